@@ -1,0 +1,170 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.  ctypes front-end to oracle/_build/liboracle.so.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+PARITY UNPINNED: see oracle/dense.hpp.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+
+MODEL_ST_LANE, MODEL_ST_CIRC, MODEL_LQR, MODEL_PENDULUM, MODEL_ROCKET = range(5)
+STRATEGY_CENTRALIZED, STRATEGY_SEQUENTIAL, STRATEGY_LINESEARCH, STRATEGY_TRUSTREGION = range(4)
+TRIG_GLIBC, TRIG_PORTABLE = 0, 1
+STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_TIME_LIMIT = 0, 1, 2
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with its Makefile (g++ only, a few seconds)."""
+    if force or not os.path.exists(_LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+    return _lib
+
+
+def _p(a, ct=ctypes.c_double):
+    if a is None:
+        return None
+    return a.ctypes.data_as(ctypes.POINTER(ct))
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def model_dims(model: int, horizon: int = 0):
+    n, m, T, dt = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+    rc = lib().oracle_model_dims(model, horizon, ctypes.byref(n), ctypes.byref(m), ctypes.byref(T), ctypes.byref(dt))
+    if rc:
+        raise ValueError(f"oracle: unknown model {model}")
+    return n.value, m.value, T.value, dt.value
+
+
+def max_threads() -> int:
+    return lib().oracle_max_threads()
+
+
+def default_controls(model: int, horizon: int = 0) -> np.ndarray:
+    n, m, T, _ = model_dims(model, horizon)
+    U = np.zeros((T, m))
+    if lib().oracle_default_controls(model, horizon, _p(U)):
+        raise RuntimeError("oracle_default_controls failed")
+    return U
+
+
+def rollout_cost(model, x0, U, params=None, horizon=0, trig=TRIG_GLIBC):
+    x0 = _f64(x0)
+    U = _f64(U)
+    batch = x0.shape[0]
+    n, m, T, _ = model_dims(model, horizon)
+    params = _f64(params)
+    np_ = 0 if params is None else params.shape[1]
+    X = np.zeros((batch, T + 1, n))
+    cost = np.zeros(batch)
+    rc = lib().oracle_rollout_cost(model, batch, _p(x0), _p(params), np_, horizon, _p(U), trig, _p(X), _p(cost))
+    if rc:
+        raise RuntimeError("oracle_rollout_cost failed")
+    return X, cost
+
+
+def ilqr_solve_batch(model, x0, U_init=None, params=None, horizon=0, max_iterations=10, tolerance=1e-5, max_ms=float("inf"),
+                     trig=TRIG_GLIBC, aliased_sym=True, threads=0):
+    """Returns dict(X[batch,T+1,n], U[batch,T,m], cost, iterations, status, rollouts, alpha_trials, reg_retries)."""
+    x0 = _f64(x0)
+    batch = x0.shape[0]
+    n, m, T, _ = model_dims(model, horizon)
+    if U_init is None:
+        U = np.broadcast_to(default_controls(model, horizon), (batch, T, m)).copy()
+    else:
+        U = np.array(U_init, dtype=np.float64, order="C").reshape(batch, T, m).copy()
+    params = _f64(params)
+    np_ = 0 if params is None else params.shape[1]
+    X = np.zeros((batch, T + 1, n))
+    cost = np.zeros(batch)
+    iters = np.zeros(batch, dtype=np.int32)
+    status = np.zeros(batch, dtype=np.int32)
+    stats = np.zeros((batch, 3), dtype=np.int32)
+    rc = lib().oracle_ilqr_solve_batch(
+        model, batch, _p(x0), _p(params), np_, horizon, _p(U), int(max_iterations), ctypes.c_double(tolerance), ctypes.c_double(max_ms),
+        int(trig), int(bool(aliased_sym)), int(threads), _p(X), _p(cost), _p(iters, ctypes.c_int), _p(status, ctypes.c_int),
+        _p(stats, ctypes.c_int))
+    if rc:
+        raise RuntimeError("oracle_ilqr_solve_batch failed")
+    return dict(X=X, U=U, cost=cost, iterations=iters, status=status, rollouts=stats[:, 0], alpha_trials=stats[:, 1], reg_retries=stats[:, 2])
+
+
+def ilqr_solve_trace(model, x0, U_init=None, params=None, horizon=0, max_iterations=10, tolerance=1e-5, trig=TRIG_GLIBC, aliased_sym=True):
+    x0 = _f64(x0).reshape(-1)
+    n, m, T, _ = model_dims(model, horizon)
+    U = default_controls(model, horizon) if U_init is None else np.array(U_init, dtype=np.float64).reshape(T, m).copy()
+    params = _f64(params)
+    np_ = 0 if params is None else params.size
+    cost_trace = np.zeros(max_iterations)
+    alpha_trace = np.zeros(max_iterations, dtype=np.int32)
+    n_trace = ctypes.c_int()
+    stats = np.zeros(3, dtype=np.int32)
+    rc = lib().oracle_ilqr_solve_trace(model, _p(x0), _p(params), np_, horizon, _p(U), int(max_iterations), ctypes.c_double(tolerance), int(trig),
+                                       int(bool(aliased_sym)), _p(cost_trace), _p(alpha_trace, ctypes.c_int), ctypes.byref(n_trace),
+                                       _p(stats, ctypes.c_int))
+    if rc:
+        raise RuntimeError("oracle_ilqr_solve_trace failed")
+    k = n_trace.value
+    return dict(U=U, cost_trace=cost_trace[:k], alpha_index=alpha_trace[:k], rollouts=int(stats[0]), alpha_trials=int(stats[1]),
+                reg_retries=int(stats[2]))
+
+
+def strategy_run_batch(kind, model, x0, params=None, horizon=0, max_outer=10, max_iterations=100, tolerance=1e-5, max_ms=float("inf"),
+                       trig=TRIG_GLIBC, aliased_sym=True, threads=0):
+    """x0: [scenarios, agents, n].  Returns dict(X, U, costs, total_cost, trace_iters, trace_accept, trace_cost)."""
+    x0 = _f64(x0)
+    S, A = x0.shape[0], x0.shape[1]
+    n, m, T, _ = model_dims(model, horizon)
+    params = _f64(params)
+    np_ = 0 if params is None else params.shape[-1]
+    X = np.zeros((S, A, T + 1, n))
+    U = np.zeros((S, A, T, m))
+    costs = np.zeros((S, A))
+    total = np.zeros(S)
+    t_it = np.zeros((S, max_outer, A), dtype=np.int32)
+    t_acc = np.zeros((S, max_outer, A), dtype=np.int32)
+    t_cost = np.zeros((S, max_outer, A))
+    rc = lib().oracle_strategy_run_batch(
+        int(kind), model, S, A, _p(x0), _p(params), np_, horizon, int(max_outer), int(max_iterations), ctypes.c_double(tolerance),
+        ctypes.c_double(max_ms), int(trig), int(bool(aliased_sym)), int(threads), _p(X), _p(U), _p(costs), _p(total), _p(t_it, ctypes.c_int),
+        _p(t_acc, ctypes.c_int), _p(t_cost))
+    if rc:
+        raise RuntimeError("oracle_strategy_run_batch failed")
+    return dict(X=X, U=U, costs=costs, total_cost=total, trace_iters=t_it, trace_accept=t_acc, trace_cost=t_cost)
+
+
+def global_ocp_eval(model, x0, X, U, params=None, horizon=0):
+    x0 = _f64(x0)
+    A = x0.shape[0]
+    params = _f64(params)
+    np_ = 0 if params is None else params.shape[-1]
+    X = _f64(X)
+    U = _f64(U)
+    dyn = np.zeros(X.size)
+    stage = ctypes.c_double()
+    term = ctypes.c_double()
+    dims = np.zeros(3, dtype=np.int32)
+    rc = lib().oracle_global_ocp_eval(model, A, _p(x0), _p(params), np_, horizon, _p(X), _p(U), _p(dyn), ctypes.byref(stage), ctypes.byref(term),
+                                      _p(dims, ctypes.c_int))
+    if rc:
+        raise RuntimeError("oracle_global_ocp_eval failed")
+    return dyn, stage.value, term.value, dims
