@@ -1,0 +1,209 @@
+/*
+ * mas_b200.h -- C ABI of the B200 batched iLQR engine (libmas_b200.so).
+ *
+ * Drop-in boundary for the iLQR path of markomiz/multi_agent_solver.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference repository root).  Plain
+ * pointers and sizes only; all host arrays are caller-owned, row-major as written below, which for a
+ * single problem is exactly the memory of the reference's column-major Eigen matrices
+ * (StateTrajectory n x (T+1) column-major == [T+1][n] row-major; ControlTrajectory m x T == [T][m]).
+ *
+ * The reference passes problems as std::function callbacks (types.hpp:21-50), which cannot run on
+ * a GPU; here a problem is `model_id` + a POD parameter block selecting a registered device functor
+ * set (multi_agent_solver_b200/csrc/models.cuh), and `deriv_mask` states which derivative callbacks
+ * are analytic -- the rest use the finite-difference defaults OCP::initialize_problem() installs
+ * (ocp.hpp:117-135).
+ *
+ * Every function returns MAS_B200_OK or an error code; mas_b200_last_error() gives the message of
+ * the calling thread's last failure.  There is no CPU fallback: without a CUDA device every call
+ * that touches a context fails with MAS_B200_ERR_CUDA.
+ */
+#ifndef MAS_B200_H
+#define MAS_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes; the C++ facade rethrows them as the reference's exception types ------------- */
+#define MAS_B200_OK 0
+#define MAS_B200_ERR_INVALID_ARGUMENT 1 /* std::invalid_argument (examples/example_utils.hpp:77-110) */
+#define MAS_B200_ERR_OUT_OF_RANGE 2     /* std::out_of_range, missing required solver param (solvers/ilqr.hpp:42-44) */
+#define MAS_B200_ERR_CUDA 3             /* std::runtime_error */
+#define MAS_B200_ERR_NCCL 4             /* std::runtime_error */
+#define MAS_B200_ERR_UNSUPPORTED 5      /* std::runtime_error: feature of the reference not on the device path */
+
+/* ---- registered models (the reference's example OCPs) ---------------------------------------- */
+#define MAS_B200_MODEL_SINGLE_TRACK_LANE 0 /* examples/single_track_ocp.cpp:14-116         n4 m2 */
+#define MAS_B200_MODEL_SINGLE_TRACK_CIRC 1 /* examples/multi_agent_single_track.cpp:31-72  n4 m2 */
+#define MAS_B200_MODEL_LQR4 2              /* examples/multi_agent_lqr.cpp:21-76           n4 m4 */
+#define MAS_B200_MODEL_PENDULUM 3          /* examples/pendulum_swing_up.cpp:29-117        n2 m1 */
+#define MAS_B200_MODEL_ROCKET 4            /* examples/rocket_max_altitude.cpp:31-137      n3 m1 */
+#define MAS_B200_NUM_MODELS 5
+
+/* derivative-mode bits: set = analytic callback installed, clear = finite-difference default */
+#define MAS_B200_DERIV_A (1u << 0)   /* OCP::dynamics_state_jacobian   (ocp.hpp:71)  */
+#define MAS_B200_DERIV_B (1u << 1)   /* OCP::dynamics_control_jacobian (ocp.hpp:72)  */
+#define MAS_B200_DERIV_LX (1u << 2)  /* OCP::cost_state_gradient       (ocp.hpp:73)  */
+#define MAS_B200_DERIV_LU (1u << 3)  /* OCP::cost_control_gradient     (ocp.hpp:74)  */
+#define MAS_B200_DERIV_LXX (1u << 4) /* OCP::cost_state_hessian        (ocp.hpp:75)  */
+#define MAS_B200_DERIV_LUU (1u << 5) /* OCP::cost_control_hessian      (ocp.hpp:76)  */
+#define MAS_B200_DERIV_LUX (1u << 6) /* OCP::cost_cross_term           (ocp.hpp:77)  */
+#define MAS_B200_DERIV_VX (1u << 7)  /* OCP::terminal_cost_gradient    (ocp.hpp:78)  */
+#define MAS_B200_DERIV_VXX (1u << 8) /* OCP::terminal_cost_hessian     (ocp.hpp:79)  */
+
+/* per-problem result flag; the reference's solve() returns void, the definition is SURVEY 8a */
+#define MAS_B200_STATUS_CONVERGED 0  /* break at solvers/ilqr.hpp:269-271 */
+#define MAS_B200_STATUS_MAX_ITER 1   /* loop at :82 exhausted */
+#define MAS_B200_STATUS_TIME_LIMIT 2 /* break at :85-90 */
+
+/* strategies (strategies/strategy.hpp:13, examples/example_utils.hpp:94-110) */
+#define MAS_B200_STRATEGY_CENTRALIZED 0
+#define MAS_B200_STRATEGY_SEQUENTIAL 1
+#define MAS_B200_STRATEGY_LINESEARCH 2
+#define MAS_B200_STRATEGY_TRUSTREGION 3
+
+#define MAS_B200_MAX_CONTROL_DIM 8
+#define MAS_B200_MAX_PARAMS 8
+
+typedef struct mas_b200_context* mas_b200_context_t; /* one device + one stream; single owner, not thread-safe */
+typedef struct mas_b200_batch* mas_b200_batch_t;     /* a batch of same-shaped OCPs resident in HBM */
+
+/* struct OCP as far as iLQR reads it (ocp.hpp:30-81): dims, horizon, dt, input bounds, which
+ * derivative callbacks are analytic, and the cost/dynamics constants of the selected model. */
+typedef struct {
+  int model_id;
+  int state_dim;     /* must equal the model's; checked */
+  int control_dim;
+  int horizon_steps; /* OCP::horizon_steps */
+  double dt;         /* OCP::dt */
+  unsigned deriv_mask;
+  int has_input_bounds; /* both input_lower_bounds and input_upper_bounds set (ilqr.hpp:213) */
+  double input_lower[MAS_B200_MAX_CONTROL_DIM];
+  double input_upper[MAS_B200_MAX_CONTROL_DIM];
+  int num_params; /* 0 = the example's constants */
+  double params[MAS_B200_MAX_PARAMS];
+} mas_b200_ocp_desc;
+
+/* iLQR::set_params keys (solvers/ilqr.hpp:40-55); defaults of the constructor (:26-37) */
+typedef struct {
+  int max_iterations;
+  double tolerance;
+  double max_ms; /* wall-clock budget for the whole batch, checked before each iteration; INFINITY disables */
+  int debug;
+  double penalty;
+  double penalty_increase;
+  double constraint_tolerance;
+  double inequality_activation_tolerance;
+} mas_b200_ilqr_params;
+
+/* Raw HBM view of a batch for callers that keep data resident (layout: DESIGN.md "HBM layout"). */
+typedef struct {
+  int batch, ld, state_dim, control_dim, horizon_steps;
+  double* x0;     /* [n][ld] */
+  double* X;      /* [T+1][n][ld]  best_states   */
+  double* U;      /* [T][m][ld]    best_controls */
+  double* cost;   /* [ld]          best_cost     */
+  int* iterations;
+  int* status;
+  double* params; /* [np][ld] or NULL */
+} mas_b200_device_view;
+
+typedef struct {
+  long long iterations;   /* sum over problems */
+  long long alpha_trials; /* candidates the sequential reference would evaluate */
+  long long reg_retries;
+  long long kernel_launches; /* since batch creation */
+  int outer_iterations_run;  /* host loop trips of the last solve */
+  int forward_lanes, forward_chains;
+} mas_b200_batch_stats;
+
+/* Per-kernel device time of the solves run while profiling was enabled: CUDA events recorded on the
+ * context stream around every launch (the kernels run back to back on that one stream). */
+typedef struct {
+  double prologue_ms, backward_ms, forward_ms;
+  long long prologue_launches, backward_launches, forward_launches;
+  long long problem_iterations; /* sum over iterations of the problems still active = units one backward+forward pair processed */
+  long long solves;
+} mas_b200_profile;
+
+const char* mas_b200_last_error(void);
+int mas_b200_version(void);
+
+/* iLQR::iLQR() defaults (solvers/ilqr.hpp:26-37) */
+void mas_b200_ilqr_default_params(mas_b200_ilqr_params* p);
+
+/* Model registry: examples::make_* equivalents.  default_params may be NULL. */
+int mas_b200_model_info(int model_id, int* state_dim, int* control_dim, int* num_params, unsigned* available_mask, unsigned* example_mask,
+                        double* default_params);
+/* The example's OCP as the reference main builds it (dims, T, dt, bounds, derivative mode). */
+int mas_b200_example_desc(int model_id, mas_b200_ocp_desc* out);
+/* The example's initial_controls, [T][m] (zeros except pendulum sinusoid / rocket half thrust). */
+int mas_b200_example_controls(int model_id, int horizon_steps, double* U);
+
+/* device_id < 0: current device.  stream: a cudaStream_t to run on, or NULL to create one. */
+int mas_b200_context_create(int device_id, void* stream, mas_b200_context_t* out);
+int mas_b200_context_destroy(mas_b200_context_t ctx);
+int mas_b200_context_synchronize(mas_b200_context_t ctx);
+
+/* Pinned host memory for callers that want full-speed copies. */
+int mas_b200_host_alloc(size_t bytes, void** out);
+int mas_b200_host_free(void* p);
+
+/* ---- batch of OCPs: struct OCP x batch ---------------------------------------------------------- */
+int mas_b200_batch_create(mas_b200_context_t ctx, const mas_b200_ocp_desc* desc, int batch, mas_b200_batch_t* out);
+int mas_b200_batch_destroy(mas_b200_batch_t b);
+/* OCP::initial_state, [batch][n] */
+int mas_b200_batch_set_initial_states(mas_b200_batch_t b, const double* x0);
+/* per-problem model constants, [batch][num_params]; NULL = desc.params for all */
+int mas_b200_batch_set_params(mas_b200_batch_t b, const double* params);
+/* OCP::initial_controls -> best_controls, [batch][T][m]; NULL = zeros */
+int mas_b200_batch_set_controls(mas_b200_batch_t b, const double* U);
+/* OCP::initialize_problem (ocp.hpp:102-183): rollout of the controls and best_cost */
+int mas_b200_batch_initialize(mas_b200_batch_t b);
+/* mas::solve(Solver&, OCP&) (solvers/solver.hpp:28-32 -> iLQR::solve, solvers/ilqr.hpp:59-273) for
+ * every problem of the batch; warm-starts from best_controls.  Asynchronous on the context stream. */
+int mas_b200_batch_solve(mas_b200_batch_t b, const mas_b200_ilqr_params* params);
+/* OCP::best_states [batch][T+1][n], best_controls [batch][T][m], best_cost [batch], plus the
+ * counters the reference lacks.  Any pointer may be NULL.  Synchronises. */
+int mas_b200_batch_get_solution(mas_b200_batch_t b, double* X, double* U, double* cost, int* iterations, int* status);
+int mas_b200_batch_get_device_view(mas_b200_batch_t b, mas_b200_device_view* out);
+int mas_b200_batch_get_stats(mas_b200_batch_t b, mas_b200_batch_stats* out);
+int mas_b200_batch_set_profiling(mas_b200_batch_t b, int enable); /* resets the accumulated profile */
+int mas_b200_batch_get_profile(mas_b200_batch_t b, mas_b200_profile* out);
+/* Tuning of the line-search kernel: lanes per problem (1,2,4,8,16; 0 = auto from batch size) and
+ * step sizes rolled out together per lane (1 or 2; 0 = auto). */
+int mas_b200_batch_set_tuning(mas_b200_batch_t b, int forward_lanes, int forward_chains);
+
+/* One-shot: set_initial_states + set_controls + initialize + solve + get_solution on host buffers.
+ * U is in/out (initial_controls in, best_controls out; NULL = zero initial controls, not returned). */
+int mas_b200_ilqr_solve_batch(mas_b200_context_t ctx, const mas_b200_ocp_desc* desc, const mas_b200_ilqr_params* params, int batch,
+                              const double* x0, const double* model_params, double* U, double* X, double* cost, int* iterations, int* status);
+
+/* ---- multi-agent strategies: mas::solve(Strategy&, MultiAgentProblem&) (strategies/strategy.hpp:15-19)
+ * on n_scenarios independent scenarios of n_agents agents each; agents have ids 0..n_agents-1 in
+ * array order (already the id-sorted block order of MultiAgentProblem::compute_offsets,
+ * multi_agent_problem.hpp:37-50).  Arrays are [scenario][agent][...].  trace_* may be NULL:
+ * [scenario][outer][agent] inner iteration counts / accepted flags / best_cost after the round. */
+int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_ocp_desc* agent_desc, const mas_b200_ilqr_params* params,
+                          int max_outer, int n_scenarios, int n_agents, const double* x0, const double* model_params, double* X, double* U,
+                          double* costs, double* total_cost, int* trace_iterations, int* trace_accepted, double* trace_cost);
+
+/* ---- multi-GPU (one process per GPU).  unique_id: 128 bytes from mas_b200_nccl_unique_id on rank 0,
+ * distributed by the caller (torch.distributed / MPI / file). ------------------------------------- */
+int mas_b200_nccl_unique_id(void* id128);
+int mas_b200_context_init_nccl(mas_b200_context_t ctx, const void* id128, int rank, int world_size);
+
+/* Synthetic inputs of the headline batch: x0_i = (0, Y, psi, v) with Y~U(-2,2),
+ * psi~U(-0.5,0.5), v~U(0,2) from std::mt19937_64(seed), drawn in that order, problem-major.
+ * Host-only helper (no device needed); x0 is [batch][4]. */
+int mas_b200_synthetic_single_track_x0(unsigned long long seed, int batch, double* x0);
+
+/* fp64 pipe peak probe (DFMA throughput in TFLOP/s on the context device) for roofline reporting */
+int mas_b200_probe_fp64_peak(mas_b200_context_t ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAS_B200_H */

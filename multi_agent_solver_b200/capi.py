@@ -1,0 +1,317 @@
+"""ctypes binding of include/mas_b200.h (libmas_b200.so).  No algorithm lives here."""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_PKG, "libmas_b200.so")
+_lib: Optional[ctypes.CDLL] = None
+
+MAX_CONTROL_DIM = 8
+MAX_PARAMS = 8
+
+
+class Model:
+    SINGLE_TRACK_LANE, SINGLE_TRACK_CIRC, LQR4, PENDULUM, ROCKET = range(5)
+
+
+class Status:
+    CONVERGED, MAX_ITER, TIME_LIMIT = range(3)
+
+
+class Strategy:
+    CENTRALIZED, SEQUENTIAL, LINESEARCH, TRUSTREGION = range(4)
+
+
+class DerivBits:
+    A, B, LX, LU, LXX, LUU, LUX, VX, VXX = (1 << i for i in range(9))
+
+
+class MasB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"mas_b200 error {code}: {msg}")
+        self.code = code
+
+
+class OcpDesc(ctypes.Structure):
+    _fields_ = [
+        ("model_id", ctypes.c_int),
+        ("state_dim", ctypes.c_int),
+        ("control_dim", ctypes.c_int),
+        ("horizon_steps", ctypes.c_int),
+        ("dt", ctypes.c_double),
+        ("deriv_mask", ctypes.c_uint),
+        ("has_input_bounds", ctypes.c_int),
+        ("input_lower", ctypes.c_double * MAX_CONTROL_DIM),
+        ("input_upper", ctypes.c_double * MAX_CONTROL_DIM),
+        ("num_params", ctypes.c_int),
+        ("params", ctypes.c_double * MAX_PARAMS),
+    ]
+
+
+class IlqrParams(ctypes.Structure):
+    _fields_ = [
+        ("max_iterations", ctypes.c_int),
+        ("tolerance", ctypes.c_double),
+        ("max_ms", ctypes.c_double),
+        ("debug", ctypes.c_int),
+        ("penalty", ctypes.c_double),
+        ("penalty_increase", ctypes.c_double),
+        ("constraint_tolerance", ctypes.c_double),
+        ("inequality_activation_tolerance", ctypes.c_double),
+    ]
+
+    @staticmethod
+    def make(max_iterations: int, tolerance: float, max_ms: float = float("inf")) -> "IlqrParams":
+        p = IlqrParams()
+        load_library().mas_b200_ilqr_default_params(ctypes.byref(p))
+        p.max_iterations = int(max_iterations)
+        p.tolerance = float(tolerance)
+        p.max_ms = float(max_ms)
+        return p
+
+
+class DeviceView(ctypes.Structure):
+    _fields_ = [
+        ("batch", ctypes.c_int), ("ld", ctypes.c_int), ("state_dim", ctypes.c_int), ("control_dim", ctypes.c_int), ("horizon_steps", ctypes.c_int),
+        ("x0", ctypes.c_void_p), ("X", ctypes.c_void_p), ("U", ctypes.c_void_p), ("cost", ctypes.c_void_p),
+        ("iterations", ctypes.c_void_p), ("status", ctypes.c_void_p), ("params", ctypes.c_void_p),
+    ]
+
+
+class BatchStats(ctypes.Structure):
+    _fields_ = [
+        ("iterations", ctypes.c_longlong), ("alpha_trials", ctypes.c_longlong), ("reg_retries", ctypes.c_longlong),
+        ("kernel_launches", ctypes.c_longlong), ("outer_iterations_run", ctypes.c_int), ("forward_lanes", ctypes.c_int),
+        ("forward_chains", ctypes.c_int),
+    ]
+
+
+class Profile(ctypes.Structure):
+    _fields_ = [
+        ("prologue_ms", ctypes.c_double), ("backward_ms", ctypes.c_double), ("forward_ms", ctypes.c_double),
+        ("prologue_launches", ctypes.c_longlong), ("backward_launches", ctypes.c_longlong), ("forward_launches", ctypes.c_longlong),
+        ("problem_iterations", ctypes.c_longlong), ("solves", ctypes.c_longlong),
+    ]
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def load_library() -> ctypes.CDLL:
+    """Loads libmas_b200.so.  Raises if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise ImportError(f"{_LIB_PATH} is missing: build it with `python -m multi_agent_solver_b200.build` (needs nvcc). "
+                              "multi_agent_solver_b200 has no CPU fallback.")
+        lib = ctypes.CDLL(_LIB_PATH)
+        lib.mas_b200_last_error.restype = ctypes.c_char_p
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise MasB200Error(rc, load_library().mas_b200_last_error().decode())
+
+
+def _dptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _iptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def model_info(model_id: int):
+    nx, nu, npar = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    avail, ex = ctypes.c_uint(), ctypes.c_uint()
+    dp = (ctypes.c_double * MAX_PARAMS)()
+    _check(load_library().mas_b200_model_info(model_id, ctypes.byref(nx), ctypes.byref(nu), ctypes.byref(npar), ctypes.byref(avail),
+                                               ctypes.byref(ex), dp))
+    return dict(state_dim=nx.value, control_dim=nu.value, num_params=npar.value, available_mask=avail.value, example_mask=ex.value,
+                default_params=list(dp)[: npar.value])
+
+
+def example_desc(model_id: int, horizon_steps: int = 0) -> OcpDesc:
+    d = OcpDesc()
+    _check(load_library().mas_b200_example_desc(model_id, ctypes.byref(d)))
+    if horizon_steps > 0:
+        d.horizon_steps = horizon_steps
+        if model_id == Model.PENDULUM:
+            d.params[0] = float(horizon_steps)
+    return d
+
+
+def synthetic_single_track_x0(batch: int, seed: int = 20240607) -> np.ndarray:
+    """Config-3 initial states: std::mt19937_64(seed), Y, psi, v per problem."""
+    x0 = np.empty((batch, 4))
+    _check(load_library().mas_b200_synthetic_single_track_x0(ctypes.c_ulonglong(seed), int(batch), _dptr(x0)))
+    return x0
+
+
+def example_controls(model_id: int, horizon_steps: int) -> np.ndarray:
+    nu = model_info(model_id)["control_dim"]
+    U = np.zeros((horizon_steps, nu))
+    _check(load_library().mas_b200_example_controls(model_id, horizon_steps, _dptr(U)))
+    return U
+
+
+class Context:
+    """mas_b200_context_t: one device, one stream."""
+
+    def __init__(self, device_id: int = -1, stream: int = 0):
+        self._h = ctypes.c_void_p()
+        _check(load_library().mas_b200_context_create(int(device_id), ctypes.c_void_p(stream or None), ctypes.byref(self._h)))
+
+    def synchronize(self) -> None:
+        _check(load_library().mas_b200_context_synchronize(self._h))
+
+    def init_nccl(self, unique_id: bytes, rank: int, world_size: int) -> None:
+        buf = ctypes.create_string_buffer(unique_id, 128)
+        _check(load_library().mas_b200_context_init_nccl(self._h, buf, int(rank), int(world_size)))
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        _check(load_library().mas_b200_nccl_unique_id(buf))
+        return buf.raw
+
+    def probe_fp64_peak(self) -> float:
+        tf = ctypes.c_double()
+        _check(load_library().mas_b200_probe_fp64_peak(self._h, ctypes.byref(tf)))
+        return tf.value
+
+    def close(self) -> None:
+        if self._h:
+            load_library().mas_b200_context_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch:
+    """mas_b200_batch_t: `batch` same-shaped OCPs resident in HBM."""
+
+    def __init__(self, ctx: Context, desc: OcpDesc, batch: int):
+        self.ctx = ctx
+        self.desc = desc
+        self.batch = int(batch)
+        self.nx, self.nu, self.T = desc.state_dim, desc.control_dim, desc.horizon_steps
+        self._h = ctypes.c_void_p()
+        _check(load_library().mas_b200_batch_create(ctx._h, ctypes.byref(desc), self.batch, ctypes.byref(self._h)))
+
+    def set_initial_states(self, x0) -> None:
+        x0 = _f64(x0)
+        assert x0.shape == (self.batch, self.nx)
+        self._x0_keep = x0
+        _check(load_library().mas_b200_batch_set_initial_states(self._h, _dptr(x0)))
+
+    def set_params(self, params) -> None:
+        params = _f64(params)
+        self._p_keep = params
+        _check(load_library().mas_b200_batch_set_params(self._h, _dptr(params)))
+
+    def set_controls(self, U=None) -> None:
+        U = _f64(U)
+        if U is not None:
+            assert U.shape == (self.batch, self.T, self.nu)
+        self._u_keep = U
+        _check(load_library().mas_b200_batch_set_controls(self._h, _dptr(U)))
+
+    def initialize(self) -> None:
+        _check(load_library().mas_b200_batch_initialize(self._h))
+
+    def solve(self, params: IlqrParams) -> None:
+        _check(load_library().mas_b200_batch_solve(self._h, ctypes.byref(params)))
+
+    def set_profiling(self, enable: bool) -> None:
+        _check(load_library().mas_b200_batch_set_profiling(self._h, int(bool(enable))))
+
+    def profile(self) -> dict:
+        p = Profile()
+        _check(load_library().mas_b200_batch_get_profile(self._h, ctypes.byref(p)))
+        return {k: getattr(p, k) for k, _ in Profile._fields_}
+
+    def set_tuning(self, forward_lanes: int = 0, forward_chains: int = 0) -> None:
+        _check(load_library().mas_b200_batch_set_tuning(self._h, int(forward_lanes), int(forward_chains)))
+
+    def get_solution(self, out=None):
+        if out is None:
+            out = dict(X=np.empty((self.batch, self.T + 1, self.nx)), U=np.empty((self.batch, self.T, self.nu)), cost=np.empty(self.batch),
+                       iterations=np.empty(self.batch, dtype=np.int32), status=np.empty(self.batch, dtype=np.int32))
+        _check(load_library().mas_b200_batch_get_solution(self._h, _dptr(out.get("X")), _dptr(out.get("U")), _dptr(out.get("cost")),
+                                                           _iptr(out.get("iterations")), _iptr(out.get("status"))))
+        return out
+
+    def device_view(self) -> DeviceView:
+        v = DeviceView()
+        _check(load_library().mas_b200_batch_get_device_view(self._h, ctypes.byref(v)))
+        return v
+
+    def stats(self) -> dict:
+        s = BatchStats()
+        _check(load_library().mas_b200_batch_get_stats(self._h, ctypes.byref(s)))
+        return {k: getattr(s, k) for k, _ in BatchStats._fields_}
+
+    def close(self) -> None:
+        if self._h:
+            load_library().mas_b200_batch_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ilqr_solve_batch(ctx: Context, desc: OcpDesc, params: IlqrParams, x0, U=None, model_params=None):
+    """mas_b200_ilqr_solve_batch: one-shot solve on host arrays."""
+    x0 = _f64(x0)
+    batch = x0.shape[0]
+    T, nx, nu = desc.horizon_steps, desc.state_dim, desc.control_dim
+    Uio = None if U is None else np.array(U, dtype=np.float64, order="C").reshape(batch, T, nu).copy()
+    model_params = _f64(model_params)
+    X = np.empty((batch, T + 1, nx))
+    cost = np.empty(batch)
+    it = np.empty(batch, dtype=np.int32)
+    st = np.empty(batch, dtype=np.int32)
+    if Uio is None:
+        Uio = np.zeros((batch, T, nu))
+    _check(load_library().mas_b200_ilqr_solve_batch(ctx._h, ctypes.byref(desc), ctypes.byref(params), batch, _dptr(x0), _dptr(model_params),
+                                                     _dptr(Uio), _dptr(X), _dptr(cost), _iptr(it), _iptr(st)))
+    return dict(X=X, U=Uio, cost=cost, iterations=it, status=st)
+
+
+def strategy_run(ctx: Context, strategy: int, desc: OcpDesc, params: IlqrParams, max_outer: int, x0, model_params=None, trace: bool = True):
+    """mas_b200_strategy_run.  x0: [scenarios, agents, n]."""
+    x0 = _f64(x0)
+    S, A = x0.shape[0], x0.shape[1]
+    T, nx, nu = desc.horizon_steps, desc.state_dim, desc.control_dim
+    model_params = _f64(model_params)
+    X = np.empty((S, A, T + 1, nx))
+    U = np.empty((S, A, T, nu))
+    costs = np.empty((S, A))
+    total = np.empty(S)
+    t_it = np.zeros((S, max_outer, A), dtype=np.int32) if trace else None
+    t_acc = np.zeros((S, max_outer, A), dtype=np.int32) if trace else None
+    t_cost = np.zeros((S, max_outer, A)) if trace else None
+    _check(load_library().mas_b200_strategy_run(ctx._h, int(strategy), ctypes.byref(desc), ctypes.byref(params), int(max_outer), S, A, _dptr(x0),
+                                                 _dptr(model_params), _dptr(X), _dptr(U), _dptr(costs), _dptr(total), _iptr(t_it), _iptr(t_acc),
+                                                 _dptr(t_cost)))
+    return dict(X=X, U=U, costs=costs, total_cost=total, trace_iters=t_it, trace_accept=t_acc, trace_cost=t_cost)

@@ -1,0 +1,585 @@
+// capi.cu -- extern "C" entry points declared in include/mas_b200.h.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <limits>
+#include <new>
+#include <random>
+
+#include "engine.cuh"
+
+namespace mas_b200 {
+const std::string& last_error();
+
+struct ModelInfo {
+  int nx, nu, np;
+  unsigned available, example_mask;
+  double default_params[kMaxParams];
+  BatchBase* (*make)();
+};
+
+static const ModelInfo kModels[MAS_B200_NUM_MODELS] = {
+    {StLane::NX, StLane::NU, StLane::NP, StLane::AVAILABLE, StLane::EXAMPLE_MASK, {1.0, 10.0, 1.0, 0.1, 0.1}, make_batch_st_lane},
+    {StCirc::NX, StCirc::NU, StCirc::NP, StCirc::AVAILABLE, StCirc::EXAMPLE_MASK, {20.0, 5.0, 1.0, 1.0, 0.001, 0.001}, make_batch_st_circ},
+    {Lqr4::NX, Lqr4::NU, Lqr4::NP, Lqr4::AVAILABLE, Lqr4::EXAMPLE_MASK, {0}, make_batch_lqr4},
+    {Pendulum::NX, Pendulum::NU, Pendulum::NP, Pendulum::AVAILABLE, Pendulum::EXAMPLE_MASK, {60.0}, make_batch_pendulum},
+    {Rocket::NX, Rocket::NU, Rocket::NP, Rocket::AVAILABLE, Rocket::EXAMPLE_MASK, {9.81, 50.0, 5e-3, 15.0, 2.0, 0.0}, make_batch_rocket},
+};
+
+static int fail(int code, const std::string& msg) {
+  set_last_error(msg);
+  return code;
+}
+
+// ---- NCCL, resolved at run time so the library loads without it ------------------------------------
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.handle) return MAS_B200_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(MAS_B200_ERR_NCCL, std::string("dlopen libnccl.so.2 failed: ") + dlerror());
+  g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+  g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+  g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+  g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(dlsym(h, "ncclAllGather"));
+  g_nccl.GroupStart = reinterpret_cast<decltype(g_nccl.GroupStart)>(dlsym(h, "ncclGroupStart"));
+  g_nccl.GroupEnd = reinterpret_cast<decltype(g_nccl.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
+  g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.GroupStart || !g_nccl.GroupEnd || !g_nccl.CommDestroy)
+    return fail(MAS_B200_ERR_NCCL, "libnccl is missing required symbols");
+  g_nccl.handle = h;
+  return MAS_B200_OK;
+}
+
+#define MAS_NCCL_CHECK(expr)                                                                                        \
+  do {                                                                                                              \
+    ncclResult_t r__ = (expr);                                                                                      \
+    if (r__ != ncclSuccess)                                                                                         \
+      return fail(MAS_B200_ERR_NCCL, std::string(#expr) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error")); \
+  } while (0)
+
+static int validate_desc(const mas_b200_ocp_desc* d) {
+  if (!d) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "desc is NULL");
+  if (d->model_id < 0 || d->model_id >= MAS_B200_NUM_MODELS) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "unknown model_id");
+  const ModelInfo& m = kModels[d->model_id];
+  if (d->state_dim != m.nx || d->control_dim != m.nu)
+    return fail(MAS_B200_ERR_INVALID_ARGUMENT, "state_dim/control_dim do not match the registered model");
+  if (d->horizon_steps <= 0) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "horizon_steps must be positive");
+  if (!(d->dt != 0.0)) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "dt is 0.0");
+  if (d->deriv_mask & ~m.available) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "deriv_mask asks for an analytic derivative the model does not provide");
+  if (d->num_params != 0 && d->num_params != m.np) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "num_params must be 0 or the model's parameter count");
+  return MAS_B200_OK;
+}
+
+static int validate_params(const mas_b200_ilqr_params* p) {
+  if (!p) return fail(MAS_B200_ERR_OUT_OF_RANGE, "solver params missing (max_iterations, tolerance, max_ms are required)");
+  if (p->max_iterations < 0) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "max_iterations < 0");
+  if (std::isnan(p->tolerance) || std::isnan(p->max_ms)) return fail(MAS_B200_ERR_OUT_OF_RANGE, "tolerance / max_ms not set");
+  return MAS_B200_OK;
+}
+
+}  // namespace mas_b200
+
+using namespace mas_b200;
+
+struct mas_b200_context {
+  Context c;
+};
+struct mas_b200_batch {
+  BatchBase* b;
+};
+
+extern "C" {
+
+const char* mas_b200_last_error(void) { return last_error().c_str(); }
+int mas_b200_version(void) { return 100; }
+
+void mas_b200_ilqr_default_params(mas_b200_ilqr_params* p) {
+  if (!p) return;
+  p->max_iterations = 50;
+  p->tolerance = 1e-6;
+  p->max_ms = std::numeric_limits<double>::infinity();
+  p->debug = 0;
+  p->penalty = 10.0;
+  p->penalty_increase = 5.0;
+  p->constraint_tolerance = 1e-4;
+  p->inequality_activation_tolerance = 1e-6;
+}
+
+int mas_b200_model_info(int model_id, int* state_dim, int* control_dim, int* num_params, unsigned* available_mask, unsigned* example_mask,
+                        double* default_params) {
+  if (model_id < 0 || model_id >= MAS_B200_NUM_MODELS) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "unknown model_id");
+  const ModelInfo& m = kModels[model_id];
+  if (state_dim) *state_dim = m.nx;
+  if (control_dim) *control_dim = m.nu;
+  if (num_params) *num_params = m.np;
+  if (available_mask) *available_mask = m.available;
+  if (example_mask) *example_mask = m.example_mask;
+  if (default_params)
+    for (int i = 0; i < m.np; ++i) default_params[i] = m.default_params[i];
+  return MAS_B200_OK;
+}
+
+int mas_b200_example_desc(int model_id, mas_b200_ocp_desc* out) {
+  if (model_id < 0 || model_id >= MAS_B200_NUM_MODELS || !out) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "unknown model_id or NULL desc");
+  const ModelInfo& m = kModels[model_id];
+  std::memset(out, 0, sizeof(*out));
+  out->model_id = model_id;
+  out->state_dim = m.nx;
+  out->control_dim = m.nu;
+  out->deriv_mask = m.example_mask;
+  out->num_params = m.np;
+  for (int i = 0; i < m.np; ++i) out->params[i] = m.default_params[i];
+  switch (model_id) {
+    case MAS_B200_MODEL_SINGLE_TRACK_LANE:  // single_track_ocp.cpp:21-24,105-109
+      out->horizon_steps = 80;
+      out->dt = 0.1;
+      out->has_input_bounds = 1;
+      out->input_lower[0] = -0.7;
+      out->input_lower[1] = -1.0;
+      out->input_upper[0] = 0.7;
+      out->input_upper[1] = 1.0;
+      break;
+    case MAS_B200_MODEL_SINGLE_TRACK_CIRC:  // multi_agent_single_track.cpp:36-39,66-67,108
+      out->horizon_steps = 10;
+      out->dt = 0.5;
+      out->has_input_bounds = 1;
+      out->input_lower[0] = out->input_lower[1] = -0.5;
+      out->input_upper[0] = out->input_upper[1] = 0.5;
+      break;
+    case MAS_B200_MODEL_LQR4:  // multi_agent_lqr.cpp:108-109
+      out->horizon_steps = 10;
+      out->dt = 0.1;
+      break;
+    case MAS_B200_MODEL_PENDULUM:  // pendulum_swing_up.cpp:36-37,101-103
+      out->horizon_steps = 60;
+      out->dt = 0.05;
+      out->has_input_bounds = 1;
+      out->input_lower[0] = -5.0;
+      out->input_upper[0] = 5.0;
+      break;
+    case MAS_B200_MODEL_ROCKET:  // rocket_max_altitude.cpp:42-43,116-120
+      out->horizon_steps = 50;
+      out->dt = 0.1;
+      out->has_input_bounds = 1;
+      out->input_lower[0] = 0.0;
+      out->input_upper[0] = 20.0;
+      break;
+  }
+  return MAS_B200_OK;
+}
+
+int mas_b200_example_controls(int model_id, int horizon_steps, double* U) {
+  if (model_id < 0 || model_id >= MAS_B200_NUM_MODELS || !U || horizon_steps <= 0) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "bad arguments");
+  const int nu = kModels[model_id].nu;
+  for (int i = 0; i < horizon_steps * nu; ++i) U[i] = 0.0;
+  if (model_id == MAS_B200_MODEL_PENDULUM) {  // pendulum_swing_up.cpp:109-112 (host-side setup, libm sin)
+    const double torque_max = 5.0, dt = 0.05;
+    for (int k = 0; k < horizon_steps; ++k) {
+      const double t = k * dt;
+      U[k] = 0.2 * torque_max * std::sin(2.0 * M_PI * t);
+    }
+  } else if (model_id == MAS_B200_MODEL_ROCKET) {  // rocket_max_altitude.cpp:131
+    for (int k = 0; k < horizon_steps; ++k) U[k] = 20.0 / 2.0;
+  }
+  return MAS_B200_OK;
+}
+
+int mas_b200_context_create(int device_id, void* stream, mas_b200_context_t* out) {
+  if (!out) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "out is NULL");
+  int count = 0;
+  MAS_CUDA_CHECK(cudaGetDeviceCount(&count));
+  if (count <= 0) return fail(MAS_B200_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (device_id < 0) MAS_CUDA_CHECK(cudaGetDevice(&device_id));
+  if (device_id >= count) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "device_id out of range");
+  MAS_CUDA_CHECK(cudaSetDevice(device_id));
+  auto* ctx = new (std::nothrow) mas_b200_context();
+  if (!ctx) return fail(MAS_B200_ERR_CUDA, "out of host memory");
+  ctx->c.device = device_id;
+  if (stream) {
+    ctx->c.stream = static_cast<cudaStream_t>(stream);
+  } else {
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete ctx;
+      return fail(MAS_B200_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    ctx->c.own_stream = true;
+  }
+  cudaDeviceGetAttribute(&ctx->c.sm_count, cudaDevAttrMultiProcessorCount, device_id);
+  *out = ctx;
+  return MAS_B200_OK;
+}
+
+int mas_b200_context_destroy(mas_b200_context_t ctx) {
+  if (!ctx) return MAS_B200_OK;
+  cudaSetDevice(ctx->c.device);
+  if (ctx->c.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(static_cast<ncclComm_t>(ctx->c.nccl_comm));
+  if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
+  delete ctx;
+  return MAS_B200_OK;
+}
+
+int mas_b200_context_synchronize(mas_b200_context_t ctx) {
+  if (!ctx) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  MAS_CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+  return MAS_B200_OK;
+}
+
+int mas_b200_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "out is NULL");
+  MAS_CUDA_CHECK(cudaMallocHost(out, bytes));
+  return MAS_B200_OK;
+}
+int mas_b200_host_free(void* p) {
+  if (p) MAS_CUDA_CHECK(cudaFreeHost(p));
+  return MAS_B200_OK;
+}
+
+int mas_b200_batch_create(mas_b200_context_t ctx, const mas_b200_ocp_desc* desc, int batch, mas_b200_batch_t* out) {
+  if (!ctx || !out) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "ctx/out is NULL");
+  int rc = validate_desc(desc);
+  if (rc) return rc;
+  if (batch <= 0) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "batch must be positive");
+  const ModelInfo& m = kModels[desc->model_id];
+  BatchBase* b = m.make();
+  b->ctx = &ctx->c;
+  b->desc = *desc;
+  if (desc->num_params == 0) {
+    b->desc.num_params = m.np;
+    for (int i = 0; i < m.np; ++i) b->desc.params[i] = m.default_params[i];
+    if (desc->model_id == MAS_B200_MODEL_PENDULUM) b->desc.params[0] = static_cast<double>(desc->horizon_steps);
+  }
+  b->batch = batch;
+  b->nx = m.nx;
+  b->nu = m.nu;
+  b->np = m.np;
+  b->T = desc->horizon_steps;
+  rc = b->allocate();
+  if (rc) {
+    delete b;
+    return rc;
+  }
+  *out = new mas_b200_batch{b};
+  return MAS_B200_OK;
+}
+
+int mas_b200_batch_destroy(mas_b200_batch_t h) {
+  if (!h) return MAS_B200_OK;
+  if (h->b) {
+    cudaSetDevice(h->b->ctx->device);
+    cudaStreamSynchronize(h->b->ctx->stream);
+    delete h->b;
+  }
+  delete h;
+  return MAS_B200_OK;
+}
+
+#define MAS_BATCH_GUARD(h)                                                      \
+  if (!(h) || !(h)->b) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "batch is NULL"); \
+  BatchBase* b = (h)->b;                                                        \
+  MAS_CUDA_CHECK(cudaSetDevice(b->ctx->device));
+
+int mas_b200_batch_set_initial_states(mas_b200_batch_t h, const double* x0) {
+  MAS_BATCH_GUARD(h);
+  if (!x0) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "x0 is NULL");
+  return b->upload_rows(x0, b->d_x0, b->nx);
+}
+
+int mas_b200_batch_set_params(mas_b200_batch_t h, const double* params) {
+  MAS_BATCH_GUARD(h);
+  if (!params || b->np == 0) {
+    b->per_problem_params = false;
+    return MAS_B200_OK;
+  }
+  b->per_problem_params = true;
+  return b->upload_rows(params, b->d_params, b->np);
+}
+
+int mas_b200_batch_set_controls(mas_b200_batch_t h, const double* U) {
+  MAS_BATCH_GUARD(h);
+  if (!U) {
+    MAS_CUDA_CHECK(cudaMemsetAsync(b->d_U, 0, static_cast<size_t>(b->ld) * b->nu * b->T * sizeof(double), b->ctx->stream));
+    return MAS_B200_OK;
+  }
+  return b->upload_rows(U, b->d_U, b->nu * b->T);
+}
+
+int mas_b200_batch_initialize(mas_b200_batch_t h) {
+  MAS_BATCH_GUARD(h);
+  return b->initialize();
+}
+
+int mas_b200_batch_solve(mas_b200_batch_t h, const mas_b200_ilqr_params* params) {
+  MAS_BATCH_GUARD(h);
+  int rc = validate_params(params);
+  if (rc) return rc;
+  return b->solve(*params);
+}
+
+int mas_b200_batch_get_solution(mas_b200_batch_t h, double* X, double* U, double* cost, int* iterations, int* status) {
+  MAS_BATCH_GUARD(h);
+  int rc = MAS_B200_OK;
+  if (X && (rc = b->download_rows(b->d_X, X, b->nx * (b->T + 1)))) return rc;
+  if (U && (rc = b->download_rows(b->d_U, U, b->nu * b->T))) return rc;
+  if (cost) MAS_CUDA_CHECK(cudaMemcpyAsync(cost, b->d_cost, b->batch * sizeof(double), cudaMemcpyDeviceToHost, b->ctx->stream));
+  if (iterations) MAS_CUDA_CHECK(cudaMemcpyAsync(iterations, b->d_iters, b->batch * sizeof(int), cudaMemcpyDeviceToHost, b->ctx->stream));
+  if (status) MAS_CUDA_CHECK(cudaMemcpyAsync(status, b->d_status, b->batch * sizeof(int), cudaMemcpyDeviceToHost, b->ctx->stream));
+  MAS_CUDA_CHECK(cudaStreamSynchronize(b->ctx->stream));
+  return MAS_B200_OK;
+}
+
+int mas_b200_batch_get_device_view(mas_b200_batch_t h, mas_b200_device_view* out) {
+  MAS_BATCH_GUARD(h);
+  if (!out) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "out is NULL");
+  out->batch = b->batch;
+  out->ld = b->ld;
+  out->state_dim = b->nx;
+  out->control_dim = b->nu;
+  out->horizon_steps = b->T;
+  out->x0 = b->d_x0;
+  out->X = b->d_X;
+  out->U = b->d_U;
+  out->cost = b->d_cost;
+  out->iterations = b->d_iters;
+  out->status = b->d_status;
+  out->params = b->d_params;
+  return MAS_B200_OK;
+}
+
+int mas_b200_batch_get_stats(mas_b200_batch_t h, mas_b200_batch_stats* out) {
+  MAS_BATCH_GUARD(h);
+  if (!out) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "out is NULL");
+  int rc = b->collect_stats();
+  if (rc) return rc;
+  *out = b->stats;
+  return MAS_B200_OK;
+}
+
+int mas_b200_batch_set_profiling(mas_b200_batch_t h, int enable) {
+  MAS_BATCH_GUARD(h);
+  b->profiling = enable != 0;
+  b->profile = mas_b200_profile{};
+  return MAS_B200_OK;
+}
+
+int mas_b200_batch_get_profile(mas_b200_batch_t h, mas_b200_profile* out) {
+  MAS_BATCH_GUARD(h);
+  if (!out) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = b->profile;
+  return MAS_B200_OK;
+}
+
+int mas_b200_batch_set_tuning(mas_b200_batch_t h, int forward_lanes, int forward_chains) {
+  MAS_BATCH_GUARD(h);
+  if (forward_lanes != 0 && forward_lanes != 1 && forward_lanes != 2 && forward_lanes != 4 && forward_lanes != 8 && forward_lanes != 16)
+    return fail(MAS_B200_ERR_INVALID_ARGUMENT, "forward_lanes must be 0,1,2,4,8 or 16");
+  if (forward_chains < 0 || forward_chains > 2) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "forward_chains must be 0,1 or 2");
+  b->tune_L = forward_lanes;
+  b->tune_C = forward_chains;
+  return MAS_B200_OK;
+}
+
+int mas_b200_ilqr_solve_batch(mas_b200_context_t ctx, const mas_b200_ocp_desc* desc, const mas_b200_ilqr_params* params, int batch,
+                              const double* x0, const double* model_params, double* U, double* X, double* cost, int* iterations, int* status) {
+  int rc = validate_params(params);
+  if (rc) return rc;
+  mas_b200_batch_t h = nullptr;
+  rc = mas_b200_batch_create(ctx, desc, batch, &h);
+  if (rc) return rc;
+  rc = mas_b200_batch_set_initial_states(h, x0);
+  if (!rc) rc = mas_b200_batch_set_params(h, model_params);
+  if (!rc) rc = mas_b200_batch_set_controls(h, U);
+  if (!rc) rc = mas_b200_batch_solve(h, params);
+  if (!rc) rc = mas_b200_batch_get_solution(h, X, U, cost, iterations, status);
+  mas_b200_batch_destroy(h);
+  return rc;
+}
+
+// ---- strategies ------------------------------------------------------------------------------------------
+int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_ocp_desc* agent_desc, const mas_b200_ilqr_params* params,
+                          int max_outer, int n_scenarios, int n_agents, const double* x0, const double* model_params, double* X, double* U,
+                          double* costs, double* total_cost, int* trace_iterations, int* trace_accepted, double* trace_cost) {
+  if (!ctx) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  int rc = validate_params(params);
+  if (rc) return rc;
+  if (n_scenarios <= 0 || n_agents <= 0 || max_outer < 0) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "bad scenario/agent/outer counts");
+  if (strategy == MAS_B200_STRATEGY_CENTRALIZED || strategy == MAS_B200_STRATEGY_LINESEARCH)
+    return fail(MAS_B200_ERR_UNSUPPORTED, "strategy not on the device path yet (centralized, linesearch)");
+  if (strategy != MAS_B200_STRATEGY_SEQUENTIAL && strategy != MAS_B200_STRATEGY_TRUSTREGION)
+    return fail(MAS_B200_ERR_INVALID_ARGUMENT, "unknown strategy");
+  const int batch = n_scenarios * n_agents;
+  mas_b200_batch_t h = nullptr;
+  rc = mas_b200_batch_create(ctx, agent_desc, batch, &h);
+  if (rc) return rc;
+  BatchBase* b = h->b;
+  cudaStream_t st = ctx->c.stream;
+  std::vector<int> tmp_i(batch);
+  std::vector<double> tmp_c(batch);
+  auto run = [&]() -> int {
+    int r = mas_b200_batch_set_initial_states(h, x0);
+    if (!r) r = mas_b200_batch_set_params(h, model_params);
+    if (!r) r = mas_b200_batch_set_controls(h, nullptr);
+    if (!r) r = b->initialize();  // OCP::initialize_problem of every agent
+    if (r) return r;
+    const size_t L = static_cast<size_t>(b->ld);
+    if (strategy == MAS_B200_STRATEGY_TRUSTREGION) {
+      r = b->ensure_strategy_scratch();
+      if (r) return r;
+      std::vector<double> ones(b->ld, 1.0);  // radii = 1.0 (nash.hpp:194)
+      MAS_CUDA_CHECK(cudaMemcpyAsync(b->d_radius, ones.data(), L * sizeof(double), cudaMemcpyHostToDevice, st));
+      MAS_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    // joint buffers for the per-round exchange of every agent's (X, U, cost) across ranks
+    double *g_X = nullptr, *g_U = nullptr, *g_c = nullptr;
+    const size_t nX = L * b->nx * (b->T + 1), nU = L * b->nu * b->T;
+    if (ctx->c.nccl_comm) {
+      MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&g_X), nX * ctx->c.world * sizeof(double)));
+      MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&g_U), nU * ctx->c.world * sizeof(double)));
+      MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&g_c), L * ctx->c.world * sizeof(double)));
+    }
+    for (int outer = 0; outer < max_outer; ++outer) {
+      if (strategy == MAS_B200_STRATEGY_TRUSTREGION) {  // nash.hpp:208-210
+        MAS_CUDA_CHECK(cudaMemcpyAsync(b->d_U_old, b->d_U, nU * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        MAS_CUDA_CHECK(cudaMemcpyAsync(b->d_X_old, b->d_X, nX * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        MAS_CUDA_CHECK(cudaMemcpyAsync(b->d_cost_old, b->d_cost, L * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      }
+      r = b->solve(*params);  // nash.hpp:59-64 / :212, one warm-started solve per agent
+      if (r) return r;
+      if (strategy == MAS_B200_STRATEGY_TRUSTREGION) {
+        r = b->trust_region_step();  // nash.hpp:218-243
+        if (r) return r;
+      }
+      if (ctx->c.nccl_comm) {  // every rank ends the round holding all agents' trajectories
+        ncclComm_t comm = static_cast<ncclComm_t>(ctx->c.nccl_comm);
+        MAS_NCCL_CHECK(g_nccl.GroupStart());
+        MAS_NCCL_CHECK(g_nccl.AllGather(b->d_X, g_X, nX, ncclDouble, comm, st));
+        MAS_NCCL_CHECK(g_nccl.AllGather(b->d_U, g_U, nU, ncclDouble, comm, st));
+        MAS_NCCL_CHECK(g_nccl.AllGather(b->d_cost, g_c, L, ncclDouble, comm, st));
+        MAS_NCCL_CHECK(g_nccl.GroupEnd());
+      }
+      if (trace_iterations || trace_accepted || trace_cost) {
+        const size_t off = static_cast<size_t>(outer) * n_agents;  // [scenario][outer][agent]
+        if (trace_iterations) {
+          MAS_CUDA_CHECK(cudaMemcpyAsync(tmp_i.data(), b->d_iters, batch * sizeof(int), cudaMemcpyDeviceToHost, st));
+          MAS_CUDA_CHECK(cudaStreamSynchronize(st));
+          for (int s = 0; s < n_scenarios; ++s)
+            for (int a = 0; a < n_agents; ++a) trace_iterations[static_cast<size_t>(s) * max_outer * n_agents + off + a] = tmp_i[s * n_agents + a];
+        }
+        if (trace_accepted) {
+          if (strategy == MAS_B200_STRATEGY_TRUSTREGION) {
+            MAS_CUDA_CHECK(cudaMemcpyAsync(tmp_i.data(), b->d_accepted, batch * sizeof(int), cudaMemcpyDeviceToHost, st));
+            MAS_CUDA_CHECK(cudaStreamSynchronize(st));
+          } else {
+            for (auto& v : tmp_i) v = 1;
+          }
+          for (int s = 0; s < n_scenarios; ++s)
+            for (int a = 0; a < n_agents; ++a) trace_accepted[static_cast<size_t>(s) * max_outer * n_agents + off + a] = tmp_i[s * n_agents + a];
+        }
+        if (trace_cost) {
+          MAS_CUDA_CHECK(cudaMemcpyAsync(tmp_c.data(), b->d_cost, batch * sizeof(double), cudaMemcpyDeviceToHost, st));
+          MAS_CUDA_CHECK(cudaStreamSynchronize(st));
+          for (int s = 0; s < n_scenarios; ++s)
+            for (int a = 0; a < n_agents; ++a) trace_cost[static_cast<size_t>(s) * max_outer * n_agents + off + a] = tmp_c[s * n_agents + a];
+        }
+      }
+    }
+    if (g_X) cudaFree(g_X);
+    if (g_U) cudaFree(g_U);
+    if (g_c) cudaFree(g_c);
+    // collect_solution (nash.hpp:23-37): per-agent trajectories and costs, total in block order
+    std::vector<double> c(batch);
+    r = mas_b200_batch_get_solution(h, X, U, c.data(), nullptr, nullptr);
+    if (r) return r;
+    for (int s = 0; s < n_scenarios; ++s) {
+      double tot = 0.0;
+      for (int a = 0; a < n_agents; ++a) tot += c[static_cast<size_t>(s) * n_agents + a];
+      if (total_cost) total_cost[s] = tot;
+    }
+    if (costs) std::memcpy(costs, c.data(), sizeof(double) * batch);
+    return MAS_B200_OK;
+  };
+  rc = run();
+  mas_b200_batch_destroy(h);
+  return rc;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------------------------
+int mas_b200_nccl_unique_id(void* id128) {
+  if (!id128) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "id128 is NULL");
+  int rc = load_nccl();
+  if (rc) return rc;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+  MAS_NCCL_CHECK(g_nccl.GetUniqueId(static_cast<ncclUniqueId*>(id128)));
+  return MAS_B200_OK;
+}
+
+int mas_b200_context_init_nccl(mas_b200_context_t ctx, const void* id128, int rank, int world_size) {
+  if (!ctx || !id128 || world_size <= 0 || rank < 0 || rank >= world_size) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "bad NCCL arguments");
+  int rc = load_nccl();
+  if (rc) return rc;
+  MAS_CUDA_CHECK(cudaSetDevice(ctx->c.device));
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  ncclComm_t comm = nullptr;
+  MAS_NCCL_CHECK(g_nccl.CommInitRank(&comm, world_size, id, rank));
+  ctx->c.nccl_comm = comm;
+  ctx->c.rank = rank;
+  ctx->c.world = world_size;
+  return MAS_B200_OK;
+}
+
+int mas_b200_synthetic_single_track_x0(unsigned long long seed, int batch, double* x0) {
+  if (!x0 || batch < 0) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "bad arguments");
+  std::mt19937_64 rng(seed);
+  std::uniform_real_distribution<double> dy(-2.0, 2.0), dpsi(-0.5, 0.5), dv(0.0, 2.0);
+  for (int i = 0; i < batch; ++i) {
+    x0[4 * i + 0] = 0.0;
+    x0[4 * i + 1] = dy(rng);
+    x0[4 * i + 2] = dpsi(rng);
+    x0[4 * i + 3] = dv(rng);
+  }
+  return MAS_B200_OK;
+}
+
+int mas_b200_probe_fp64_peak(mas_b200_context_t ctx, double* tflops) {
+  if (!ctx || !tflops) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "bad arguments");
+  MAS_CUDA_CHECK(cudaSetDevice(ctx->c.device));
+  const int blocks = ctx->c.sm_count * 8, threads = 256, iters = 20000;
+  double* d = nullptr;
+  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d), static_cast<size_t>(blocks) * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  MAS_CUDA_CHECK(cudaEventCreate(&e0));
+  MAS_CUDA_CHECK(cudaEventCreate(&e1));
+  dfma_probe_kernel<<<blocks, threads, 0, ctx->c.stream>>>(d, 1000);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    MAS_CUDA_CHECK(cudaEventRecord(e0, ctx->c.stream));
+    dfma_probe_kernel<<<blocks, threads, 0, ctx->c.stream>>>(d, iters);
+    MAS_CUDA_CHECK(cudaEventRecord(e1, ctx->c.stream));
+    MAS_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    MAS_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * iters * static_cast<double>(blocks) * threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return MAS_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+// engine.cu -- model-independent parts of the batch engine: HBM allocation, layout transposes,
+// host<->device staging, statistics.
+#include "engine.cuh"
+
+namespace mas_b200 {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const std::string& last_error() { return g_last_error; }
+
+// [batch][rows] (row-major, problem-major) -> [rows][ld]; 32x32 shared-memory tiles so both the
+// global read (along rows) and the global write (along the batch) are coalesced.
+__global__ void aos_to_soa_kernel(const double* __restrict__ src, double* __restrict__ dst, int batch, int rows, int ld) {
+  __shared__ double tile[32][33];
+  const int b0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int b = b0 + j, r = r0 + threadIdx.x;
+    if (b < batch && r < rows) tile[j][threadIdx.x] = src[static_cast<size_t>(b) * rows + r];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, b = b0 + threadIdx.x;
+    if (b < batch && r < rows) dst[static_cast<size_t>(r) * ld + b] = tile[threadIdx.x][j];
+  }
+}
+
+__global__ void soa_to_aos_kernel(const double* __restrict__ src, double* __restrict__ dst, int batch, int rows, int ld) {
+  __shared__ double tile[32][33];
+  const int b0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, b = b0 + threadIdx.x;
+    if (b < batch && r < rows) tile[j][threadIdx.x] = src[static_cast<size_t>(r) * ld + b];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int b = b0 + j, r = r0 + threadIdx.x;
+    if (b < batch && r < rows) dst[static_cast<size_t>(b) * rows + r] = tile[threadIdx.x][j];
+  }
+}
+
+__global__ void fill_kernel(double* dst, size_t n, double value) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = value;
+}
+
+__global__ void time_limit_kernel(const int* __restrict__ list, const int* __restrict__ count, int* status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < *count) status[list[i]] = STATUS_TIME_LIMIT;
+}
+
+// 8 independent DFMA chains per thread; reports 2 flops per fma.
+__global__ void dfma_probe_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+  const double m = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c);
+    a1 = fma(a1, m, c);
+    a2 = fma(a2, m, c);
+    a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c);
+    a5 = fma(a5, m, c);
+    a6 = fma(a6, m, c);
+    a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+BatchBase::~BatchBase() {
+  if (ctx) cudaSetDevice(ctx->device);
+  double* dptrs[] = {d_x0, d_X, d_U, d_K, d_k, d_cost, d_merit, d_params, d_stage, d_U_old, d_X_old, d_cost_old, d_radius};
+  for (double* p : dptrs)
+    if (p) cudaFree(p);
+  int* iptrs[] = {d_iters, d_status, d_trials, d_reg, d_list[0], d_list[1], d_count, d_accepted};
+  for (int* p : iptrs)
+    if (p) cudaFree(p);
+  if (h_counts) cudaFreeHost(h_counts);
+  if (d_count_hist) cudaFree(d_count_hist);
+  for (auto& tl : timed) {
+    cudaEventDestroy(tl.e0);
+    cudaEventDestroy(tl.e1);
+  }
+  for (auto& e : event_pool) cudaEventDestroy(e);
+  for (auto& e : ev)
+    if (e) cudaEventDestroy(e);
+}
+
+int BatchBase::allocate() {
+  MAS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  ld = ((batch + 31) / 32) * 32;
+  const size_t L = static_cast<size_t>(ld);
+  auto dalloc = [&](double** p, size_t n) -> cudaError_t {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, n * sizeof(double), ctx->stream);
+    return e;
+  };
+  auto ialloc = [&](int** p, size_t n) -> cudaError_t {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, n * sizeof(int), ctx->stream);
+    return e;
+  };
+  MAS_CUDA_CHECK(dalloc(&d_x0, L * nx));
+  MAS_CUDA_CHECK(dalloc(&d_X, L * nx * (T + 1)));
+  MAS_CUDA_CHECK(dalloc(&d_U, L * nu * T));
+  MAS_CUDA_CHECK(dalloc(&d_K, L * nu * nx * T));
+  MAS_CUDA_CHECK(dalloc(&d_k, L * nu * T));
+  MAS_CUDA_CHECK(dalloc(&d_cost, L));
+  MAS_CUDA_CHECK(dalloc(&d_merit, L));
+  const size_t stage_rows = static_cast<size_t>(nx) * (T + 1) > static_cast<size_t>(nu) * T ? static_cast<size_t>(nx) * (T + 1) : static_cast<size_t>(nu) * T;
+  MAS_CUDA_CHECK(dalloc(&d_stage, static_cast<size_t>(batch) * stage_rows));
+  if (np > 0) MAS_CUDA_CHECK(dalloc(&d_params, L * np));
+  MAS_CUDA_CHECK(ialloc(&d_iters, L));
+  MAS_CUDA_CHECK(ialloc(&d_status, L));
+  MAS_CUDA_CHECK(ialloc(&d_trials, L));
+  MAS_CUDA_CHECK(ialloc(&d_reg, L));
+  MAS_CUDA_CHECK(ialloc(&d_list[0], L));
+  MAS_CUDA_CHECK(ialloc(&d_list[1], L));
+  MAS_CUDA_CHECK(ialloc(&d_count, 2));
+  MAS_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&h_counts), 4 * sizeof(int)));
+  MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  return MAS_B200_OK;
+}
+
+int BatchBase::ensure_strategy_scratch() {
+  if (d_U_old) return MAS_B200_OK;
+  const size_t L = static_cast<size_t>(ld);
+  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_U_old), L * nu * T * sizeof(double)));
+  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_X_old), L * nx * (T + 1) * sizeof(double)));
+  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_cost_old), L * sizeof(double)));
+  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_radius), L * sizeof(double)));
+  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_accepted), L * sizeof(int)));
+  return MAS_B200_OK;
+}
+
+int BatchBase::upload_rows(const double* host, double* dev, int rows) {
+  const size_t bytes = static_cast<size_t>(batch) * rows * sizeof(double);
+  MAS_CUDA_CHECK(cudaMemcpyAsync(d_stage, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  dim3 block(32, 8), grid(div_up(batch, 32), div_up(rows, 32));
+  aos_to_soa_kernel<<<grid, block, 0, ctx->stream>>>(d_stage, dev, batch, rows, ld);
+  stats.kernel_launches++;
+  MAS_CUDA_CHECK(cudaGetLastError());
+  return MAS_B200_OK;
+}
+
+int BatchBase::download_rows(const double* dev, double* host, int rows) {
+  const size_t bytes = static_cast<size_t>(batch) * rows * sizeof(double);
+  dim3 block(32, 8), grid(div_up(batch, 32), div_up(rows, 32));
+  soa_to_aos_kernel<<<grid, block, 0, ctx->stream>>>(dev, d_stage, batch, rows, ld);
+  stats.kernel_launches++;
+  MAS_CUDA_CHECK(cudaGetLastError());
+  MAS_CUDA_CHECK(cudaMemcpyAsync(host, d_stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return MAS_B200_OK;
+}
+
+void BatchBase::prof_begin(int kind) {
+  if (!profiling) return;
+  TimedLaunch tl{};
+  for (cudaEvent_t* e : {&tl.e0, &tl.e1}) {
+    if (!event_pool.empty()) {
+      *e = event_pool.back();
+      event_pool.pop_back();
+    } else {
+      cudaEventCreate(e);
+    }
+  }
+  tl.kind = kind;
+  cudaEventRecord(tl.e0, ctx->stream);
+  timed.push_back(tl);
+}
+
+void BatchBase::prof_end() {
+  if (!profiling || timed.empty()) return;
+  cudaEventRecord(timed.back().e1, ctx->stream);
+}
+
+// Sums the per-launch durations of the solve that just ran and the exact active-problem counts.
+int BatchBase::prof_collect(int trips) {
+  MAS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  for (auto& tl : timed) {
+    float ms = 0.f;
+    MAS_CUDA_CHECK(cudaEventElapsedTime(&ms, tl.e0, tl.e1));
+    if (tl.kind == 0) {
+      profile.prologue_ms += ms;
+      profile.prologue_launches++;
+    } else if (tl.kind == 1) {
+      profile.backward_ms += ms;
+      profile.backward_launches++;
+    } else {
+      profile.forward_ms += ms;
+      profile.forward_launches++;
+    }
+    event_pool.push_back(tl.e0);
+    event_pool.push_back(tl.e1);
+  }
+  timed.clear();
+  if (trips > 0) {
+    std::vector<int> hist(trips);
+    MAS_CUDA_CHECK(cudaMemcpy(hist.data(), d_count_hist, trips * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int c : hist) profile.problem_iterations += c;
+  }
+  profile.solves++;
+  return MAS_B200_OK;
+}
+
+int BatchBase::collect_stats() {
+  MAS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  std::vector<int> it(batch), tr(batch), rg(batch);
+  MAS_CUDA_CHECK(cudaMemcpy(it.data(), d_iters, batch * sizeof(int), cudaMemcpyDeviceToHost));
+  MAS_CUDA_CHECK(cudaMemcpy(tr.data(), d_trials, batch * sizeof(int), cudaMemcpyDeviceToHost));
+  MAS_CUDA_CHECK(cudaMemcpy(rg.data(), d_reg, batch * sizeof(int), cudaMemcpyDeviceToHost));
+  long long a = 0, b = 0, c = 0;
+  for (int i = 0; i < batch; ++i) {
+    a += it[i];
+    b += tr[i];
+    c += rg[i];
+  }
+  stats.iterations = a;
+  stats.alpha_trials = b;
+  stats.reg_retries = c;
+  return MAS_B200_OK;
+}
+
+}  // namespace mas_b200

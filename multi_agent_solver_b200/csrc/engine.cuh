@@ -1,0 +1,426 @@
+// engine.cuh -- kernels and the host-side batch engine behind the C ABI (include/mas_b200.h).
+//
+// One Batch = `batch` same-shaped OCPs resident in HBM in the [T][dim][ld] layout of ilqr_core.cuh.
+// An iLQR solve of the whole batch (mas::solve(Solver&, OCP&) for every problem,
+// solvers/solver.hpp:28-32 -> solvers/ilqr.hpp:59-273) is a host loop over iterations that launches
+//   backward_kernel : one thread per still-active problem; derivatives + Riccati + gains (ilqr.hpp:92-193)
+//   forward_kernel  : L lanes per still-active problem; the line search with its step sizes rolled
+//                     out concurrently, warp-shuffle selection of the first improving one, accepted
+//                     step written in place, stop test, compaction of the active list (ilqr.hpp:195-271)
+// Problems leave the active list as they converge, so later iterations only pay for what is left.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ilqr_core.cuh"
+#include "mas_b200.h"
+
+namespace mas_b200 {
+
+void set_last_error(const std::string& msg);
+
+#define MAS_CUDA_CHECK(expr)                                                                              \
+  do {                                                                                                    \
+    cudaError_t err__ = (expr);                                                                           \
+    if (err__ != cudaSuccess) {                                                                           \
+      set_last_error(std::string(#expr) + ": " + cudaGetErrorString(err__));                              \
+      return MAS_B200_ERR_CUDA;                                                                           \
+    }                                                                                                     \
+  } while (0)
+
+struct Context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  void* nccl_comm = nullptr;  // ncclComm_t when multi-GPU is initialised
+  int rank = 0, world = 1;
+};
+
+// ---- kernels ------------------------------------------------------------------------------------
+// Batched transposes between the caller's [batch][rows] arrays and the [rows][ld] HBM layout.
+__global__ void aos_to_soa_kernel(const double* __restrict__ src, double* __restrict__ dst, int batch, int rows, int ld);
+__global__ void soa_to_aos_kernel(const double* __restrict__ src, double* __restrict__ dst, int batch, int rows, int ld);
+__global__ void fill_kernel(double* dst, size_t n, double value);
+__global__ void dfma_probe_kernel(double* out, int iters);
+
+// OCP::initialize_problem / iLQR prologue: rollout + cost, reset of the per-solve counters and of
+// the active list (identity).  ilqr.hpp:75-78, ocp.hpp:110-113,182.
+template <class M>
+__global__ void __launch_bounds__(128) prologue_kernel(BatchView<M::NX, M::NU> v, int batch, int* list, int* count, int max_iterations) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p == 0) *count = (max_iterations > 0) ? batch : 0;
+  if (p >= batch) return;
+  const double c = rollout_thread<M>(v, p);
+  v.cost[p] = c;
+  v.merit[p] = c;  // compute_merit == objective without constraint callbacks (ilqr.hpp:380-407)
+  v.iters[p] = 0;
+  v.trials[p] = 0;
+  v.reg_retries[p] = 0;
+  v.status[p] = STATUS_MAX_ITER;
+  list[p] = p;
+}
+
+template <class M, int MASK_CT>
+__global__ void __launch_bounds__(128) backward_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
+                                                       int* next_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *next_count = 0;
+  if (i >= *count) return;
+  const int p = list[i];
+  const int r = backward_thread<M, MASK_CT>(v, p);
+  if (r) v.reg_retries[p] += r;
+}
+
+// L lanes per problem (a power of two <= 16, aligned inside the warp); lane l rolls out step sizes
+// l, l+L, ...; the group picks the first improving candidate with shuffles; lane 0 commits.
+template <class M, int L, int C>
+__global__ void __launch_bounds__(128) forward_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
+                                                      int* next_list, int* next_count) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = gid / L;
+  const int lane = gid % L;
+  const bool valid = i < *count;
+  const int p = valid ? list[i] : 0;
+  bool again = false;
+  double prm[M::NP > 0 ? M::NP : 1];
+  int best_j = kNumAlphas;
+  double best_merit = 0.0, current_merit = 0.0;
+  if (valid) {
+    load_params<M>(v, p, prm);
+    current_merit = v.merit[p];
+    lane_line_search<M, L, C>(v, p, prm, lane, current_merit, &best_j, &best_merit);
+  }
+  if (L > 1) {
+    // first improving candidate of the group = minimum index; its merit travels with it.
+    // Executed by every lane of the warp (idle groups carry kNumAlphas) so the full mask is legal.
+#pragma unroll
+    for (int off = L / 2; off > 0; off >>= 1) {
+      const int oj = __shfl_xor_sync(0xffffffffu, best_j, off, L);
+      const double om = __shfl_xor_sync(0xffffffffu, best_merit, off, L);
+      if (oj < best_j) {
+        best_j = oj;
+        best_merit = om;
+      }
+    }
+  }
+  if (valid && lane == 0) again = finish_iteration<M>(v, p, prm, current_merit, best_j, best_merit);
+  // warp-aggregated append to the next active list
+  const unsigned vote = __ballot_sync(0xffffffffu, again);
+  if (vote) {
+    const int wl = threadIdx.x & 31;
+    int base = 0;
+    if (wl == 0) base = atomicAdd(next_count, __popc(vote));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (again) next_list[base + __popc(vote & ((1u << wl) - 1u))] = p;
+  }
+}
+
+// Re-rollout of given controls (strategy layer, nash.hpp:224-225): X and cost from U.
+template <class M>
+__global__ void __launch_bounds__(128) rollout_kernel(BatchView<M::NX, M::NU> v, int batch) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= batch) return;
+  const double c = rollout_thread<M>(v, p);
+  v.cost[p] = c;
+}
+
+// Trust-region accept/scale (TrustRegionNashStrategy, strategies/nash.hpp:208-243) for every agent:
+// delta = U_new - U_old, Frobenius norm in column-major order; if it exceeds the radius the step is
+// scaled, re-rolled out and re-costed; accept iff cand_cost < old_cost (strict) -> radius *= 1.5,
+// otherwise restore the old trajectory and radius *= 0.5.
+template <class M>
+__global__ void __launch_bounds__(128) trust_region_kernel(BatchView<M::NX, M::NU> v, int batch, const double* __restrict__ U_old,
+                                                           const double* __restrict__ X_old, const double* __restrict__ cost_old, double* radius,
+                                                           int* accepted) {
+  constexpr int NX = M::NX, NU = M::NU;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= batch) return;
+  const int T = v.T;
+  double sq = 0.0;
+  for (int t = 0; t < T; ++t)
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      const size_t idx = soa_index<NU>(t, i, v.ld, p);
+      const double d = v.U[idx] - U_old[idx];
+      sq += d * d;
+    }
+  const double norm = sqrt(sq);
+  double rad = radius[p];
+  double cand_cost = v.cost[p];
+  if (norm > rad) {
+    const double scale = rad / norm;
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        const size_t idx = soa_index<NU>(t, i, v.ld, p);
+        const double d = v.U[idx] - U_old[idx];
+        v.U[idx] = U_old[idx] + scale * d;
+      }
+    cand_cost = rollout_thread<M>(v, p);
+  }
+  const double oc = cost_old[p];
+  if (cand_cost < oc) {
+    v.cost[p] = cand_cost;
+    radius[p] = rad * 1.5;
+    accepted[p] = 1;
+  } else {
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        const size_t idx = soa_index<NU>(t, i, v.ld, p);
+        v.U[idx] = U_old[idx];
+      }
+    for (int t = 0; t <= T; ++t)
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        const size_t idx = soa_index<NX>(t, i, v.ld, p);
+        v.X[idx] = X_old[idx];
+      }
+    v.cost[p] = oc;
+    radius[p] = rad * 0.5;
+    accepted[p] = 0;
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+struct BatchBase {
+  Context* ctx = nullptr;
+  mas_b200_ocp_desc desc{};
+  int batch = 0, ld = 0, nx = 0, nu = 0, np = 0, T = 0;
+  // HBM
+  double *d_x0 = nullptr, *d_X = nullptr, *d_U = nullptr, *d_K = nullptr, *d_k = nullptr, *d_cost = nullptr, *d_merit = nullptr,
+         *d_params = nullptr;
+  int *d_iters = nullptr, *d_status = nullptr, *d_trials = nullptr, *d_reg = nullptr;
+  int* d_list[2] = {nullptr, nullptr};
+  int* d_count = nullptr;  // [2]
+  double* d_stage = nullptr;  // staging for AoS<->SoA transposes (max(nx*(T+1), nu*T) * batch doubles)
+  // strategy scratch (allocated on demand)
+  double *d_U_old = nullptr, *d_X_old = nullptr, *d_cost_old = nullptr, *d_radius = nullptr;
+  int* d_accepted = nullptr;
+  int* h_counts = nullptr;  // pinned, [4]
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool per_problem_params = false;
+  int tune_L = 0, tune_C = 0;
+  // optional per-launch timing (CUDA events on the launching stream), see mas_b200_batch_set_profiling
+  bool profiling = false;
+  struct TimedLaunch {
+    cudaEvent_t e0, e1;
+    int kind;  // 0 prologue, 1 backward, 2 forward
+  };
+  std::vector<TimedLaunch> timed;
+  std::vector<cudaEvent_t> event_pool;
+  mas_b200_profile profile{};
+  int* d_count_hist = nullptr;  // active problems at the start of every iteration of the last solve
+  int hist_capacity = 0;
+  void prof_begin(int kind);
+  void prof_end();
+  int prof_collect(int trips);
+  mas_b200_batch_stats stats{};
+  int last_L = 0, last_C = 0;
+
+  virtual ~BatchBase();
+  int allocate();
+  int upload_rows(const double* host, double* dev, int rows);      // [batch][rows] host -> [rows][ld]
+  int download_rows(const double* dev, double* host, int rows);    // [rows][ld] -> [batch][rows] host
+  int ensure_strategy_scratch();
+  virtual int initialize() = 0;
+  virtual int solve(const mas_b200_ilqr_params& prm) = 0;
+  virtual int rollout_all() = 0;                 // X, cost from U
+  virtual int trust_region_step() = 0;           // uses d_*_old, d_radius, d_accepted
+  int collect_stats();
+};
+
+inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+template <class M>
+struct BatchImpl : BatchBase {
+  using View = BatchView<M::NX, M::NU>;
+  View view{};
+
+  void make_view() {
+    view.ld = ld;
+    view.T = T;
+    view.dt = desc.dt;
+    view.deriv_mask = desc.deriv_mask;
+    view.has_bounds = desc.has_input_bounds;
+    for (int i = 0; i < M::NU; ++i) {
+      view.lo[i] = desc.input_lower[i];
+      view.hi[i] = desc.input_upper[i];
+    }
+    view.per_problem_params = per_problem_params ? 1 : 0;
+    for (int i = 0; i < kMaxParams; ++i) view.shared_p[i] = i < desc.num_params ? desc.params[i] : 0.0;
+    view.params = d_params;
+    view.x0 = d_x0;
+    view.X = d_X;
+    view.U = d_U;
+    view.K = d_K;
+    view.kff = d_k;
+    view.cost = d_cost;
+    view.merit = d_merit;
+    view.iters = d_iters;
+    view.status = d_status;
+    view.trials = d_trials;
+    view.reg_retries = d_reg;
+    view.tolerance = 0.0;
+    view.max_iterations = 0;
+  }
+
+  int launch_prologue(int max_iterations) {
+    make_view();
+    prologue_kernel<M><<<div_up(batch, 128), 128, 0, ctx->stream>>>(view, batch, d_list[0], d_count, max_iterations);
+    stats.kernel_launches++;
+    MAS_CUDA_CHECK(cudaGetLastError());
+    return MAS_B200_OK;
+  }
+
+  int initialize() override { return launch_prologue(0); }
+
+  int rollout_all() override {
+    make_view();
+    rollout_kernel<M><<<div_up(batch, 128), 128, 0, ctx->stream>>>(view, batch);
+    stats.kernel_launches++;
+    MAS_CUDA_CHECK(cudaGetLastError());
+    return MAS_B200_OK;
+  }
+
+  int trust_region_step() override {
+    make_view();
+    trust_region_kernel<M><<<div_up(batch, 128), 128, 0, ctx->stream>>>(view, batch, d_U_old, d_X_old, d_cost_old, d_radius, d_accepted);
+    stats.kernel_launches++;
+    MAS_CUDA_CHECK(cudaGetLastError());
+    return MAS_B200_OK;
+  }
+
+  void launch_backward(int n_upper, int cur) {
+    const int grid = div_up(n_upper, 128);
+    const unsigned mask = desc.deriv_mask;
+    if (mask == M::EXAMPLE_MASK)
+      backward_kernel<M, static_cast<int>(M::EXAMPLE_MASK)><<<grid, 128, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
+    else if (mask == 0u)
+      backward_kernel<M, 0><<<grid, 128, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
+    else
+      backward_kernel<M, -1><<<grid, 128, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
+    stats.kernel_launches++;
+  }
+
+  template <int L, int C>
+  void launch_forward_lc(int n_upper, int cur) {
+    const long long threads = static_cast<long long>(n_upper) * L;
+    const int grid = static_cast<int>((threads + 127) / 128);
+    forward_kernel<M, L, C><<<grid, 128, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1], d_count + (cur ^ 1));
+    stats.kernel_launches++;
+  }
+
+  void launch_forward(int n_upper, int cur, int L, int C) {
+    if (L == 1 && C == 2) launch_forward_lc<1, 2>(n_upper, cur);
+    else if (L == 1) launch_forward_lc<1, 1>(n_upper, cur);
+    else if (L == 2) launch_forward_lc<2, 1>(n_upper, cur);
+    else if (L == 4) launch_forward_lc<4, 1>(n_upper, cur);
+    else if (L == 8) launch_forward_lc<8, 1>(n_upper, cur);
+    else launch_forward_lc<16, 1>(n_upper, cur);
+  }
+
+  // Lanes per problem: enough lanes to fill the device (about 512 resident per SM) without
+  // evaluating more step sizes than needed when the batch alone already fills it.
+  void choose_forward(int n_active, int* L, int* C) const {
+    int l = tune_L, c = tune_C;
+    if (l == 0) {
+      const long long target = static_cast<long long>(ctx->sm_count) * 384;
+      l = 1;
+      while (l < 16 && static_cast<long long>(n_active) * l < target) l *= 2;
+    }
+    if (c == 0) c = (l == 1) ? 2 : 1;
+    if (l != 1) c = 1;
+    *L = l;
+    *C = c;
+  }
+
+  int solve(const mas_b200_ilqr_params& prm) override {
+    using clock = std::chrono::steady_clock;
+    const auto start = clock::now();
+    prof_begin(0);
+    int rc = launch_prologue(prm.max_iterations);
+    prof_end();
+    if (rc) return rc;
+    if (profiling && prm.max_iterations > hist_capacity) {
+      if (d_count_hist) cudaFree(d_count_hist);
+      MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_count_hist), prm.max_iterations * sizeof(int)));
+      hist_capacity = prm.max_iterations;
+    }
+    view.tolerance = prm.tolerance;
+    view.max_iterations = prm.max_iterations;
+    const bool timed = std::isfinite(prm.max_ms);
+    int n_upper = prm.max_iterations > 0 ? batch : 0;
+    int cur = 0;
+    int trips = 0;
+    for (int it = 0; it < prm.max_iterations && n_upper > 0; ++it) {
+      if (timed) {
+        // the reference checks an integer-millisecond clock at the top of every iteration
+        // (ilqr.hpp:84-90); here the budget covers the whole batch, so drain the stream first
+        MAS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        const double elapsed_ms =
+            static_cast<double>(std::chrono::duration_cast<std::chrono::milliseconds>(clock::now() - start).count());
+        if (elapsed_ms > prm.max_ms) {
+          rc = mark_time_limit(cur);
+          if (rc) return rc;
+          break;
+        }
+      }
+      int L, C;
+      choose_forward(n_upper, &L, &C);
+      last_L = L;
+      last_C = C;
+      prof_begin(1);
+      launch_backward(n_upper, cur);
+      prof_end();
+      prof_begin(2);
+      launch_forward(n_upper, cur, L, C);
+      prof_end();
+      MAS_CUDA_CHECK(cudaGetLastError());
+      if (profiling)
+        MAS_CUDA_CHECK(cudaMemcpyAsync(d_count_hist + it, d_count + cur, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+      MAS_CUDA_CHECK(cudaMemcpyAsync(h_counts + (it & 1), d_count + (cur ^ 1), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      MAS_CUDA_CHECK(cudaEventRecord(ev[it & 1], ctx->stream));
+      if (it >= 1) {
+        // active count after iteration it-1: an upper bound for iteration it+1 (the list only shrinks)
+        MAS_CUDA_CHECK(cudaEventSynchronize(ev[(it - 1) & 1]));
+        n_upper = h_counts[(it - 1) & 1];
+      }
+      cur ^= 1;
+      ++trips;
+    }
+    stats.outer_iterations_run = trips;
+    stats.forward_lanes = last_L;
+    stats.forward_chains = last_C;
+    if (profiling) return prof_collect(trips);
+    return MAS_B200_OK;
+  }
+
+  int mark_time_limit(int cur);
+};
+
+__global__ void time_limit_kernel(const int* __restrict__ list, const int* __restrict__ count, int* status);
+
+template <class M>
+int BatchImpl<M>::mark_time_limit(int cur) {
+  time_limit_kernel<<<div_up(batch, 128), 128, 0, ctx->stream>>>(d_list[cur], d_count + cur, d_status);
+  stats.kernel_launches++;
+  MAS_CUDA_CHECK(cudaGetLastError());
+  return MAS_B200_OK;
+}
+
+// factories, one translation unit per model (model_*.cu)
+BatchBase* make_batch_st_lane();
+BatchBase* make_batch_st_circ();
+BatchBase* make_batch_lqr4();
+BatchBase* make_batch_pendulum();
+BatchBase* make_batch_rocket();
+
+}  // namespace mas_b200

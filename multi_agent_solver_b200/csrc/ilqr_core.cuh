@@ -1,0 +1,665 @@
+// ilqr_core.cuh -- per-problem bodies of the batched iLQR kernels (one problem per thread / lane group).
+//
+// Hot path being replaced: mas::iLQR::solve, include/multi_agent_solver/solvers/ilqr.hpp:59-273, and
+// what it calls per iteration: integrate_rk4 / integrate_horizon (integrator.hpp:19-48),
+// compute_trajectory_cost (ocp.hpp:14-28), the finite-difference defaults
+// (finite_differences.hpp:53-287) and clamp_controls (constraint_helpers.hpp:107-114).
+//
+// Data layout (HBM, structure of arrays, `ld` = padded batch stride, problem index fastest):
+//   x0 [NX][ld]   X [T+1][NX][ld]   U [T][NU][ld]   K [T][NU*NX][ld] (K(i,j) at i + j*NU)   k [T][NU][ld]
+// so the 32 lanes of a warp working on 32 neighbouring problems read 32 consecutive doubles.
+//
+// Arithmetic contract: every sum below is written in the operation order of the reference
+// expression it restates (k-ascending dot products starting from the first product, no fused
+// multiply-add: compile with -fmad=false).  The functions are __host__ __device__ so the very same
+// source can be emulated on the CPU by tests/csrc/host_emulation.cpp.
+#pragma once
+#include "models.cuh"
+
+namespace mas_b200 {
+
+enum SolveStatus : int { STATUS_CONVERGED = 0, STATUS_MAX_ITER = 1, STATUS_TIME_LIMIT = 2 };
+
+constexpr int kNumAlphas = 10;  // alpha = 1, 1/2, ... while alpha >= 1e-3 (ilqr.hpp:199-206,227)
+constexpr int kMaxParams = 8;
+
+template <int NX, int NU>
+struct BatchView {
+  int ld;
+  int T;
+  double dt;
+  unsigned deriv_mask;
+  int has_bounds;  // both input bounds present (ilqr.hpp:213)
+  double lo[NU], hi[NU];
+  int per_problem_params;  // 0: shared_p, 1: params[NP][ld]
+  double shared_p[kMaxParams];
+  const double* params;
+  const double* x0;
+  double* X;
+  double* U;
+  double* K;
+  double* kff;
+  double* cost;
+  double* merit;
+  int* iters;
+  int* status;
+  int* trials;       // line-search candidates the sequential reference would have evaluated
+  int* reg_retries;  // Q_uu + reg*I retries (ilqr.hpp:175-182)
+  double tolerance;
+  int max_iterations;
+};
+
+template <int DIM>
+MAS_HD size_t soa_index(int t, int d, int ld, int p) {
+  return (static_cast<size_t>(t) * DIM + d) * static_cast<size_t>(ld) + p;
+}
+
+template <class M, int NX, int NU>
+MAS_HD void load_params(const BatchView<NX, NU>& v, int p, double* prm) {
+#pragma unroll
+  for (int i = 0; i < (M::NP > 0 ? M::NP : 1); ++i) {
+    if (i < M::NP) prm[i] = v.per_problem_params ? v.params[static_cast<size_t>(i) * v.ld + p] : v.shared_p[i];
+  }
+}
+
+// ---- small dense helpers (column-major, compile-time sizes, reference summation order) -----------
+// C[R x CC] = A^T * B with A stored KD x R, B stored KD x CC
+template <int KD, int R, int CC>
+MAS_HD void mat_tn(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int j = 0; j < CC; ++j)
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      double s = A[0 + i * KD] * B[0 + j * KD];
+#pragma unroll
+      for (int k = 1; k < KD; ++k) s = s + A[k + i * KD] * B[k + j * KD];
+      C[i + j * R] = s;
+    }
+}
+// C[R x CC] = A * B with A stored R x KD, B stored KD x CC
+template <int R, int KD, int CC>
+MAS_HD void mat_nn(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int j = 0; j < CC; ++j)
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      double s = A[i + 0 * R] * B[0 + j * KD];
+#pragma unroll
+      for (int k = 1; k < KD; ++k) s = s + A[i + k * R] * B[k + j * KD];
+      C[i + j * R] = s;
+    }
+}
+
+// `m = 0.5 * (m + m.transpose())` evaluated in place, columns outer / rows inner, as the reference's
+// aliased Eigen expression does (ilqr.hpp:102,192).
+template <int N>
+MAS_HD void symmetrize_aliased(double* m) {
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+#pragma unroll
+    for (int i = 0; i < N; ++i) m[i + j * N] = 0.5 * (m[i + j * N] + m[j + i * N]);
+}
+
+// ---- integrator.hpp:19-28 ---------------------------------------------------------------------
+template <class M>
+MAS_HD void rk4_step(const double* x, const double* u, const double* prm, double dt, double* xn) {
+  constexpr int NX = M::NX;
+  double k1[NX], k2[NX], k3[NX], k4[NX], xs[NX];
+  const double hdt = 0.5 * dt;
+  M::dynamics(x, u, prm, k1);
+#pragma unroll
+  for (int i = 0; i < NX; ++i) xs[i] = x[i] + hdt * k1[i];
+  M::dynamics(xs, u, prm, k2);
+#pragma unroll
+  for (int i = 0; i < NX; ++i) xs[i] = x[i] + hdt * k2[i];
+  M::dynamics(xs, u, prm, k3);
+#pragma unroll
+  for (int i = 0; i < NX; ++i) xs[i] = x[i] + dt * k3[i];
+  M::dynamics(xs, u, prm, k4);
+  const double sixth = dt / 6.0;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) xn[i] = x[i] + sixth * (((k1[i] + 2.0 * k2[i]) + 2.0 * k3[i]) + k4[i]);
+}
+
+// ---- prologue: X = integrate_horizon(x0, U); cost = objective(X, U)  (ilqr.hpp:75-78) -----------
+// Also used by the strategy layer's re-rollouts (nash.hpp:140,224).  Returns the cost.
+template <class M>
+MAS_HD double rollout_thread(const BatchView<M::NX, M::NU>& v, int p) {
+  constexpr int NX = M::NX, NU = M::NU;
+  double prm[M::NP > 0 ? M::NP : 1];
+  load_params<M>(v, p, prm);
+  double x[NX], u[NU], xn[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    x[i] = v.x0[static_cast<size_t>(i) * v.ld + p];
+    v.X[soa_index<NX>(0, i, v.ld, p)] = x[i];
+  }
+  double cost = 0.0;
+  for (int t = 0; t < v.T; ++t) {
+#pragma unroll
+    for (int i = 0; i < NU; ++i) u[i] = v.U[soa_index<NU>(t, i, v.ld, p)];
+    cost += M::stage(x, u, t, prm);
+    rk4_step<M>(x, u, prm, v.dt, xn);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      x[i] = xn[i];
+      v.X[soa_index<NX>(t + 1, i, v.ld, p)] = x[i];
+    }
+  }
+  cost += M::terminal(x, prm);
+  return cost;
+}
+
+// ---- finite-difference defaults (finite_differences.hpp) ------------------------------------------
+MAS_HD double finite_or_zero(double v) { return isfinite(v) ? v : 0.0; }  // safe_eval, :95-107
+
+template <class M>
+MAS_HD void fd_jac_x(const double* x, const double* u, const double* prm, double* A) {  // :53-72
+  constexpr int NX = M::NX;
+  const double eps = 1e-6;
+  double xp[NX], fp[NX], fm[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+#pragma unroll
+    for (int k = 0; k < NX; ++k) xp[k] = x[k];
+    xp[i] = x[i] + eps;
+    M::dynamics(xp, u, prm, fp);
+    xp[i] = x[i] - eps;
+    M::dynamics(xp, u, prm, fm);
+#pragma unroll
+    for (int r = 0; r < NX; ++r) A[r + i * NX] = (fp[r] - fm[r]) / (2 * eps);
+  }
+}
+template <class M>
+MAS_HD void fd_jac_u(const double* x, const double* u, const double* prm, double* B) {  // :74-92
+  constexpr int NX = M::NX, NU = M::NU;
+  const double eps = 1e-6;
+  double up[NU], fp[NX], fm[NX];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) {
+#pragma unroll
+    for (int k = 0; k < NU; ++k) up[k] = u[k];
+    up[i] = u[i] + eps;
+    M::dynamics(x, up, prm, fp);
+    up[i] = u[i] - eps;
+    M::dynamics(x, up, prm, fm);
+#pragma unroll
+    for (int r = 0; r < NX; ++r) B[r + i * NX] = (fp[r] - fm[r]) / (2 * eps);
+  }
+}
+template <class M>
+MAS_HD void fd_l_x(const double* x, const double* u, int t, const double* prm, double* g) {  // :110-122
+  constexpr int NX = M::NX;
+  const double eps = 1e-6;
+  double xp[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+#pragma unroll
+    for (int k = 0; k < NX; ++k) xp[k] = x[k];
+    xp[i] = x[i] + eps;
+    const double fp = M::stage(xp, u, t, prm);
+    xp[i] = x[i] - eps;
+    const double fm = M::stage(xp, u, t, prm);
+    g[i] = (fp - fm) / (2 * eps);
+  }
+}
+template <class M>
+MAS_HD void fd_l_u(const double* x, const double* u, int t, const double* prm, double* g) {  // :124-136
+  constexpr int NU = M::NU;
+  const double eps = 1e-6;
+  double up[NU];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) {
+#pragma unroll
+    for (int k = 0; k < NU; ++k) up[k] = u[k];
+    up[i] = u[i] + eps;
+    const double fp = M::stage(x, up, t, prm);
+    up[i] = u[i] - eps;
+    const double fm = M::stage(x, up, t, prm);
+    g[i] = (fp - fm) / (2 * eps);
+  }
+}
+// Hessian of F(z) in z (either the state or the control slot), :138-210 and :229-261.
+// F is a functor double(const double* z).
+template <int N, class F>
+MAS_HD void fd_hessian(const double* z, const F& f, double* H) {
+  const double eps = 1e-5;
+  double zp[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) zp[k] = z[k];
+    zp[i] = z[i] + eps;
+    const double fp = finite_or_zero(f(zp));
+    const double f0 = finite_or_zero(f(z));
+    zp[i] = z[i] - eps;
+    const double fm = finite_or_zero(f(zp));
+    H[i + i * N] = (fp - 2 * f0 + fm) / (eps * eps);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (i != j) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) zp[k] = z[k];
+        zp[i] = z[i] + eps;
+        zp[j] = z[j] + eps;
+        const double fpp = finite_or_zero(f(zp));
+        zp[j] = z[j] - eps;
+        const double fpm = finite_or_zero(f(zp));
+        zp[i] = z[i] - eps;
+        zp[j] = z[j] + eps;
+        const double fmp = finite_or_zero(f(zp));
+        zp[j] = z[j] - eps;
+        const double fmm = finite_or_zero(f(zp));
+        H[i + j * N] = (fpp - fpm - fmp + fmm) / (4 * eps * eps);
+      }
+}
+template <class M>
+MAS_HD void fd_l_ux(const double* x, const double* u, int t, const double* prm, double* H) {  // :263-287
+  constexpr int NX = M::NX, NU = M::NU;
+  const double eps = 1e-6;
+  double xp[NX], up[NU];
+#pragma unroll
+  for (int i = 0; i < NU; ++i)
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+#pragma unroll
+      for (int k = 0; k < NX; ++k) xp[k] = x[k];
+#pragma unroll
+      for (int k = 0; k < NU; ++k) up[k] = u[k];
+      xp[j] = x[j] + eps;
+      up[i] = u[i] + eps;
+      const double fpp = finite_or_zero(M::stage(xp, up, t, prm));
+      xp[j] = x[j] - eps;
+      const double fpm = finite_or_zero(M::stage(xp, up, t, prm));
+      xp[j] = x[j] + eps;
+      up[i] = u[i] - eps;
+      const double fmp = finite_or_zero(M::stage(xp, up, t, prm));
+      xp[j] = x[j] - eps;
+      const double fmm = finite_or_zero(M::stage(xp, up, t, prm));
+      H[i + j * NU] = (fpp - fpm - fmp + fmm) / (4 * eps * eps);
+    }
+}
+template <class M>
+struct StageInX {
+  const double* u;
+  const double* prm;
+  int t;
+  MAS_HD double operator()(const double* x) const { return M::stage(x, u, t, prm); }
+};
+template <class M>
+struct StageInU {
+  const double* x;
+  const double* prm;
+  int t;
+  MAS_HD double operator()(const double* u) const { return M::stage(x, u, t, prm); }
+};
+template <class M>
+struct TerminalInX {
+  const double* prm;
+  MAS_HD double operator()(const double* x) const { return M::terminal(x, prm); }
+};
+template <class M>
+MAS_HD void fd_v_x(const double* x, const double* prm, double* g) {  // :212-225
+  constexpr int NX = M::NX;
+  const double eps = 1e-6;
+  double xp[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+#pragma unroll
+    for (int k = 0; k < NX; ++k) xp[k] = x[k];
+    xp[i] = x[i] + eps;
+    const double fp = M::terminal(xp, prm);
+    xp[i] = x[i] - eps;
+    const double fm = M::terminal(xp, prm);
+    g[i] = (fp - fm) / (2 * eps);
+  }
+}
+
+// ---- Q_uu regularisation + LLT + explicit inverse (ilqr.hpp:172-183) -----------------------------
+// Unblocked lower Cholesky reading the lower triangle only; fails at column k iff the pivot
+// x = a_kk - sum_j L_kj^2 is <= 0 (NaN passes), as Eigen::LLT does for these sizes.
+template <int N>
+MAS_HD bool llt_factor(const double* a, double* L) {
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) L[i] = a[i];
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    if (ok) {
+      double x = L[k + k * N];
+      if (k > 0) {
+        double sq = 0.0;
+#pragma unroll
+        for (int j = 0; j < k; ++j) sq += L[k + j * N] * L[k + j * N];
+        x -= sq;
+      }
+      if (x <= 0.0) {
+        ok = false;
+      } else {
+        x = sqrt(x);
+        L[k + k * N] = x;
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+          double s = L[i + k * N];
+          if (k > 0) {
+            double acc = L[i + 0 * N] * L[k + 0 * N];
+#pragma unroll
+            for (int j = 1; j < k; ++j) acc = acc + L[i + j * N] * L[k + j * N];
+            s -= acc;
+          }
+          L[i + k * N] = s / x;
+        }
+      }
+    }
+  }
+  return ok;
+}
+// inv = A^{-1} via L y = e_c, L^T x = y for each column c of the identity.
+template <int N>
+MAS_HD void llt_inverse(const double* L, double* inv) {
+#pragma unroll
+  for (int c = 0; c < N; ++c) {
+    double x[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double s = x[i];
+#pragma unroll
+      for (int j = 0; j < i; ++j) s -= L[i + j * N] * x[j];
+      x[i] = s / L[i + i * N];
+    }
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+      double s = x[i];
+#pragma unroll
+      for (int j = i + 1; j < N; ++j) s -= L[j + i * N] * x[j];
+      x[i] = s / L[i + i * N];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) inv[i + c * N] = x[i];
+  }
+}
+
+// ---- backward pass for one problem (ilqr.hpp:92-193) --------------------------------------------
+// MASK_CT >= 0 fixes the derivative mode at compile time (dead branches vanish); -1 reads it from
+// the view.  Writes K, k for every t.  Returns the number of regularisation retries.
+template <class M, int MASK_CT>
+MAS_HD int backward_thread(const BatchView<M::NX, M::NU>& v, int p) {
+  constexpr int NX = M::NX, NU = M::NU;
+  const unsigned mask = (MASK_CT >= 0) ? static_cast<unsigned>(MASK_CT) : v.deriv_mask;
+  double prm[M::NP > 0 ? M::NP : 1];
+  load_params<M>(v, p, prm);
+  const int T = v.T;
+  int retries = 0;
+
+  double x[NX], u[NU];
+  double v_x[NX], v_xx[NX * NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) x[i] = v.X[soa_index<NX>(T, i, v.ld, p)];
+  // :92-102 terminal value
+  if (mask & D_VX) M::v_x(x, prm, v_x);
+  else fd_v_x<M>(x, prm, v_x);
+  if (mask & D_VXX) M::v_xx(x, prm, v_xx);
+  else fd_hessian<NX>(x, TerminalInX<M>{prm}, v_xx);
+  symmetrize_aliased<NX>(v_xx);
+
+  for (int t = T - 1; t >= 0; --t) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = v.X[soa_index<NX>(t, i, v.ld, p)];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) u[i] = v.U[soa_index<NU>(t, i, v.ld, p)];
+
+    // :106-113
+    double A[NX * NX], B[NX * NU], l_x[NX], l_u[NU], l_xx[NX * NX], l_uu[NU * NU], l_ux[NU * NX];
+    if (mask & D_A) M::jac_x(x, u, prm, A);
+    else fd_jac_x<M>(x, u, prm, A);
+    if (mask & D_B) M::jac_u(x, u, prm, B);
+    else fd_jac_u<M>(x, u, prm, B);
+    if (mask & D_LX) M::l_x(x, u, t, prm, l_x);
+    else fd_l_x<M>(x, u, t, prm, l_x);
+    if (mask & D_LU) M::l_u(x, u, t, prm, l_u);
+    else fd_l_u<M>(x, u, t, prm, l_u);
+    if (mask & D_LXX) M::l_xx(x, u, t, prm, l_xx);
+    else fd_hessian<NX>(x, StageInX<M>{u, prm, t}, l_xx);
+    if (mask & D_LUU) M::l_uu(x, u, t, prm, l_uu);
+    else fd_hessian<NU>(u, StageInU<M>{x, prm, t}, l_uu);
+    if (mask & D_LUX) M::l_ux(x, u, t, prm, l_ux);
+    else fd_l_ux<M>(x, u, t, prm, l_ux);
+
+    // :115-119
+    double q_x[NX], q_u[NU], q_xx[NX * NX], q_ux[NU * NX], q_uu[NU * NU];
+    constexpr int TMPN = (NX > NU ? NX : NU) * (NX > NU ? NX : NU);
+    double AtV[NX * NX], BtV[NU * NX], tmp[TMPN];
+    mat_tn<NX, NX, 1>(A, v_x, tmp);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) q_x[i] = l_x[i] + tmp[i];
+    mat_tn<NX, NU, 1>(B, v_x, tmp);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) q_u[i] = l_u[i] + tmp[i];
+    mat_tn<NX, NX, NX>(A, v_xx, AtV);
+    mat_tn<NX, NU, NX>(B, v_xx, BtV);
+    mat_nn<NX, NX, NX>(AtV, A, tmp);
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) q_xx[i] = l_xx[i] + tmp[i];
+    mat_nn<NU, NX, NX>(BtV, A, tmp);
+#pragma unroll
+    for (int i = 0; i < NU * NX; ++i) q_ux[i] = l_ux[i] + tmp[i];
+    mat_nn<NU, NX, NU>(BtV, B, tmp);
+#pragma unroll
+    for (int i = 0; i < NU * NU; ++i) q_uu[i] = l_uu[i] + tmp[i];
+
+    // :172-183
+    double q_reg[NU * NU], L[NU * NU], inv[NU * NU];
+#pragma unroll
+    for (int i = 0; i < NU * NU; ++i) q_reg[i] = q_uu[i];
+    double reg = 1e-6;
+    while (!llt_factor<NU>(q_reg, L)) {
+#pragma unroll
+      for (int i = 0; i < NU; ++i) q_reg[i + i * NU] += reg;
+      reg *= 10.0;
+      ++retries;
+      if (!(reg < 1e300)) break;  // reference loops forever on NaN-free garbage; bail out instead
+    }
+    llt_inverse<NU>(L, inv);
+
+    // :185-186  k = (-Q_uu_inv) q_u,  K = (-Q_uu_inv) Q_ux
+    double ninv[NU * NU], kv[NU], Km[NU * NX];
+#pragma unroll
+    for (int i = 0; i < NU * NU; ++i) ninv[i] = -inv[i];
+    mat_nn<NU, NU, 1>(ninv, q_u, kv);
+    mat_nn<NU, NU, NX>(ninv, q_ux, Km);
+
+#pragma unroll
+    for (int i = 0; i < NU; ++i) v.kff[soa_index<NU>(t, i, v.ld, p)] = kv[i];
+#pragma unroll
+    for (int i = 0; i < NU * NX; ++i) v.K[soa_index<NU * NX>(t, i, v.ld, p)] = Km[i];
+
+    // :188-192 value update with the unregularised Q_uu
+    double KtQuu[NX * NU], t1[NX], t2[NX], t3[NX];
+    mat_tn<NU, NX, NU>(Km, q_uu, KtQuu);
+    mat_tn<NU, NX, 1>(Km, q_u, t1);
+    mat_tn<NU, NX, 1>(q_ux, kv, t2);
+    mat_nn<NX, NU, 1>(KtQuu, kv, t3);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) v_x[i] = ((q_x[i] + t1[i]) + t2[i]) + t3[i];
+    double m1[NX * NX], m2[NX * NX], m3[NX * NX];
+    mat_tn<NU, NX, NX>(Km, q_ux, m1);
+    mat_tn<NU, NX, NX>(q_ux, Km, m2);
+    mat_nn<NX, NU, NX>(KtQuu, Km, m3);
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) v_xx[i] = ((q_xx[i] + m1[i]) + m2[i]) + m3[i];
+    symmetrize_aliased<NX>(v_xx);
+  }
+  return retries;
+}
+
+// ---- forward pass (ilqr.hpp:206-217) for C step sizes at once, merit only ------------------------
+// The C rollouts share the loads of the nominal trajectory and gains and give the fp64 pipe C
+// independent dependency chains.  merit[c] = sum_t stage + terminal, accumulated in t order.
+template <class M, int C>
+MAS_HD void trial_rollout(const BatchView<M::NX, M::NU>& v, int p, const double* prm, const double* alpha, double* merit) {
+  constexpr int NX = M::NX, NU = M::NU;
+  double xt[C][NX], cost[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    cost[c] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xt[c][i] = v.x0[static_cast<size_t>(i) * v.ld + p];
+  }
+  for (int t = 0; t < v.T; ++t) {
+    double xn[NX], un[NU], kv[NU], Km[NU * NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xn[i] = v.X[soa_index<NX>(t, i, v.ld, p)];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) un[i] = v.U[soa_index<NU>(t, i, v.ld, p)];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) kv[i] = v.kff[soa_index<NU>(t, i, v.ld, p)];
+#pragma unroll
+    for (int i = 0; i < NU * NX; ++i) Km[i] = v.K[soa_index<NU * NX>(t, i, v.ld, p)];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      double dx[NX], u[NU], xnext[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) dx[i] = xt[c][i] - xn[i];
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        double kdx = Km[i + 0 * NU] * dx[0];
+#pragma unroll
+        for (int j = 1; j < NX; ++j) kdx = kdx + Km[i + j * NU] * dx[j];
+        double ui = (un[i] + alpha[c] * kv[i]) + kdx;
+        if (v.has_bounds) {  // clamp_controls: cwiseMin(upper) then cwiseMax(lower)
+          ui = (v.hi[i] < ui) ? v.hi[i] : ui;
+          ui = (v.lo[i] > ui) ? v.lo[i] : ui;
+        }
+        u[i] = ui;
+      }
+      cost[c] += M::stage(xt[c], u, t, prm);
+      rk4_step<M>(xt[c], u, prm, v.dt, xnext);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) xt[c][i] = xnext[i];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    cost[c] += M::terminal(xt[c], prm);
+    merit[c] = cost[c];
+  }
+}
+
+// ---- accepted step: same arithmetic as trial_rollout, writing X and U in place -------------------
+// Step t reads the nominal x_t, u_t, K_t, k_t before U[t] and X[t+1] are overwritten, and the
+// nominal x_{t+1} is fetched before X[t+1] is stored, so one buffer serves as old and new trajectory.
+template <class M>
+MAS_HD double commit_rollout(const BatchView<M::NX, M::NU>& v, int p, const double* prm, double alpha) {
+  constexpr int NX = M::NX, NU = M::NU;
+  double xt[NX], xn[NX], cost = 0.0;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    xt[i] = v.x0[static_cast<size_t>(i) * v.ld + p];
+    xn[i] = v.X[soa_index<NX>(0, i, v.ld, p)];
+  }
+  for (int t = 0; t < v.T; ++t) {
+    double un[NU], kv[NU], Km[NU * NX], xn_next[NX];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) un[i] = v.U[soa_index<NU>(t, i, v.ld, p)];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) kv[i] = v.kff[soa_index<NU>(t, i, v.ld, p)];
+#pragma unroll
+    for (int i = 0; i < NU * NX; ++i) Km[i] = v.K[soa_index<NU * NX>(t, i, v.ld, p)];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xn_next[i] = v.X[soa_index<NX>(t + 1, i, v.ld, p)];
+    double dx[NX], u[NU], xnext[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) dx[i] = xt[i] - xn[i];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      double kdx = Km[i + 0 * NU] * dx[0];
+#pragma unroll
+      for (int j = 1; j < NX; ++j) kdx = kdx + Km[i + j * NU] * dx[j];
+      double ui = (un[i] + alpha * kv[i]) + kdx;
+      if (v.has_bounds) {
+        ui = (v.hi[i] < ui) ? v.hi[i] : ui;
+        ui = (v.lo[i] > ui) ? v.lo[i] : ui;
+      }
+      u[i] = ui;
+      v.U[soa_index<NU>(t, i, v.ld, p)] = ui;
+    }
+    cost += M::stage(xt, u, t, prm);
+    rk4_step<M>(xt, u, prm, v.dt, xnext);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      xt[i] = xnext[i];
+      xn[i] = xn_next[i];
+      v.X[soa_index<NX>(t + 1, i, v.ld, p)] = xnext[i];
+    }
+  }
+  cost += M::terminal(xt, prm);
+  return cost;
+}
+
+// Step size of candidate j: alpha starts at 1.0 and is halved (ilqr.hpp:200,227) -> exact 2^-j.
+MAS_HD double alpha_of(int j) {
+  double a = 1.0;
+  for (int i = 0; i < j; ++i) a *= 0.5;
+  return a;
+}
+
+// One lane's share of the line search: candidates j = lane, lane + L, ... in chunks of C, stopping
+// after the first chunk that holds an improving candidate (later candidates of this lane cannot win).
+// Returns the lane's first improving candidate (kNumAlphas if none) and its merit.
+template <class M, int L, int C>
+MAS_HD void lane_line_search(const BatchView<M::NX, M::NU>& v, int p, const double* prm, int lane, double current_merit, int* best_j,
+                             double* best_merit) {
+  *best_j = kNumAlphas;
+  *best_merit = current_merit;
+  for (int base = lane; base < kNumAlphas; base += L * C) {
+    double alpha[C], merit[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int j = base + c * L;
+      alpha[c] = alpha_of(j < kNumAlphas ? j : kNumAlphas - 1);
+    }
+    trial_rollout<M, C>(v, p, prm, alpha, merit);
+    bool found = false;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int j = base + c * L;
+      if (!found && j < kNumAlphas && merit[c] < current_merit) {  // strict <, NaN never improves (:220)
+        found = true;
+        *best_j = j;
+        *best_merit = merit[c];
+      }
+    }
+    if (found) break;
+  }
+}
+
+// Accept / bookkeeping / stop test for one problem (ilqr.hpp:230-234,269-271).  Returns true when
+// the problem needs another iteration.
+template <class M>
+MAS_HD bool finish_iteration(const BatchView<M::NX, M::NU>& v, int p, const double* prm, double current_merit, int best_j, double best_merit) {
+  if (best_j < kNumAlphas) {
+    const double c = commit_rollout<M>(v, p, prm, alpha_of(best_j));
+    v.cost[p] = c;  // objective(x,u) recomputed on the accepted trajectory: same arithmetic as the trial merit
+    v.merit[p] = best_merit;
+  }
+  const double improvement = current_merit - best_merit;
+  const int it = v.iters[p] + 1;
+  v.iters[p] = it;
+  v.trials[p] += (best_j < kNumAlphas) ? best_j + 1 : kNumAlphas;
+  if (improvement < v.tolerance) {
+    v.status[p] = STATUS_CONVERGED;
+    return false;
+  }
+  if (it >= v.max_iterations) {
+    v.status[p] = STATUS_MAX_ITER;
+    return false;
+  }
+  return true;
+}
+
+}  // namespace mas_b200

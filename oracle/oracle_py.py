@@ -25,7 +25,7 @@ _lib = None
 def build(force: bool = False) -> str:
     """Compile the oracle with its Makefile (g++ only, a few seconds)."""
     if force or not os.path.exists(_LIB_PATH):
-        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []))
+        subprocess.check_call(["make", "-C", _HERE, "all"] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
 

@@ -1,0 +1,141 @@
+"""Shared fixtures.  GPU tests are marked `gpu`; everything else runs on a machine without one.
+
+`/root/reference` is never read here: inputs are generated, expected values come from oracle/ (a CPU
+restatement of the reference, test infrastructure) or from tests/golden/.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle_py
+
+    oracle_py.build()
+    return oracle_py
+
+
+@pytest.fixture(scope="session")
+def mas():
+    import multi_agent_solver_b200 as m
+
+    m.load_library()
+    return m
+
+
+@pytest.fixture(scope="session")
+def ctx(mas):
+    return mas.Context(0)
+
+
+# ---- host emulation of the device source (tests/csrc/host_emulation.cpp) -------------------------
+_EMU_SRC = os.path.join(ROOT, "tests", "csrc", "host_emulation.cpp")
+_EMU_LIB = os.path.join(ROOT, "tests", "_build", "libhost_emulation.so")
+
+
+def _build_emulation() -> str:
+    deps = [_EMU_SRC] + [os.path.join(ROOT, "multi_agent_solver_b200", "csrc", f) for f in ("ilqr_core.cuh", "models.cuh")]
+    deps.append(os.path.join(ROOT, "include", "mas_b200", "portable_math.h"))
+    if not os.path.exists(_EMU_LIB) or os.path.getmtime(_EMU_LIB) < max(os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(_EMU_LIB), exist_ok=True)
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-x", "c++",
+                               "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "multi_agent_solver_b200", "csrc"), _EMU_SRC,
+                               "-o", _EMU_LIB])
+    return _EMU_LIB
+
+
+# model id -> (n, m, T, dt, example mask, has_bounds, lower, upper, default params)
+MODEL_TABLE = {
+    0: (4, 2, 80, 0.1, 0x3F, 1, [-0.7, -1.0], [0.7, 1.0], [1.0, 10.0, 1.0, 0.1, 0.1]),
+    1: (4, 2, 10, 0.5, 0x0, 1, [-0.5, -0.5], [0.5, 0.5], [20.0, 5.0, 1.0, 1.0, 0.001, 0.001]),
+    2: (4, 4, 10, 0.1, 0x1FF, 0, [0.0] * 4, [0.0] * 4, []),
+    3: (2, 1, 60, 0.05, 0x0, 1, [-5.0], [5.0], [60.0]),
+    4: (3, 1, 50, 0.1, 0x1BF, 1, [0.0], [20.0], [9.81, 50.0, 5e-3, 15.0, 2.0, 0.0]),
+}
+
+
+class HostEmulation:
+    def __init__(self):
+        self.lib = ctypes.CDLL(_build_emulation())
+
+    def solve(self, model, x0, U, max_iterations, tolerance, L=1, C=2, mask=None, per_problem_params=None):
+        n, m, T, dt, emask, hb, lo, hi, prm = MODEL_TABLE[model]
+        mask = emask if mask is None else mask
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        B = x0.shape[0]
+        U = np.array(U, dtype=np.float64, order="C").reshape(B, T, m).copy()
+        X = np.zeros((B, T + 1, n))
+        cost = np.zeros(B)
+        it = np.zeros(B, np.int32)
+        st = np.zeros(B, np.int32)
+        tr = np.zeros(B, np.int32)
+        rg = np.zeros(B, np.int32)
+        lo = np.array(list(lo) + [0.0] * 8)
+        hi = np.array(list(hi) + [0.0] * 8)
+        sp = np.array(list(prm) + [0.0] * 8)
+        P = ctypes.POINTER(ctypes.c_double)
+        PI = ctypes.POINTER(ctypes.c_int)
+        pp = None
+        if per_problem_params is not None:
+            ppa = np.ascontiguousarray(per_problem_params, dtype=np.float64)
+            pp = ppa.ctypes.data_as(P)
+        rc = self.lib.emu_ilqr_solve_batch(model, B, T, ctypes.c_double(dt), ctypes.c_uint(mask), hb, lo.ctypes.data_as(P), hi.ctypes.data_as(P),
+                                           sp.ctypes.data_as(P), pp, x0.ctypes.data_as(P), U.ctypes.data_as(P), X.ctypes.data_as(P),
+                                           cost.ctypes.data_as(P), it.ctypes.data_as(PI), st.ctypes.data_as(PI), tr.ctypes.data_as(PI),
+                                           rg.ctypes.data_as(PI), int(max_iterations), ctypes.c_double(tolerance), int(L), int(C))
+        assert rc == 0
+        return dict(X=X, U=U, cost=cost, iterations=it, status=st, alpha_trials=tr, reg_retries=rg)
+
+
+@pytest.fixture(scope="session")
+def emu():
+    return HostEmulation()
+
+
+# ---- synthetic inputs ------------------------------------------------------------------------------
+def random_x0(model: int, batch: int, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    if model == 0:  # config 3 ranges
+        return np.stack([np.zeros(batch), rng.uniform(-2, 2, batch), rng.uniform(-0.5, 0.5, batch), rng.uniform(0, 2, batch)], -1)
+    if model == 1:  # agents on the circle, tangential heading (multi_agent_single_track.cpp:41-44)
+        th = rng.uniform(0, 2 * np.pi, batch)
+        return np.stack([20 * np.cos(th), 20 * np.sin(th), 1.57 + th, np.full(batch, 4.0)], -1)
+    if model == 2:
+        return rng.uniform(-1, 1, (batch, 4))
+    if model == 3:
+        return np.stack([np.pi - 0.05 + rng.uniform(-0.1, 0.1, batch), rng.uniform(-0.1, 0.1, batch)], -1)
+    if model == 4:
+        return np.stack([rng.uniform(0, 1, batch), rng.uniform(-1, 1, batch), rng.uniform(0.8, 1.2, batch)], -1)
+    raise ValueError(model)
+
+
+# solver params of the example mains: (max_iterations, tolerance)
+EXAMPLE_SOLVER_PARAMS = {0: (10, 1e-5), 1: (100, 1e-5), 2: (100, 1e-5), 3: (1000, 1e-4), 4: (25, 1e-6)}
+
+
+def assert_parity(got, ref, cost_rtol=1e-9, traj_atol=1e-7):
+    """BASELINE.json north_star tolerances: cost 1e-9 relative, trajectories 1e-7 absolute, identical
+    iteration counts and convergence flags."""
+    np.testing.assert_array_equal(got["iterations"], ref["iterations"])
+    np.testing.assert_array_equal(got["status"], ref["status"])
+    denom = np.maximum(np.abs(ref["cost"]), 1e-300)
+    assert np.max(np.abs(got["cost"] - ref["cost"]) / denom) <= cost_rtol
+    assert np.max(np.abs(got["X"] - ref["X"])) <= traj_atol
+    assert np.max(np.abs(got["U"] - ref["U"])) <= traj_atol
+
+
+def is_bit_exact(got, ref) -> bool:
+    return bool(np.array_equal(got["X"], ref["X"]) and np.array_equal(got["U"], ref["U"]) and np.array_equal(got["cost"], ref["cost"]))

@@ -1,0 +1,132 @@
+// host_emulation.cpp -- TEST HARNESS, not a product path.
+//
+// Compiles the per-thread bodies of the CUDA kernels (multi_agent_solver_b200/csrc/ilqr_core.cuh,
+// models.cuh -- all __host__ __device__) with g++ and drives them with the same schedule the engine
+// uses on the GPU (prologue, then per iteration: backward for each active problem, L-lane line
+// search with the group reduction done by a loop instead of warp shuffles, commit, stop test,
+// active-list compaction).  This lets the "-m 'not gpu'" tests check the device source against the
+// oracle bit for bit on a machine without a GPU.  Nothing in the product links or loads this file.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "ilqr_core.cuh"
+
+using namespace mas_b200;
+
+namespace {
+
+template <class M>
+int emulate(int batch, int T, double dt, unsigned mask, int has_bounds, const double* lo, const double* hi, const double* shared_p,
+            const double* per_problem_p, const double* x0, double* U, double* X, double* cost, int* iters, int* status, int* trials, int* reg,
+            int max_iterations, double tolerance, int L, int C) {
+  constexpr int NX = M::NX, NU = M::NU;
+  const int ld = ((batch + 31) / 32) * 32;
+  std::vector<double> sx0(static_cast<size_t>(NX) * ld), sX(static_cast<size_t>(NX) * (T + 1) * ld), sU(static_cast<size_t>(NU) * T * ld),
+      sK(static_cast<size_t>(NU) * NX * T * ld), sk(static_cast<size_t>(NU) * T * ld), scost(ld), smerit(ld), sp(static_cast<size_t>(kMaxParams) * ld);
+  std::vector<int> sit(ld), sst(ld), str(ld), srg(ld);
+  for (int b = 0; b < batch; ++b) {
+    for (int i = 0; i < NX; ++i) sx0[static_cast<size_t>(i) * ld + b] = x0[static_cast<size_t>(b) * NX + i];
+    for (int r = 0; r < NU * T; ++r) sU[static_cast<size_t>(r) * ld + b] = U[static_cast<size_t>(b) * NU * T + r];
+    if (per_problem_p)
+      for (int i = 0; i < M::NP; ++i) sp[static_cast<size_t>(i) * ld + b] = per_problem_p[static_cast<size_t>(b) * M::NP + i];
+  }
+  BatchView<NX, NU> v{};
+  v.ld = ld;
+  v.T = T;
+  v.dt = dt;
+  v.deriv_mask = mask;
+  v.has_bounds = has_bounds;
+  for (int i = 0; i < NU; ++i) {
+    v.lo[i] = lo[i];
+    v.hi[i] = hi[i];
+  }
+  v.per_problem_params = per_problem_p ? 1 : 0;
+  for (int i = 0; i < kMaxParams; ++i) v.shared_p[i] = shared_p ? shared_p[i] : 0.0;
+  v.params = sp.data();
+  v.x0 = sx0.data();
+  v.X = sX.data();
+  v.U = sU.data();
+  v.K = sK.data();
+  v.kff = sk.data();
+  v.cost = scost.data();
+  v.merit = smerit.data();
+  v.iters = sit.data();
+  v.status = sst.data();
+  v.trials = str.data();
+  v.reg_retries = srg.data();
+  v.tolerance = tolerance;
+  v.max_iterations = max_iterations;
+
+  std::vector<int> list(batch), next;
+  for (int p = 0; p < batch; ++p) {  // prologue_kernel
+    const double c = rollout_thread<M>(v, p);
+    v.cost[p] = c;
+    v.merit[p] = c;
+    v.iters[p] = 0;
+    v.trials[p] = 0;
+    v.reg_retries[p] = 0;
+    v.status[p] = STATUS_MAX_ITER;
+    list[p] = p;
+  }
+  if (max_iterations <= 0) list.clear();
+  for (int it = 0; it < max_iterations && !list.empty(); ++it) {
+    for (int p : list) {  // backward_kernel
+      int r;
+      if (mask == M::EXAMPLE_MASK) r = backward_thread<M, static_cast<int>(M::EXAMPLE_MASK)>(v, p);
+      else if (mask == 0u) r = backward_thread<M, 0>(v, p);
+      else r = backward_thread<M, -1>(v, p);
+      v.reg_retries[p] += r;
+    }
+    next.clear();
+    for (int p : list) {  // forward_kernel, lanes emulated one after the other
+      double prm[M::NP > 0 ? M::NP : 1];
+      load_params<M>(v, p, prm);
+      const double current_merit = v.merit[p];
+      int best_j = kNumAlphas;
+      double best_merit = 0.0;
+      for (int lane = 0; lane < L; ++lane) {
+        int bj;
+        double bm;
+        if (L == 1 && C == 2) lane_line_search<M, 1, 2>(v, p, prm, lane, current_merit, &bj, &bm);
+        else if (L == 1) lane_line_search<M, 1, 1>(v, p, prm, lane, current_merit, &bj, &bm);
+        else if (L == 2) lane_line_search<M, 2, 1>(v, p, prm, lane, current_merit, &bj, &bm);
+        else if (L == 4) lane_line_search<M, 4, 1>(v, p, prm, lane, current_merit, &bj, &bm);
+        else if (L == 8) lane_line_search<M, 8, 1>(v, p, prm, lane, current_merit, &bj, &bm);
+        else lane_line_search<M, 16, 1>(v, p, prm, lane, current_merit, &bj, &bm);
+        if (bj < best_j) {
+          best_j = bj;
+          best_merit = bm;
+        }
+      }
+      if (best_j == kNumAlphas) best_merit = current_merit;
+      if (finish_iteration<M>(v, p, prm, current_merit, best_j, best_merit)) next.push_back(p);
+    }
+    list.swap(next);
+  }
+  for (int b = 0; b < batch; ++b) {
+    for (int r = 0; r < NX * (T + 1); ++r) X[static_cast<size_t>(b) * NX * (T + 1) + r] = sX[static_cast<size_t>(r) * ld + b];
+    for (int r = 0; r < NU * T; ++r) U[static_cast<size_t>(b) * NU * T + r] = sU[static_cast<size_t>(r) * ld + b];
+    cost[b] = scost[b];
+    iters[b] = sit[b];
+    status[b] = sst[b];
+    if (trials) trials[b] = str[b];
+    if (reg) reg[b] = srg[b];
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int emu_ilqr_solve_batch(int model, int batch, int T, double dt, unsigned mask, int has_bounds, const double* lo, const double* hi,
+                                    const double* shared_p, const double* per_problem_p, const double* x0, double* U, double* X, double* cost,
+                                    int* iters, int* status, int* trials, int* reg, int max_iterations, double tolerance, int L, int C) {
+  switch (model) {
+    case 0: return emulate<StLane>(batch, T, dt, mask, has_bounds, lo, hi, shared_p, per_problem_p, x0, U, X, cost, iters, status, trials, reg, max_iterations, tolerance, L, C);
+    case 1: return emulate<StCirc>(batch, T, dt, mask, has_bounds, lo, hi, shared_p, per_problem_p, x0, U, X, cost, iters, status, trials, reg, max_iterations, tolerance, L, C);
+    case 2: return emulate<Lqr4>(batch, T, dt, mask, has_bounds, lo, hi, shared_p, per_problem_p, x0, U, X, cost, iters, status, trials, reg, max_iterations, tolerance, L, C);
+    case 3: return emulate<Pendulum>(batch, T, dt, mask, has_bounds, lo, hi, shared_p, per_problem_p, x0, U, X, cost, iters, status, trials, reg, max_iterations, tolerance, L, C);
+    case 4: return emulate<Rocket>(batch, T, dt, mask, has_bounds, lo, hi, shared_p, per_problem_p, x0, U, X, cost, iters, status, trials, reg, max_iterations, tolerance, L, C);
+  }
+  return 1;
+}

@@ -1,0 +1,187 @@
+"""GPU parity: libmas_b200.so (through the C ABI) against the oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): final cost 1e-9 relative, trajectories 1e-7 absolute, identical
+iteration counts and convergence flags.  The oracle runs in its portable-trig mode, i.e. with the same
+sin/cos/tan implementation as the kernels (include/mas_b200/portable_math.h); the kernels are written
+to reproduce the oracle's rounded operations one for one, so these tests additionally require
+bit-identical trajectories.
+"""
+import numpy as np
+import pytest
+
+from conftest import EXAMPLE_SOLVER_PARAMS, assert_parity, is_bit_exact, random_x0
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_solve(mas, ctx, model, x0, U0, max_iterations, tolerance, lanes=0, chains=0, mask=None, params=None):
+    desc = mas.example_desc(model)
+    if mask is not None:
+        desc.deriv_mask = mask
+    b = mas.Batch(ctx, desc, x0.shape[0])
+    b.set_tuning(lanes, chains)
+    b.set_initial_states(x0)
+    if params is not None:
+        b.set_params(params)
+    b.set_controls(U0)
+    b.solve(mas.IlqrParams.make(max_iterations, tolerance))
+    out = b.get_solution()
+    out["stats"] = b.stats()
+    b.close()
+    return out
+
+
+@pytest.mark.parametrize("model,batch", [(0, 257), (1, 96), (2, 64), (3, 40), (4, 64)])
+def test_example_models_match_oracle(mas, ctx, oracle, model, batch):
+    max_it, tol = EXAMPLE_SOLVER_PARAMS[model]
+    max_it = min(max_it, 60)
+    x0 = random_x0(model, batch, seed=100 + model)
+    desc = mas.example_desc(model)
+    U0 = np.broadcast_to(mas.example_controls(model, desc.horizon_steps), (batch, desc.horizon_steps, desc.control_dim)).copy()
+    ref = oracle.ilqr_solve_batch(model, x0, U_init=U0, max_iterations=max_it, tolerance=tol, trig=oracle.TRIG_PORTABLE)
+    got = gpu_solve(mas, ctx, model, x0, U0, max_it, tol)
+    assert_parity(got, ref)
+    assert is_bit_exact(got, ref)
+    assert got["stats"]["iterations"] == int(ref["iterations"].sum())
+    assert got["stats"]["alpha_trials"] == int(ref["alpha_trials"].sum())
+    assert got["stats"]["reg_retries"] == int(ref["reg_retries"].sum())
+
+
+def test_config1_single_track_ocp(mas, ctx, oracle):
+    """BASELINE config 1: the single_track_ocp example, x0 = (0,1,0,0), 10 / 1e-5."""
+    x0 = np.array([[0.0, 1.0, 0.0, 0.0]])
+    got = gpu_solve(mas, ctx, 0, x0, None, 10, 1e-5)
+    ref = oracle.ilqr_solve_batch(0, x0, max_iterations=10, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    assert_parity(got, ref)
+    assert got["iterations"][0] == 3 and got["status"][0] == mas.Status.CONVERGED
+    assert abs(got["cost"][0] - 508.5930603049) < 1e-9
+
+
+@pytest.mark.parametrize("lanes,chains", [(1, 1), (1, 2), (2, 1), (4, 1), (8, 1), (16, 1)])
+def test_line_search_lane_mappings_agree(mas, ctx, oracle, lanes, chains):
+    """Every lanes-per-problem mapping of the line-search kernel picks the same first improving step."""
+    x0 = random_x0(0, 130, seed=5)
+    ref = oracle.ilqr_solve_batch(0, x0, max_iterations=10, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    got = gpu_solve(mas, ctx, 0, x0, None, 10, 1e-5, lanes=lanes, chains=chains)
+    assert_parity(got, ref)
+    assert is_bit_exact(got, ref)
+    assert got["stats"]["forward_lanes"] == lanes
+
+
+@pytest.mark.parametrize("model", [0, 4])
+def test_all_fd_mode_matches_oracle(mas, ctx, oracle, emu, model):
+    """deriv_mask = 0: every derivative from the finite-difference defaults (ocp.hpp:117-135).  The oracle's
+    example builders install analytic callbacks for these models, so the expected values come from the
+    host emulation of the device source, itself checked against the oracle in the CPU tests."""
+    max_it, tol = 8, 1e-5
+    x0 = random_x0(model, 48, seed=11)
+    desc = mas.example_desc(model)
+    U0 = np.broadcast_to(mas.example_controls(model, desc.horizon_steps), (48, desc.horizon_steps, desc.control_dim)).copy()
+    exp = emu.solve(model, x0, U0, max_it, tol, mask=0)
+    got = gpu_solve(mas, ctx, model, x0, U0, max_it, tol, mask=0)
+    assert_parity(got, exp)
+    assert is_bit_exact(got, exp)
+
+
+def test_per_problem_params(mas, ctx, oracle):
+    """ST-circ with a different track radius per problem (SURVEY 8d config 2 jitter)."""
+    rng = np.random.default_rng(3)
+    B = 64
+    R = rng.uniform(15, 25, B)
+    th = rng.uniform(0, 2 * np.pi, B)
+    x0 = np.stack([R * np.cos(th), R * np.sin(th), 1.57 + th, np.full(B, 4.0)], -1)
+    oparams = np.stack([R, np.full(B, 5.0)], -1)
+    gparams = np.stack([R, np.full(B, 5.0), np.ones(B), np.ones(B), np.full(B, 0.001), np.full(B, 0.001)], -1)
+    ref = oracle.ilqr_solve_batch(1, x0, params=oparams, max_iterations=40, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    got = gpu_solve(mas, ctx, 1, x0, None, 40, 1e-5, params=gparams)
+    assert_parity(got, ref)
+    assert is_bit_exact(got, ref)
+
+
+def test_warm_start_and_iteration_cap(mas, ctx, oracle):
+    """solve() starts from best_controls (ilqr.hpp:71-75); max_iterations = 2 ends with MAX_ITER flags."""
+    x0 = random_x0(0, 64, seed=21)
+    first = oracle.ilqr_solve_batch(0, x0, max_iterations=2, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    got1 = gpu_solve(mas, ctx, 0, x0, None, 2, 1e-5)
+    assert_parity(got1, first)
+    assert (got1["status"] == mas.Status.MAX_ITER).any()
+    second = oracle.ilqr_solve_batch(0, x0, U_init=first["U"], max_iterations=10, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    got2 = gpu_solve(mas, ctx, 0, x0, got1["U"], 10, 1e-5)
+    assert_parity(got2, second)
+    assert is_bit_exact(got2, second)
+
+
+def test_one_shot_api_and_edge_sizes(mas, ctx, oracle):
+    """mas_b200_ilqr_solve_batch on host arrays; batch sizes 1, 31, 33 (ragged against the 32-lane padding)."""
+    for batch in (1, 31, 33):
+        x0 = random_x0(2, batch, seed=batch)
+        got = mas.ilqr_solve_batch(ctx, mas.example_desc(2), mas.IlqrParams.make(100, 1e-5), x0)
+        ref = oracle.ilqr_solve_batch(2, x0, max_iterations=100, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+        assert_parity(got, ref)
+        assert is_bit_exact(got, ref)
+
+
+def test_zero_iterations_and_errors(mas, ctx, oracle):
+    x0 = random_x0(0, 8, seed=1)
+    got = gpu_solve(mas, ctx, 0, x0, None, 0, 1e-5)
+    assert (got["iterations"] == 0).all() and (got["status"] == mas.Status.MAX_ITER).all()
+    X, cost = oracle.rollout_cost(0, x0, np.zeros((8, 80, 2)), trig=oracle.TRIG_PORTABLE)
+    np.testing.assert_array_equal(got["cost"], cost)
+    np.testing.assert_array_equal(got["X"], X)
+    desc = mas.example_desc(1)
+    desc.deriv_mask = mas.DerivBits.LX  # ST-circ has no analytic cost gradient
+    with pytest.raises(mas.MasB200Error) as e:
+        mas.Batch(ctx, desc, 4)
+    assert e.value.code == 1
+    desc = mas.example_desc(0)
+    desc.state_dim = 5
+    with pytest.raises(mas.MasB200Error):
+        mas.Batch(ctx, desc, 4)
+
+
+def test_time_limit_flag(mas, ctx):
+    """max_ms = 0 with a clock already past it: the batch stops before the first backward pass (ilqr.hpp:84-90)."""
+    x0 = random_x0(0, 16, seed=2)
+    desc = mas.example_desc(0)
+    b = mas.Batch(ctx, desc, 16)
+    b.set_initial_states(x0)
+    b.set_controls(None)
+    b.solve(mas.IlqrParams.make(10, 1e-5, max_ms=-1.0))
+    out = b.get_solution()
+    assert (out["status"] == mas.Status.TIME_LIMIT).all() and (out["iterations"] == 0).all()
+
+
+def test_full_size_batch_properties(mas, ctx, oracle):
+    """BASELINE config 3 at full size (65,536 ST-lane problems): size-independent properties.
+    (a) a strided sample of 512 problems equals the oracle; (b) solving the two halves separately
+    gives the same bits as the whole batch (no cross-problem coupling, any lane mapping);
+    (c) a second solve warm-started from the solution stops after one iteration without changing it."""
+    B = 65536
+    x0 = mas.synthetic_single_track_x0(B)
+    desc = mas.example_desc(0)
+    prm = mas.IlqrParams.make(10, 1e-5)
+    b = mas.Batch(ctx, desc, B)
+    b.set_initial_states(x0)
+    b.set_controls(None)
+    b.solve(prm)
+    full = b.get_solution()
+    idx = np.arange(0, B, 128)
+    ref = oracle.ilqr_solve_batch(0, x0[idx], max_iterations=10, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    sub = {k: full[k][idx] for k in ("X", "U", "cost", "iterations", "status")}
+    assert_parity(sub, ref)
+    assert is_bit_exact(sub, ref)
+    # (c) idempotence on the device-resident solution
+    b.solve(prm)
+    again = b.get_solution()
+    conv = full["status"] == mas.Status.CONVERGED
+    assert conv.mean() > 0.9
+    assert (again["iterations"][conv] == 1).all()
+    np.testing.assert_array_equal(again["U"][conv], full["U"][conv])
+    np.testing.assert_array_equal(again["cost"][conv], full["cost"][conv])
+    b.close()
+    # (b) halves
+    for lo, hi, lanes in ((0, B // 2, 2), (B // 2, B, 4)):
+        h = gpu_solve(mas, ctx, 0, x0[lo:hi], None, 10, 1e-5, lanes=lanes)
+        np.testing.assert_array_equal(h["X"], full["X"][lo:hi])
+        np.testing.assert_array_equal(h["cost"], full["cost"][lo:hi])
+        np.testing.assert_array_equal(h["iterations"], full["iterations"][lo:hi])
