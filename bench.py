@@ -169,6 +169,8 @@ def run_b200(args):
     batch = mas.Batch(ctx, desc, per_rank)
     if args.lanes or args.chains:
         batch.set_tuning(args.lanes, args.chains)
+    if args.ls_mode:
+        batch.set_line_search_mode(args.ls_mode)
 
     # pinned host buffers of the e2e path
     x0_pin = torch.from_numpy(x0).pin_memory()
@@ -223,9 +225,18 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     ms_step, wall_step = timed(resident_step, args.steps)
+    if args.resident_only and rank == 0:
+        sampler.stop()
     st = batch.stats()
     launches = st["kernel_launches"] - launches0
     value = total / (ms_step * 1e-3)
+
+    if args.resident_only:  # short form for ncu captures: only the resident steps above
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_step, "gpu_launches": int(launches),
+                              "note": "resident-only run (profiling aid), not a bench line"}), flush=True)
+        batch.close()
+        return
 
     # ---- e2e number ------------------------------------------------------------------------------------
     for _ in range(2):
@@ -310,6 +321,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-sample", type=int, default=8192, help="problems per CPU-baseline pass")
+    ap.add_argument("--resident-only", action="store_true", help="run only warm-up + timed resident steps (for ncu)")
+    ap.add_argument("--ls-mode", type=int, default=0, help="line search scheduling: 0 auto, 1 concurrent lanes, 2 compacted rounds")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--chains", type=int, default=0)
     args = ap.parse_args()

@@ -175,6 +175,10 @@ int mas_b200_batch_get_profile(mas_b200_batch_t b, mas_b200_profile* out);
 /* Tuning of the line-search kernel: lanes per problem (1,2,4,8,16; 0 = auto from batch size) and
  * step sizes rolled out together per lane (1 or 2; 0 = auto). */
 int mas_b200_batch_set_tuning(mas_b200_batch_t b, int forward_lanes, int forward_chains);
+/* How the line search (solvers/ilqr.hpp:195-228) is scheduled: 0 = auto (by active-set size),
+ * 1 = all step sizes concurrently on `forward_lanes` lanes per problem, 2 = compacted rounds of two
+ * step sizes over the problems still searching.  Results are bit-identical in every mode. */
+int mas_b200_batch_set_line_search_mode(mas_b200_batch_t b, int mode);
 
 /* One-shot: set_initial_states + set_controls + initialize + solve + get_solution on host buffers.
  * U is in/out (initial_controls in, best_controls out; NULL = zero initial controls, not returned). */

@@ -250,6 +250,10 @@ class Batch:
     def set_tuning(self, forward_lanes: int = 0, forward_chains: int = 0) -> None:
         _check(load_library().mas_b200_batch_set_tuning(self._h, int(forward_lanes), int(forward_chains)))
 
+    def set_line_search_mode(self, mode: int) -> None:
+        """0 auto, 1 concurrent lanes, 2 compacted rounds."""
+        _check(load_library().mas_b200_batch_set_line_search_mode(self._h, int(mode)))
+
     def get_solution(self, out=None):
         if out is None:
             out = dict(X=np.empty((self.batch, self.T + 1, self.nx)), U=np.empty((self.batch, self.T, self.nu)), cost=np.empty(self.batch),

@@ -391,6 +391,13 @@ int mas_b200_batch_set_tuning(mas_b200_batch_t h, int forward_lanes, int forward
   return MAS_B200_OK;
 }
 
+int mas_b200_batch_set_line_search_mode(mas_b200_batch_t h, int mode) {
+  MAS_BATCH_GUARD(h);
+  if (mode < 0 || mode > 2) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "line search mode must be 0 (auto), 1 (lanes) or 2 (rounds)");
+  b->ls_mode = mode;
+  return MAS_B200_OK;
+}
+
 int mas_b200_ilqr_solve_batch(mas_b200_context_t ctx, const mas_b200_ocp_desc* desc, const mas_b200_ilqr_params* params, int batch,
                               const double* x0, const double* model_params, double* U, double* X, double* cost, int* iterations, int* status) {
   int rc = validate_params(params);

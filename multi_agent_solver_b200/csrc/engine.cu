@@ -67,10 +67,10 @@ __global__ void dfma_probe_kernel(double* out, int iters) {
 
 BatchBase::~BatchBase() {
   if (ctx) cudaSetDevice(ctx->device);
-  double* dptrs[] = {d_x0, d_X, d_U, d_K, d_k, d_cost, d_merit, d_params, d_stage, d_U_old, d_X_old, d_cost_old, d_radius};
+  double* dptrs[] = {d_x0, d_X, d_U, d_K, d_k, d_cost, d_merit, d_params, d_stage, d_U_old, d_X_old, d_cost_old, d_radius, d_accept_merit};
   for (double* p : dptrs)
     if (p) cudaFree(p);
-  int* iptrs[] = {d_iters, d_status, d_trials, d_reg, d_list[0], d_list[1], d_count, d_accepted};
+  int* iptrs[] = {d_iters, d_status, d_trials, d_reg, d_list[0], d_list[1], d_count, d_accepted, d_ls_list[0], d_ls_list[1], d_round_count, d_accept_idx};
   for (int* p : iptrs)
     if (p) cudaFree(p);
   if (h_counts) cudaFreeHost(h_counts);
@@ -115,6 +115,12 @@ int BatchBase::allocate() {
   MAS_CUDA_CHECK(ialloc(&d_list[0], L));
   MAS_CUDA_CHECK(ialloc(&d_list[1], L));
   MAS_CUDA_CHECK(ialloc(&d_count, 2));
+  MAS_CUDA_CHECK(ialloc(&d_ls_list[0], L));
+  MAS_CUDA_CHECK(ialloc(&d_ls_list[1], L));
+  MAS_CUDA_CHECK(ialloc(&d_round_count, 8));
+  MAS_CUDA_CHECK(ialloc(&d_accept_idx, L));
+  MAS_CUDA_CHECK(cudaMemsetAsync(d_accept_idx, 0xFF, L * sizeof(int), ctx->stream));  // -1: no accepted step size
+  MAS_CUDA_CHECK(dalloc(&d_accept_merit, L));
   MAS_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&h_counts), 4 * sizeof(int)));
   MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
   MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));

@@ -34,6 +34,11 @@ void set_last_error(const std::string& msg);
     }                                                                                                     \
   } while (0)
 
+// 64-thread CTAs: the iLQR kernels need 120-250 registers per thread, and with 2-warp CTAs the
+// register file of an SM (64K) divides into more resident CTAs than with 4-warp ones (e.g. 7 x 64
+// instead of 3 x 128 threads at 134 registers), which turns the 65,536-problem batch into one wave.
+constexpr int kBlock = 64;
+
 struct Context {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -53,7 +58,7 @@ __global__ void dfma_probe_kernel(double* out, int iters);
 // OCP::initialize_problem / iLQR prologue: rollout + cost, reset of the per-solve counters and of
 // the active list (identity).  ilqr.hpp:75-78, ocp.hpp:110-113,182.
 template <class M>
-__global__ void __launch_bounds__(128) prologue_kernel(BatchView<M::NX, M::NU> v, int batch, int* list, int* count, int max_iterations) {
+__global__ void __launch_bounds__(kBlock) prologue_kernel(BatchView<M::NX, M::NU> v, int batch, int* list, int* count, int max_iterations) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p == 0) *count = (max_iterations > 0) ? batch : 0;
   if (p >= batch) return;
@@ -68,7 +73,7 @@ __global__ void __launch_bounds__(128) prologue_kernel(BatchView<M::NX, M::NU> v
 }
 
 template <class M, int MASK_CT>
-__global__ void __launch_bounds__(128) backward_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
+__global__ void __launch_bounds__(kBlock, 7) backward_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
                                                        int* next_count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) *next_count = 0;
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(128) backward_kernel(BatchView<M::NX, M::NU> v
 // L lanes per problem (a power of two <= 16, aligned inside the warp); lane l rolls out step sizes
 // l, l+L, ...; the group picks the first improving candidate with shuffles; lane 0 commits.
 template <class M, int L, int C>
-__global__ void __launch_bounds__(128) forward_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
+__global__ void __launch_bounds__(kBlock, 7) forward_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
                                                       int* next_list, int* next_count) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = gid / L;
@@ -122,9 +127,79 @@ __global__ void __launch_bounds__(128) forward_kernel(BatchView<M::NX, M::NU> v,
   }
 }
 
+// ---- line search as compacted rounds (large active sets) ------------------------------------------------
+// Round r rolls out step sizes r*C .. r*C+C-1 for the problems that have not found an improving one
+// yet; those that still have not are appended (warp-aggregated) to the next round's list.  Every warp
+// of every round is full, and a problem stops costing rollouts at its first improving step size, as
+// in the reference's sequential loop (ilqr.hpp:206-228).  counts[r] holds the size of round r's list.
+template <class M, int C>
+__global__ void __launch_bounds__(kBlock, 7) trial_round_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
+                                                               int* next_list, int* next_count, int base_j, int* accept_idx,
+                                                               double* accept_merit) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < *count;
+  const int p = valid ? list[i] : 0;
+  bool keep = false;
+  if (valid) {
+    double prm[M::NP > 0 ? M::NP : 1];
+    load_params<M>(v, p, prm);
+    const double current_merit = v.merit[p];
+    double alpha[C], merit[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) alpha[c] = alpha_of(base_j + c < kNumAlphas ? base_j + c : kNumAlphas - 1);
+    trial_rollout<M, C>(v, p, prm, alpha, merit);
+    int found = -1;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      if (found < 0 && base_j + c < kNumAlphas && merit[c] < current_merit) found = c;
+    if (found >= 0) {
+      accept_idx[p] = base_j + found;
+      accept_merit[p] = merit[found];
+    } else {
+      keep = base_j + C < kNumAlphas;
+    }
+  }
+  const unsigned vote = __ballot_sync(0xffffffffu, keep);
+  if (vote) {
+    const int wl = threadIdx.x & 31;
+    int base = 0;
+    if (wl == 0) base = atomicAdd(next_count, __popc(vote));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) next_list[base + __popc(vote & ((1u << wl) - 1u))] = p;
+  }
+}
+
+// After the rounds: commit the accepted step (if any), bookkeeping, stop test, next active list.
+template <class M>
+__global__ void __launch_bounds__(kBlock, 7) finish_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
+                                                          int* next_list, int* next_count, int* accept_idx, const double* __restrict__ accept_merit) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < *count;
+  const int p = valid ? list[i] : 0;
+  bool again = false;
+  if (valid) {
+    double prm[M::NP > 0 ? M::NP : 1];
+    load_params<M>(v, p, prm);
+    const double current_merit = v.merit[p];
+    const int aj = accept_idx[p];
+    accept_idx[p] = -1;
+    const int best_j = aj >= 0 ? aj : kNumAlphas;
+    const double best_merit = aj >= 0 ? accept_merit[p] : current_merit;
+    again = finish_iteration<M>(v, p, prm, current_merit, best_j, best_merit);
+  }
+  const unsigned vote = __ballot_sync(0xffffffffu, again);
+  if (vote) {
+    const int wl = threadIdx.x & 31;
+    int base = 0;
+    if (wl == 0) base = atomicAdd(next_count, __popc(vote));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (again) next_list[base + __popc(vote & ((1u << wl) - 1u))] = p;
+  }
+}
+
 // Re-rollout of given controls (strategy layer, nash.hpp:224-225): X and cost from U.
 template <class M>
-__global__ void __launch_bounds__(128) rollout_kernel(BatchView<M::NX, M::NU> v, int batch) {
+__global__ void __launch_bounds__(kBlock) rollout_kernel(BatchView<M::NX, M::NU> v, int batch) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= batch) return;
   const double c = rollout_thread<M>(v, p);
@@ -136,7 +211,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(BatchView<M::NX, M::NU> v,
 // scaled, re-rolled out and re-costed; accept iff cand_cost < old_cost (strict) -> radius *= 1.5,
 // otherwise restore the old trajectory and radius *= 0.5.
 template <class M>
-__global__ void __launch_bounds__(128) trust_region_kernel(BatchView<M::NX, M::NU> v, int batch, const double* __restrict__ U_old,
+__global__ void __launch_bounds__(kBlock) trust_region_kernel(BatchView<M::NX, M::NU> v, int batch, const double* __restrict__ U_old,
                                                            const double* __restrict__ X_old, const double* __restrict__ cost_old, double* radius,
                                                            int* accepted) {
   constexpr int NX = M::NX, NU = M::NU;
@@ -208,6 +283,13 @@ struct BatchBase {
   cudaEvent_t ev[2] = {nullptr, nullptr};
   bool per_problem_params = false;
   int tune_L = 0, tune_C = 0;
+  int ls_mode = 0;  // 0 auto, 1 concurrent lanes (forward_kernel), 2 compacted rounds (trial_round_kernel + finish_kernel)
+  // compacted-rounds line search scratch
+  int* d_ls_list[2] = {nullptr, nullptr};
+  int* d_round_count = nullptr;  // [8]
+  int* d_accept_idx = nullptr;   // [ld], -1 = none
+  double* d_accept_merit = nullptr;
+  int rounds_used = 0;
   // optional per-launch timing (CUDA events on the launching stream), see mas_b200_batch_set_profiling
   bool profiling = false;
   struct TimedLaunch {
@@ -274,7 +356,7 @@ struct BatchImpl : BatchBase {
 
   int launch_prologue(int max_iterations) {
     make_view();
-    prologue_kernel<M><<<div_up(batch, 128), 128, 0, ctx->stream>>>(view, batch, d_list[0], d_count, max_iterations);
+    prologue_kernel<M><<<div_up(batch, kBlock), kBlock, 0, ctx->stream>>>(view, batch, d_list[0], d_count, max_iterations);
     stats.kernel_launches++;
     MAS_CUDA_CHECK(cudaGetLastError());
     return MAS_B200_OK;
@@ -284,7 +366,7 @@ struct BatchImpl : BatchBase {
 
   int rollout_all() override {
     make_view();
-    rollout_kernel<M><<<div_up(batch, 128), 128, 0, ctx->stream>>>(view, batch);
+    rollout_kernel<M><<<div_up(batch, kBlock), kBlock, 0, ctx->stream>>>(view, batch);
     stats.kernel_launches++;
     MAS_CUDA_CHECK(cudaGetLastError());
     return MAS_B200_OK;
@@ -292,29 +374,29 @@ struct BatchImpl : BatchBase {
 
   int trust_region_step() override {
     make_view();
-    trust_region_kernel<M><<<div_up(batch, 128), 128, 0, ctx->stream>>>(view, batch, d_U_old, d_X_old, d_cost_old, d_radius, d_accepted);
+    trust_region_kernel<M><<<div_up(batch, kBlock), kBlock, 0, ctx->stream>>>(view, batch, d_U_old, d_X_old, d_cost_old, d_radius, d_accepted);
     stats.kernel_launches++;
     MAS_CUDA_CHECK(cudaGetLastError());
     return MAS_B200_OK;
   }
 
   void launch_backward(int n_upper, int cur) {
-    const int grid = div_up(n_upper, 128);
+    const int grid = div_up(n_upper, kBlock);
     const unsigned mask = desc.deriv_mask;
     if (mask == M::EXAMPLE_MASK)
-      backward_kernel<M, static_cast<int>(M::EXAMPLE_MASK)><<<grid, 128, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
+      backward_kernel<M, static_cast<int>(M::EXAMPLE_MASK)><<<grid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
     else if (mask == 0u)
-      backward_kernel<M, 0><<<grid, 128, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
+      backward_kernel<M, 0><<<grid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
     else
-      backward_kernel<M, -1><<<grid, 128, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
+      backward_kernel<M, -1><<<grid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
     stats.kernel_launches++;
   }
 
   template <int L, int C>
   void launch_forward_lc(int n_upper, int cur) {
     const long long threads = static_cast<long long>(n_upper) * L;
-    const int grid = static_cast<int>((threads + 127) / 128);
-    forward_kernel<M, L, C><<<grid, 128, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1], d_count + (cur ^ 1));
+    const int grid = static_cast<int>((threads + kBlock - 1) / kBlock);
+    forward_kernel<M, L, C><<<grid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1], d_count + (cur ^ 1));
     stats.kernel_launches++;
   }
 
@@ -327,14 +409,57 @@ struct BatchImpl : BatchBase {
     else launch_forward_lc<16, 1>(n_upper, cur);
   }
 
-  // Lanes per problem: enough lanes to fill the device (about 512 resident per SM) without
-  // evaluating more step sizes than needed when the batch alone already fills it.
-  void choose_forward(int n_active, int* L, int* C) const {
+  // Line search as compacted rounds of two step sizes each, then commit + stop test.
+  int launch_rounds(int n_upper, int cur) {
+    constexpr int C = 2;
+    constexpr int R = (kNumAlphas + C - 1) / C;
+    const int grid = div_up(n_upper, kBlock);
+    MAS_CUDA_CHECK(cudaMemsetAsync(d_round_count, 0, 8 * sizeof(int), ctx->stream));
+    for (int r = 0; r < R; ++r) {
+      const int* in_list = r == 0 ? d_list[cur] : d_ls_list[(r - 1) & 1];
+      const int* in_count = r == 0 ? d_count + cur : d_round_count + r;
+      trial_round_kernel<M, C><<<grid, kBlock, 0, ctx->stream>>>(view, in_list, in_count, d_ls_list[r & 1], d_round_count + r + 1, r * C,
+                                                                d_accept_idx, d_accept_merit);
+      stats.kernel_launches++;
+    }
+    finish_kernel<M><<<grid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1], d_count + (cur ^ 1), d_accept_idx,
+                                                      d_accept_merit);
+    stats.kernel_launches++;
+    rounds_used++;
+    return MAS_B200_OK;
+  }
+
+  // Resident lanes of every forward_kernel variant on this device (occupancy x SMs), queried once.
+  long long resident_lanes[5] = {0, 0, 0, 0, 0};  // L = 1 (C=2), 2, 4, 8, 16
+  template <int L, int C>
+  long long query_resident() const {
+    int blocks = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, forward_kernel<M, L, C>, kBlock, 0) != cudaSuccess || blocks <= 0) blocks = 4;
+    return static_cast<long long>(blocks) * kBlock * ctx->sm_count;
+  }
+  void query_occupancy() {
+    if (resident_lanes[0]) return;
+    resident_lanes[0] = query_resident<1, 2>();
+    resident_lanes[1] = query_resident<2, 1>();
+    resident_lanes[2] = query_resident<4, 1>();
+    resident_lanes[3] = query_resident<8, 1>();
+    resident_lanes[4] = query_resident<16, 1>();
+  }
+
+  // Lanes per problem: the widest mapping whose lanes all fit on the device at once.  Every kernel
+  // here is bound by the latency of the T sequential time steps, so a launch that needs a second
+  // wave costs a whole extra pass; within one wave more lanes per problem mean fewer step sizes per
+  // lane and a shorter pass.  When even one lane per problem overflows the device, one lane it is.
+  void choose_forward(int n_active, int* L, int* C) {
     int l = tune_L, c = tune_C;
     if (l == 0) {
-      const long long target = static_cast<long long>(ctx->sm_count) * 384;
+      query_occupancy();
       l = 1;
-      while (l < 16 && static_cast<long long>(n_active) * l < target) l *= 2;
+      for (int k = 4; k >= 1; --k)
+        if (static_cast<long long>(n_active) * (1 << k) <= resident_lanes[k]) {
+          l = 1 << k;
+          break;
+        }
     }
     if (c == 0) c = (l == 1) ? 2 : 1;
     if (l != 1) c = 1;
@@ -356,6 +481,7 @@ struct BatchImpl : BatchBase {
     }
     view.tolerance = prm.tolerance;
     view.max_iterations = prm.max_iterations;
+    query_occupancy();
     const bool timed = std::isfinite(prm.max_ms);
     int n_upper = prm.max_iterations > 0 ? batch : 0;
     int cur = 0;
@@ -381,7 +507,19 @@ struct BatchImpl : BatchBase {
       launch_backward(n_upper, cur);
       prof_end();
       prof_begin(2);
-      launch_forward(n_upper, cur, L, C);
+      // Large active sets: compacted rounds (full warps, work stops at the first improving step size).
+      // Small ones, where a pass is pure latency: all step sizes at once on L lanes per problem.
+      // (measured on B200, 65,536 ST-lane problems: every round pays the latency of T sequential steps,
+      //  0.4 ms, so rounds lose to the lane mapping, 26.6 vs 16.9 ms per solve; auto therefore = lanes)
+      const bool rounds = ls_mode == 2;
+      if (rounds) {
+        rc = launch_rounds(n_upper, cur);
+        if (rc) return rc;
+        last_L = 0;
+        last_C = 2;
+      } else {
+        launch_forward(n_upper, cur, L, C);
+      }
       prof_end();
       MAS_CUDA_CHECK(cudaGetLastError());
       if (profiling)
@@ -410,7 +548,7 @@ __global__ void time_limit_kernel(const int* __restrict__ list, const int* __res
 
 template <class M>
 int BatchImpl<M>::mark_time_limit(int cur) {
-  time_limit_kernel<<<div_up(batch, 128), 128, 0, ctx->stream>>>(d_list[cur], d_count + cur, d_status);
+  time_limit_kernel<<<div_up(batch, kBlock), kBlock, 0, ctx->stream>>>(d_list[cur], d_count + cur, d_status);
   stats.kernel_launches++;
   MAS_CUDA_CHECK(cudaGetLastError());
   return MAS_B200_OK;

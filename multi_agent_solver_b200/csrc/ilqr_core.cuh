@@ -49,6 +49,17 @@ struct BatchView {
   int max_iterations;
 };
 
+// Pulls the line holding *p into L1 ahead of use.  Every kernel below walks the trajectory one time
+// step at a time with a long dependent fp64 chain per step; asking for step t+1's lines while step
+// t computes hides the ~800-cycle HBM latency without spending registers on double buffering.
+MAS_HD void prefetch_l1(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 template <int DIM>
 MAS_HD size_t soa_index(int t, int d, int ld, int p) {
   return (static_cast<size_t>(t) * DIM + d) * static_cast<size_t>(ld) + p;
@@ -106,16 +117,18 @@ MAS_HD void rk4_step(const double* x, const double* u, const double* prm, double
   constexpr int NX = M::NX;
   double k1[NX], k2[NX], k3[NX], k4[NX], xs[NX];
   const double hdt = 0.5 * dt;
-  M::dynamics(x, u, prm, k1);
+  double cu[M::NCU];
+  M::control_terms(u, prm, cu);  // control-only terms, shared by the four stages
+  M::dynamics_c(x, u, cu, prm, k1);
 #pragma unroll
   for (int i = 0; i < NX; ++i) xs[i] = x[i] + hdt * k1[i];
-  M::dynamics(xs, u, prm, k2);
+  M::dynamics_c(xs, u, cu, prm, k2);
 #pragma unroll
   for (int i = 0; i < NX; ++i) xs[i] = x[i] + hdt * k2[i];
-  M::dynamics(xs, u, prm, k3);
+  M::dynamics_c(xs, u, cu, prm, k3);
 #pragma unroll
   for (int i = 0; i < NX; ++i) xs[i] = x[i] + dt * k3[i];
-  M::dynamics(xs, u, prm, k4);
+  M::dynamics_c(xs, u, cu, prm, k4);
   const double sixth = dt / 6.0;
 #pragma unroll
   for (int i = 0; i < NX; ++i) xn[i] = x[i] + sixth * (((k1[i] + 2.0 * k2[i]) + 2.0 * k3[i]) + k4[i]);
@@ -157,15 +170,16 @@ template <class M>
 MAS_HD void fd_jac_x(const double* x, const double* u, const double* prm, double* A) {  // :53-72
   constexpr int NX = M::NX;
   const double eps = 1e-6;
-  double xp[NX], fp[NX], fm[NX];
+  double xp[NX], fp[NX], fm[NX], cu[M::NCU];
+  M::control_terms(u, prm, cu);  // u is not perturbed here
 #pragma unroll
   for (int i = 0; i < NX; ++i) {
 #pragma unroll
     for (int k = 0; k < NX; ++k) xp[k] = x[k];
     xp[i] = x[i] + eps;
-    M::dynamics(xp, u, prm, fp);
+    M::dynamics_c(xp, u, cu, prm, fp);
     xp[i] = x[i] - eps;
-    M::dynamics(xp, u, prm, fm);
+    M::dynamics_c(xp, u, cu, prm, fm);
 #pragma unroll
     for (int r = 0; r < NX; ++r) A[r + i * NX] = (fp[r] - fm[r]) / (2 * eps);
   }
@@ -412,6 +426,12 @@ MAS_HD int backward_thread(const BatchView<M::NX, M::NU>& v, int p) {
     for (int i = 0; i < NX; ++i) x[i] = v.X[soa_index<NX>(t, i, v.ld, p)];
 #pragma unroll
     for (int i = 0; i < NU; ++i) u[i] = v.U[soa_index<NU>(t, i, v.ld, p)];
+    if (t > 0) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) prefetch_l1(&v.X[soa_index<NX>(t - 1, i, v.ld, p)]);
+#pragma unroll
+      for (int i = 0; i < NU; ++i) prefetch_l1(&v.U[soa_index<NU>(t - 1, i, v.ld, p)]);
+    }
 
     // :106-113
     double A[NX * NX], B[NX * NU], l_x[NX], l_u[NU], l_xx[NX * NX], l_uu[NU * NU], l_ux[NU * NX];
@@ -520,6 +540,16 @@ MAS_HD void trial_rollout(const BatchView<M::NX, M::NU>& v, int p, const double*
     for (int i = 0; i < NU; ++i) kv[i] = v.kff[soa_index<NU>(t, i, v.ld, p)];
 #pragma unroll
     for (int i = 0; i < NU * NX; ++i) Km[i] = v.K[soa_index<NU * NX>(t, i, v.ld, p)];
+    if (t + 1 < v.T) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) prefetch_l1(&v.X[soa_index<NX>(t + 1, i, v.ld, p)]);
+#pragma unroll
+      for (int i = 0; i < NU; ++i) prefetch_l1(&v.U[soa_index<NU>(t + 1, i, v.ld, p)]);
+#pragma unroll
+      for (int i = 0; i < NU; ++i) prefetch_l1(&v.kff[soa_index<NU>(t + 1, i, v.ld, p)]);
+#pragma unroll
+      for (int i = 0; i < NU * NX; ++i) prefetch_l1(&v.K[soa_index<NU * NX>(t + 1, i, v.ld, p)]);
+    }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       double dx[NX], u[NU], xnext[NX];
@@ -572,6 +602,16 @@ MAS_HD double commit_rollout(const BatchView<M::NX, M::NU>& v, int p, const doub
     for (int i = 0; i < NU * NX; ++i) Km[i] = v.K[soa_index<NU * NX>(t, i, v.ld, p)];
 #pragma unroll
     for (int i = 0; i < NX; ++i) xn_next[i] = v.X[soa_index<NX>(t + 1, i, v.ld, p)];
+    if (t + 1 < v.T) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) prefetch_l1(&v.X[soa_index<NX>(t + 2, i, v.ld, p)]);
+#pragma unroll
+      for (int i = 0; i < NU; ++i) prefetch_l1(&v.U[soa_index<NU>(t + 1, i, v.ld, p)]);
+#pragma unroll
+      for (int i = 0; i < NU; ++i) prefetch_l1(&v.kff[soa_index<NU>(t + 1, i, v.ld, p)]);
+#pragma unroll
+      for (int i = 0; i < NU * NX; ++i) prefetch_l1(&v.K[soa_index<NU * NX>(t + 1, i, v.ld, p)]);
+    }
     double dx[NX], u[NU], xnext[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) dx[i] = xt[i] - xn[i];

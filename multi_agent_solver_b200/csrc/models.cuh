@@ -40,15 +40,24 @@ enum DerivBits : unsigned {
 
 // ---- single-track kinematic bicycle, shared by StLane and StCirc ---------------------------------
 struct SingleTrackDyn {
-  MAS_HD static void f(const double* x, const double* u, double* d) {
-    const double psi = x[2], v = x[3], delta = u[0], a = u[1];
+  // The control enters only through tan(delta); RK4 evaluates f four times with the same control
+  // (integrator.hpp:22-25), so the tangent is computed once per step and reused: same bits, a
+  // quarter of the work.
+  MAS_HD static void control_terms(const double* u, double* cu) { cu[0] = pm::tan_(u[0]); }
+  MAS_HD static void f_c(const double* x, const double* u, const double* cu, double* d) {
+    const double psi = x[2], v = x[3], a = u[1];
     const double L = 2.5;
     double s, c;
     pm::sincos_(psi, &s, &c);
     d[0] = v * c;
     d[1] = v * s;
-    d[2] = v * pm::tan_(delta) / L;
+    d[2] = v * cu[0] / L;
     d[3] = a;
+  }
+  MAS_HD static void f(const double* x, const double* u, double* d) {
+    double cu[1];
+    control_terms(u, cu);
+    f_c(x, u, cu, d);
   }
   MAS_HD static void jac_x(const double* x, const double* u, double* A) {
     const double psi = x[2], v = x[3], delta = u[0];
@@ -78,6 +87,9 @@ struct StLane {
   static constexpr unsigned AVAILABLE = D_A | D_B | D_LX | D_LU | D_LXX | D_LUU;
   static constexpr unsigned EXAMPLE_MASK = AVAILABLE;  // l_ux and terminal derivatives are FD
   // p = {desired_velocity, w_lane, w_speed, w_delta, w_acc}
+  static constexpr int NCU = 1;
+  MAS_HD static void control_terms(const double* u, const double*, double* cu) { SingleTrackDyn::control_terms(u, cu); }
+  MAS_HD static void dynamics_c(const double* x, const double* u, const double* cu, const double*, double* d) { SingleTrackDyn::f_c(x, u, cu, d); }
   MAS_HD static void dynamics(const double* x, const double* u, const double*, double* d) { SingleTrackDyn::f(x, u, d); }
   MAS_HD static double stage(const double* x, const double* u, int, const double* p) {
     const double lane_error = x[1], speed_error = (x[3] - p[0]);
@@ -119,6 +131,9 @@ struct StCirc {
   static constexpr unsigned AVAILABLE = D_A | D_B;
   static constexpr unsigned EXAMPLE_MASK = 0;  // the example installs no derivative callback: all FD
   // p = {track_radius, target_velocity, w_track, w_speed, w_delta, w_acc}
+  static constexpr int NCU = 1;
+  MAS_HD static void control_terms(const double* u, const double*, double* cu) { SingleTrackDyn::control_terms(u, cu); }
+  MAS_HD static void dynamics_c(const double* x, const double* u, const double* cu, const double*, double* d) { SingleTrackDyn::f_c(x, u, cu, d); }
   MAS_HD static void dynamics(const double* x, const double* u, const double*, double* d) { SingleTrackDyn::f(x, u, d); }
   MAS_HD static double stage(const double* s, const double* c, int, const double* p) {
     const double x = s[0], y = s[1], vx = s[3];
@@ -147,6 +162,9 @@ struct Lqr4 {
   static constexpr int NX = 4, NU = 4, NP = 0;
   static constexpr unsigned AVAILABLE = D_ALL;
   static constexpr unsigned EXAMPLE_MASK = D_ALL;
+  static constexpr int NCU = 1;
+  MAS_HD static void control_terms(const double*, const double*, double* cu) { cu[0] = 0.0; }
+  MAS_HD static void dynamics_c(const double* x, const double* u, const double*, const double* p, double* d) { dynamics(x, u, p, d); }
   MAS_HD static void dynamics(const double* x, const double* u, const double*, double* d) {
     for (int i = 0; i < 4; ++i) d[i] = x[i] + u[i];
   }
@@ -202,6 +220,9 @@ struct Pendulum {
   static constexpr unsigned AVAILABLE = D_A | D_B;
   static constexpr unsigned EXAMPLE_MASK = 0;  // pendulum_swing_up.cpp installs no derivative callback
   // p = {horizon_steps as double}
+  static constexpr int NCU = 1;
+  MAS_HD static void control_terms(const double*, const double*, double* cu) { cu[0] = 0.0; }
+  MAS_HD static void dynamics_c(const double* x, const double* u, const double*, const double* p, double* d) { dynamics(x, u, p, d); }
   MAS_HD static void dynamics(const double* x, const double* u, const double*, double* d) {
     const double g = 9.81, l = 1.0, m = 1.0, b = 0.1;
     d[0] = x[1];
@@ -258,6 +279,9 @@ struct Rocket {
   static constexpr unsigned AVAILABLE = D_A | D_B | D_LX | D_LU | D_LXX | D_LUU | D_VX | D_VXX;
   static constexpr unsigned EXAMPLE_MASK = AVAILABLE;  // only l_ux is FD
   // p = {gravity, exhaust_velocity, w_thrust, w_terminal_altitude, w_terminal_velocity, desired_terminal_vel}
+  static constexpr int NCU = 1;
+  MAS_HD static void control_terms(const double*, const double*, double* cu) { cu[0] = 0.0; }
+  MAS_HD static void dynamics_c(const double* x, const double* u, const double*, const double* p, double* d) { dynamics(x, u, p, d); }
   MAS_HD static void dynamics(const double* s, const double* c, const double* p, double* d) {
     const double mass = s[2] > 1e-6 ? s[2] : 1e-6;
     const double thrust = mass > 0 ? c[0] : 0.0;

@@ -1,0 +1,51 @@
+"""GPU: the multi-agent strategy layer (mas::solve(Strategy&, MultiAgentProblem&)) through the C ABI
+against the oracle, round by round: inner iteration counts, accept/reject flags, per-agent costs, final
+trajectories and totals.  Oracle in portable-trig mode; bit-identical results required.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def circ_x0(n_scenarios, n_agents, jitter_seed=None):
+    th = 2.0 * np.pi * np.arange(n_agents) / n_agents
+    R = np.full((n_scenarios, 1), 20.0)
+    if jitter_seed is not None:
+        R = np.random.default_rng(jitter_seed).uniform(15, 25, (n_scenarios, 1))
+    x0 = np.stack([R * np.cos(th), R * np.sin(th), np.broadcast_to(1.57 + th, (n_scenarios, n_agents)), np.full((n_scenarios, n_agents), 4.0)], -1)
+    return x0, R
+
+
+def test_trust_region_config2(mas, ctx, oracle):
+    """multi_agent_single_track --agents 3 --strategy trustregion, replicated scenarios with a jittered
+    track radius per scenario (BASELINE configs[1])."""
+    S, A = 24, 3
+    x0, R = circ_x0(S, A, jitter_seed=4)
+    op = np.broadcast_to(np.stack([R[:, 0], np.full(S, 5.0)], -1)[:, None, :], (S, A, 2)).copy()
+    gp = np.broadcast_to(np.stack([R[:, 0], np.full(S, 5.0), np.ones(S), np.ones(S), np.full(S, 1e-3), np.full(S, 1e-3)], -1)[:, None, :],
+                         (S, A, 6)).copy()
+    ref = oracle.strategy_run_batch(oracle.STRATEGY_TRUSTREGION, oracle.MODEL_ST_CIRC, x0, params=op, max_outer=10, max_iterations=100,
+                                    tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    got = mas.strategy_run(ctx, mas.Strategy.TRUSTREGION, mas.example_desc(1), mas.IlqrParams.make(100, 1e-5), 10, x0, model_params=gp)
+    for k in ("trace_iters", "trace_accept", "trace_cost", "costs", "total_cost", "X", "U"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert (ref["trace_accept"] == 0).any() and (ref["trace_accept"] == 1).any()
+
+
+def test_sequential_config4(mas, ctx, oracle):
+    """multi_agent_lqr, sequential/Nash: exactly max_outer Jacobi rounds (BASELINE configs[3])."""
+    x0 = np.random.default_rng(8).uniform(-1, 1, (6, 16, 4))
+    ref = oracle.strategy_run_batch(oracle.STRATEGY_SEQUENTIAL, oracle.MODEL_LQR, x0, max_outer=10, max_iterations=100, tolerance=1e-5,
+                                    trig=oracle.TRIG_PORTABLE)
+    got = mas.strategy_run(ctx, mas.Strategy.SEQUENTIAL, mas.example_desc(2), mas.IlqrParams.make(100, 1e-5), 10, x0)
+    for k in ("trace_iters", "trace_cost", "costs", "total_cost", "X", "U"):
+        assert np.array_equal(got[k], ref[k]), k
+
+
+def test_unsupported_strategies_fail_loudly(mas, ctx):
+    x0, _ = circ_x0(1, 3)
+    for kind in (7,):
+        with pytest.raises(mas.MasB200Error) as e:
+            mas.strategy_run(ctx, kind, mas.example_desc(1), mas.IlqrParams.make(100, 1e-5), 2, x0)
+        assert e.value.code == 1

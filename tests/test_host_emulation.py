@@ -1,0 +1,86 @@
+"""The device source (multi_agent_solver_b200/csrc/ilqr_core.cuh + models.cuh, all __host__ __device__)
+compiled with g++ and driven with the engine's schedule, against the oracle in portable-trig mode.
+Bit-identical results are required: the kernels restate the oracle's rounded operations one for one.
+This is the CPU-side check of the CUDA code; the same comparison runs on the GPU in test_gpu_parity.py.
+"""
+import numpy as np
+import pytest
+
+from conftest import EXAMPLE_SOLVER_PARAMS, MODEL_TABLE, assert_parity, is_bit_exact, random_x0
+
+
+def _defaults(oracle, model, batch):
+    n, m, T = MODEL_TABLE[model][:3]
+    return np.broadcast_to(oracle.default_controls(model), (batch, T, m)).copy()
+
+
+@pytest.mark.parametrize("model,batch,cap", [(0, 48, 10), (1, 12, 100), (2, 16, 100), (3, 6, 40), (4, 12, 25)])
+def test_models_bit_exact(emu, oracle, model, batch, cap):
+    max_it, tol = EXAMPLE_SOLVER_PARAMS[model]
+    max_it = min(max_it, cap)
+    x0 = random_x0(model, batch, seed=40 + model)
+    U0 = _defaults(oracle, model, batch)
+    ref = oracle.ilqr_solve_batch(model, x0, U_init=U0, max_iterations=max_it, tolerance=tol, trig=oracle.TRIG_PORTABLE)
+    got = emu.solve(model, x0, U0, max_it, tol)
+    assert_parity(got, ref)
+    assert is_bit_exact(got, ref)
+    assert np.array_equal(got["alpha_trials"], ref["alpha_trials"])
+    assert np.array_equal(got["reg_retries"], ref["reg_retries"])
+
+
+@pytest.mark.parametrize("L,C", [(1, 1), (1, 2), (2, 1), (4, 1), (8, 1), (16, 1)])
+def test_lane_mappings_pick_the_first_improving_step(emu, oracle, L, C):
+    x0 = random_x0(0, 24, seed=9)
+    U0 = np.zeros((24, 80, 2))
+    ref = oracle.ilqr_solve_batch(0, x0, U_init=U0, max_iterations=10, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    got = emu.solve(0, x0, U0, 10, 1e-5, L=L, C=C)
+    assert is_bit_exact(got, ref)
+    assert np.array_equal(got["iterations"], ref["iterations"]) and np.array_equal(got["alpha_trials"], ref["alpha_trials"])
+
+
+def test_regularisation_path(emu, oracle):
+    """ST-circ from rest-like states exercises Q_uu + reg*I retries (ilqr.hpp:175-182)."""
+    x0 = random_x0(1, 8, seed=3)
+    U0 = np.zeros((8, 10, 2))
+    ref = oracle.ilqr_solve_batch(1, x0, U_init=U0, max_iterations=30, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    got = emu.solve(1, x0, U0, 30, 1e-5)
+    assert ref["reg_retries"].sum() > 0
+    assert np.array_equal(got["reg_retries"], ref["reg_retries"])
+    assert is_bit_exact(got, ref)
+
+
+def test_runtime_mask_equals_compile_time_mask(emu):
+    """backward_thread<M, -1> (mask read at run time) and the specialised instantiation agree."""
+    x0 = random_x0(0, 8, seed=12)
+    U0 = np.zeros((8, 80, 2))
+    a = emu.solve(0, x0, U0, 6, 1e-5, mask=0x3F)          # specialised (example mask)
+    b = emu.solve(0, x0, U0, 6, 1e-5, mask=0x3F & ~0x20)  # generic path, l_uu from finite differences
+    c = emu.solve(0, x0, U0, 6, 1e-5, mask=0)             # all finite differences
+    assert np.array_equal(a["iterations"] > 0, np.ones(8, bool))
+    # l_uu is constant for this cost, its FD estimate is close but not equal: results differ slightly
+    assert np.max(np.abs(a["cost"] - b["cost"]) / a["cost"]) < 1e-2
+    assert np.max(np.abs(a["cost"] - c["cost"]) / a["cost"]) < 1e-1
+
+
+def test_per_problem_params(emu, oracle):
+    rng = np.random.default_rng(5)
+    B = 10
+    R = rng.uniform(15, 25, B)
+    th = rng.uniform(0, 2 * np.pi, B)
+    x0 = np.stack([R * np.cos(th), R * np.sin(th), 1.57 + th, np.full(B, 4.0)], -1)
+    ref = oracle.ilqr_solve_batch(1, x0, params=np.stack([R, np.full(B, 5.0)], -1), max_iterations=30, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    pp = np.stack([R, np.full(B, 5.0), np.ones(B), np.ones(B), np.full(B, 0.001), np.full(B, 0.001)], -1)
+    got = emu.solve(1, x0, np.zeros((B, 10, 2)), 30, 1e-5, per_problem_params=pp)
+    assert is_bit_exact(got, ref)
+
+
+def test_nan_initial_state_matches_oracle(emu, oracle):
+    """Non-finite costs propagate silently (SURVEY 8b error conventions): a NaN merit never accepts a
+    candidate and `improvement < tolerance` is false for NaN, so the loop runs to max_iterations."""
+    x0 = np.array([[0.0, np.nan, 0.0, 1.0]])
+    U0 = np.zeros((1, 80, 2))
+    ref = oracle.ilqr_solve_batch(0, x0, U_init=U0, max_iterations=10, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    got = emu.solve(0, x0, U0, 10, 1e-5)
+    assert got["iterations"][0] == ref["iterations"][0]
+    assert got["status"][0] == ref["status"][0]
+    assert np.isnan(got["cost"][0]) and np.isnan(ref["cost"][0])
