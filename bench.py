@@ -53,6 +53,17 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, averaged over the launches of one
+    solve, from the committed ncu capture of this same workload (profiles/r01_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
 
@@ -277,7 +288,8 @@ def run_b200(args):
         trials_seq = st["alpha_trials"]
         alg_flops = T * (st["iterations"] * BWD_FLOPS_STEP + (trials_seq + per_rank) * FWD_FLOPS_STEP)
         roofline = {
-            "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+            "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "traffic": load_traffic(dom),
             "peak_source": peak_src,
             "avg_launch_ms": k["ms_per_step"] / n_launch,
             "alg_bytes_per_launch": k["alg_bytes_per_step"] / n_launch,

@@ -1,0 +1,196 @@
+// mas_b200_examples.cpp -- the reference's five example programs on the B200 engine, one binary.
+//
+// The program is selected by the name it is invoked under (build.sh creates the links) or by a first
+// argument, and keeps the reference's command line and output grammar so scripts/compare_solvers.py
+// and scripts/plot_example.py of the reference parse it unchanged:
+//   single_track_ocp       [--solver NAME]                                   examples/single_track_ocp.cpp:133-174
+//   pendulum_swing_up      [--solver NAME]                                   examples/pendulum_swing_up.cpp:135-176
+//   rocket_max_altitude    [--solver NAME] [--dump]                          examples/rocket_max_altitude.cpp:149-197
+//   multi_agent_single_track / multi_agent_lqr
+//       [--agents N | N] [--solver NAME] [--strategy NAME] [--max-outer N]   examples/cli.hpp:161-220
+// output: "solver=<s> [strategy=<t> agents=<n>] cost=<c> time_ms=<ms>" with 6 decimals, then
+// "<label>_states" / "<label>_controls" CSV blocks (examples/example_utils.hpp:123-167).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <iomanip>
+#include <iostream>
+#include <string>
+
+#include "mas_b200/mas_b200.hpp"
+
+namespace mb = mas_b200;
+
+namespace {
+
+struct Options {
+  bool help = false, dump = false;
+  int agents = 10, max_outer = 10;               // examples/cli.hpp:163-167
+  std::string solver = "ilqr", strategy = "centralized";
+};
+
+std::string dashed(std::string opt) {  // "--max_outer=3" -> "--max-outer=3"
+  if (opt.rfind("--", 0) != 0) return opt;
+  const std::size_t stop = std::min(opt.find('='), opt.size());
+  for (std::size_t i = 2; i < stop; ++i)
+    if (opt[i] == '_') opt[i] = '-';
+  return opt;
+}
+
+int to_int(const std::string& label, const std::string& text) {
+  std::size_t used = 0;
+  int v = 0;
+  try {
+    v = std::stoi(text, &used);
+  } catch (...) {
+    used = 0;
+  }
+  if (used != text.size() || text.empty()) throw std::invalid_argument("Invalid value for " + label + ": '" + text + "'");
+  return v;
+}
+
+Options parse(int argc, char** argv, int first, bool multi_agent, bool rocket) {
+  Options o;
+  bool positional_seen = false;
+  for (int i = first; i < argc; ++i) {
+    const std::string raw = argv[i];
+    std::string arg = dashed(raw), value;
+    auto option = [&](const char* name) {
+      const std::string n = name;
+      if (arg == n) {
+        if (i + 1 >= argc) throw std::invalid_argument("Missing value for option '" + n + "'");
+        value = argv[++i];
+        return true;
+      }
+      if (arg.rfind(n + "=", 0) == 0) {
+        value = arg.substr(n.size() + 1);
+        return true;
+      }
+      return false;
+    };
+    if (arg == "--help" || arg == "-h") o.help = true;
+    else if (rocket && arg == "--dump") o.dump = true;
+    else if (option("--solver")) o.solver = value;
+    else if (multi_agent && option("--agents")) o.agents = to_int("--agents", value);
+    else if (multi_agent && option("--strategy")) o.strategy = value;
+    else if (multi_agent && option("--max-outer")) o.max_outer = to_int("--max-outer", value);
+    else if (multi_agent && !positional_seen && !raw.empty() && raw[0] != '-') {
+      o.agents = to_int("agents", raw);
+      positional_seen = true;
+    } else throw std::invalid_argument("Unknown argument '" + raw + "'");
+  }
+  return o;
+}
+
+void print_block(const mb::Matrix& m, double dt, const std::string& label, const char* suffix, char var) {
+  if (m.size() == 0) return;
+  std::cout << label << suffix << "\ntime";
+  for (int r = 0; r < m.rows(); ++r) std::cout << ',' << var << r;
+  std::cout << '\n';
+  for (int c = 0; c < m.cols(); ++c) {
+    std::cout << (dt > 0.0 ? static_cast<double>(c) * dt : static_cast<double>(c));
+    for (int r = 0; r < m.rows(); ++r) std::cout << ',' << m(r, c);
+    std::cout << '\n';
+  }
+  std::cout << '\n';
+}
+
+void usage(const std::string& prog, bool multi) {
+  if (multi) std::cout << "Usage: " << prog << " [--agents N] [--solver NAME] [--strategy NAME] [--max-outer N]\n       " << prog << " N\n\n";
+  else std::cout << "Usage: " << prog << " [--solver NAME]\n\n";
+  std::cout << "Available solvers: ilqr\nAvailable strategies: centralized, sequential, linesearch, trustregion\n";
+}
+
+int run_single(const std::string& prog, const Options& o) {
+  mb::OCP problem;
+  mb::SolverParams params;
+  std::string label;
+  if (prog == "single_track_ocp") {  // single_track_ocp.cpp:146-151
+    problem = mb::examples::create_single_track_lane_following_ocp();
+    params = {{"max_iterations", 10}, {"tolerance", 1e-5}, {"max_ms", 100}};
+    label = "single_track";
+  } else if (prog == "pendulum_swing_up") {  // pendulum_swing_up.cpp:148-153
+    problem = mb::examples::create_pendulum_swingup_ocp();
+    params = {{"max_iterations", 1000}, {"tolerance", 1e-4}, {"max_ms", 5000}};
+    label = "pendulum";
+  } else {  // rocket_max_altitude.cpp:163-168
+    problem = mb::examples::create_max_altitude_rocket_ocp();
+    params = {{"max_iterations", 25}, {"tolerance", 1e-6}, {"max_ms", 200}};
+    label = "rocket";
+  }
+  mb::Solver solver = mb::registry::make_solver(o.solver);
+  mb::set_params(solver, params);
+  const auto t0 = std::chrono::steady_clock::now();
+  mb::solve(solver, problem);
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  std::cout << std::fixed << std::setprecision(6) << "solver=" << mb::registry::canonical_solver_name(o.solver) << " cost=" << problem.best_cost
+            << " time_ms=" << ms << '\n';
+  print_block(problem.best_states, problem.dt, label, "_states", 'x');
+  print_block(problem.best_controls, problem.dt, label, "_controls", 'u');
+  return 0;
+}
+
+int run_multi(const std::string& prog, const Options& o) {
+  mb::MultiAgentProblem problem;
+  mb::SolverParams params;
+  if (prog == "multi_agent_single_track") {  // multi_agent_single_track.cpp:103-119
+    params = {{"max_iterations", 100}, {"tolerance", 1e-5}, {"max_ms", 1000}};
+    for (int i = 0; i < o.agents; ++i) {
+      const double theta = 2.0 * M_PI * i / o.agents;
+      auto ocp = std::make_shared<mb::OCP>(mb::examples::create_single_track_circular_ocp(theta, 20.0, 5.0, 10));
+      problem.add_agent(std::make_shared<mb::Agent>(i, ocp));
+    }
+  } else {  // multi_agent_lqr.cpp:108-122
+    params = {{"max_iterations", 100}, {"tolerance", 1e-5}, {"max_ms", 100}};
+    for (int i = 0; i < o.agents; ++i) {
+      auto ocp = std::make_shared<mb::OCP>(mb::examples::create_linear_lqr_ocp(4, 4, 0.1, 10));
+      problem.add_agent(std::make_shared<mb::Agent>(i, ocp));
+    }
+  }
+  mb::Strategy strategy = mb::registry::make_strategy(o.strategy, mb::registry::make_solver(o.solver), params, o.max_outer);
+  const auto t0 = std::chrono::steady_clock::now();
+  const mb::Solution sol = mb::solve(strategy, problem);
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  std::cout << std::fixed << std::setprecision(6) << "solver=" << mb::registry::canonical_solver_name(o.solver)
+            << " strategy=" << mb::registry::canonical_strategy_name(o.strategy) << " agents=" << o.agents << " cost=" << sol.total_cost
+            << " time_ms=" << ms << '\n';
+  if (problem.blocks.empty()) problem.compute_offsets();
+  for (std::size_t i = 0; i < sol.states.size() && i < problem.blocks.size(); ++i) {
+    const std::string label = "agent_" + std::to_string(problem.blocks[i].agent_id);
+    print_block(sol.states[i], problem.blocks[i].agent->ocp->dt, label, "_states", 'x');
+    print_block(sol.controls[i], problem.blocks[i].agent->ocp->dt, label, "_controls", 'u');
+  }
+  return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  std::string prog = argv[0];
+  prog = prog.substr(prog.find_last_of('/') + 1);
+  int first = 1;
+  const char* names[] = {"single_track_ocp", "pendulum_swing_up", "rocket_max_altitude", "multi_agent_single_track", "multi_agent_lqr"};
+  bool known = false;
+  for (const char* n : names) known = known || prog == n;
+  if (!known && argc > 1) {
+    prog = argv[1];
+    first = 2;
+    for (const char* n : names) known = known || prog == n;
+  }
+  if (!known) {
+    std::cerr << "usage: mas_b200_examples <single_track_ocp|pendulum_swing_up|rocket_max_altitude|multi_agent_single_track|multi_agent_lqr> [options]\n";
+    return 2;
+  }
+  const bool multi = prog.rfind("multi_agent", 0) == 0;
+  try {
+    const Options o = parse(argc, argv, first, multi, prog == "rocket_max_altitude");
+    if (o.help) {
+      usage(prog, multi);
+      return 0;
+    }
+    return multi ? run_multi(prog, o) : run_single(prog, o);
+  } catch (const std::exception& e) {
+    std::cerr << "Error: " << e.what() << "\nUse --help to see available options.\n";
+    return 1;
+  }
+}

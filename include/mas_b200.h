@@ -188,11 +188,12 @@ int mas_b200_ilqr_solve_batch(mas_b200_context_t ctx, const mas_b200_ocp_desc* d
 /* ---- multi-agent strategies: mas::solve(Strategy&, MultiAgentProblem&) (strategies/strategy.hpp:15-19)
  * on n_scenarios independent scenarios of n_agents agents each; agents have ids 0..n_agents-1 in
  * array order (already the id-sorted block order of MultiAgentProblem::compute_offsets,
- * multi_agent_problem.hpp:37-50).  Arrays are [scenario][agent][...].  trace_* may be NULL:
+ * multi_agent_problem.hpp:37-50).  Arrays are [scenario][agent][...].  U_init: every agent's
+ * initial_controls / best_controls before the first round, NULL = zeros.  trace_* may be NULL:
  * [scenario][outer][agent] inner iteration counts / accepted flags / best_cost after the round. */
 int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_ocp_desc* agent_desc, const mas_b200_ilqr_params* params,
-                          int max_outer, int n_scenarios, int n_agents, const double* x0, const double* model_params, double* X, double* U,
-                          double* costs, double* total_cost, int* trace_iterations, int* trace_accepted, double* trace_cost);
+                          int max_outer, int n_scenarios, int n_agents, const double* x0, const double* model_params, const double* U_init,
+                          double* X, double* U, double* costs, double* total_cost, int* trace_iterations, int* trace_accepted, double* trace_cost);
 
 /* ---- multi-GPU (one process per GPU).  unique_id: 128 bytes from mas_b200_nccl_unique_id on rank 0,
  * distributed by the caller (torch.distributed / MPI / file). ------------------------------------- */

@@ -302,12 +302,14 @@ def ilqr_solve_batch(ctx: Context, desc: OcpDesc, params: IlqrParams, x0, U=None
     return dict(X=X, U=Uio, cost=cost, iterations=it, status=st)
 
 
-def strategy_run(ctx: Context, strategy: int, desc: OcpDesc, params: IlqrParams, max_outer: int, x0, model_params=None, trace: bool = True):
+def strategy_run(ctx: Context, strategy: int, desc: OcpDesc, params: IlqrParams, max_outer: int, x0, model_params=None, trace: bool = True,
+                 U_init=None):
     """mas_b200_strategy_run.  x0: [scenarios, agents, n]."""
     x0 = _f64(x0)
     S, A = x0.shape[0], x0.shape[1]
     T, nx, nu = desc.horizon_steps, desc.state_dim, desc.control_dim
     model_params = _f64(model_params)
+    U_init = _f64(U_init)
     X = np.empty((S, A, T + 1, nx))
     U = np.empty((S, A, T, nu))
     costs = np.empty((S, A))
@@ -316,6 +318,6 @@ def strategy_run(ctx: Context, strategy: int, desc: OcpDesc, params: IlqrParams,
     t_acc = np.zeros((S, max_outer, A), dtype=np.int32) if trace else None
     t_cost = np.zeros((S, max_outer, A)) if trace else None
     _check(load_library().mas_b200_strategy_run(ctx._h, int(strategy), ctypes.byref(desc), ctypes.byref(params), int(max_outer), S, A, _dptr(x0),
-                                                 _dptr(model_params), _dptr(X), _dptr(U), _dptr(costs), _dptr(total), _iptr(t_it), _iptr(t_acc),
+                                                 _dptr(model_params), _dptr(U_init), _dptr(X), _dptr(U), _dptr(costs), _dptr(total), _iptr(t_it), _iptr(t_acc),
                                                  _dptr(t_cost)))
     return dict(X=X, U=U, costs=costs, total_cost=total, trace_iters=t_it, trace_accept=t_acc, trace_cost=t_cost)

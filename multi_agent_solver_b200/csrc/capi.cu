@@ -416,8 +416,8 @@ int mas_b200_ilqr_solve_batch(mas_b200_context_t ctx, const mas_b200_ocp_desc* d
 
 // ---- strategies ------------------------------------------------------------------------------------------
 int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_ocp_desc* agent_desc, const mas_b200_ilqr_params* params,
-                          int max_outer, int n_scenarios, int n_agents, const double* x0, const double* model_params, double* X, double* U,
-                          double* costs, double* total_cost, int* trace_iterations, int* trace_accepted, double* trace_cost) {
+                          int max_outer, int n_scenarios, int n_agents, const double* x0, const double* model_params, const double* U_init,
+                          double* X, double* U, double* costs, double* total_cost, int* trace_iterations, int* trace_accepted, double* trace_cost) {
   if (!ctx) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
   int rc = validate_params(params);
   if (rc) return rc;
@@ -437,7 +437,7 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
   auto run = [&]() -> int {
     int r = mas_b200_batch_set_initial_states(h, x0);
     if (!r) r = mas_b200_batch_set_params(h, model_params);
-    if (!r) r = mas_b200_batch_set_controls(h, nullptr);
+    if (!r) r = mas_b200_batch_set_controls(h, U_init);
     if (!r) r = b->initialize();  // OCP::initialize_problem of every agent
     if (r) return r;
     const size_t L = static_cast<size_t>(b->ld);
