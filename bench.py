@@ -114,7 +114,8 @@ def cpu_reference_run(n_problems: int, steps: int, warmup: int, threads: int = 0
     import multi_agent_solver_b200 as mas
 
     x0 = mas.synthetic_single_track_x0(PROBLEMS)[:n_problems]
-    threads = threads or o.max_threads()
+    # all host cores this process may use (torchrun sets OMP_NUM_THREADS=1; the num_threads clause overrides it)
+    threads = threads or len(os.sched_getaffinity(0))
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
@@ -298,7 +299,12 @@ def run_b200(args):
                      "frac": alg_flops / (ms_step * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
                      "note": "algorithmic flops of the sequential reference (SURVEY 8d convention) / step time; the line search evaluates more candidates than the reference"},
         }
-        cpu_val, cpu_threads, cpu_ms = cpu_reference_run(args.cpu_sample, 1, 1)
+        cpu_baseline = None
+        if n_gpus == 1:  # reported on rank 0 at N=1 only
+            cpu_val, cpu_threads, cpu_ms = cpu_reference_run(args.cpu_sample, 1, 1)
+            cpu_baseline = {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                            "sample": f"first {args.cpu_sample} of the 65,536 problems, one pass ({cpu_ms:.0f} ms); oracle/ C++ restatement of the "
+                                      "reference (glibc libm, OpenMP static over problems); the reference needs Eigen 3.4, absent here"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -312,9 +318,7 @@ def run_b200(args):
                     "wall_ms_per_step": e2e_wall * 1e3},
             "gpu_launches": int(launches),
             "roofline": roofline,
-            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": "port",
-                             "sample": f"first {args.cpu_sample} of the 65,536 problems, one pass ({cpu_ms:.0f} ms); oracle/ C++ restatement of the "
-                                       "reference (glibc libm, OpenMP static over problems); the reference needs Eigen 3.4, absent here"},
+            "cpu_baseline": cpu_baseline,
             "clocks": clocks,
             "wall_ms_per_step": wall_step * 1e3,
         }
