@@ -6,6 +6,7 @@
 #include <new>
 #include <random>
 
+#include "centralized_host.cuh"
 #include "engine.cuh"
 
 namespace mas_b200 {
@@ -422,8 +423,27 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
   int rc = validate_params(params);
   if (rc) return rc;
   if (n_scenarios <= 0 || n_agents <= 0 || max_outer < 0) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "bad scenario/agent/outer counts");
-  if (strategy == MAS_B200_STRATEGY_CENTRALIZED || strategy == MAS_B200_STRATEGY_LINESEARCH)
-    return fail(MAS_B200_ERR_UNSUPPORTED, "strategy not on the device path yet (centralized, linesearch)");
+  if (strategy == MAS_B200_STRATEGY_CENTRALIZED) {
+    // stack -> one solve -> scatter (strategies/centralized.hpp:18-38); the stacked problem is always all-FD
+    rc = validate_desc(agent_desc);
+    if (rc) return rc;
+    if (n_agents * agent_desc->state_dim > 256) return fail(MAS_B200_ERR_UNSUPPORTED, "stacked state dimension above 256");
+    CentralizedFn fn = centralized_entry(agent_desc->model_id);
+    if (!fn) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "unknown model_id");
+    mas_b200_ocp_desc d = *agent_desc;
+    if (d.num_params == 0) {
+      d.num_params = kModels[d.model_id].np;
+      for (int i = 0; i < d.num_params; ++i) d.params[i] = kModels[d.model_id].default_params[i];
+      if (d.model_id == MAS_B200_MODEL_PENDULUM) d.params[0] = static_cast<double>(d.horizon_steps);
+    }
+    std::vector<int> its(n_scenarios);
+    rc = fn(&ctx->c, d, *params, n_scenarios, n_agents, x0, model_params, U_init, X, U, costs, total_cost, its.data(), nullptr, nullptr);
+    if (rc) return rc;
+    if (trace_iterations)
+      for (int s = 0; s < n_scenarios; ++s) trace_iterations[static_cast<size_t>(s) * (max_outer > 0 ? max_outer : 1) * n_agents] = its[s];
+    return MAS_B200_OK;
+  }
+  if (strategy == MAS_B200_STRATEGY_LINESEARCH) return fail(MAS_B200_ERR_UNSUPPORTED, "LineSearchNashStrategy is not on the device path yet");
   if (strategy != MAS_B200_STRATEGY_SEQUENTIAL && strategy != MAS_B200_STRATEGY_TRUSTREGION)
     return fail(MAS_B200_ERR_INVALID_ARGUMENT, "unknown strategy");
   const int batch = n_scenarios * n_agents;

@@ -1,0 +1,653 @@
+// centralized.cuh -- CentralizedStrategy on the device (strategies/centralized.hpp:18-38): the agents of a
+// scenario are stacked into one OCP (MultiAgentProblem::build_global_ocp, multi_agent_problem.hpp:52-127) with
+// block-diagonal dynamics, stage / terminal costs summed in block order, concatenated bounds, and -- because
+// build_global_ocp drops the agents' analytic callbacks (ocp.hpp:117-135 re-installs the defaults) -- finite
+// differences for *every* derivative of the stacked functions.  One CTA solves one scenario start to finish
+// (T is 10 in the reference's multi-agent examples; state n_s = A*NX up to 128, controls m_s = A*NU up to 64).
+//
+// Bit-compatibility with the oracle's dense evaluation is kept while exploiting the structure:
+//  * a finite difference of the stacked cost changes one or two agents' terms; the stacked value is re-formed
+//    as the same left-to-right sum (prefix up to the first changed agent, then the remaining terms in order),
+//    so the rounding noise of the 4-point stencils (finite_differences.hpp:155-171,271-285) is reproduced;
+//  * FD Jacobians of block-diagonal dynamics are exactly block diagonal (equal values subtract to 0.0), and a
+//    dot product that skips exact-zero terms has the same value, so products with A and B touch one block;
+//  * everything else (Q_uu LLT with its retry loop, explicit inverse, gains, value update, aliased
+//    symmetrisation, line search, stop test) follows ilqr.hpp:92-271 with k-ascending sums per output element,
+//    one thread per element.
+//
+// The body is written as data-parallel phases `for (idx = tid; idx < n; idx += nthr)` separated by barriers, with
+// all cross-phase state in the workspace, so tests/csrc/host_emulation.cpp can run it with tid = 0, nthr = 1.
+#pragma once
+#include "ilqr_core.cuh"
+
+namespace mas_b200 {
+
+#if defined(__CUDA_ARCH__)
+#define MAS_CTA_SYNC() __syncthreads()
+#else
+#define MAS_CTA_SYNC() ((void)0)
+#endif
+
+template <class M>
+struct StackedProblem {
+  int A, T;
+  double dt;
+  int has_bounds;
+  double lo[M::NU], hi[M::NU];
+  double tolerance;
+  int max_iterations;
+  // per scenario (pointers already offset to the scenario)
+  const double* x0;   // [ns]
+  const double* prm;  // [A][NPs]   NPs = max(NP,1)
+  double *X, *U, *Xt, *Ut;     // [(T+1)*ns], [T*ms] nominal and trial, column t at t*ns
+  double *K, *kff;             // [T][ms*ns] (K(i,j) at i + j*ms), [T][ms]
+  double* work;                // scratch, layout in StackedWork
+  double* out_cost;            // [1 + A]: stacked best_cost, then per-agent costs
+  int* out_int;                // iterations, status, reg_retries, alpha_trials
+};
+
+// Offsets into the double workspace of one scenario.
+struct StackedWork {
+  int ns, ms, A, NX, NU;
+  size_t Vx, Vxx, Ab, Bb, lx, lu, lxx, luu, lux, Qx, Qu, Qxx, Qux, Quu, Qreg, L, inv, AtV, BtV, KtQ, cb, pref, S5, R5, S6, R6, dx, scal, total;
+  MAS_HD StackedWork(int A_, int NX_, int NU_) : A(A_), NX(NX_), NU(NU_) {
+    ns = A * NX;
+    ms = A * NU;
+    size_t o = 0;
+    auto take = [&](size_t n) {
+      const size_t r = o;
+      o += n;
+      return r;
+    };
+    Vx = take(ns);
+    Vxx = take(static_cast<size_t>(ns) * ns);
+    Ab = take(static_cast<size_t>(A) * NX * NX);
+    Bb = take(static_cast<size_t>(A) * NX * NU);
+    lx = take(ns);
+    lu = take(ms);
+    lxx = take(static_cast<size_t>(ns) * ns);
+    luu = take(static_cast<size_t>(ms) * ms);
+    lux = take(static_cast<size_t>(ms) * ns);
+    Qx = take(ns);
+    Qu = take(ms);
+    Qxx = take(static_cast<size_t>(ns) * ns);
+    Qux = take(static_cast<size_t>(ms) * ns);
+    Quu = take(static_cast<size_t>(ms) * ms);
+    Qreg = take(static_cast<size_t>(ms) * ms);
+    L = take(static_cast<size_t>(ms) * ms);
+    inv = take(static_cast<size_t>(ms) * ms);
+    AtV = take(static_cast<size_t>(ns) * ns);
+    BtV = take(static_cast<size_t>(ms) * ns);
+    KtQ = take(static_cast<size_t>(ns) * ms);
+    cb = take(A);
+    pref = take(A + 1);
+    S5 = take(static_cast<size_t>(A) * NX * 2);
+    R5 = take(static_cast<size_t>(A) * NU * 2);
+    S6 = take(static_cast<size_t>(A) * NX * 2);
+    R6 = take(static_cast<size_t>(A) * NU * 2);
+    dx = take(ns);
+    scal = take(16);
+    total = o;
+  }
+};
+
+enum StackedScalar { SC_COST = 0, SC_MERIT = 1, SC_TRIAL = 2, SC_REG = 3, SC_PIVOT = 4, SC_FLAG = 5, SC_INNER = 6 };
+
+// stacked value with agent a's term replaced by va: ((pref[a] + va) + c[a+1]) + ... + c[A-1]
+MAS_HD double stacked_sum1(const double* c, const double* pref, int A, int a, double va) {
+  double s = pref[a] + va;
+  for (int k = a + 1; k < A; ++k) s += c[k];
+  return s;
+}
+// two agents replaced (a != b)
+MAS_HD double stacked_sum2(const double* c, const double* pref, int A, int a, double va, int b, double vb) {
+  if (a > b) {
+    const int ti = a;
+    a = b;
+    b = ti;
+    const double tv = va;
+    va = vb;
+    vb = tv;
+  }
+  double s = pref[a] + va;
+  for (int k = a + 1; k < b; ++k) s += c[k];
+  s += vb;
+  for (int k = b + 1; k < A; ++k) s += c[k];
+  return s;
+}
+
+// cost of one agent at (x + sx*eps*e_i + ..., u + ...) helpers
+template <class M>
+MAS_HD double agent_stage_pert(const double* x, const double* u, int t, const double* prm, int ix, double dxv, int jx, double djv, int iu, double duv,
+                               int ju, double dju) {
+  double xp[M::NX], up[M::NU];
+#pragma unroll
+  for (int k = 0; k < M::NX; ++k) xp[k] = x[k];
+#pragma unroll
+  for (int k = 0; k < M::NU; ++k) up[k] = u[k];
+  if (ix >= 0) xp[ix] = xp[ix] + dxv;
+  if (jx >= 0) xp[jx] = xp[jx] + djv;
+  if (iu >= 0) up[iu] = up[iu] + duv;
+  if (ju >= 0) up[ju] = up[ju] + dju;
+  return M::stage(xp, up, t, prm);
+}
+
+// One backward pass over the stacked problem (ilqr.hpp:92-193).  Returns nothing; retries are counted in out_int[2].
+template <class M>
+MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, int tid, int nthr) {
+  constexpr int NX = M::NX, NU = M::NU, NPs = (M::NP > 0 ? M::NP : 1);
+  const int A = P.A, ns = W.ns, ms = W.ms, T = P.T;
+  double* w = P.work;
+  double *Vx = w + W.Vx, *Vxx = w + W.Vxx, *Ab = w + W.Ab, *Bb = w + W.Bb, *lx = w + W.lx, *lu = w + W.lu, *lxx = w + W.lxx, *luu = w + W.luu,
+         *lux = w + W.lux, *Qx = w + W.Qx, *Qu = w + W.Qu, *Qxx = w + W.Qxx, *Qux = w + W.Qux, *Quu = w + W.Quu, *Qreg = w + W.Qreg, *Lm = w + W.L,
+         *inv = w + W.inv, *AtV = w + W.AtV, *BtV = w + W.BtV, *KtQ = w + W.KtQ, *cb = w + W.cb, *pref = w + W.pref, *S5 = w + W.S5, *R5 = w + W.R5,
+         *S6 = w + W.S6, *R6 = w + W.R6, *scal = w + W.scal;
+  const double e5 = 1e-5, e6 = 1e-6;
+
+  // ---- terminal value (ilqr.hpp:92-102): FD gradient (eps 1e-6) and Hessian (eps 1e-5) of the stacked terminal cost
+  const double* xT = P.X + static_cast<size_t>(T) * ns;
+  for (int a = tid; a < A; a += nthr) {
+    const double* xa = xT + a * NX;
+    const double* pa = P.prm + a * NPs;
+    cb[a] = M::terminal(xa, pa);
+    for (int i = 0; i < NX; ++i)
+      for (int sgn = 0; sgn < 2; ++sgn) {
+        double xp[NX];
+        for (int k = 0; k < NX; ++k) xp[k] = xa[k];
+        xp[i] = sgn ? xa[i] - e5 : xa[i] + e5;
+        S5[(a * NX + i) * 2 + sgn] = M::terminal(xp, pa);
+        xp[i] = sgn ? xa[i] - e6 : xa[i] + e6;
+        S6[(a * NX + i) * 2 + sgn] = M::terminal(xp, pa);
+      }
+  }
+  MAS_CTA_SYNC();
+  if (tid == 0) {
+    double s = 0.0;
+    pref[0] = s;
+    for (int a = 0; a < A; ++a) {
+      s += cb[a];
+      pref[a + 1] = s;
+    }
+  }
+  MAS_CTA_SYNC();
+  for (int idx = tid; idx < ns + ns * ns; idx += nthr) {
+    if (idx < ns) {
+      const int a = idx / NX, il = idx % NX;
+      const double fp = stacked_sum1(cb, pref, A, a, S6[(a * NX + il) * 2 + 0]);
+      const double fm = stacked_sum1(cb, pref, A, a, S6[(a * NX + il) * 2 + 1]);
+      Vx[idx] = (fp - fm) / (2 * e6);
+    } else {
+      const int e = idx - ns, i = e % ns, j = e / ns;
+      const int a = i / NX, il = i % NX, b = j / NX, jl = j % NX;
+      double h;
+      if (i == j) {
+        const double fp = finite_or_zero(stacked_sum1(cb, pref, A, a, S5[(a * NX + il) * 2 + 0]));
+        const double f0 = finite_or_zero(pref[A]);
+        const double fm = finite_or_zero(stacked_sum1(cb, pref, A, a, S5[(a * NX + il) * 2 + 1]));
+        h = (fp - 2 * f0 + fm) / (e5 * e5);
+      } else if (a == b) {
+        const double* xa = xT + a * NX;
+        const double* pa = P.prm + a * NPs;
+        double v[4];
+        for (int q = 0; q < 4; ++q) {
+          double xp[NX];
+          for (int k = 0; k < NX; ++k) xp[k] = xa[k];
+          xp[il] = (q & 2) ? xa[il] - e5 : xa[il] + e5;
+          xp[jl] = (q & 1) ? xa[jl] - e5 : xa[jl] + e5;
+          v[q] = finite_or_zero(stacked_sum1(cb, pref, A, a, M::terminal(xp, pa)));
+        }
+        h = (v[0] - v[1] - v[2] + v[3]) / (4 * e5 * e5);
+      } else {
+        double v[4];
+        for (int q = 0; q < 4; ++q)
+          v[q] = finite_or_zero(stacked_sum2(cb, pref, A, a, S5[(a * NX + il) * 2 + ((q >> 1) & 1)], b, S5[(b * NX + jl) * 2 + (q & 1)]));
+        h = (v[0] - v[1] - v[2] + v[3]) / (4 * e5 * e5);
+      }
+      Vxx[i + static_cast<size_t>(j) * ns] = h;
+    }
+  }
+  MAS_CTA_SYNC();
+  // v_xx = 0.5 * (v_xx + v_xx^T), aliased: lower triangle from old values, then upper from the new lower
+  for (int e = tid; e < ns * ns; e += nthr) {
+    const int i = e % ns, j = e / ns;
+    if (i > j) Vxx[i + static_cast<size_t>(j) * ns] = 0.5 * (Vxx[i + static_cast<size_t>(j) * ns] + Vxx[j + static_cast<size_t>(i) * ns]);
+  }
+  MAS_CTA_SYNC();
+  for (int e = tid; e < ns * ns; e += nthr) {
+    const int i = e % ns, j = e / ns;
+    if (i <= j) Vxx[i + static_cast<size_t>(j) * ns] = 0.5 * (Vxx[i + static_cast<size_t>(j) * ns] + Vxx[j + static_cast<size_t>(i) * ns]);
+  }
+  MAS_CTA_SYNC();
+
+  for (int t = T - 1; t >= 0; --t) {
+    const double* xt = P.X + static_cast<size_t>(t) * ns;
+    const double* ut = P.U + static_cast<size_t>(t) * ms;
+    // ---- per-agent pieces: FD Jacobian blocks, base stage cost, singly perturbed stage costs
+    for (int a = tid; a < A; a += nthr) {
+      const double* xa = xt + a * NX;
+      const double* ua = ut + a * NU;
+      const double* pa = P.prm + a * NPs;
+      fd_jac_x<M>(xa, ua, pa, Ab + static_cast<size_t>(a) * NX * NX);
+      fd_jac_u<M>(xa, ua, pa, Bb + static_cast<size_t>(a) * NX * NU);
+      cb[a] = M::stage(xa, ua, t, pa);
+    }
+    for (int e = tid; e < A * (NX + NU) * 2; e += nthr) {
+      const int a = e / ((NX + NU) * 2), r = e % ((NX + NU) * 2), v = r / 2, sgn = r % 2;
+      const double* xa = xt + a * NX;
+      const double* ua = ut + a * NU;
+      const double* pa = P.prm + a * NPs;
+      if (v < NX) {
+        S5[(a * NX + v) * 2 + sgn] = agent_stage_pert<M>(xa, ua, t, pa, v, sgn ? -e5 : e5, -1, 0, -1, 0, -1, 0);
+        S6[(a * NX + v) * 2 + sgn] = agent_stage_pert<M>(xa, ua, t, pa, v, sgn ? -e6 : e6, -1, 0, -1, 0, -1, 0);
+      } else {
+        const int iu = v - NX;
+        R5[(a * NU + iu) * 2 + sgn] = agent_stage_pert<M>(xa, ua, t, pa, -1, 0, -1, 0, iu, sgn ? -e5 : e5, -1, 0);
+        R6[(a * NU + iu) * 2 + sgn] = agent_stage_pert<M>(xa, ua, t, pa, -1, 0, -1, 0, iu, sgn ? -e6 : e6, -1, 0);
+      }
+    }
+    MAS_CTA_SYNC();
+    if (tid == 0) {
+      double s = 0.0;
+      pref[0] = s;
+      for (int a = 0; a < A; ++a) {
+        s += cb[a];
+        pref[a + 1] = s;
+      }
+    }
+    MAS_CTA_SYNC();
+    // ---- FD derivatives of the stacked stage cost (finite_differences.hpp:110-210,263-287)
+    const int n_lx = ns, n_lu = ms, n_lxx = ns * ns, n_luu = ms * ms, n_lux = ms * ns;
+    for (int idx = tid; idx < n_lx + n_lu + n_lxx + n_luu + n_lux; idx += nthr) {
+      int e = idx;
+      if (e < n_lx) {
+        const int a = e / NX, il = e % NX;
+        const double fp = stacked_sum1(cb, pref, A, a, S6[(a * NX + il) * 2 + 0]);
+        const double fm = stacked_sum1(cb, pref, A, a, S6[(a * NX + il) * 2 + 1]);
+        lx[e] = (fp - fm) / (2 * e6);
+        continue;
+      }
+      e -= n_lx;
+      if (e < n_lu) {
+        const int a = e / NU, il = e % NU;
+        const double fp = stacked_sum1(cb, pref, A, a, R6[(a * NU + il) * 2 + 0]);
+        const double fm = stacked_sum1(cb, pref, A, a, R6[(a * NU + il) * 2 + 1]);
+        lu[e] = (fp - fm) / (2 * e6);
+        continue;
+      }
+      e -= n_lu;
+      if (e < n_lxx + n_luu) {
+        const bool is_x = e < n_lxx;
+        if (!is_x) e -= n_lxx;
+        const int dim = is_x ? ns : ms, per = is_x ? NX : NU;
+        const double* tab = is_x ? S5 : R5;
+        const int i = e % dim, j = e / dim;
+        const int a = i / per, il = i % per, b = j / per, jl = j % per;
+        double h;
+        if (i == j) {
+          const double fp = finite_or_zero(stacked_sum1(cb, pref, A, a, tab[(a * per + il) * 2 + 0]));
+          const double f0 = finite_or_zero(pref[A]);
+          const double fm = finite_or_zero(stacked_sum1(cb, pref, A, a, tab[(a * per + il) * 2 + 1]));
+          h = (fp - 2 * f0 + fm) / (e5 * e5);
+        } else if (a == b) {
+          const double* xa = xt + a * NX;
+          const double* ua = ut + a * NU;
+          const double* pa = P.prm + a * NPs;
+          double v[4];
+          for (int q = 0; q < 4; ++q) {
+            const double di = (q & 2) ? -e5 : e5, dj = (q & 1) ? -e5 : e5;
+            const double c = is_x ? agent_stage_pert<M>(xa, ua, t, pa, il, di, jl, dj, -1, 0, -1, 0)
+                                  : agent_stage_pert<M>(xa, ua, t, pa, -1, 0, -1, 0, il, di, jl, dj);
+            v[q] = finite_or_zero(stacked_sum1(cb, pref, A, a, c));
+          }
+          h = (v[0] - v[1] - v[2] + v[3]) / (4 * e5 * e5);
+        } else {
+          double v[4];
+          for (int q = 0; q < 4; ++q)
+            v[q] = finite_or_zero(stacked_sum2(cb, pref, A, a, tab[(a * per + il) * 2 + ((q >> 1) & 1)], b, tab[(b * per + jl) * 2 + (q & 1)]));
+          h = (v[0] - v[1] - v[2] + v[3]) / (4 * e5 * e5);
+        }
+        (is_x ? lxx : luu)[i + static_cast<size_t>(j) * dim] = h;
+        continue;
+      }
+      e -= n_lxx + n_luu;
+      {  // cross term H(i,j): control i, state j; f_pp=(x+,u+) f_pm=(x-,u+) f_mp=(x+,u-) f_mm=(x-,u-)
+        const int i = e % ms, j = e / ms;
+        const int a = i / NU, il = i % NU, b = j / NX, jl = j % NX;
+        double v[4];
+        for (int q = 0; q < 4; ++q) {
+          const int sx = q & 1, su = (q >> 1) & 1;  // q: 0 pp, 1 pm (x-), 2 mp (u-), 3 mm
+          if (a == b) {
+            const double c = agent_stage_pert<M>(xt + a * NX, ut + a * NU, t, P.prm + a * NPs, jl, sx ? -e6 : e6, -1, 0, il, su ? -e6 : e6, -1, 0);
+            v[q] = finite_or_zero(stacked_sum1(cb, pref, A, a, c));
+          } else {
+            v[q] = finite_or_zero(stacked_sum2(cb, pref, A, a, R6[(a * NU + il) * 2 + su], b, S6[(b * NX + jl) * 2 + sx]));
+          }
+        }
+        lux[i + static_cast<size_t>(j) * ms] = (v[0] - v[1] - v[2] + v[3]) / (4 * e6 * e6);
+      }
+    }
+    MAS_CTA_SYNC();
+    // ---- Q_x, Q_u, A^T V_xx, B^T V_xx (ilqr.hpp:115-119); A, B block diagonal
+    for (int idx = tid; idx < ns + ms + ns * ns + ms * ns; idx += nthr) {
+      int e = idx;
+      if (e < ns) {
+        const int a = e / NX, il = e % NX;
+        const double* Aa = Ab + static_cast<size_t>(a) * NX * NX;
+        double s = Aa[0 + il * NX] * Vx[a * NX + 0];
+        for (int k = 1; k < NX; ++k) s = s + Aa[k + il * NX] * Vx[a * NX + k];
+        Qx[e] = lx[e] + s;
+        continue;
+      }
+      e -= ns;
+      if (e < ms) {
+        const int a = e / NU, il = e % NU;
+        const double* Ba = Bb + static_cast<size_t>(a) * NX * NU;
+        double s = Ba[0 + il * NX] * Vx[a * NX + 0];
+        for (int k = 1; k < NX; ++k) s = s + Ba[k + il * NX] * Vx[a * NX + k];
+        Qu[e] = lu[e] + s;
+        continue;
+      }
+      e -= ms;
+      if (e < ns * ns) {
+        const int i = e % ns, j = e / ns, a = i / NX, il = i % NX;
+        const double* Aa = Ab + static_cast<size_t>(a) * NX * NX;
+        double s = Aa[0 + il * NX] * Vxx[a * NX + 0 + static_cast<size_t>(j) * ns];
+        for (int k = 1; k < NX; ++k) s = s + Aa[k + il * NX] * Vxx[a * NX + k + static_cast<size_t>(j) * ns];
+        AtV[i + static_cast<size_t>(j) * ns] = s;
+        continue;
+      }
+      e -= ns * ns;
+      {
+        const int i = e % ms, j = e / ms, a = i / NU, il = i % NU;
+        const double* Ba = Bb + static_cast<size_t>(a) * NX * NU;
+        double s = Ba[0 + il * NX] * Vxx[a * NX + 0 + static_cast<size_t>(j) * ns];
+        for (int k = 1; k < NX; ++k) s = s + Ba[k + il * NX] * Vxx[a * NX + k + static_cast<size_t>(j) * ns];
+        BtV[i + static_cast<size_t>(j) * ms] = s;
+      }
+    }
+    MAS_CTA_SYNC();
+    // ---- Q_xx = l_xx + (A^T V) A,  Q_ux = l_ux + (B^T V) A,  Q_uu = l_uu + (B^T V) B
+    for (int idx = tid; idx < ns * ns + ms * ns + ms * ms; idx += nthr) {
+      int e = idx;
+      if (e < ns * ns) {
+        const int i = e % ns, j = e / ns, b = j / NX, jl = j % NX;
+        const double* Aj = Ab + static_cast<size_t>(b) * NX * NX;
+        double s = AtV[i + static_cast<size_t>(b * NX + 0) * ns] * Aj[0 + jl * NX];
+        for (int k = 1; k < NX; ++k) s = s + AtV[i + static_cast<size_t>(b * NX + k) * ns] * Aj[k + jl * NX];
+        Qxx[i + static_cast<size_t>(j) * ns] = lxx[i + static_cast<size_t>(j) * ns] + s;
+        continue;
+      }
+      e -= ns * ns;
+      if (e < ms * ns) {
+        const int i = e % ms, j = e / ms, b = j / NX, jl = j % NX;
+        const double* Aj = Ab + static_cast<size_t>(b) * NX * NX;
+        double s = BtV[i + static_cast<size_t>(b * NX + 0) * ms] * Aj[0 + jl * NX];
+        for (int k = 1; k < NX; ++k) s = s + BtV[i + static_cast<size_t>(b * NX + k) * ms] * Aj[k + jl * NX];
+        Qux[i + static_cast<size_t>(j) * ms] = lux[i + static_cast<size_t>(j) * ms] + s;
+        continue;
+      }
+      e -= ms * ns;
+      {
+        const int i = e % ms, j = e / ms, b = j / NU, jl = j % NU;
+        const double* Bj = Bb + static_cast<size_t>(b) * NX * NU;
+        double s = BtV[i + static_cast<size_t>(b * NX + 0) * ms] * Bj[0 + jl * NX];
+        for (int k = 1; k < NX; ++k) s = s + BtV[i + static_cast<size_t>(b * NX + k) * ms] * Bj[k + jl * NX];
+        Quu[i + static_cast<size_t>(j) * ms] = luu[i + static_cast<size_t>(j) * ms] + s;
+        Qreg[i + static_cast<size_t>(j) * ms] = Quu[i + static_cast<size_t>(j) * ms];
+      }
+    }
+    if (tid == 0) scal[SC_REG] = 1e-6;
+    MAS_CTA_SYNC();
+    // ---- LLT of Q_uu_reg with the cumulative-shift retry loop (ilqr.hpp:172-182); unblocked, lower
+    for (;;) {
+      for (int e = tid; e < ms * ms; e += nthr) Lm[e] = Qreg[e];
+      if (tid == 0) scal[SC_FLAG] = 0.0;
+      MAS_CTA_SYNC();
+      bool failed = false;
+      for (int k = 0; k < ms; ++k) {
+        if (tid == 0) {
+          double x = Lm[k + static_cast<size_t>(k) * ms];
+          if (k > 0) {
+            double sq = 0.0;
+            for (int j = 0; j < k; ++j) sq += Lm[k + static_cast<size_t>(j) * ms] * Lm[k + static_cast<size_t>(j) * ms];
+            x -= sq;
+          }
+          if (x <= 0.0) {
+            scal[SC_FLAG] = 1.0;
+          } else {
+            x = sqrt(x);
+            Lm[k + static_cast<size_t>(k) * ms] = x;
+            scal[SC_PIVOT] = x;
+          }
+        }
+        MAS_CTA_SYNC();
+        if (scal[SC_FLAG] != 0.0) {
+          failed = true;
+          break;
+        }
+        const double x = scal[SC_PIVOT];
+        for (int i = k + 1 + tid; i < ms; i += nthr) {
+          double s = Lm[i + static_cast<size_t>(k) * ms];
+          if (k > 0) {
+            double acc = Lm[i + 0 * static_cast<size_t>(ms)] * Lm[k + 0 * static_cast<size_t>(ms)];
+            for (int j = 1; j < k; ++j) acc = acc + Lm[i + static_cast<size_t>(j) * ms] * Lm[k + static_cast<size_t>(j) * ms];
+            s -= acc;
+          }
+          Lm[i + static_cast<size_t>(k) * ms] = s / x;
+        }
+        MAS_CTA_SYNC();
+      }
+      if (!failed) break;
+      const double reg = scal[SC_REG];
+      MAS_CTA_SYNC();
+      for (int i = tid; i < ms; i += nthr) Qreg[i + static_cast<size_t>(i) * ms] += reg;
+      if (tid == 0) {
+        scal[SC_REG] = reg * 10.0;
+        P.out_int[2] += 1;
+      }
+      MAS_CTA_SYNC();
+      if (!(reg < 1e300)) break;
+    }
+    // ---- Q_uu_inv = llt.solve(I), one column per thread, the column is its own work vector
+    for (int c = tid; c < ms; c += nthr) {
+      double* x = inv + static_cast<size_t>(c) * ms;
+      for (int i = 0; i < ms; ++i) x[i] = (i == c) ? 1.0 : 0.0;
+      for (int i = 0; i < ms; ++i) {
+        double s = x[i];
+        for (int j = 0; j < i; ++j) s -= Lm[i + static_cast<size_t>(j) * ms] * x[j];
+        x[i] = s / Lm[i + static_cast<size_t>(i) * ms];
+      }
+      for (int i = ms - 1; i >= 0; --i) {
+        double s = x[i];
+        for (int j = i + 1; j < ms; ++j) s -= Lm[j + static_cast<size_t>(i) * ms] * x[j];
+        x[i] = s / Lm[i + static_cast<size_t>(i) * ms];
+      }
+    }
+    MAS_CTA_SYNC();
+    // ---- gains k = (-inv) Q_u, K = (-inv) Q_ux (ilqr.hpp:185-186)
+    double* Kt = P.K + static_cast<size_t>(t) * ms * ns;
+    double* kt = P.kff + static_cast<size_t>(t) * ms;
+    for (int idx = tid; idx < ms + ms * ns; idx += nthr) {
+      if (idx < ms) {
+        const int i = idx;
+        double s = (-inv[i + 0 * static_cast<size_t>(ms)]) * Qu[0];
+        for (int k = 1; k < ms; ++k) s = s + (-inv[i + static_cast<size_t>(k) * ms]) * Qu[k];
+        kt[i] = s;
+      } else {
+        const int e = idx - ms, i = e % ms, j = e / ms;
+        double s = (-inv[i + 0 * static_cast<size_t>(ms)]) * Qux[0 + static_cast<size_t>(j) * ms];
+        for (int k = 1; k < ms; ++k) s = s + (-inv[i + static_cast<size_t>(k) * ms]) * Qux[k + static_cast<size_t>(j) * ms];
+        Kt[i + static_cast<size_t>(j) * ms] = s;
+      }
+    }
+    MAS_CTA_SYNC();
+    // ---- K^T Q_uu (unregularised), then the value update (ilqr.hpp:188-192)
+    for (int e = tid; e < ns * ms; e += nthr) {
+      const int i = e % ns, j = e / ns;
+      double s = Kt[0 + static_cast<size_t>(i) * ms] * Quu[0 + static_cast<size_t>(j) * ms];
+      for (int k = 1; k < ms; ++k) s = s + Kt[k + static_cast<size_t>(i) * ms] * Quu[k + static_cast<size_t>(j) * ms];
+      KtQ[i + static_cast<size_t>(j) * ns] = s;
+    }
+    MAS_CTA_SYNC();
+    for (int idx = tid; idx < ns + ns * ns; idx += nthr) {
+      if (idx < ns) {
+        const int i = idx;
+        double t1 = Kt[0 + static_cast<size_t>(i) * ms] * Qu[0];
+        for (int k = 1; k < ms; ++k) t1 = t1 + Kt[k + static_cast<size_t>(i) * ms] * Qu[k];
+        double t2 = Qux[0 + static_cast<size_t>(i) * ms] * kt[0];
+        for (int k = 1; k < ms; ++k) t2 = t2 + Qux[k + static_cast<size_t>(i) * ms] * kt[k];
+        double t3 = KtQ[i + 0 * static_cast<size_t>(ns)] * kt[0];
+        for (int k = 1; k < ms; ++k) t3 = t3 + KtQ[i + static_cast<size_t>(k) * ns] * kt[k];
+        Vx[i] = ((Qx[i] + t1) + t2) + t3;
+      } else {
+        const int e = idx - ns, i = e % ns, j = e / ns;
+        double m1 = Kt[0 + static_cast<size_t>(i) * ms] * Qux[0 + static_cast<size_t>(j) * ms];
+        for (int k = 1; k < ms; ++k) m1 = m1 + Kt[k + static_cast<size_t>(i) * ms] * Qux[k + static_cast<size_t>(j) * ms];
+        double m2 = Qux[0 + static_cast<size_t>(i) * ms] * Kt[0 + static_cast<size_t>(j) * ms];
+        for (int k = 1; k < ms; ++k) m2 = m2 + Qux[k + static_cast<size_t>(i) * ms] * Kt[k + static_cast<size_t>(j) * ms];
+        double m3 = KtQ[i + 0 * static_cast<size_t>(ns)] * Kt[0 + static_cast<size_t>(j) * ms];
+        for (int k = 1; k < ms; ++k) m3 = m3 + KtQ[i + static_cast<size_t>(k) * ns] * Kt[k + static_cast<size_t>(j) * ms];
+        Vxx[i + static_cast<size_t>(j) * ns] = ((Qxx[i + static_cast<size_t>(j) * ns] + m1) + m2) + m3;
+      }
+    }
+    MAS_CTA_SYNC();
+    for (int e = tid; e < ns * ns; e += nthr) {
+      const int i = e % ns, j = e / ns;
+      if (i > j) Vxx[i + static_cast<size_t>(j) * ns] = 0.5 * (Vxx[i + static_cast<size_t>(j) * ns] + Vxx[j + static_cast<size_t>(i) * ns]);
+    }
+    MAS_CTA_SYNC();
+    for (int e = tid; e < ns * ns; e += nthr) {
+      const int i = e % ns, j = e / ns;
+      if (i <= j) Vxx[i + static_cast<size_t>(j) * ns] = 0.5 * (Vxx[i + static_cast<size_t>(j) * ns] + Vxx[j + static_cast<size_t>(i) * ns]);
+    }
+    MAS_CTA_SYNC();
+  }
+}
+
+// Rollout of the stacked system.  alpha < 0: plain rollout of the controls in Uout (prologue, ilqr.hpp:75-76);
+// otherwise the line-search forward pass (ilqr.hpp:208-217) from the nominal (P.X, P.U) with gains.  The stacked
+// stage cost is the block-order sum of the agents' costs, accumulated over t.  Result in scal[SC_TRIAL].
+template <class M>
+MAS_HD void stacked_rollout(const StackedProblem<M>& P, const StackedWork& W, double alpha, double* Xout, double* Uout, int tid, int nthr) {
+  constexpr int NX = M::NX, NU = M::NU, NPs = (M::NP > 0 ? M::NP : 1);
+  const int A = P.A, ns = W.ns, ms = W.ms, T = P.T;
+  double* w = P.work;
+  double *cb = w + W.cb, *dxv = w + W.dx, *scal = w + W.scal;
+  for (int i = tid; i < ns; i += nthr) Xout[i] = P.x0[i];
+  if (tid == 0) scal[SC_TRIAL] = 0.0;
+  MAS_CTA_SYNC();
+  for (int t = 0; t < T; ++t) {
+    double* xt = Xout + static_cast<size_t>(t) * ns;
+    double* ut = Uout + static_cast<size_t>(t) * ms;
+    if (alpha >= 0.0) {
+      const double* xn = P.X + static_cast<size_t>(t) * ns;
+      const double* un = P.U + static_cast<size_t>(t) * ms;
+      const double* Kt = P.K + static_cast<size_t>(t) * ms * ns;
+      const double* kt = P.kff + static_cast<size_t>(t) * ms;
+      for (int i = tid; i < ns; i += nthr) dxv[i] = xt[i] - xn[i];
+      MAS_CTA_SYNC();
+      for (int i = tid; i < ms; i += nthr) {
+        double kdx = Kt[i + 0 * static_cast<size_t>(ms)] * dxv[0];
+        for (int j = 1; j < ns; ++j) kdx = kdx + Kt[i + static_cast<size_t>(j) * ms] * dxv[j];
+        double ui = (un[i] + alpha * kt[i]) + kdx;
+        if (P.has_bounds) {
+          const double hi = P.hi[i % NU], lo = P.lo[i % NU];
+          ui = (hi < ui) ? hi : ui;
+          ui = (lo > ui) ? lo : ui;
+        }
+        ut[i] = ui;
+      }
+      MAS_CTA_SYNC();
+    }
+    for (int a = tid; a < A; a += nthr) {
+      const double* pa = P.prm + a * NPs;
+      cb[a] = M::stage(xt + a * NX, ut + a * NU, t, pa);
+      double xn1[NX];
+      rk4_step<M>(xt + a * NX, ut + a * NU, pa, P.dt, xn1);
+      for (int k = 0; k < NX; ++k) xt[ns + a * NX + k] = xn1[k];
+    }
+    MAS_CTA_SYNC();
+    if (tid == 0) {
+      double inner = 0.0;
+      for (int a = 0; a < A; ++a) inner += cb[a];
+      scal[SC_TRIAL] += inner;
+    }
+    MAS_CTA_SYNC();
+  }
+  for (int a = tid; a < A; a += nthr) cb[a] = M::terminal(Xout + static_cast<size_t>(T) * ns + a * NX, P.prm + a * NPs);
+  MAS_CTA_SYNC();
+  if (tid == 0) {
+    double inner = 0.0;
+    for (int a = 0; a < A; ++a) inner += cb[a];
+    scal[SC_TRIAL] += inner;
+  }
+  MAS_CTA_SYNC();
+}
+
+// The whole centralized solve of one scenario: iLQR::solve on the stacked OCP, then the per-agent cost
+// re-evaluation of centralized.hpp:27-36.
+template <class M>
+MAS_HD void stacked_solve(const StackedProblem<M>& P, int tid, int nthr) {
+  constexpr int NX = M::NX, NU = M::NU, NPs = (M::NP > 0 ? M::NP : 1);
+  const StackedWork W(P.A, NX, NU);
+  const int ns = W.ns, ms = W.ms, T = P.T;
+  double* scal = P.work + W.scal;
+  if (tid == 0) {
+    P.out_int[0] = 0;
+    P.out_int[1] = STATUS_MAX_ITER;
+    P.out_int[2] = 0;
+    P.out_int[3] = 0;
+  }
+  stacked_rollout<M>(P, W, -1.0, P.X, P.U, tid, nthr);
+  if (tid == 0) {
+    scal[SC_COST] = scal[SC_TRIAL];
+    scal[SC_MERIT] = scal[SC_TRIAL];
+  }
+  MAS_CTA_SYNC();
+  for (int iter = 0; iter < P.max_iterations; ++iter) {
+    if (tid == 0) P.out_int[0] = iter + 1;
+    stacked_backward<M>(P, W, tid, nthr);
+    const double current_merit = scal[SC_MERIT];
+    int accepted = -1;
+    double best_merit = current_merit;
+    double alpha = 1.0;
+    for (int j = 0; j < kNumAlphas; ++j) {
+      stacked_rollout<M>(P, W, alpha, P.Xt, P.Ut, tid, nthr);
+      const double trial = scal[SC_TRIAL];
+      MAS_CTA_SYNC();
+      if (tid == 0) P.out_int[3] += 1;
+      if (trial < best_merit) {
+        best_merit = trial;
+        accepted = j;
+        break;
+      }
+      alpha *= 0.5;
+    }
+    if (accepted >= 0) {
+      for (int i = tid; i < (T + 1) * ns; i += nthr) P.X[i] = P.Xt[i];
+      for (int i = tid; i < T * ms; i += nthr) P.U[i] = P.Ut[i];
+      if (tid == 0) {
+        scal[SC_COST] = best_merit;  // objective re-evaluated on the accepted trajectory: the same sum
+        scal[SC_MERIT] = best_merit;
+      }
+    }
+    MAS_CTA_SYNC();
+    const double improvement = current_merit - best_merit;
+    if (improvement < P.tolerance) {
+      if (tid == 0) P.out_int[1] = STATUS_CONVERGED;
+      break;
+    }
+  }
+  MAS_CTA_SYNC();
+  // per-agent best_cost = objective of the agent's own block (centralized.hpp:32), total = stacked best_cost (:27)
+  for (int a = tid; a < P.A; a += nthr) {
+    const double* pa = P.prm + a * NPs;
+    double c = 0.0;
+    for (int t = 0; t < T; ++t) c += M::stage(P.X + static_cast<size_t>(t) * ns + a * NX, P.U + static_cast<size_t>(t) * ms + a * NU, t, pa);
+    c += M::terminal(P.X + static_cast<size_t>(T) * ns + a * NX, pa);
+    P.out_cost[1 + a] = c;
+  }
+  if (tid == 0) P.out_cost[0] = scal[SC_COST];
+}
+
+}  // namespace mas_b200

@@ -1,0 +1,137 @@
+// centralized_host.cuh -- kernel wrapper and host launcher of the stacked (centralized) solve.
+#pragma once
+#include "centralized.cuh"
+#include "engine.cuh"
+
+namespace mas_b200 {
+
+constexpr int kCentralizedThreads = 256;
+
+// One CTA per scenario.  `base` holds the pointers of scenario 0; the strides select the others.
+template <class M>
+__global__ void __launch_bounds__(kCentralizedThreads) centralized_kernel(StackedProblem<M> base, int n_scenarios, size_t work_stride) {
+  const int s = blockIdx.x;
+  if (s >= n_scenarios) return;
+  constexpr int NPs = (M::NP > 0 ? M::NP : 1);
+  const int ns = base.A * M::NX, ms = base.A * M::NU, T = base.T;
+  StackedProblem<M> P = base;
+  P.x0 = base.x0 + static_cast<size_t>(s) * ns;
+  P.prm = base.prm + static_cast<size_t>(s) * base.A * NPs;
+  P.X = base.X + static_cast<size_t>(s) * (T + 1) * ns;
+  P.Xt = base.Xt + static_cast<size_t>(s) * (T + 1) * ns;
+  P.U = base.U + static_cast<size_t>(s) * T * ms;
+  P.Ut = base.Ut + static_cast<size_t>(s) * T * ms;
+  P.K = base.K + static_cast<size_t>(s) * T * ms * ns;
+  P.kff = base.kff + static_cast<size_t>(s) * T * ms;
+  P.work = base.work + static_cast<size_t>(s) * work_stride;
+  P.out_cost = base.out_cost + static_cast<size_t>(s) * (1 + base.A);
+  P.out_int = base.out_int + static_cast<size_t>(s) * 4;
+  stacked_solve<M>(P, threadIdx.x, blockDim.x);
+}
+
+// CentralizedStrategy::operator() for n_scenarios scenarios of n_agents agents (host arrays as in
+// mas_b200_strategy_run).  trace_iterations (optional): [scenario] iterations of the stacked solve.
+template <class M>
+int run_centralized(Context* ctx, const mas_b200_ocp_desc& d, const mas_b200_ilqr_params& prm, int S, int A, const double* x0,
+                    const double* model_params, const double* U_init, double* X, double* U, double* costs, double* total_cost,
+                    int* iterations_out, int* status_out, long long* launches) {
+  constexpr int NX = M::NX, NU = M::NU, NPs = (M::NP > 0 ? M::NP : 1);
+  const int T = d.horizon_steps, ns = A * NX, ms = A * NU;
+  const StackedWork W(A, NX, NU);
+  cudaStream_t st = ctx->stream;
+  MAS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  // host staging in the stacked layout: X [S][T+1][ns], U [S][T][ms], params [S][A][NPs]
+  std::vector<double> hU(static_cast<size_t>(S) * T * ms, 0.0), hP(static_cast<size_t>(S) * A * NPs, 0.0);
+  for (int s = 0; s < S; ++s)
+    for (int a = 0; a < A; ++a) {
+      for (int i = 0; i < M::NP; ++i)
+        hP[(static_cast<size_t>(s) * A + a) * NPs + i] = model_params ? model_params[(static_cast<size_t>(s) * A + a) * M::NP + i] : d.params[i];
+      if (U_init)
+        for (int t = 0; t < T; ++t)
+          for (int i = 0; i < NU; ++i)
+            hU[(static_cast<size_t>(s) * T + t) * ms + a * NU + i] = U_init[((static_cast<size_t>(s) * A + a) * T + t) * NU + i];
+    }
+  struct Buffers {
+    double *x0 = nullptr, *prm = nullptr, *X = nullptr, *Xt = nullptr, *U = nullptr, *Ut = nullptr, *K = nullptr, *k = nullptr, *work = nullptr,
+           *oc = nullptr;
+    int* oi = nullptr;
+    ~Buffers() {
+      for (double* p : {x0, prm, X, Xt, U, Ut, K, k, work, oc})
+        if (p) cudaFree(p);
+      if (oi) cudaFree(oi);
+    }
+  } b;
+  auto dalloc = [&](double** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(double)); };
+  const size_t Ss = static_cast<size_t>(S);
+  MAS_CUDA_CHECK(dalloc(&b.x0, Ss * ns));
+  MAS_CUDA_CHECK(dalloc(&b.prm, Ss * A * NPs));
+  MAS_CUDA_CHECK(dalloc(&b.X, Ss * (T + 1) * ns));
+  MAS_CUDA_CHECK(dalloc(&b.Xt, Ss * (T + 1) * ns));
+  MAS_CUDA_CHECK(dalloc(&b.U, Ss * T * ms));
+  MAS_CUDA_CHECK(dalloc(&b.Ut, Ss * T * ms));
+  MAS_CUDA_CHECK(dalloc(&b.K, Ss * T * ms * ns));
+  MAS_CUDA_CHECK(dalloc(&b.k, Ss * T * ms));
+  MAS_CUDA_CHECK(dalloc(&b.work, Ss * W.total));
+  MAS_CUDA_CHECK(dalloc(&b.oc, Ss * (1 + A)));
+  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&b.oi), Ss * 4 * sizeof(int)));
+  MAS_CUDA_CHECK(cudaMemcpyAsync(b.x0, x0, Ss * ns * sizeof(double), cudaMemcpyHostToDevice, st));  // [S][A][NX] is already [S][ns]
+  MAS_CUDA_CHECK(cudaMemcpyAsync(b.prm, hP.data(), hP.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  MAS_CUDA_CHECK(cudaMemcpyAsync(b.U, hU.data(), hU.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+
+  StackedProblem<M> P{};
+  P.A = A;
+  P.T = T;
+  P.dt = d.dt;
+  P.has_bounds = d.has_input_bounds;
+  for (int i = 0; i < NU; ++i) {
+    P.lo[i] = d.input_lower[i];
+    P.hi[i] = d.input_upper[i];
+  }
+  P.tolerance = prm.tolerance;
+  P.max_iterations = prm.max_iterations;
+  P.x0 = b.x0;
+  P.prm = b.prm;
+  P.X = b.X;
+  P.U = b.U;
+  P.Xt = b.Xt;
+  P.Ut = b.Ut;
+  P.K = b.K;
+  P.kff = b.k;
+  P.work = b.work;
+  P.out_cost = b.oc;
+  P.out_int = b.oi;
+  centralized_kernel<M><<<S, kCentralizedThreads, 0, st>>>(P, S, W.total);
+  if (launches) (*launches)++;
+  MAS_CUDA_CHECK(cudaGetLastError());
+
+  std::vector<double> hX(Ss * (T + 1) * ns), hUo(Ss * T * ms), hc(Ss * (1 + A));
+  std::vector<int> hi(Ss * 4);
+  MAS_CUDA_CHECK(cudaMemcpyAsync(hX.data(), b.X, hX.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  MAS_CUDA_CHECK(cudaMemcpyAsync(hUo.data(), b.U, hUo.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  MAS_CUDA_CHECK(cudaMemcpyAsync(hc.data(), b.oc, hc.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  MAS_CUDA_CHECK(cudaMemcpyAsync(hi.data(), b.oi, hi.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+  MAS_CUDA_CHECK(cudaStreamSynchronize(st));
+  // scatter the stacked trajectories back to the agents' blocks (centralized.hpp:30-31)
+  for (int s = 0; s < S; ++s) {
+    for (int a = 0; a < A; ++a) {
+      const size_t ag = static_cast<size_t>(s) * A + a;
+      if (X)
+        for (int t = 0; t <= T; ++t)
+          for (int i = 0; i < NX; ++i) X[(ag * (T + 1) + t) * NX + i] = hX[(static_cast<size_t>(s) * (T + 1) + t) * ns + a * NX + i];
+      if (U)
+        for (int t = 0; t < T; ++t)
+          for (int i = 0; i < NU; ++i) U[(ag * T + t) * NU + i] = hUo[(static_cast<size_t>(s) * T + t) * ms + a * NU + i];
+      if (costs) costs[ag] = hc[static_cast<size_t>(s) * (1 + A) + 1 + a];
+    }
+    if (total_cost) total_cost[s] = hc[static_cast<size_t>(s) * (1 + A)];
+    if (iterations_out) iterations_out[s] = hi[static_cast<size_t>(s) * 4 + 0];
+    if (status_out) status_out[s] = hi[static_cast<size_t>(s) * 4 + 1];
+  }
+  return MAS_B200_OK;
+}
+
+using CentralizedFn = int (*)(Context*, const mas_b200_ocp_desc&, const mas_b200_ilqr_params&, int, int, const double*, const double*, const double*,
+                              double*, double*, double*, double*, int*, int*, long long*);
+CentralizedFn centralized_entry(int model_id);
+
+}  // namespace mas_b200

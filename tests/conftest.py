@@ -47,7 +47,7 @@ _EMU_LIB = os.path.join(ROOT, "tests", "_build", "libhost_emulation.so")
 
 
 def _build_emulation() -> str:
-    deps = [_EMU_SRC] + [os.path.join(ROOT, "multi_agent_solver_b200", "csrc", f) for f in ("ilqr_core.cuh", "models.cuh")]
+    deps = [_EMU_SRC] + [os.path.join(ROOT, "multi_agent_solver_b200", "csrc", f) for f in ("ilqr_core.cuh", "models.cuh", "centralized.cuh")]
     deps.append(os.path.join(ROOT, "include", "mas_b200", "portable_math.h"))
     if not os.path.exists(_EMU_LIB) or os.path.getmtime(_EMU_LIB) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(_EMU_LIB), exist_ok=True)
@@ -100,9 +100,37 @@ class HostEmulation:
         return dict(X=X, U=U, cost=cost, iterations=it, status=st, alpha_trials=tr, reg_retries=rg)
 
 
+    def solve_centralized(self, model, x0, max_iterations=100, tolerance=1e-5):
+        """stacked_solve<M> (centralized.cuh) with tid = 0, nthr = 1.  x0: [agents, n]."""
+        n, m, T, dt, _, hb, lo, hi, prm = MODEL_TABLE[model]
+        A = x0.shape[0]
+        ns, ms = A * n, A * m
+        U = np.zeros((T, ms))
+        X = np.zeros((T + 1, ns))
+        oc = np.zeros(1 + A)
+        oi = np.zeros(4, np.int32)
+        pp = np.tile(np.array(list(prm) + [0.0])[: max(len(prm), 1)], (A, 1)).copy()
+        lo = np.array(list(lo) + [0.0] * 8)
+        hi = np.array(list(hi) + [0.0] * 8)
+        x0f = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1)
+        P = ctypes.POINTER(ctypes.c_double)
+        rc = self.lib.emu_centralized_solve(model, A, T, ctypes.c_double(dt), hb, lo.ctypes.data_as(P), hi.ctypes.data_as(P), pp.ctypes.data_as(P),
+                                            x0f.ctypes.data_as(P), U.ctypes.data_as(P), X.ctypes.data_as(P), oc.ctypes.data_as(P),
+                                            oi.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), int(max_iterations), ctypes.c_double(tolerance))
+        assert rc == 0
+        return dict(X=X.reshape(T + 1, A, n).transpose(1, 0, 2).copy(), U=U.reshape(T, A, m).transpose(1, 0, 2).copy(), total_cost=oc[0],
+                    costs=oc[1:].copy(), iterations=int(oi[0]), status=int(oi[1]), reg_retries=int(oi[2]), alpha_trials=int(oi[3]))
+
+
 @pytest.fixture(scope="session")
 def emu():
     return HostEmulation()
+
+
+def circle_x0(n_agents: int, radius: float = 20.0) -> np.ndarray:
+    """Agents evenly spaced on the circular track (multi_agent_single_track.cpp:41-44,114-119)."""
+    th = 2.0 * np.pi * np.arange(n_agents) / n_agents
+    return np.stack([radius * np.cos(th), radius * np.sin(th), 1.57 + th, np.full(n_agents, 4.0)], -1)
 
 
 # ---- synthetic inputs ------------------------------------------------------------------------------

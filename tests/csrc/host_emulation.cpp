@@ -130,3 +130,55 @@ extern "C" int emu_ilqr_solve_batch(int model, int batch, int T, double dt, unsi
   }
   return 1;
 }
+
+// ---- centralized (stacked) solve, run with tid = 0, nthr = 1 -----------------------------------------------
+#include "centralized.cuh"
+
+namespace {
+template <class M>
+int emulate_centralized(int A, int T, double dt, int has_bounds, const double* lo, const double* hi, const double* params_per_agent,
+                        const double* x0, double* U /* [T][ms] in/out */, double* X /* [T+1][ns] */, double* out_cost, int* out_int,
+                        int max_iterations, double tolerance) {
+  constexpr int NPs = (M::NP > 0 ? M::NP : 1);
+  const StackedWork W(A, M::NX, M::NU);
+  const int ns = W.ns, ms = W.ms;
+  std::vector<double> Xt(static_cast<size_t>(T + 1) * ns), Ut(static_cast<size_t>(T) * ms), K(static_cast<size_t>(T) * ms * ns), k(static_cast<size_t>(T) * ms),
+      work(W.total, 0.0), prm(static_cast<size_t>(A) * NPs, 0.0);
+  for (int a = 0; a < A; ++a)
+    for (int i = 0; i < M::NP; ++i) prm[a * NPs + i] = params_per_agent[a * M::NP + i];
+  StackedProblem<M> P{};
+  P.A = A;
+  P.T = T;
+  P.dt = dt;
+  P.has_bounds = has_bounds;
+  for (int i = 0; i < M::NU; ++i) {
+    P.lo[i] = lo[i];
+    P.hi[i] = hi[i];
+  }
+  P.tolerance = tolerance;
+  P.max_iterations = max_iterations;
+  P.x0 = x0;
+  P.prm = prm.data();
+  P.X = X;
+  P.U = U;
+  P.Xt = Xt.data();
+  P.Ut = Ut.data();
+  P.K = K.data();
+  P.kff = k.data();
+  P.work = work.data();
+  P.out_cost = out_cost;
+  P.out_int = out_int;
+  stacked_solve<M>(P, 0, 1);
+  return 0;
+}
+}  // namespace
+
+extern "C" int emu_centralized_solve(int model, int A, int T, double dt, int has_bounds, const double* lo, const double* hi,
+                                     const double* params_per_agent, const double* x0, double* U, double* X, double* out_cost, int* out_int,
+                                     int max_iterations, double tolerance) {
+  switch (model) {
+    case 1: return emulate_centralized<StCirc>(A, T, dt, has_bounds, lo, hi, params_per_agent, x0, U, X, out_cost, out_int, max_iterations, tolerance);
+    case 2: return emulate_centralized<Lqr4>(A, T, dt, has_bounds, lo, hi, params_per_agent, x0, U, X, out_cost, out_int, max_iterations, tolerance);
+  }
+  return 1;
+}

@@ -68,6 +68,12 @@ def main():
     r = o.strategy_run_batch(o.STRATEGY_CENTRALIZED, o.MODEL_ST_CIRC, x0, max_outer=1, max_iterations=100, tolerance=1e-5, trig=o.TRIG_PORTABLE)
     np.savez_compressed(os.path.join(HERE, "config5_centralized_4agents.npz"), x0=x0, iterations=r["trace_iters"][:, 0, 0],
                         **{k: r[k] for k in ("X", "U", "costs", "total_cost")})
+    # config 5 at full size: 32 stacked circular-track agents (n = 128, m = 64); ~10 s in the oracle
+    th = 2.0 * np.pi * np.arange(32) / 32
+    x0 = np.stack([20 * np.cos(th), 20 * np.sin(th), 1.57 + th, np.full(32, 4.0)], -1)[None]
+    r = o.strategy_run_batch(o.STRATEGY_CENTRALIZED, o.MODEL_ST_CIRC, x0, max_outer=1, max_iterations=100, tolerance=1e-5, trig=o.TRIG_PORTABLE)
+    np.savez_compressed(os.path.join(HERE, "config5_centralized_32agents.npz"), x0=x0, iterations=r["trace_iters"][:, 0, 0],
+                        **{k: r[k] for k in ("X", "U", "costs", "total_cost")})
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 

@@ -43,6 +43,24 @@ def test_sequential_config4(mas, ctx, oracle):
         assert np.array_equal(got[k], ref[k]), k
 
 
+@pytest.mark.parametrize("model,agents", [(1, 3), (1, 10), (2, 6)])
+def test_centralized(mas, ctx, oracle, model, agents):
+    """CentralizedStrategy (BASELINE configs[4] shape, smaller): stacked all-FD solve, per-agent cost re-evaluation."""
+    S = 5
+    rng = np.random.default_rng(agents)
+    if model == 1:
+        x0 = circ_x0(S, agents, jitter_seed=None)[0]
+        x0[:, :, 2] += rng.uniform(-0.05, 0.05, (S, agents))
+    else:
+        x0 = rng.uniform(-1, 1, (S, agents, 4))
+    ref = oracle.strategy_run_batch(oracle.STRATEGY_CENTRALIZED, model, x0, max_outer=1, max_iterations=100, tolerance=1e-5,
+                                    trig=oracle.TRIG_PORTABLE)
+    got = mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, mas.example_desc(model), mas.IlqrParams.make(100, 1e-5), 1, x0)
+    assert np.array_equal(got["trace_iters"][:, 0, 0], ref["trace_iters"][:, 0, 0])
+    for k in ("total_cost", "costs", "X", "U"):
+        assert np.array_equal(got[k], ref[k]), k
+
+
 def test_unsupported_strategies_fail_loudly(mas, ctx):
     x0, _ = circ_x0(1, 3)
     for kind in (7,):

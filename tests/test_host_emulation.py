@@ -74,6 +74,22 @@ def test_per_problem_params(emu, oracle):
     assert is_bit_exact(got, ref)
 
 
+@pytest.mark.parametrize("model,agents", [(1, 3), (1, 8), (2, 5)])
+def test_centralized_stacked_solve_bit_exact(emu, oracle, model, agents):
+    """CentralizedStrategy: the structure-exploiting stacked solve (centralized.cuh) reproduces the oracle's
+    dense evaluation of build_global_ocp + iLQR with all-FD derivatives bit for bit, noise included."""
+    from conftest import circle_x0
+
+    x0 = circle_x0(agents) if model == 1 else np.random.default_rng(0).uniform(-1, 1, (agents, 4))
+    ref = oracle.strategy_run_batch(oracle.STRATEGY_CENTRALIZED, model, x0[None], max_outer=1, max_iterations=100, tolerance=1e-5,
+                                    trig=oracle.TRIG_PORTABLE)
+    got = emu.solve_centralized(model, x0)
+    assert got["iterations"] == ref["trace_iters"][0, 0, 0]
+    assert got["total_cost"] == ref["total_cost"][0]
+    assert np.array_equal(got["costs"], ref["costs"][0])
+    assert np.array_equal(got["X"], ref["X"][0]) and np.array_equal(got["U"], ref["U"][0])
+
+
 def test_nan_initial_state_matches_oracle(emu, oracle):
     """Non-finite costs propagate silently (SURVEY 8b error conventions): a NaN merit never accepts a
     candidate and `improvement < tolerance` is false for NaN, so the loop runs to max_iterations."""
