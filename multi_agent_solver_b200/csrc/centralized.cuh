@@ -5,7 +5,7 @@
 // differences for *every* derivative of the stacked functions.  One CTA solves one scenario start to finish
 // (T is 10 in the reference's multi-agent examples; state n_s = A*NX up to 128, controls m_s = A*NU up to 64).
 //
-// Bit-compatibility with the oracle's dense evaluation is kept while exploiting the structure:
+// Bit-compatibility with the reference's dense evaluation order is kept while exploiting the structure:
 //  * a finite difference of the stacked cost changes one or two agents' terms; the stacked value is re-formed
 //    as the same left-to-right sum (prefix up to the first changed agent, then the remaining terms in order),
 //    so the rounding noise of the 4-point stencils (finite_differences.hpp:155-171,271-285) is reproduced;
