@@ -443,9 +443,9 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
       for (int s = 0; s < n_scenarios; ++s) trace_iterations[static_cast<size_t>(s) * (max_outer > 0 ? max_outer : 1) * n_agents] = its[s];
     return MAS_B200_OK;
   }
-  if (strategy == MAS_B200_STRATEGY_LINESEARCH) return fail(MAS_B200_ERR_UNSUPPORTED, "LineSearchNashStrategy is not on the device path yet");
-  if (strategy != MAS_B200_STRATEGY_SEQUENTIAL && strategy != MAS_B200_STRATEGY_TRUSTREGION)
+  if (strategy != MAS_B200_STRATEGY_SEQUENTIAL && strategy != MAS_B200_STRATEGY_TRUSTREGION && strategy != MAS_B200_STRATEGY_LINESEARCH)
     return fail(MAS_B200_ERR_INVALID_ARGUMENT, "unknown strategy");
+  const bool keeps_old = strategy == MAS_B200_STRATEGY_TRUSTREGION || strategy == MAS_B200_STRATEGY_LINESEARCH;
   const int batch = n_scenarios * n_agents;
   mas_b200_batch_t h = nullptr;
   rc = mas_b200_batch_create(ctx, agent_desc, batch, &h);
@@ -461,9 +461,15 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
     if (!r) r = b->initialize();  // OCP::initialize_problem of every agent
     if (r) return r;
     const size_t L = static_cast<size_t>(b->ld);
-    if (strategy == MAS_B200_STRATEGY_TRUSTREGION) {
+    if (keeps_old) {
       r = b->ensure_strategy_scratch();
       if (r) return r;
+    }
+    if (strategy == MAS_B200_STRATEGY_LINESEARCH) {
+      r = b->nash_ls_reduce(n_scenarios, n_agents, -1);  // base_cost = total_cost(problem), nash.hpp:103
+      if (r) return r;
+    }
+    if (strategy == MAS_B200_STRATEGY_TRUSTREGION) {
       std::vector<double> ones(b->ld, 1.0);  // radii = 1.0 (nash.hpp:194)
       MAS_CUDA_CHECK(cudaMemcpyAsync(b->d_radius, ones.data(), L * sizeof(double), cudaMemcpyHostToDevice, st));
       MAS_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -476,8 +482,36 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
       MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&g_U), nU * ctx->c.world * sizeof(double)));
       MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&g_c), L * ctx->c.world * sizeof(double)));
     }
+    // per-round record: inner iteration counts, accept flags, costs ([scenario][outer][agent])
+    auto record_trace = [&](int outer) -> int {
+      if (!(trace_iterations || trace_accepted || trace_cost)) return MAS_B200_OK;
+      const size_t off = static_cast<size_t>(outer) * n_agents;
+      if (trace_iterations) {
+        MAS_CUDA_CHECK(cudaMemcpyAsync(tmp_i.data(), b->d_iters, batch * sizeof(int), cudaMemcpyDeviceToHost, st));
+        MAS_CUDA_CHECK(cudaStreamSynchronize(st));
+        for (int s = 0; s < n_scenarios; ++s)
+          for (int a = 0; a < n_agents; ++a) trace_iterations[static_cast<size_t>(s) * max_outer * n_agents + off + a] = tmp_i[s * n_agents + a];
+      }
+      if (trace_accepted) {
+        if (strategy == MAS_B200_STRATEGY_TRUSTREGION) {
+          MAS_CUDA_CHECK(cudaMemcpyAsync(tmp_i.data(), b->d_accepted, batch * sizeof(int), cudaMemcpyDeviceToHost, st));
+          MAS_CUDA_CHECK(cudaStreamSynchronize(st));
+        } else {
+          for (auto& v : tmp_i) v = 1;
+        }
+        for (int s = 0; s < n_scenarios; ++s)
+          for (int a = 0; a < n_agents; ++a) trace_accepted[static_cast<size_t>(s) * max_outer * n_agents + off + a] = tmp_i[s * n_agents + a];
+      }
+      if (trace_cost) {
+        MAS_CUDA_CHECK(cudaMemcpyAsync(tmp_c.data(), b->d_cost, batch * sizeof(double), cudaMemcpyDeviceToHost, st));
+        MAS_CUDA_CHECK(cudaStreamSynchronize(st));
+        for (int s = 0; s < n_scenarios; ++s)
+          for (int a = 0; a < n_agents; ++a) trace_cost[static_cast<size_t>(s) * max_outer * n_agents + off + a] = tmp_c[s * n_agents + a];
+      }
+      return MAS_B200_OK;
+    };
     for (int outer = 0; outer < max_outer; ++outer) {
-      if (strategy == MAS_B200_STRATEGY_TRUSTREGION) {  // nash.hpp:208-210
+      if (keeps_old) {  // nash.hpp:108-115 / :208-210
         MAS_CUDA_CHECK(cudaMemcpyAsync(b->d_U_old, b->d_U, nU * sizeof(double), cudaMemcpyDeviceToDevice, st));
         MAS_CUDA_CHECK(cudaMemcpyAsync(b->d_X_old, b->d_X, nX * sizeof(double), cudaMemcpyDeviceToDevice, st));
         MAS_CUDA_CHECK(cudaMemcpyAsync(b->d_cost_old, b->d_cost, L * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -488,6 +522,20 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
         r = b->trust_region_step();  // nash.hpp:218-243
         if (r) return r;
       }
+      if (strategy == MAS_B200_STRATEGY_LINESEARCH) {
+        r = record_trace(outer);  // the reference's per-solve record sits inside sequential_solve, before the joint search
+        if (r) return r;
+        MAS_CUDA_CHECK(cudaMemcpyAsync(b->d_U_cand, b->d_U, nU * sizeof(double), cudaMemcpyDeviceToDevice, st));  // nash.hpp:123-125
+        r = b->nash_ls_reduce(n_scenarios, n_agents, 0);  // new_cost >= base_cost ? search : base_cost = new_cost
+        if (r) return r;
+        for (double alpha = 0.5; alpha > 1e-3; alpha *= 0.5) {  // nash.hpp:127-158
+          r = b->nash_ls_trial(n_agents, alpha);
+          if (!r) r = b->nash_ls_reduce(n_scenarios, n_agents, 1);
+          if (r) return r;
+        }
+        r = b->nash_ls_restore(n_agents);  // nash.hpp:161-171
+        if (r) return r;
+      }
       if (ctx->c.nccl_comm) {  // every rank ends the round holding all agents' trajectories
         ncclComm_t comm = static_cast<ncclComm_t>(ctx->c.nccl_comm);
         MAS_NCCL_CHECK(g_nccl.GroupStart());
@@ -496,30 +544,9 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
         MAS_NCCL_CHECK(g_nccl.AllGather(b->d_cost, g_c, L, ncclDouble, comm, st));
         MAS_NCCL_CHECK(g_nccl.GroupEnd());
       }
-      if (trace_iterations || trace_accepted || trace_cost) {
-        const size_t off = static_cast<size_t>(outer) * n_agents;  // [scenario][outer][agent]
-        if (trace_iterations) {
-          MAS_CUDA_CHECK(cudaMemcpyAsync(tmp_i.data(), b->d_iters, batch * sizeof(int), cudaMemcpyDeviceToHost, st));
-          MAS_CUDA_CHECK(cudaStreamSynchronize(st));
-          for (int s = 0; s < n_scenarios; ++s)
-            for (int a = 0; a < n_agents; ++a) trace_iterations[static_cast<size_t>(s) * max_outer * n_agents + off + a] = tmp_i[s * n_agents + a];
-        }
-        if (trace_accepted) {
-          if (strategy == MAS_B200_STRATEGY_TRUSTREGION) {
-            MAS_CUDA_CHECK(cudaMemcpyAsync(tmp_i.data(), b->d_accepted, batch * sizeof(int), cudaMemcpyDeviceToHost, st));
-            MAS_CUDA_CHECK(cudaStreamSynchronize(st));
-          } else {
-            for (auto& v : tmp_i) v = 1;
-          }
-          for (int s = 0; s < n_scenarios; ++s)
-            for (int a = 0; a < n_agents; ++a) trace_accepted[static_cast<size_t>(s) * max_outer * n_agents + off + a] = tmp_i[s * n_agents + a];
-        }
-        if (trace_cost) {
-          MAS_CUDA_CHECK(cudaMemcpyAsync(tmp_c.data(), b->d_cost, batch * sizeof(double), cudaMemcpyDeviceToHost, st));
-          MAS_CUDA_CHECK(cudaStreamSynchronize(st));
-          for (int s = 0; s < n_scenarios; ++s)
-            for (int a = 0; a < n_agents; ++a) trace_cost[static_cast<size_t>(s) * max_outer * n_agents + off + a] = tmp_c[s * n_agents + a];
-        }
+      if (strategy != MAS_B200_STRATEGY_LINESEARCH) {
+        r = record_trace(outer);
+        if (r) return r;
       }
     }
     if (g_X) cudaFree(g_X);

@@ -67,10 +67,10 @@ __global__ void dfma_probe_kernel(double* out, int iters) {
 
 BatchBase::~BatchBase() {
   if (ctx) cudaSetDevice(ctx->device);
-  double* dptrs[] = {d_x0, d_X, d_U, d_K, d_k, d_cost, d_merit, d_params, d_stage, d_U_old, d_X_old, d_cost_old, d_radius, d_accept_merit};
+  double* dptrs[] = {d_x0, d_X, d_U, d_K, d_k, d_cost, d_merit, d_params, d_stage, d_U_old, d_X_old, d_cost_old, d_radius, d_accept_merit, d_U_cand, d_base_cost};
   for (double* p : dptrs)
     if (p) cudaFree(p);
-  int* iptrs[] = {d_iters, d_status, d_trials, d_reg, d_list[0], d_list[1], d_count, d_accepted, d_ls_list[0], d_ls_list[1], d_round_count, d_accept_idx};
+  int* iptrs[] = {d_iters, d_status, d_trials, d_reg, d_list[0], d_list[1], d_count, d_accepted, d_ls_list[0], d_ls_list[1], d_round_count, d_accept_idx, d_ls_state};
   for (int* p : iptrs)
     if (p) cudaFree(p);
   if (h_counts) cudaFreeHost(h_counts);
@@ -135,6 +135,42 @@ int BatchBase::ensure_strategy_scratch() {
   MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_cost_old), L * sizeof(double)));
   MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_radius), L * sizeof(double)));
   MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_accepted), L * sizeof(int)));
+  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_U_cand), L * nu * T * sizeof(double)));
+  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_base_cost), L * sizeof(double)));
+  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_ls_state), L * sizeof(int)));
+  MAS_CUDA_CHECK(cudaMemsetAsync(d_ls_state, 0, L * sizeof(int), ctx->stream));
+  return MAS_B200_OK;
+}
+
+// phase -1: base = joint cost (nash.hpp:103).  phase 0, after the Jacobi solve (:119-122,173-176): joint cost not
+// lower than base -> state 1 (search), else base = joint cost, state 0.  phase 1, after a trial (:143-153):
+// searching scenarios whose trial joint cost is below base accept it -> state 2.
+__global__ void nash_ls_reduce_kernel(const double* __restrict__ cost, int n_scenarios, int n_agents, double* base_cost, int* state, int phase) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_scenarios) return;
+  if (phase == 1 && state[s] != 1) return;
+  double c = 0.0;
+  for (int a = 0; a < n_agents; ++a) c += cost[static_cast<size_t>(s) * n_agents + a];
+  if (phase < 0) {
+    base_cost[s] = c;
+    state[s] = 0;
+  } else if (phase == 0) {
+    if (c >= base_cost[s]) {
+      state[s] = 1;
+    } else {
+      base_cost[s] = c;
+      state[s] = 0;
+    }
+  } else if (c < base_cost[s]) {
+    base_cost[s] = c;
+    state[s] = 2;
+  }
+}
+
+int BatchBase::nash_ls_reduce(int n_scenarios, int n_agents, int phase) {
+  nash_ls_reduce_kernel<<<div_up(n_scenarios, 128), 128, 0, ctx->stream>>>(d_cost, n_scenarios, n_agents, d_base_cost, d_ls_state, phase);
+  stats.kernel_launches++;
+  MAS_CUDA_CHECK(cudaGetLastError());
   return MAS_B200_OK;
 }
 

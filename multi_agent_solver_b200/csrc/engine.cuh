@@ -264,6 +264,51 @@ __global__ void __launch_bounds__(kBlock) trust_region_kernel(BatchView<M::NX, M
   }
 }
 
+// ---- LineSearchNashStrategy (strategies/nash.hpp:92-180), scenario = n_agents consecutive problems -------------
+// state per scenario: 0 = round accepted as solved, 1 = joint cost did not drop, searching along old -> cand,
+// 2 = a trial step was accepted.  Joint costs are summed in block order from 0.0 (oracle convention; the
+// reference's OpenMP reduction order is unspecified, nash.hpp:45,134).
+__global__ void nash_ls_reduce_kernel(const double* __restrict__ cost, int n_scenarios, int n_agents, double* base_cost, int* state, int phase);
+
+// trial_controls = old + alpha * (cand - old); trial_states = rollout; trial cost (nash.hpp:136-142)
+template <class M>
+__global__ void __launch_bounds__(kBlock) nash_ls_trial_kernel(BatchView<M::NX, M::NU> v, int batch, int n_agents, const double* __restrict__ U_old,
+                                                            const double* __restrict__ U_cand, const int* __restrict__ state, double alpha) {
+  constexpr int NU = M::NU;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= batch || state[p / n_agents] != 1) return;
+  for (int t = 0; t < v.T; ++t)
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      const size_t idx = soa_index<NU>(t, i, v.ld, p);
+      v.U[idx] = U_old[idx] + alpha * (U_cand[idx] - U_old[idx]);
+    }
+  v.cost[p] = rollout_thread<M>(v, p);
+}
+
+// no trial accepted: back to the old trajectories and costs (nash.hpp:161-171)
+template <class M>
+__global__ void __launch_bounds__(kBlock) nash_ls_restore_kernel(BatchView<M::NX, M::NU> v, int batch, int n_agents, const double* __restrict__ U_old,
+                                                              const double* __restrict__ X_old, const double* __restrict__ cost_old,
+                                                              const int* __restrict__ state) {
+  constexpr int NX = M::NX, NU = M::NU;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= batch || state[p / n_agents] != 1) return;
+  for (int t = 0; t < v.T; ++t)
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      const size_t idx = soa_index<NU>(t, i, v.ld, p);
+      v.U[idx] = U_old[idx];
+    }
+  for (int t = 0; t <= v.T; ++t)
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      const size_t idx = soa_index<NX>(t, i, v.ld, p);
+      v.X[idx] = X_old[idx];
+    }
+  v.cost[p] = cost_old[p];
+}
+
 // ---- host side --------------------------------------------------------------------------------------
 struct BatchBase {
   Context* ctx = nullptr;
@@ -316,6 +361,12 @@ struct BatchBase {
   virtual int solve(const mas_b200_ilqr_params& prm) = 0;
   virtual int rollout_all() = 0;                 // X, cost from U
   virtual int trust_region_step() = 0;           // uses d_*_old, d_radius, d_accepted
+  // LineSearchNashStrategy pieces; d_U_cand, d_base_cost, d_ls_state allocated by ensure_strategy_scratch
+  double *d_U_cand = nullptr, *d_base_cost = nullptr;
+  int* d_ls_state = nullptr;
+  int nash_ls_reduce(int n_scenarios, int n_agents, int phase);
+  virtual int nash_ls_trial(int n_agents, double alpha) = 0;
+  virtual int nash_ls_restore(int n_agents) = 0;
   int collect_stats();
 };
 
@@ -375,6 +426,22 @@ struct BatchImpl : BatchBase {
   int trust_region_step() override {
     make_view();
     trust_region_kernel<M><<<div_up(batch, kBlock), kBlock, 0, ctx->stream>>>(view, batch, d_U_old, d_X_old, d_cost_old, d_radius, d_accepted);
+    stats.kernel_launches++;
+    MAS_CUDA_CHECK(cudaGetLastError());
+    return MAS_B200_OK;
+  }
+
+  int nash_ls_trial(int n_agents, double alpha) override {
+    make_view();
+    nash_ls_trial_kernel<M><<<div_up(batch, kBlock), kBlock, 0, ctx->stream>>>(view, batch, n_agents, d_U_old, d_U_cand, d_ls_state, alpha);
+    stats.kernel_launches++;
+    MAS_CUDA_CHECK(cudaGetLastError());
+    return MAS_B200_OK;
+  }
+
+  int nash_ls_restore(int n_agents) override {
+    make_view();
+    nash_ls_restore_kernel<M><<<div_up(batch, kBlock), kBlock, 0, ctx->stream>>>(view, batch, n_agents, d_U_old, d_X_old, d_cost_old, d_ls_state);
     stats.kernel_launches++;
     MAS_CUDA_CHECK(cudaGetLastError());
     return MAS_B200_OK;

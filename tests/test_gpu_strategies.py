@@ -43,6 +43,24 @@ def test_sequential_config4(mas, ctx, oracle):
         assert np.array_equal(got[k], ref[k]), k
 
 
+@pytest.mark.parametrize("model,agents", [(1, 3), (1, 7), (2, 4)])
+def test_line_search_nash(mas, ctx, oracle, model, agents):
+    """LineSearchNashStrategy (strategies/nash.hpp:92-180): Jacobi solve, then a joint backtracking step
+    old + alpha (cand - old) whenever the scenario's summed cost did not drop."""
+    S = 12
+    rng = np.random.default_rng(30 + agents)
+    if model == 1:
+        x0 = circ_x0(S, agents)[0]
+        x0[:, :, 2] += rng.uniform(-0.2, 0.2, (S, agents))
+        x0[:, :, 3] += rng.uniform(-1.0, 1.0, (S, agents))
+    else:
+        x0 = rng.uniform(-1, 1, (S, agents, 4))
+    ref = oracle.strategy_run_batch(oracle.STRATEGY_LINESEARCH, model, x0, max_outer=6, max_iterations=100, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    got = mas.strategy_run(ctx, mas.Strategy.LINESEARCH, mas.example_desc(model), mas.IlqrParams.make(100, 1e-5), 6, x0)
+    for k in ("trace_iters", "trace_cost", "costs", "total_cost", "X", "U"):
+        assert np.array_equal(got[k], ref[k]), k
+
+
 @pytest.mark.parametrize("model,agents", [(1, 3), (1, 10), (2, 6)])
 def test_centralized(mas, ctx, oracle, model, agents):
     """CentralizedStrategy (BASELINE configs[4] shape, smaller): stacked all-FD solve, per-agent cost re-evaluation."""
