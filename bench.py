@@ -6,7 +6,10 @@ lane-following OCPs (n=4, m=2, T=80, dt=0.1, bounds as examples/single_track_ocp
 x0 = (0, Y, psi, v) from std::mt19937_64(20240607), U_init = 0, iLQR params 10 / 1e-5 / max_ms=inf.
 A "step" is one solve of the whole batch.  With N > 1 every rank solves its own 65,536-problem shard
 (independent problems, no data-path collective): weak scaling; --scaling strong splits one 65,536
-batch across the ranks instead.
+batch across the ranks instead.  Throughput is measured with --depth (default 4) independent solves in
+flight per GPU -- each a whole step on its own stream, driven by its own host thread, starts staggered --
+because the last iterations of a solve are bound by the latency of T sequential time steps and leave
+the GPU nearly idle; the time of one solve alone is reported as config.single_solve_ms.
 
   value : solves/s, inputs (x0) resident in HBM in the engine's layout when the timed region starts
   e2e   : same metric through the C ABI with HOST buffers: x0 host->device, solve, and X, U, cost,
@@ -147,6 +150,28 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+
+
+class Lane:
+    """One solve pipeline: its own CUDA stream, engine context, resident batch and pinned result buffers."""
+
+    def __init__(self, torch, mas, device, desc, per_rank, args, with_host_buffers):
+        self.stream = torch.cuda.Stream()
+        self.ctx = mas.Context(device, self.stream.cuda_stream)
+        self.batch = mas.Batch(self.ctx, desc, per_rank)
+        if args.lanes or args.chains:
+            self.batch.set_tuning(args.lanes, args.chains)
+        if args.ls_mode:
+            self.batch.set_line_search_mode(args.ls_mode)
+        self.out = None
+        if with_host_buffers:
+            self.out = dict(X=torch.empty((per_rank, T + 1, NX), dtype=torch.float64).pin_memory().numpy(),
+                            U=torch.empty((per_rank, T, NU), dtype=torch.float64).pin_memory().numpy(),
+                            cost=torch.empty(per_rank, dtype=torch.float64).pin_memory().numpy(),
+                            iterations=torch.empty(per_rank, dtype=torch.int32).pin_memory().numpy(),
+                            status=torch.empty(per_rank, dtype=torch.int32).pin_memory().numpy())
+
+
 def run_b200(args):
     import torch
     import multi_agent_solver_b200 as mas
@@ -173,131 +198,152 @@ def run_b200(args):
         x0 = np.roll(x0_all, -rank * 4099, axis=0).copy()
     else:
         x0 = x0_all[rank * per_rank:(rank + 1) * per_rank].copy()
+    x0_host = torch.from_numpy(x0).pin_memory().numpy()
 
-    stream = torch.cuda.Stream()
-    ctx = mas.Context(local_rank, stream.cuda_stream)
     desc = mas.example_desc(mas.Model.SINGLE_TRACK_LANE)
     prm = mas.IlqrParams.make(MAX_ITER, TOL)
-    batch = mas.Batch(ctx, desc, per_rank)
-    if args.lanes or args.chains:
-        batch.set_tuning(args.lanes, args.chains)
-    if args.ls_mode:
-        batch.set_line_search_mode(args.ls_mode)
-
-    # pinned host buffers of the e2e path
-    x0_pin = torch.from_numpy(x0).pin_memory()
-    out_pin = dict(X=torch.empty((per_rank, T + 1, NX), dtype=torch.float64).pin_memory().numpy(),
-                   U=torch.empty((per_rank, T, NU), dtype=torch.float64).pin_memory().numpy(),
-                   cost=torch.empty(per_rank, dtype=torch.float64).pin_memory().numpy(),
-                   iterations=torch.empty(per_rank, dtype=torch.int32).pin_memory().numpy(),
-                   status=torch.empty(per_rank, dtype=torch.int32).pin_memory().numpy())
-    x0_host = x0_pin.numpy()
+    depth = max(1, args.depth)
+    lanes = [Lane(torch, mas, local_rank, desc, per_rank, args, with_host_buffers=not args.resident_only) for _ in range(depth)]
+    for ln in lanes:
+        ln.batch.set_initial_states(x0_host)  # resident input of the `value` measurement
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def resident_step():
-        batch.set_controls(None)  # U_init = 0 (device memset); x0 is already resident
-        batch.solve(prm)
+    def resident_step(ln):
+        ln.batch.set_controls(None)  # U_init = 0 (device memset); x0 is already resident
+        ln.batch.solve(prm)
 
-    def e2e_step():
-        batch.set_initial_states(x0_host)
-        batch.set_controls(None)
-        batch.solve(prm)
-        batch.get_solution(out_pin)
+    def e2e_step(ln):
+        ln.batch.set_initial_states(x0_host)  # H2D from pinned memory
+        ln.batch.set_controls(None)
+        ln.batch.solve(prm)
+        ln.batch.get_solution(ln.out)  # D2H of X, U, cost, iterations, status into pinned memory; synchronises
 
-    def timed(fn, steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def timed(fn, steps, use_lanes, stagger_ms):
+        """Runs exactly `steps` steps spread over `use_lanes` pipelines, each driven by its own host thread and
+        started stagger_ms/len(use_lanes) apart so one solve's latency-bound tail overlaps another's bulk.
+        Device time = latest end event - earliest start event over the lanes' streams (then max over ranks)."""
+        n = len(use_lanes)
+        counts = [steps // n + (1 if i < steps % n else 0) for i in range(n)]
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+        go = threading.Barrier(n + 1)
+        errors = []
+
+        def work(i):
+            try:
+                torch.cuda.set_device(local_rank)  # the current device is per host thread
+                ln = use_lanes[i]
+                go.wait()
+                if i:
+                    time.sleep(i * stagger_ms * 1e-3 / n)
+                e0[i].record(ln.stream)
+                for _ in range(counts[i]):
+                    fn(ln)
+                e1[i].record(ln.stream)
+                e1[i].synchronize()
+            except Exception as exc:  # surfaced after join
+                errors.append(exc)
+
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+        for t in threads:
+            t.start()
         barrier()
         w0 = time.perf_counter()
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            for _ in range(steps):
-                fn()
-            e1.record(stream)
-        e1.synchronize()
-        barrier()
+        go.wait()
+        for t in threads:
+            t.join()
+        torch.cuda.synchronize()
         wall = time.perf_counter() - w0
-        ms = e0.elapsed_time(e1)
+        if errors:
+            raise errors[0]
+        active = [i for i in range(n) if counts[i] > 0]
+        starts = [e0[active[0]].elapsed_time(e0[i]) for i in active]
+        ends = [e0[active[0]].elapsed_time(e1[i]) for i in active]
+        ms = max(ends) - min(starts)
+        barrier()
         if dist is not None:
             t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1]) / 1e3
         return ms / steps, wall / steps
 
-    # ---- resident (kernel-path) number -------------------------------------------------------------
-    batch.set_initial_states(x0_host)
+    # ---- one solve at a time: latency of a 65,536-problem solve, and the reference for kernel shares ------------
     for _ in range(max(args.warmup, 3)):
-        resident_step()
-    ctx.synchronize()
-    launches0 = batch.stats()["kernel_launches"]
+        for ln in lanes:
+            resident_step(ln)
+    barrier()
+    single_ms, _ = timed(resident_step, max(3, min(args.steps, 6)), lanes[:1], 0.0)
+
+    # ---- resident throughput: `depth` solves in flight ----------------------------------------------------------
+    launches0 = sum(ln.batch.stats()["kernel_launches"] for ln in lanes)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_step, wall_step = timed(resident_step, args.steps)
-    if args.resident_only and rank == 0:
-        sampler.stop()
-    st = batch.stats()
-    launches = st["kernel_launches"] - launches0
+    ms_step, wall_step = timed(resident_step, args.steps, lanes, single_ms)
+    launches = sum(ln.batch.stats()["kernel_launches"] for ln in lanes) - launches0
+    st = lanes[0].batch.stats()
     value = total / (ms_step * 1e-3)
 
     if args.resident_only:  # short form for ncu captures: only the resident steps above
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_step, "gpu_launches": int(launches),
-                              "note": "resident-only run (profiling aid), not a bench line"}), flush=True)
-        batch.close()
+            sampler.stop()
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_step, "single_solve_ms": single_ms,
+                              "gpu_launches": int(launches), "note": "resident-only run (profiling aid), not a bench line"}), flush=True)
+        for ln in lanes:
+            ln.batch.close()
         return
 
-    # ---- e2e number ------------------------------------------------------------------------------------
-    for _ in range(2):
-        e2e_step()
-    e2e_ms, e2e_wall = timed(e2e_step, args.steps)
+    # ---- e2e: host buffers in, host buffers out, every step ---------------------------------------------------------
+    for ln in lanes:
+        e2e_step(ln)
+    e2e_ms, e2e_wall = timed(e2e_step, args.steps, lanes, single_ms)
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = total / (max(e2e_ms * 1e-3, e2e_wall))
     h2d = per_rank * NX * 8
     d2h = per_rank * (((T + 1) * NX + T * NU + 1) * 8 + 2 * 4)
 
-    # ---- per-kernel timing for the roofline (separate pass so the events do not sit in the timed region)
+    # ---- per-kernel timing for the roofline: one solve at a time, CUDA events around every launch inside the engine
+    batch = lanes[0].batch
     batch.set_profiling(True)
     for _ in range(max(2, min(args.steps, 5))):
-        resident_step()
+        resident_step(lanes[0])
     prof = batch.profile()
     batch.set_profiling(False)
-    fp64_peak = ctx.probe_fp64_peak()
-
+    fp64_peak = lanes[0].ctx.probe_fp64_peak()
     out = batch.get_solution()
+
     if rank == 0:
         hbm_peak, peak_src = load_peaks()
         iters_total = int(out["iterations"].sum())
-        pit = prof["problem_iterations"] / max(prof["solves"], 1)  # problem-iterations per solve of this rank's shard
-        bwd_ms = prof["backward_ms"] / max(prof["solves"], 1)
-        fwd_ms = prof["forward_ms"] / max(prof["solves"], 1)
-        pro_ms = prof["prologue_ms"] / max(prof["solves"], 1)
+        n_solves = max(prof["solves"], 1)
+        pit = prof["problem_iterations"] / n_solves  # problem-iterations per solve of this rank's shard
         kernels = {
-            "forward_kernel": {"ms_per_step": fwd_ms, "launches_per_step": prof["forward_launches"] / max(prof["solves"], 1),
-                               "alg_bytes_per_step": pit * FWD_BYTES},
-            "backward_kernel": {"ms_per_step": bwd_ms, "launches_per_step": prof["backward_launches"] / max(prof["solves"], 1),
-                                "alg_bytes_per_step": pit * BWD_BYTES},
-            "prologue_kernel": {"ms_per_step": pro_ms, "launches_per_step": 1, "alg_bytes_per_step": per_rank * 8 * ((T + 1) * NX + T * NU)},
+            "forward_kernel": {"ms_per_solve": prof["forward_ms"] / n_solves, "launches_per_solve": prof["forward_launches"] / n_solves,
+                               "alg_bytes_per_solve": pit * FWD_BYTES},
+            "backward_kernel": {"ms_per_solve": prof["backward_ms"] / n_solves, "launches_per_solve": prof["backward_launches"] / n_solves,
+                                "alg_bytes_per_solve": pit * BWD_BYTES},
+            "prologue_kernel": {"ms_per_solve": prof["prologue_ms"] / n_solves, "launches_per_solve": 1,
+                                "alg_bytes_per_solve": per_rank * 8 * ((T + 1) * NX + T * NU)},
         }
-        dom = max(("forward_kernel", "backward_kernel"), key=lambda k: kernels[k]["ms_per_step"])
+        dom = max(("forward_kernel", "backward_kernel"), key=lambda k: kernels[k]["ms_per_solve"])
         k = kernels[dom]
-        n_launch = max(k["launches_per_step"], 1)
-        achieved = (k["alg_bytes_per_step"] / n_launch) / (k["ms_per_step"] / n_launch * 1e-3) / 1e9
-        trials_seq = st["alpha_trials"]
-        alg_flops = T * (st["iterations"] * BWD_FLOPS_STEP + (trials_seq + per_rank) * FWD_FLOPS_STEP)
+        n_launch = max(k["launches_per_solve"], 1)
+        achieved = (k["alg_bytes_per_solve"] / n_launch) / (k["ms_per_solve"] / n_launch * 1e-3) / 1e9
+        alg_flops = T * (st["iterations"] * BWD_FLOPS_STEP + (st["alpha_trials"] + per_rank) * FWD_FLOPS_STEP)
         roofline = {
             "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": load_traffic(dom),
-            "peak_source": peak_src,
-            "avg_launch_ms": k["ms_per_step"] / n_launch,
-            "alg_bytes_per_launch": k["alg_bytes_per_step"] / n_launch,
-            "kernel_share_of_step": {name: v["ms_per_step"] / ms_step for name, v in kernels.items()},
+            "traffic": load_traffic(dom), "peak_source": peak_src,
+            "avg_launch_ms": k["ms_per_solve"] / n_launch, "alg_bytes_per_launch": k["alg_bytes_per_solve"] / n_launch,
+            "kernel_share_of_single_solve": {name: v["ms_per_solve"] / single_ms for name, v in kernels.items()},
+            "note": "kernel durations: CUDA events around every launch on the engine's stream, one solve in flight; the kernels are bound by the "
+                    "fp64 pipe and by the latency of T sequential steps, not by HBM (profiles/README.md)",
             "fp64": {"alg_tflops": alg_flops / (ms_step * 1e-3) / 1e12, "dfma_peak_tflops_measured": fp64_peak,
                      "frac": alg_flops / (ms_step * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
-                     "note": "algorithmic flops of the sequential reference (SURVEY 8d convention) / step time; the line search evaluates more candidates than the reference"},
+                     "note": "algorithmic flops of the sequential reference (SURVEY 8d convention) / step time"},
         }
         cpu_baseline = None
         if n_gpus == 1:  # reported on rank 0 at N=1 only
@@ -311,7 +357,11 @@ def run_b200(args):
             "config": {"workload": "batched single-track iLQR, 65,536 independent OCPs with randomised initial states (BASELINE configs[2])",
                        "problems_per_gpu": per_rank, "problems_total": total, "horizon": T, "state_dim": NX, "control_dim": NU,
                        "max_iterations": MAX_ITER, "tolerance": TOL, "max_ms": "inf", "parallelism": f"independent shards x{n_gpus}",
-                       "l2": "working set 670 MB per GPU (X,U,K,k) > 126 MB L2, no flush needed",
+                       "solves_in_flight": depth,
+                       "pipelining": f"{depth} independent 65,536-problem solves in flight per GPU, each a whole step on its own stream and host "
+                                     "thread, starts staggered; ms_per_step = device time of the K steps / K",
+                       "single_solve_ms": single_ms,
+                       "l2": "working set 670 MB per solve (X,U,K,k) > 126 MB L2, no flush needed",
                        "forward_lanes": st["forward_lanes"], "forward_chains": st["forward_chains"],
                        "mean_iterations": iters_total / per_rank},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
@@ -323,7 +373,8 @@ def run_b200(args):
             "wall_ms_per_step": wall_step * 1e3,
         }
         print(json.dumps(line), flush=True)
-    batch.close()
+    for ln in lanes:
+        ln.batch.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -332,10 +383,11 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--depth", type=int, default=4, help="independent solves in flight per GPU (1 = one at a time)")
     ap.add_argument("--cpu-sample", type=int, default=8192, help="problems per CPU-baseline pass")
     ap.add_argument("--resident-only", action="store_true", help="run only warm-up + timed resident steps (for ncu)")
     ap.add_argument("--ls-mode", type=int, default=0, help="line search scheduling: 0 auto, 1 concurrent lanes, 2 compacted rounds")
