@@ -177,7 +177,8 @@ int mas_b200_batch_get_profile(mas_b200_batch_t b, mas_b200_profile* out);
 int mas_b200_batch_set_tuning(mas_b200_batch_t b, int forward_lanes, int forward_chains);
 /* How the line search (solvers/ilqr.hpp:195-228) is scheduled: 0 = auto (by active-set size),
  * 1 = all step sizes concurrently on `forward_lanes` lanes per problem, 2 = compacted rounds of two
- * step sizes over the problems still searching.  Results are bit-identical in every mode. */
+ * step sizes over the problems still searching, 3 = warp-cooperative (a warp owns 32 problems and deals
+ * its lanes out to the (problem, step size) tasks still needed).  Results are bit-identical in every mode. */
 int mas_b200_batch_set_line_search_mode(mas_b200_batch_t b, int mode);
 
 /* One-shot: set_initial_states + set_controls + initialize + solve + get_solution on host buffers.

@@ -394,7 +394,7 @@ int mas_b200_batch_set_tuning(mas_b200_batch_t h, int forward_lanes, int forward
 
 int mas_b200_batch_set_line_search_mode(mas_b200_batch_t h, int mode) {
   MAS_BATCH_GUARD(h);
-  if (mode < 0 || mode > 2) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "line search mode must be 0 (auto), 1 (lanes) or 2 (rounds)");
+  if (mode < 0 || mode > 3) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "line search mode must be 0 (auto), 1 (lanes), 2 (rounds) or 3 (warp-cooperative)");
   b->ls_mode = mode;
   return MAS_B200_OK;
 }

@@ -127,6 +127,77 @@ __global__ void __launch_bounds__(kBlock, 7) forward_kernel(BatchView<M::NX, M::
   }
 }
 
+// ---- warp-cooperative line search (large active sets) ----------------------------------------------------
+// One warp owns 32 active problems.  In every round the 32 lanes are dealt out to the problems still searching
+// (coop_assign): each lane rolls out one (problem, step size) task, merits go to the owner through shared memory,
+// the owner takes its first improving candidate in index order -- the reference's sequential semantics
+// (ilqr.hpp:206-228) -- and lanes of finished problems take over candidates of the ones that need many.  A warp's
+// search costs about (candidates actually needed)/32 rollout times instead of 10.  Then owners commit / stop-test.
+template <class M>
+__global__ void __launch_bounds__(kBlock, 7) forward_coop_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
+                                                                int* next_list, int* next_count) {
+  constexpr int kWarps = kBlock / 32;
+  __shared__ double s_merit[kWarps][32][kNumAlphas];
+  __shared__ double s_cur[kWarps][32];
+  __shared__ int s_p[kWarps][32], s_done[kWarps][32], s_next[kWarps][32];
+  __shared__ CoopPlan s_plan[kWarps];
+  const int w = threadIdx.x / 32, lane = threadIdx.x & 31;
+  const int first = (blockIdx.x * kWarps + w) * 32;
+  const int n_total = *count;
+  int n_valid = n_total - first;
+  n_valid = n_valid < 0 ? 0 : (n_valid > 32 ? 32 : n_valid);
+  const bool owner = lane < n_valid;
+  const int p = owner ? list[first + lane] : 0;
+  const double current_merit = owner ? v.merit[p] : 0.0;
+  int accepted = -1;
+  double accepted_merit = 0.0;
+  s_p[w][lane] = p;
+  s_cur[w][lane] = current_merit;
+  s_done[w][lane] = owner ? 0 : 1;
+  s_next[w][lane] = 0;
+  __syncwarp();
+  if (n_valid > 0) {
+    for (int round = 0; round < kNumAlphas; ++round) {  // at most ten rounds: every searching problem advances by >= 1
+      if (lane == 0) coop_assign(s_done[w], s_next[w], n_valid, &s_plan[w]);
+      __syncwarp();
+      bool any = false;
+      for (int i = 0; i < n_valid; ++i) any = any || s_plan[w].quota[i] > 0;
+      if (!any) break;
+      const int o = s_plan[w].owner[lane];
+      if (o >= 0) {
+        const int po = s_p[w][o], j = s_plan[w].cand[lane];
+        double prm[M::NP > 0 ? M::NP : 1];
+        load_params<M>(v, po, prm);
+        const double alpha = alpha_of(j);
+        double merit;
+        trial_rollout<M, 1>(v, po, prm, &alpha, &merit);
+        s_merit[w][o][j] = merit;
+      }
+      __syncwarp();
+      if (owner && !s_done[w][lane]) {
+        int nx = s_next[w][lane];
+        const bool fin = coop_owner_update(s_merit[w][lane], current_merit, s_plan[w].quota[lane], &nx, &accepted, &accepted_merit);
+        s_next[w][lane] = nx;
+        s_done[w][lane] = fin ? 1 : 0;
+      }
+      __syncwarp();
+    }
+  }
+  bool again = false;
+  if (owner) {
+    double prm[M::NP > 0 ? M::NP : 1];
+    load_params<M>(v, p, prm);
+    again = finish_iteration<M>(v, p, prm, current_merit, accepted >= 0 ? accepted : kNumAlphas, accepted >= 0 ? accepted_merit : current_merit);
+  }
+  const unsigned vote = __ballot_sync(0xffffffffu, again);
+  if (vote) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(next_count, __popc(vote));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (again) next_list[base + __popc(vote & ((1u << lane) - 1u))] = p;
+  }
+}
+
 // ---- line search as compacted rounds (large active sets) ------------------------------------------------
 // Round r rolls out step sizes r*C .. r*C+C-1 for the problems that have not found an improving one
 // yet; those that still have not are appended (warp-aggregated) to the next round's list.  Every warp
@@ -584,6 +655,13 @@ struct BatchImpl : BatchBase {
         if (rc) return rc;
         last_L = 0;
         last_C = 2;
+      } else if (ls_mode == 3 || (ls_mode == 0 && tune_L == 0 && L == 1)) {
+        // more problems than the device holds lanes: warp-cooperative search (32 problems per warp)
+        forward_coop_kernel<M><<<div_up(n_upper, kBlock), kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1],
+                                                                                  d_count + (cur ^ 1));
+        stats.kernel_launches++;
+        last_L = 32;
+        last_C = 1;
       } else {
         launch_forward(n_upper, cur, L, C);
       }

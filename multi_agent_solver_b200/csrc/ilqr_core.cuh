@@ -678,6 +678,57 @@ MAS_HD void lane_line_search(const BatchView<M::NX, M::NU>& v, int p, const doub
   }
 }
 
+// ---- warp-cooperative line search: task assignment ----------------------------------------------------
+// A warp owns up to 32 problems; a task is (problem, step-size index).  Each round the 32 lanes are dealt out
+// evenly to the problems still searching: a problem's share q covers its next q untried step sizes, so a
+// problem that needs many candidates gets them evaluated side by side by the lanes of problems that are
+// already done.  Sequential semantics are preserved by the owner scanning its results in index order.
+// Arrays are per warp (shared memory on the device); `next` = first untried index, `done` = search over.
+struct CoopPlan {
+  int owner[32];   // lane -> owning problem slot, -1 = idle this round
+  int cand[32];    // lane -> step-size index
+  int quota[32];   // slot -> candidates evaluated this round
+};
+MAS_HD void coop_assign(const int* done, const int* next, int n_valid, CoopPlan* plan) {
+  int n_act = 0;
+  for (int i = 0; i < n_valid; ++i) n_act += done[i] ? 0 : 1;
+  for (int l = 0; l < 32; ++l) {
+    plan->owner[l] = -1;
+    plan->cand[l] = 0;
+    plan->quota[l] = 0;
+  }
+  if (n_act == 0) return;
+  const int base = 32 / n_act, rem = 32 % n_act;
+  int lane = 0, rank = 0;
+  for (int i = 0; i < n_valid; ++i) {
+    if (done[i]) continue;
+    int q = base + (rank < rem ? 1 : 0);
+    const int left = kNumAlphas - next[i];
+    if (q > left) q = left;
+    plan->quota[i] = q;
+    for (int k = 0; k < q; ++k) {
+      plan->owner[lane] = i;
+      plan->cand[lane] = next[i] + k;
+      ++lane;
+    }
+    ++rank;
+  }
+}
+
+// Owner's verdict after a round: first improving candidate among those just evaluated (strict <, ilqr.hpp:220).
+// Returns true when the problem's search is over (accepted, or all ten tried); *accepted = index or -1.
+MAS_HD bool coop_owner_update(const double* merits /* [kNumAlphas] of this problem */, double current_merit, int quota, int* next, int* accepted,
+                              double* accepted_merit) {
+  for (int j = *next; j < *next + quota; ++j)
+    if (merits[j] < current_merit) {
+      *accepted = j;
+      *accepted_merit = merits[j];
+      return true;
+    }
+  *next += quota;
+  return *next >= kNumAlphas;
+}
+
 // Accept / bookkeeping / stop test for one problem (ilqr.hpp:230-234,269-271).  Returns true when
 // the problem needs another iteration.
 template <class M>

@@ -6,6 +6,7 @@
 // search with the group reduction done by a loop instead of warp shuffles, commit, stop test,
 // active-list compaction).  This lets the "-m 'not gpu'" tests check the device source against the
 // oracle bit for bit on a machine without a GPU.  Nothing in the product links or loads this file.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -79,6 +80,46 @@ int emulate(int batch, int T, double dt, unsigned mask, int has_bounds, const do
       v.reg_retries[p] += r;
     }
     next.clear();
+    if (L == 32) {  // forward_coop_kernel: a warp owns 32 consecutive list entries, lanes emulated by loops
+      for (size_t first = 0; first < list.size(); first += 32) {
+        const int n_valid = static_cast<int>(std::min<size_t>(32, list.size() - first));
+        int done[32], nxt[32], acc[32];
+        double cur[32], accm[32], merits[32][kNumAlphas];
+        CoopPlan plan;
+        for (int i = 0; i < 32; ++i) {
+          done[i] = i < n_valid ? 0 : 1;
+          nxt[i] = 0;
+          acc[i] = -1;
+          accm[i] = 0.0;
+          cur[i] = i < n_valid ? v.merit[list[first + i]] : 0.0;
+        }
+        for (int round = 0; round < kNumAlphas; ++round) {
+          coop_assign(done, nxt, n_valid, &plan);
+          bool any = false;
+          for (int i = 0; i < n_valid; ++i) any = any || plan.quota[i] > 0;
+          if (!any) break;
+          for (int lane = 0; lane < 32; ++lane) {
+            const int o = plan.owner[lane];
+            if (o < 0) continue;
+            const int po = list[first + o];
+            double prm[M::NP > 0 ? M::NP : 1];
+            load_params<M>(v, po, prm);
+            const double alpha = alpha_of(plan.cand[lane]);
+            trial_rollout<M, 1>(v, po, prm, &alpha, &merits[o][plan.cand[lane]]);
+          }
+          for (int i = 0; i < n_valid; ++i)
+            if (!done[i]) done[i] = coop_owner_update(merits[i], cur[i], plan.quota[i], &nxt[i], &acc[i], &accm[i]) ? 1 : 0;
+        }
+        for (int i = 0; i < n_valid; ++i) {
+          const int p = list[first + i];
+          double prm[M::NP > 0 ? M::NP : 1];
+          load_params<M>(v, p, prm);
+          if (finish_iteration<M>(v, p, prm, cur[i], acc[i] >= 0 ? acc[i] : kNumAlphas, acc[i] >= 0 ? accm[i] : cur[i])) next.push_back(p);
+        }
+      }
+      list.swap(next);
+      continue;
+    }
     for (int p : list) {  // forward_kernel, lanes emulated one after the other
       double prm[M::NP > 0 ? M::NP : 1];
       load_params<M>(v, p, prm);

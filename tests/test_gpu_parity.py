@@ -68,7 +68,7 @@ def test_line_search_lane_mappings_agree(mas, ctx, oracle, lanes, chains):
     assert got["stats"]["forward_lanes"] == lanes
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("model", [0, 1, 2])
 def test_line_search_schedules_agree(mas, ctx, oracle, model, mode):
     """Concurrent-lanes and compacted-rounds scheduling of the line search give the same bits."""
