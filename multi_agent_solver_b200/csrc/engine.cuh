@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kBlock) trust_region_kernel(BatchView<M::NX, M
 
 // ---- LineSearchNashStrategy (strategies/nash.hpp:92-180), scenario = n_agents consecutive problems -------------
 // state per scenario: 0 = round accepted as solved, 1 = joint cost did not drop, searching along old -> cand,
-// 2 = a trial step was accepted.  Joint costs are summed in block order from 0.0 (oracle convention; the
+// 2 = a trial step was accepted.  Joint costs are summed in block order from 0.0 (a fixed convention; the
 // reference's OpenMP reduction order is unspecified, nash.hpp:45,134).
 __global__ void nash_ls_reduce_kernel(const double* __restrict__ cost, int n_scenarios, int n_agents, double* base_cost, int* state, int phase);
 
