@@ -6,7 +6,7 @@ lane-following OCPs (n=4, m=2, T=80, dt=0.1, bounds as examples/single_track_ocp
 x0 = (0, Y, psi, v) from std::mt19937_64(20240607), U_init = 0, iLQR params 10 / 1e-5 / max_ms=inf.
 A "step" is one solve of the whole batch.  With N > 1 every rank solves its own 65,536-problem shard
 (independent problems, no data-path collective): weak scaling; --scaling strong splits one 65,536
-batch across the ranks instead.  Throughput is measured with --depth (default 4) independent solves in
+batch across the ranks instead.  Throughput is measured with --depth (default 6) independent solves in
 flight per GPU -- each a whole step on its own stream, driven by its own host thread, starts staggered --
 because the last iterations of a solve are bound by the latency of T sequential time steps and leave
 the GPU nearly idle; the time of one solve alone is reported as config.single_solve_ms.
@@ -387,7 +387,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--depth", type=int, default=4, help="independent solves in flight per GPU (1 = one at a time)")
+    ap.add_argument("--depth", type=int, default=6, help="independent solves in flight per GPU (1 = one at a time)")
     ap.add_argument("--cpu-sample", type=int, default=8192, help="problems per CPU-baseline pass")
     ap.add_argument("--resident-only", action="store_true", help="run only warm-up + timed resident steps (for ncu)")
     ap.add_argument("--ls-mode", type=int, default=0, help="line search scheduling: 0 auto, 1 concurrent lanes, 2 compacted rounds")
