@@ -42,6 +42,7 @@ struct StackedProblem {
   double *X, *U, *Xt, *Ut;     // [(T+1)*ns], [T*ms] nominal and trial, column t at t*ns
   double *K, *kff;             // [T][ms*ns] (K(i,j) at i + j*ms), [T][ms]
   double* work;                // scratch, layout in StackedWork
+  double* fast;                // K, Q_ux (padded columns) and L | inv | K^T Q_uu: shared memory when it fits, else in `work`
   double* out_cost;            // [1 + A]: stacked best_cost, then per-agent costs
   int* out_int;                // iterations, status, reg_retries, alpha_trials
 };
@@ -49,7 +50,7 @@ struct StackedProblem {
 // Offsets into the double workspace of one scenario.
 struct StackedWork {
   int ns, ms, A, NX, NU;
-  size_t Vx, Vxx, Ab, Bb, lx, lu, lxx, luu, lux, Qx, Qu, Qxx, Qux, Quu, Qreg, L, inv, AtV, BtV, KtQ, cb, pref, S5, R5, S6, R6, dx, scal, total;
+  size_t Vx, Vxx, Ab, Bb, lx, lu, lxx, luu, lux, Qx, Qu, Qxx, Qux, Quu, Qreg, AtV, BtV, cb, pref, S5, R5, S6, R6, dx, scal, fast, fast_doubles, total;
   MAS_HD StackedWork(int A_, int NX_, int NU_) : A(A_), NX(NX_), NU(NU_) {
     ns = A * NX;
     ms = A * NU;
@@ -74,19 +75,28 @@ struct StackedWork {
     Qux = take(static_cast<size_t>(ms) * ns);
     Quu = take(static_cast<size_t>(ms) * ms);
     Qreg = take(static_cast<size_t>(ms) * ms);
-    L = take(static_cast<size_t>(ms) * ms);
-    inv = take(static_cast<size_t>(ms) * ms);
     AtV = take(static_cast<size_t>(ns) * ns);
     BtV = take(static_cast<size_t>(ms) * ns);
-    KtQ = take(static_cast<size_t>(ns) * ms);
-    cb = take(A);
-    pref = take(A + 1);
-    S5 = take(static_cast<size_t>(A) * NX * 2);
-    R5 = take(static_cast<size_t>(A) * NU * 2);
-    S6 = take(static_cast<size_t>(A) * NX * 2);
-    R6 = take(static_cast<size_t>(A) * NU * 2);
-    dx = take(ns);
-    scal = take(16);
+    // fast scratch (offsets below are relative to StackedProblem::fast): K and Q_ux with columns padded to ms + 1
+    // (conflict-free column reads from shared memory), a region that holds L and Q_uu_inv during the
+    // factorisation and K^T Q_uu afterwards, then the per-agent cost tables of the FD stencils and the scalars
+    const size_t region = static_cast<size_t>(ns) * ms > 2 * static_cast<size_t>(ms) * ms ? static_cast<size_t>(ns) * ms : 2 * static_cast<size_t>(ms) * ms;
+    size_t fo = 2 * static_cast<size_t>(ns) * (ms + 1) + region;
+    auto ftake = [&](size_t n) {
+      const size_t r = fo;
+      fo += n;
+      return r;
+    };
+    cb = ftake(A);
+    pref = ftake(A + 1);
+    S5 = ftake(static_cast<size_t>(A) * NX * 2);
+    R5 = ftake(static_cast<size_t>(A) * NU * 2);
+    S6 = ftake(static_cast<size_t>(A) * NX * 2);
+    R6 = ftake(static_cast<size_t>(A) * NU * 2);
+    dx = ftake(ns);
+    scal = ftake(16);
+    fast_doubles = fo;
+    fast = take(fast_doubles);  // fallback location inside `work` when it does not fit in shared memory
     total = o;
   }
 };
@@ -139,10 +149,15 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
   const int A = P.A, ns = W.ns, ms = W.ms, T = P.T;
   double* w = P.work;
   double *Vx = w + W.Vx, *Vxx = w + W.Vxx, *Ab = w + W.Ab, *Bb = w + W.Bb, *lx = w + W.lx, *lu = w + W.lu, *lxx = w + W.lxx, *luu = w + W.luu,
-         *lux = w + W.lux, *Qx = w + W.Qx, *Qu = w + W.Qu, *Qxx = w + W.Qxx, *Qux = w + W.Qux, *Quu = w + W.Quu, *Qreg = w + W.Qreg, *Lm = w + W.L,
-         *inv = w + W.inv, *AtV = w + W.AtV, *BtV = w + W.BtV, *KtQ = w + W.KtQ, *cb = w + W.cb, *pref = w + W.pref, *S5 = w + W.S5, *R5 = w + W.R5,
-         *S6 = w + W.S6, *R6 = w + W.R6, *scal = w + W.scal;
+         *lux = w + W.lux, *Qx = w + W.Qx, *Qu = w + W.Qu, *Qxx = w + W.Qxx, *Qux = w + W.Qux, *Quu = w + W.Quu, *Qreg = w + W.Qreg,
+         *AtV = w + W.AtV, *BtV = w + W.BtV, *cb = P.fast + W.cb, *pref = P.fast + W.pref, *S5 = P.fast + W.S5,
+         *R5 = P.fast + W.R5, *S6 = P.fast + W.S6, *R6 = P.fast + W.R6, *scal = P.fast + W.scal;
   const double e5 = 1e-5, e6 = 1e-6;
+  const int ldk = ms + 1;
+  double* fK = P.fast;                                   // K of the current step, column i at i*ldk
+  double* fQ = fK + static_cast<size_t>(ns) * ldk;       // Q_ux, same layout
+  double* fC = fQ + static_cast<size_t>(ns) * ldk;
+  double *Lm = fC, *inv = fC + static_cast<size_t>(ms) * ms, *KtQ = fC;  // K^T Q_uu reuses the space of L and inv
 
   // ---- terminal value (ilqr.hpp:92-102): FD gradient (eps 1e-6) and Hessian (eps 1e-5) of the stacked terminal cost
   const double* xT = P.X + static_cast<size_t>(T) * ns;
@@ -384,6 +399,7 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
         double s = BtV[i + static_cast<size_t>(b * NX + 0) * ms] * Aj[0 + jl * NX];
         for (int k = 1; k < NX; ++k) s = s + BtV[i + static_cast<size_t>(b * NX + k) * ms] * Aj[k + jl * NX];
         Qux[i + static_cast<size_t>(j) * ms] = lux[i + static_cast<size_t>(j) * ms] + s;
+        fQ[i + static_cast<size_t>(j) * ldk] = Qux[i + static_cast<size_t>(j) * ms];
         continue;
       }
       e -= ms * ns;
@@ -475,38 +491,39 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
         kt[i] = s;
       } else {
         const int e = idx - ms, i = e % ms, j = e / ms;
-        double s = (-inv[i + 0 * static_cast<size_t>(ms)]) * Qux[0 + static_cast<size_t>(j) * ms];
-        for (int k = 1; k < ms; ++k) s = s + (-inv[i + static_cast<size_t>(k) * ms]) * Qux[k + static_cast<size_t>(j) * ms];
+        double s = (-inv[i + 0 * static_cast<size_t>(ms)]) * fQ[0 + static_cast<size_t>(j) * ldk];
+        for (int k = 1; k < ms; ++k) s = s + (-inv[i + static_cast<size_t>(k) * ms]) * fQ[k + static_cast<size_t>(j) * ldk];
         Kt[i + static_cast<size_t>(j) * ms] = s;
+        fK[i + static_cast<size_t>(j) * ldk] = s;
       }
     }
     MAS_CTA_SYNC();
     // ---- K^T Q_uu (unregularised), then the value update (ilqr.hpp:188-192)
     for (int e = tid; e < ns * ms; e += nthr) {
       const int i = e % ns, j = e / ns;
-      double s = Kt[0 + static_cast<size_t>(i) * ms] * Quu[0 + static_cast<size_t>(j) * ms];
-      for (int k = 1; k < ms; ++k) s = s + Kt[k + static_cast<size_t>(i) * ms] * Quu[k + static_cast<size_t>(j) * ms];
+      double s = fK[0 + static_cast<size_t>(i) * ldk] * Quu[0 + static_cast<size_t>(j) * ms];
+      for (int k = 1; k < ms; ++k) s = s + fK[k + static_cast<size_t>(i) * ldk] * Quu[k + static_cast<size_t>(j) * ms];
       KtQ[i + static_cast<size_t>(j) * ns] = s;
     }
     MAS_CTA_SYNC();
     for (int idx = tid; idx < ns + ns * ns; idx += nthr) {
       if (idx < ns) {
         const int i = idx;
-        double t1 = Kt[0 + static_cast<size_t>(i) * ms] * Qu[0];
-        for (int k = 1; k < ms; ++k) t1 = t1 + Kt[k + static_cast<size_t>(i) * ms] * Qu[k];
-        double t2 = Qux[0 + static_cast<size_t>(i) * ms] * kt[0];
-        for (int k = 1; k < ms; ++k) t2 = t2 + Qux[k + static_cast<size_t>(i) * ms] * kt[k];
+        double t1 = fK[0 + static_cast<size_t>(i) * ldk] * Qu[0];
+        for (int k = 1; k < ms; ++k) t1 = t1 + fK[k + static_cast<size_t>(i) * ldk] * Qu[k];
+        double t2 = fQ[0 + static_cast<size_t>(i) * ldk] * kt[0];
+        for (int k = 1; k < ms; ++k) t2 = t2 + fQ[k + static_cast<size_t>(i) * ldk] * kt[k];
         double t3 = KtQ[i + 0 * static_cast<size_t>(ns)] * kt[0];
         for (int k = 1; k < ms; ++k) t3 = t3 + KtQ[i + static_cast<size_t>(k) * ns] * kt[k];
         Vx[i] = ((Qx[i] + t1) + t2) + t3;
       } else {
         const int e = idx - ns, i = e % ns, j = e / ns;
-        double m1 = Kt[0 + static_cast<size_t>(i) * ms] * Qux[0 + static_cast<size_t>(j) * ms];
-        for (int k = 1; k < ms; ++k) m1 = m1 + Kt[k + static_cast<size_t>(i) * ms] * Qux[k + static_cast<size_t>(j) * ms];
-        double m2 = Qux[0 + static_cast<size_t>(i) * ms] * Kt[0 + static_cast<size_t>(j) * ms];
-        for (int k = 1; k < ms; ++k) m2 = m2 + Qux[k + static_cast<size_t>(i) * ms] * Kt[k + static_cast<size_t>(j) * ms];
-        double m3 = KtQ[i + 0 * static_cast<size_t>(ns)] * Kt[0 + static_cast<size_t>(j) * ms];
-        for (int k = 1; k < ms; ++k) m3 = m3 + KtQ[i + static_cast<size_t>(k) * ns] * Kt[k + static_cast<size_t>(j) * ms];
+        double m1 = fK[0 + static_cast<size_t>(i) * ldk] * fQ[0 + static_cast<size_t>(j) * ldk];
+        for (int k = 1; k < ms; ++k) m1 = m1 + fK[k + static_cast<size_t>(i) * ldk] * fQ[k + static_cast<size_t>(j) * ldk];
+        double m2 = fQ[0 + static_cast<size_t>(i) * ldk] * fK[0 + static_cast<size_t>(j) * ldk];
+        for (int k = 1; k < ms; ++k) m2 = m2 + fQ[k + static_cast<size_t>(i) * ldk] * fK[k + static_cast<size_t>(j) * ldk];
+        double m3 = KtQ[i + 0 * static_cast<size_t>(ns)] * fK[0 + static_cast<size_t>(j) * ldk];
+        for (int k = 1; k < ms; ++k) m3 = m3 + KtQ[i + static_cast<size_t>(k) * ns] * fK[k + static_cast<size_t>(j) * ldk];
         Vxx[i + static_cast<size_t>(j) * ns] = ((Qxx[i + static_cast<size_t>(j) * ns] + m1) + m2) + m3;
       }
     }
@@ -532,7 +549,7 @@ MAS_HD void stacked_rollout(const StackedProblem<M>& P, const StackedWork& W, do
   constexpr int NX = M::NX, NU = M::NU, NPs = (M::NP > 0 ? M::NP : 1);
   const int A = P.A, ns = W.ns, ms = W.ms, T = P.T;
   double* w = P.work;
-  double *cb = w + W.cb, *dxv = w + W.dx, *scal = w + W.scal;
+  double *cb = P.fast + W.cb, *dxv = P.fast + W.dx, *scal = P.fast + W.scal;
   for (int i = tid; i < ns; i += nthr) Xout[i] = P.x0[i];
   if (tid == 0) scal[SC_TRIAL] = 0.0;
   MAS_CTA_SYNC();
@@ -591,7 +608,7 @@ MAS_HD void stacked_solve(const StackedProblem<M>& P, int tid, int nthr) {
   constexpr int NX = M::NX, NU = M::NU, NPs = (M::NP > 0 ? M::NP : 1);
   const StackedWork W(P.A, NX, NU);
   const int ns = W.ns, ms = W.ms, T = P.T;
-  double* scal = P.work + W.scal;
+  double* scal = P.fast + W.scal;
   if (tid == 0) {
     P.out_int[0] = 0;
     P.out_int[1] = STATUS_MAX_ITER;

@@ -9,7 +9,9 @@ constexpr int kCentralizedThreads = 256;
 
 // One CTA per scenario.  `base` holds the pointers of scenario 0; the strides select the others.
 template <class M>
-__global__ void __launch_bounds__(kCentralizedThreads) centralized_kernel(StackedProblem<M> base, int n_scenarios, size_t work_stride) {
+__global__ void __launch_bounds__(kCentralizedThreads) centralized_kernel(StackedProblem<M> base, int n_scenarios, size_t work_stride,
+                                                                          size_t fast_offset, int fast_in_shared) {
+  extern __shared__ double mas_fast_scratch[];
   const int s = blockIdx.x;
   if (s >= n_scenarios) return;
   constexpr int NPs = (M::NP > 0 ? M::NP : 1);
@@ -24,6 +26,7 @@ __global__ void __launch_bounds__(kCentralizedThreads) centralized_kernel(Stacke
   P.K = base.K + static_cast<size_t>(s) * T * ms * ns;
   P.kff = base.kff + static_cast<size_t>(s) * T * ms;
   P.work = base.work + static_cast<size_t>(s) * work_stride;
+  P.fast = fast_in_shared ? mas_fast_scratch : P.work + fast_offset;
   P.out_cost = base.out_cost + static_cast<size_t>(s) * (1 + base.A);
   P.out_int = base.out_int + static_cast<size_t>(s) * 4;
   stacked_solve<M>(P, threadIdx.x, blockDim.x);
@@ -100,7 +103,14 @@ int run_centralized(Context* ctx, const mas_b200_ocp_desc& d, const mas_b200_ilq
   P.work = b.work;
   P.out_cost = b.oc;
   P.out_int = b.oi;
-  centralized_kernel<M><<<S, kCentralizedThreads, 0, st>>>(P, S, W.total);
+  // K, Q_ux and the factorisation scratch live in shared memory when they fit (A = 32 single-track agents: 199 KB)
+  const size_t fast_bytes = W.fast_doubles * sizeof(double);
+  int max_optin = 0;
+  MAS_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+  const int in_shared = fast_bytes <= static_cast<size_t>(max_optin) ? 1 : 0;
+  if (in_shared)
+    MAS_CUDA_CHECK(cudaFuncSetAttribute(centralized_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fast_bytes)));
+  centralized_kernel<M><<<S, kCentralizedThreads, in_shared ? fast_bytes : 0, st>>>(P, S, W.total, W.fast, in_shared);
   if (launches) (*launches)++;
   MAS_CUDA_CHECK(cudaGetLastError());
 

@@ -38,11 +38,6 @@ __global__ void soa_to_aos_kernel(const double* __restrict__ src, double* __rest
   }
 }
 
-__global__ void fill_kernel(double* dst, size_t n, double value) {
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = value;
-}
-
 __global__ void time_limit_kernel(const int* __restrict__ list, const int* __restrict__ count, int* status) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < *count) status[list[i]] = STATUS_TIME_LIMIT;

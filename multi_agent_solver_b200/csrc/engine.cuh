@@ -3,11 +3,15 @@
 // One Batch = `batch` same-shaped OCPs resident in HBM in the [T][dim][ld] layout of ilqr_core.cuh.
 // An iLQR solve of the whole batch (mas::solve(Solver&, OCP&) for every problem,
 // solvers/solver.hpp:28-32 -> solvers/ilqr.hpp:59-273) is a host loop over iterations that launches
-//   backward_kernel : one thread per still-active problem; derivatives + Riccati + gains (ilqr.hpp:92-193)
-//   forward_kernel  : L lanes per still-active problem; the line search with its step sizes rolled
-//                     out concurrently, warp-shuffle selection of the first improving one, accepted
-//                     step written in place, stop test, compaction of the active list (ilqr.hpp:195-271)
+//   backward_kernel      : one thread per still-active problem; derivatives + Riccati + gains (ilqr.hpp:92-193)
+//   forward_coop_kernel  : the line search (ilqr.hpp:195-271) for large active sets: a warp owns 32 problems and
+//                          deals its lanes out to the (problem, step size) rollouts still needed
+//   forward_kernel       : the line search for small active sets: L lanes per problem roll out all step sizes
+//                          concurrently, warp-shuffle selection of the first improving one
+//   both then write the accepted step in place, apply the stop test and compact the active list.
 // Problems leave the active list as they converge, so later iterations only pay for what is left.
+// The strategy layer's kernels (trust region, joint line search) and the timing hooks are here too; the
+// centralized strategy lives in centralized.cuh.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -52,7 +56,6 @@ struct Context {
 // Batched transposes between the caller's [batch][rows] arrays and the [rows][ld] HBM layout.
 __global__ void aos_to_soa_kernel(const double* __restrict__ src, double* __restrict__ dst, int batch, int rows, int ld);
 __global__ void soa_to_aos_kernel(const double* __restrict__ src, double* __restrict__ dst, int batch, int rows, int ld);
-__global__ void fill_kernel(double* dst, size_t n, double value);
 __global__ void dfma_probe_kernel(double* out, int iters);
 
 // OCP::initialize_problem / iLQR prologue: rollout + cost, reset of the per-solve counters and of

@@ -207,6 +207,7 @@ int emulate_centralized(int A, int T, double dt, int has_bounds, const double* l
   P.K = K.data();
   P.kff = k.data();
   P.work = work.data();
+  P.fast = work.data() + W.fast;
   P.out_cost = out_cost;
   P.out_int = out_int;
   stacked_solve<M>(P, 0, 1);

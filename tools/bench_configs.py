@@ -85,16 +85,26 @@ def main():
                 "cpu_oracle_ms": t_cpu * 1e3, "cpu_threads": threads, "gpu_agent_solves_per_s": 1024 * 10 / t_gpu})
 
     # config 5: 32 stacked agents (n = 128, m = 64), centralized, batch of scenarios
-    for S5 in (1, 148, 296):
-        x5, gp5, op5 = circle(S5, 32, seed=5)
-        t_gpu = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, d1, p100, 1, x5, model_params=gp5, trace=False), 2)
-        rec = {"config": 5, "what": f"multi_agent_single_track --agents 32 --strategy centralized x {S5} scenarios (stacked n=128, m=64, all-FD)",
-               "gpu_ms": t_gpu * 1e3, "gpu_scenarios_per_s": S5 / t_gpu}
+    # (a) the example's scenario (R = 20) replicated: every CTA does the same 4 iterations
+    th = 2.0 * np.pi * np.arange(32) / 32
+    xe = np.stack([20 * np.cos(th), 20 * np.sin(th), 1.57 + th, np.full(32, 4.0)], -1)[None]
+    for S5 in (1, 148, 592):
+        x5 = np.repeat(xe, S5, axis=0)
+        t_gpu = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, d1, p100, 1, x5, trace=False), 2)
+        rec = {"config": 5, "what": f"multi_agent_single_track --agents 32 --strategy centralized, the example scenario x {S5} replicas "
+                                    "(stacked n=128, m=64, all-FD, 4 iterations each)", "gpu_ms": t_gpu * 1e3, "gpu_scenarios_per_s": S5 / t_gpu}
         if S5 == 1:
             t0 = time.perf_counter()
-            o.strategy_run_batch(o.STRATEGY_CENTRALIZED, 1, x5, params=op5, max_outer=1, max_iterations=100, tolerance=1e-5, threads=1)
+            o.strategy_run_batch(o.STRATEGY_CENTRALIZED, 1, x5, max_outer=1, max_iterations=100, tolerance=1e-5, threads=1)
             rec["cpu_oracle_ms_one_scenario"] = (time.perf_counter() - t0) * 1e3
         out.append(rec)
+    # (b) track radius jittered per scenario: iteration counts spread widely and the slowest scenario sets the time
+    x5, gp5, _ = circle(296, 32, seed=5)
+    r5 = mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, d1, p100, 1, x5, model_params=gp5)
+    t_gpu = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, d1, p100, 1, x5, model_params=gp5, trace=False), 1)
+    its = r5["trace_iters"][:, 0, 0]
+    out.append({"config": 5, "what": "same, 296 scenarios with the track radius jittered in [15, 25]", "gpu_ms": t_gpu * 1e3,
+                "gpu_scenarios_per_s": 296 / t_gpu, "iterations_mean": float(its.mean()), "iterations_max": int(its.max())})
 
     for rec in out:
         print(json.dumps(rec), flush=True)
