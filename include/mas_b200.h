@@ -40,7 +40,10 @@ extern "C" {
 #define MAS_B200_MODEL_LQR4 2              /* examples/multi_agent_lqr.cpp:21-76           n4 m4 */
 #define MAS_B200_MODEL_PENDULUM 3          /* examples/pendulum_swing_up.cpp:29-117        n2 m1 */
 #define MAS_B200_MODEL_ROCKET 4            /* examples/rocket_max_altitude.cpp:31-137      n3 m1 */
-#define MAS_B200_NUM_MODELS 5
+/* not a reference example: model 0 plus one equality and one inequality path constraint (OCP::equality_constraints /
+ * inequality_constraints, ocp.hpp:59-66), the vehicle for iLQR's augmented-Lagrangian terms (ilqr.hpp:121-170,236-260) */
+#define MAS_B200_MODEL_SINGLE_TRACK_LANE_CONSTRAINED 5
+#define MAS_B200_NUM_MODELS 6
 
 /* derivative-mode bits: set = analytic callback installed, clear = finite-difference default */
 #define MAS_B200_DERIV_A (1u << 0)   /* OCP::dynamics_state_jacobian   (ocp.hpp:71)  */
@@ -169,6 +172,10 @@ int mas_b200_batch_solve(mas_b200_batch_t b, const mas_b200_ilqr_params* params)
  * counters the reference lacks.  Any pointer may be NULL.  Synchronises. */
 int mas_b200_batch_get_solution(mas_b200_batch_t b, double* X, double* U, double* cost, int* iterations, int* status);
 int mas_b200_batch_get_device_view(mas_b200_batch_t b, mas_b200_device_view* out);
+/* Constrained models only: the multipliers and the penalty parameter persist from solve to solve like the members
+ * of a reference solver object (ilqr.hpp:331-338,415); this makes the next solve start from a fresh solver
+ * (multipliers 0, penalty = params->penalty).  A new batch starts fresh. */
+int mas_b200_batch_reset_solver_state(mas_b200_batch_t b);
 int mas_b200_batch_get_stats(mas_b200_batch_t b, mas_b200_batch_stats* out);
 int mas_b200_batch_set_profiling(mas_b200_batch_t b, int enable); /* resets the accumulated profile */
 int mas_b200_batch_get_profile(mas_b200_batch_t b, mas_b200_profile* out);

@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 OBJ_DIR = os.path.join(PKG_DIR, "_obj")
 LIB_PATH = os.path.join(PKG_DIR, "libmas_b200.so")
 
-SOURCES = ["engine.cu", "capi.cu", "centralized.cu", "model_st_lane.cu", "model_st_circ.cu", "model_lqr4.cu", "model_pendulum.cu", "model_rocket.cu"]
+SOURCES = ["engine.cu", "capi.cu", "centralized.cu", "model_st_lane.cu", "model_st_lane_con.cu", "model_st_circ.cu", "model_lqr4.cu", "model_pendulum.cu", "model_rocket.cu"]
 HEADERS = ["engine.cuh", "ilqr_core.cuh", "models.cuh", "centralized.cuh", "centralized_host.cuh"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [

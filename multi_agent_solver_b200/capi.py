@@ -16,7 +16,7 @@ MAX_PARAMS = 8
 
 
 class Model:
-    SINGLE_TRACK_LANE, SINGLE_TRACK_CIRC, LQR4, PENDULUM, ROCKET = range(5)
+    SINGLE_TRACK_LANE, SINGLE_TRACK_CIRC, LQR4, PENDULUM, ROCKET, SINGLE_TRACK_LANE_CONSTRAINED = range(6)
 
 
 class Status:
@@ -238,6 +238,9 @@ class Batch:
 
     def solve(self, params: IlqrParams) -> None:
         _check(load_library().mas_b200_batch_solve(self._h, ctypes.byref(params)))
+
+    def reset_solver_state(self) -> None:
+        _check(load_library().mas_b200_batch_reset_solver_state(self._h))
 
     def set_profiling(self, enable: bool) -> None:
         _check(load_library().mas_b200_batch_set_profiling(self._h, int(bool(enable))))

@@ -25,6 +25,8 @@ static const ModelInfo kModels[MAS_B200_NUM_MODELS] = {
     {Lqr4::NX, Lqr4::NU, Lqr4::NP, Lqr4::AVAILABLE, Lqr4::EXAMPLE_MASK, {0}, make_batch_lqr4},
     {Pendulum::NX, Pendulum::NU, Pendulum::NP, Pendulum::AVAILABLE, Pendulum::EXAMPLE_MASK, {60.0}, make_batch_pendulum},
     {Rocket::NX, Rocket::NU, Rocket::NP, Rocket::AVAILABLE, Rocket::EXAMPLE_MASK, {9.81, 50.0, 5e-3, 15.0, 2.0, 0.0}, make_batch_rocket},
+    {StLaneCon::NX, StLaneCon::NU, StLaneCon::NP, StLaneCon::AVAILABLE, StLaneCon::EXAMPLE_MASK, {1.0, 10.0, 1.0, 0.1, 0.1, 0.8, 0.5},
+     make_batch_st_lane_con},
 };
 
 static int fail(int code, const std::string& msg) {
@@ -143,6 +145,7 @@ int mas_b200_example_desc(int model_id, mas_b200_ocp_desc* out) {
   out->num_params = m.np;
   for (int i = 0; i < m.np; ++i) out->params[i] = m.default_params[i];
   switch (model_id) {
+    case MAS_B200_MODEL_SINGLE_TRACK_LANE_CONSTRAINED:
     case MAS_B200_MODEL_SINGLE_TRACK_LANE:  // single_track_ocp.cpp:21-24,105-109
       out->horizon_steps = 80;
       out->dt = 0.1;
@@ -356,6 +359,12 @@ int mas_b200_batch_get_device_view(mas_b200_batch_t h, mas_b200_device_view* out
   out->iterations = b->d_iters;
   out->status = b->d_status;
   out->params = b->d_params;
+  return MAS_B200_OK;
+}
+
+int mas_b200_batch_reset_solver_state(mas_b200_batch_t h) {
+  MAS_BATCH_GUARD(h);
+  b->al_fresh = true;
   return MAS_B200_OK;
 }
 

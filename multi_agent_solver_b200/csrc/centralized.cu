@@ -10,6 +10,7 @@ CentralizedFn centralized_entry(int model_id) {
     case Lqr4::ID: return &run_centralized<Lqr4>;
     case Pendulum::ID: return &run_centralized<Pendulum>;
     case Rocket::ID: return &run_centralized<Rocket>;
+    case StLaneCon::ID: return &run_centralized<StLaneCon>;  // build_global_ocp does not stack constraints
   }
   return nullptr;
 }

@@ -62,7 +62,7 @@ __global__ void dfma_probe_kernel(double* out, int iters) {
 
 BatchBase::~BatchBase() {
   if (ctx) cudaSetDevice(ctx->device);
-  double* dptrs[] = {d_x0, d_X, d_U, d_K, d_k, d_cost, d_merit, d_params, d_stage, d_U_old, d_X_old, d_cost_old, d_radius, d_accept_merit, d_U_cand, d_base_cost};
+  double* dptrs[] = {d_x0, d_X, d_U, d_K, d_k, d_cost, d_merit, d_params, d_stage, d_U_old, d_X_old, d_cost_old, d_radius, d_accept_merit, d_U_cand, d_base_cost, d_lam_eq, d_lam_ineq, d_penalty};
   for (double* p : dptrs)
     if (p) cudaFree(p);
   int* iptrs[] = {d_iters, d_status, d_trials, d_reg, d_list[0], d_list[1], d_count, d_accepted, d_ls_list[0], d_ls_list[1], d_round_count, d_accept_idx, d_ls_state};
@@ -119,6 +119,40 @@ int BatchBase::allocate() {
   MAS_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&h_counts), 4 * sizeof(int)));
   MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
   MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  return allocate_constraint_state();
+}
+
+int BatchBase::allocate_constraint_state() {
+  if (neq == 0 && nineq == 0) return MAS_B200_OK;
+  if (T > kMaxALHorizon) {
+    set_last_error("constrained models support horizons up to 128 steps");
+    return MAS_B200_ERR_UNSUPPORTED;
+  }
+  const size_t L = static_cast<size_t>(ld);
+  if (neq > 0) MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_lam_eq), L * neq * T * sizeof(double)));
+  if (nineq > 0) MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_lam_ineq), L * nineq * T * sizeof(double)));
+  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_penalty), L * sizeof(double)));
+  // a default-constructed solver: zero multipliers, penalty 10 (ilqr.hpp:31); the first solve re-initialises both
+  // from its params (`al_fresh`)
+  mas_b200_ilqr_params defaults;
+  mas_b200_ilqr_default_params(&defaults);
+  al_fresh = true;
+  const int rc = prepare_constraint_state(defaults);
+  al_fresh = true;
+  return rc;
+}
+
+// A fresh reference solver has zero multipliers and the penalty given to set_params (ilqr.hpp:31,47-48,331-338);
+// afterwards both persist from solve to solve.
+int BatchBase::prepare_constraint_state(const mas_b200_ilqr_params& prm) {
+  if ((neq == 0 && nineq == 0) || !al_fresh) return MAS_B200_OK;
+  const size_t L = static_cast<size_t>(ld);
+  if (d_lam_eq) MAS_CUDA_CHECK(cudaMemsetAsync(d_lam_eq, 0, L * neq * T * sizeof(double), ctx->stream));
+  if (d_lam_ineq) MAS_CUDA_CHECK(cudaMemsetAsync(d_lam_ineq, 0, L * nineq * T * sizeof(double), ctx->stream));
+  std::vector<double> rho(L, prm.penalty);
+  MAS_CUDA_CHECK(cudaMemcpyAsync(d_penalty, rho.data(), L * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  MAS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  al_fresh = false;
   return MAS_B200_OK;
 }
 

@@ -67,7 +67,13 @@ __global__ void __launch_bounds__(kBlock) prologue_kernel(BatchView<M::NX, M::NU
   if (p >= batch) return;
   const double c = rollout_thread<M>(v, p);
   v.cost[p] = c;
-  v.merit[p] = c;  // compute_merit == objective without constraint callbacks (ilqr.hpp:380-407)
+  if (HasConstraints<M>::value) {
+    double prm[M::NP > 0 ? M::NP : 1];
+    load_params<M>(v, p, prm);
+    v.merit[p] = al_merit_of_stored<M>(v, p, prm, c);  // compute_merit (ilqr.hpp:78,380-407) with the current multipliers
+  } else {
+    v.merit[p] = c;  // compute_merit == objective without constraint callbacks
+  }
   v.iters[p] = 0;
   v.trials[p] = 0;
   v.reg_retries[p] = 0;
@@ -431,6 +437,13 @@ struct BatchBase {
   int upload_rows(const double* host, double* dev, int rows);      // [batch][rows] host -> [rows][ld]
   int download_rows(const double* dev, double* host, int rows);    // [rows][ld] -> [batch][rows] host
   int ensure_strategy_scratch();
+  // augmented-Lagrangian solver state of constrained models: multipliers [T][NC][ld], penalty [ld]; `al_fresh` =
+  // next solve starts like a newly constructed solver after set_params (multipliers 0, penalty from the params)
+  double *d_lam_eq = nullptr, *d_lam_ineq = nullptr, *d_penalty = nullptr;
+  int neq = 0, nineq = 0;
+  bool al_fresh = true;
+  int allocate_constraint_state();
+  int prepare_constraint_state(const mas_b200_ilqr_params& prm);
   virtual int initialize() = 0;
   virtual int solve(const mas_b200_ilqr_params& prm) = 0;
   virtual int rollout_all() = 0;                 // X, cost from U
@@ -450,6 +463,10 @@ template <class M>
 struct BatchImpl : BatchBase {
   using View = BatchView<M::NX, M::NU>;
   View view{};
+  BatchImpl() {
+    neq = M::NEQ;
+    nineq = M::NINEQ;
+  }
 
   void make_view() {
     view.ld = ld;
@@ -477,10 +494,23 @@ struct BatchImpl : BatchBase {
     view.reg_retries = d_reg;
     view.tolerance = 0.0;
     view.max_iterations = 0;
+    view.lam_eq = d_lam_eq;
+    view.lam_ineq = d_lam_ineq;
+    view.penalty = d_penalty;
+    view.penalty_increase = 5.0;
+    view.constraint_tolerance = 1e-4;
+    view.activation_tolerance = 1e-6;
   }
 
-  int launch_prologue(int max_iterations) {
+  void apply_al_params(const mas_b200_ilqr_params& prm) {
+    view.penalty_increase = prm.penalty_increase;
+    view.constraint_tolerance = prm.constraint_tolerance;
+    view.activation_tolerance = prm.inequality_activation_tolerance;
+  }
+
+  int launch_prologue(int max_iterations, const mas_b200_ilqr_params* prm = nullptr) {
     make_view();
+    if (prm) apply_al_params(*prm);
     prologue_kernel<M><<<div_up(batch, kBlock), kBlock, 0, ctx->stream>>>(view, batch, d_list[0], d_count, max_iterations);
     stats.kernel_launches++;
     MAS_CUDA_CHECK(cudaGetLastError());
@@ -611,8 +641,10 @@ struct BatchImpl : BatchBase {
   int solve(const mas_b200_ilqr_params& prm) override {
     using clock = std::chrono::steady_clock;
     const auto start = clock::now();
+    int rc = prepare_constraint_state(prm);
+    if (rc) return rc;
     prof_begin(0);
-    int rc = launch_prologue(prm.max_iterations);
+    rc = launch_prologue(prm.max_iterations, &prm);
     prof_end();
     if (rc) return rc;
     if (profiling && prm.max_iterations > hist_capacity) {
@@ -622,6 +654,7 @@ struct BatchImpl : BatchBase {
     }
     view.tolerance = prm.tolerance;
     view.max_iterations = prm.max_iterations;
+    apply_al_params(prm);
     query_occupancy();
     const bool timed = std::isfinite(prm.max_ms);
     int n_upper = prm.max_iterations > 0 ? batch : 0;
@@ -708,5 +741,6 @@ BatchBase* make_batch_st_circ();
 BatchBase* make_batch_lqr4();
 BatchBase* make_batch_pendulum();
 BatchBase* make_batch_rocket();
+BatchBase* make_batch_st_lane_con();
 
 }  // namespace mas_b200

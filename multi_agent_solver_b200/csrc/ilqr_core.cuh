@@ -47,7 +47,16 @@ struct BatchView {
   int* reg_retries;  // Q_uu + reg*I retries (ilqr.hpp:175-182)
   double tolerance;
   int max_iterations;
+  // augmented-Lagrangian state of models with path constraints (ilqr.hpp:31-34,415-418,445-453): one multiplier
+  // vector per time step and one penalty parameter per problem; they persist across solves like the members of a
+  // reference solver object.  Unused (null) for models without constraints.
+  double* lam_eq;    // [T][NEQ][ld]
+  double* lam_ineq;  // [T][NINEQ][ld]
+  double* penalty;   // [ld]
+  double penalty_increase, constraint_tolerance, activation_tolerance;
 };
+
+constexpr int kMaxALHorizon = 128;  // horizon bound of constrained models (merit addends are kept per step)
 
 // Pulls the line holding *p into L1 ahead of use.  Every kernel below walks the trajectory one time
 // step at a time with a long dependent fp64 chain per step; asking for step t+1's lines while step
@@ -398,6 +407,235 @@ MAS_HD void llt_inverse(const double* L, double* inv) {
   }
 }
 
+// ---- augmented-Lagrangian pieces for models with path constraints -------------------------------------
+template <class M>
+struct HasConstraints {
+  static constexpr bool value = (M::NEQ > 0) || (M::NINEQ > 0);
+};
+
+// Constraint Jacobians by central differences, eps = 1e-6 (compute_constraints_state_jacobian /
+// _control_jacobian, finite_differences.hpp:289-345).  J is NC x N column-major.
+template <class M, bool EQ>
+MAS_HD void fd_constraint_jacobians(const double* x, const double* u, const double* prm, double* Jx, double* Ju) {
+  constexpr int NX = M::NX, NU = M::NU, NC = EQ ? M::NEQ : M::NINEQ, NCs = NC > 0 ? NC : 1;
+  const double eps = 1e-6;
+  double xp[NX], up[NU], fp[NCs], fm[NCs];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+#pragma unroll
+    for (int k = 0; k < NX; ++k) xp[k] = x[k];
+    xp[i] = x[i] + eps;
+    if (EQ) M::eq(xp, u, prm, fp);
+    else M::ineq(xp, u, prm, fp);
+    xp[i] = x[i] - eps;
+    if (EQ) M::eq(xp, u, prm, fm);
+    else M::ineq(xp, u, prm, fm);
+#pragma unroll
+    for (int r = 0; r < NC; ++r) Jx[r + i * NC] = (fp[r] - fm[r]) / (2 * eps);
+  }
+#pragma unroll
+  for (int i = 0; i < NU; ++i) {
+#pragma unroll
+    for (int k = 0; k < NU; ++k) up[k] = u[k];
+    up[i] = u[i] + eps;
+    if (EQ) M::eq(x, up, prm, fp);
+    else M::ineq(x, up, prm, fp);
+    up[i] = u[i] - eps;
+    if (EQ) M::eq(x, up, prm, fm);
+    else M::ineq(x, up, prm, fm);
+#pragma unroll
+    for (int r = 0; r < NC; ++r) Ju[r + i * NC] = (fp[r] - fm[r]) / (2 * eps);
+  }
+}
+
+// q += J^T dual;  Q += (rho J_a^T [D]) J_b  with the reference's evaluation order (ilqr.hpp:134-140,158-168):
+// first (rho * J_a^T), then (. * D) when `active` is given (a diagonal 0/1 matrix: the off-diagonal products are
+// exact zeros), then the product with J_b, every coefficient a k-ascending sum starting from the first product.
+template <int NC, int NA, int NB>
+MAS_HD void al_add_quadratic(double rho, const double* Ja, const double* Jb, const double* active, double* Q /* NA x NB */) {
+#pragma unroll
+  for (int j = 0; j < NB; ++j)
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int r = 0; r < NC; ++r) {
+        double left = rho * Ja[r + i * NC];
+        if (active) left = left * active[r];
+        const double term = left * Jb[r + j * NC];
+        s = (r == 0) ? term : s + term;
+      }
+      Q[i + j * NA] = Q[i + j * NA] + s;
+    }
+}
+template <int NC, int N>
+MAS_HD void al_add_linear(const double* J, const double* dual, double* q) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = J[0 + i * NC] * dual[0];
+#pragma unroll
+    for (int r = 1; r < NC; ++r) s = s + J[r + i * NC] * dual[r];
+    q[i] = q[i] + s;
+  }
+}
+
+// Constraint terms of the backward pass at step t (ilqr.hpp:121-170).
+template <class M>
+MAS_HD void al_backward_terms(const BatchView<M::NX, M::NU>& v, int p, int t, const double* x, const double* u, const double* prm, double rho,
+                              double* q_x, double* q_u, double* q_xx, double* q_ux, double* q_uu) {
+  constexpr int NX = M::NX, NU = M::NU;
+  if (M::NEQ > 0) {
+    constexpr int NC = M::NEQ > 0 ? M::NEQ : 1;
+    double c[NC], Jx[NC * NX], Ju[NC * NU], dual[NC];
+    M::eq(x, u, prm, c);
+    fd_constraint_jacobians<M, true>(x, u, prm, Jx, Ju);
+#pragma unroll
+    for (int r = 0; r < NC; ++r) dual[r] = v.lam_eq[soa_index<NC>(t, r, v.ld, p)] + rho * c[r];
+    al_add_linear<NC, NX>(Jx, dual, q_x);
+    al_add_linear<NC, NU>(Ju, dual, q_u);
+    al_add_quadratic<NC, NX, NX>(rho, Jx, Jx, nullptr, q_xx);
+    al_add_quadratic<NC, NU, NX>(rho, Ju, Jx, nullptr, q_ux);
+    al_add_quadratic<NC, NU, NU>(rho, Ju, Ju, nullptr, q_uu);
+  }
+  if (M::NINEQ > 0) {
+    constexpr int NC = M::NINEQ > 0 ? M::NINEQ : 1;
+    double g[NC], Jx[NC * NX], Ju[NC * NU], dual[NC], active[NC];
+    M::ineq(x, u, prm, g);
+    fd_constraint_jacobians<M, false>(x, u, prm, Jx, Ju);
+    bool any_active = false;
+#pragma unroll
+    for (int r = 0; r < NC; ++r) {
+      const double slack = g[r] > 0.0 ? g[r] : 0.0;
+      active[r] = (g[r] > -v.activation_tolerance) ? 1.0 : 0.0;
+      any_active = any_active || active[r] != 0.0;
+      dual[r] = v.lam_ineq[soa_index<NC>(t, r, v.ld, p)] * active[r] + rho * slack * active[r];
+    }
+    al_add_linear<NC, NX>(Jx, dual, q_x);
+    al_add_linear<NC, NU>(Ju, dual, q_u);
+    if (any_active) {
+      al_add_quadratic<NC, NX, NX>(rho, Jx, Jx, active, q_xx);
+      al_add_quadratic<NC, NU, NX>(rho, Ju, Jx, active, q_ux);
+      al_add_quadratic<NC, NU, NU>(rho, Ju, Ju, active, q_uu);
+    }
+  }
+}
+
+// The up to three addends step t contributes to compute_merit after the objective (ilqr.hpp:386-403).
+template <class M>
+MAS_HD void al_merit_addends(const BatchView<M::NX, M::NU>& v, int p, int t, const double* x, const double* u, const double* prm, double rho,
+                             double* a) {
+  a[0] = a[1] = a[2] = 0.0;
+  if (M::NEQ > 0) {
+    constexpr int NC = M::NEQ > 0 ? M::NEQ : 1;
+    double r[NC];
+    M::eq(x, u, prm, r);
+    double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      d1 += v.lam_eq[soa_index<NC>(t, i, v.ld, p)] * r[i];
+      d2 += r[i] * r[i];
+    }
+    a[0] = d1 + 0.5 * rho * d2;
+  }
+  if (M::NINEQ > 0) {
+    constexpr int NC = M::NINEQ > 0 ? M::NINEQ : 1;
+    double r[NC];
+    M::ineq(x, u, prm, r);
+    double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const double slack = r[i] > 0.0 ? r[i] : 0.0;
+      const double active = (r[i] > -v.activation_tolerance) ? 1.0 : 0.0;
+      const double as = slack * active;
+      const double w = v.lam_ineq[soa_index<NC>(t, i, v.ld, p)] * active;
+      d1 += w * as;
+      d2 += as * as;
+    }
+    a[1] = d1;
+    a[2] = 0.5 * rho * d2;
+  }
+}
+// merit = objective, then the per-step addends in time order
+template <class M>
+MAS_HD double al_finish_merit(double objective, const double* addends, int T) {
+  double merit = objective;
+  for (int t = 0; t < T; ++t) {
+    if (M::NEQ > 0) merit += addends[3 * t + 0];
+    if (M::NINEQ > 0) {
+      merit += addends[3 * t + 1];
+      merit += addends[3 * t + 2];
+    }
+  }
+  return merit;
+}
+
+// compute_merit of the trajectory stored in (X, U) (ilqr.hpp:78,380-407)
+template <class M>
+MAS_HD double al_merit_of_stored(const BatchView<M::NX, M::NU>& v, int p, const double* prm, double objective) {
+  constexpr int NX = M::NX, NU = M::NU;
+  const double rho = v.penalty[p];
+  double merit = objective;
+  for (int t = 0; t < v.T; ++t) {
+    double x[NX], u[NU], a[3];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = v.X[soa_index<NX>(t, i, v.ld, p)];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) u[i] = v.U[soa_index<NU>(t, i, v.ld, p)];
+    al_merit_addends<M>(v, p, t, x, u, prm, rho, a);
+    if (M::NEQ > 0) merit += a[0];
+    if (M::NINEQ > 0) {
+      merit += a[1];
+      merit += a[2];
+    }
+  }
+  return merit;
+}
+
+// Multiplier and penalty update after an iteration (ilqr.hpp:236-260) on the stored (X, U); returns the two
+// violation norms for the stop test.
+template <class M>
+MAS_HD void al_update(const BatchView<M::NX, M::NU>& v, int p, const double* prm, double* eq_norm, double* ineq_norm) {
+  constexpr int NX = M::NX, NU = M::NU;
+  const double rho = v.penalty[p];
+  double eq_v = 0.0, ineq_v = 0.0;
+  for (int t = 0; t < v.T; ++t) {
+    double x[NX], u[NU];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = v.X[soa_index<NX>(t, i, v.ld, p)];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) u[i] = v.U[soa_index<NU>(t, i, v.ld, p)];
+    if (M::NEQ > 0) {
+      constexpr int NC = M::NEQ > 0 ? M::NEQ : 1;
+      double r[NC];
+      M::eq(x, u, prm, r);
+      double sq = 0.0;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        v.lam_eq[soa_index<NC>(t, i, v.ld, p)] += rho * r[i];
+        sq += r[i] * r[i];
+      }
+      eq_v += sq;
+    }
+    if (M::NINEQ > 0) {
+      constexpr int NC = M::NINEQ > 0 ? M::NINEQ : 1;
+      double r[NC];
+      M::ineq(x, u, prm, r);
+      double sq = 0.0;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const double pos = r[i] > 0.0 ? r[i] : 0.0;
+        const double m = v.lam_ineq[soa_index<NC>(t, i, v.ld, p)] + rho * pos;
+        v.lam_ineq[soa_index<NC>(t, i, v.ld, p)] = m > 0.0 ? m : 0.0;
+        sq += pos * pos;
+      }
+      ineq_v += sq;
+    }
+  }
+  *eq_norm = sqrt(eq_v);
+  *ineq_norm = sqrt(ineq_v);
+  if (*eq_norm > v.constraint_tolerance || *ineq_norm > v.constraint_tolerance) v.penalty[p] = rho * v.penalty_increase;
+}
+
 // ---- backward pass for one problem (ilqr.hpp:92-193) --------------------------------------------
 // MASK_CT >= 0 fixes the derivative mode at compile time (dead branches vanish); -1 reads it from
 // the view.  Writes K, k for every t.  Returns the number of regularisation retries.
@@ -409,6 +647,7 @@ MAS_HD int backward_thread(const BatchView<M::NX, M::NU>& v, int p) {
   load_params<M>(v, p, prm);
   const int T = v.T;
   int retries = 0;
+  const double al_rho = HasConstraints<M>::value ? v.penalty[p] : 0.0;
 
   double x[NX], u[NU];
   double v_x[NX], v_xx[NX * NX];
@@ -472,6 +711,9 @@ MAS_HD int backward_thread(const BatchView<M::NX, M::NU>& v, int p) {
 #pragma unroll
     for (int i = 0; i < NU * NU; ++i) q_uu[i] = l_uu[i] + tmp[i];
 
+    // :121-170 constraint terms (models with path constraints only)
+    if (HasConstraints<M>::value) al_backward_terms<M>(v, p, t, x, u, prm, al_rho, q_x, q_u, q_xx, q_ux, q_uu);
+
     // :172-183
     double q_reg[NU * NU], L[NU * NU], inv[NU * NU];
 #pragma unroll
@@ -523,7 +765,10 @@ MAS_HD int backward_thread(const BatchView<M::NX, M::NU>& v, int p) {
 template <class M, int C>
 MAS_HD void trial_rollout(const BatchView<M::NX, M::NU>& v, int p, const double* prm, const double* alpha, double* merit) {
   constexpr int NX = M::NX, NU = M::NU;
+  constexpr bool kAL = HasConstraints<M>::value;
   double xt[C][NX], cost[C];
+  double al_terms[kAL ? C : 1][kAL ? 3 * kMaxALHorizon : 1];  // merit addends per step (local memory, constrained models only)
+  const double al_rho = kAL ? v.penalty[p] : 0.0;
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     cost[c] = 0.0;
@@ -568,6 +813,7 @@ MAS_HD void trial_rollout(const BatchView<M::NX, M::NU>& v, int p, const double*
         u[i] = ui;
       }
       cost[c] += M::stage(xt[c], u, t, prm);
+      if (kAL) al_merit_addends<M>(v, p, t, xt[c], u, prm, al_rho, &al_terms[c][3 * t]);
       rk4_step<M>(xt[c], u, prm, v.dt, xnext);
 #pragma unroll
       for (int i = 0; i < NX; ++i) xt[c][i] = xnext[i];
@@ -576,7 +822,7 @@ MAS_HD void trial_rollout(const BatchView<M::NX, M::NU>& v, int p, const double*
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     cost[c] += M::terminal(xt[c], prm);
-    merit[c] = cost[c];
+    merit[c] = kAL ? al_finish_merit<M>(cost[c], al_terms[c], v.T) : cost[c];
   }
 }
 
@@ -742,7 +988,15 @@ MAS_HD bool finish_iteration(const BatchView<M::NX, M::NU>& v, int p, const doub
   const int it = v.iters[p] + 1;
   v.iters[p] = it;
   v.trials[p] += (best_j < kNumAlphas) ? best_j + 1 : kNumAlphas;
-  if (improvement < v.tolerance) {
+  bool feasible = true;
+  if (HasConstraints<M>::value) {
+    // multipliers <- multipliers + rho * residual on the new trajectory, penalty growth, and the violation
+    // norms that gate the stop test (ilqr.hpp:236-260,269-270)
+    double eq_norm, ineq_norm;
+    al_update<M>(v, p, prm, &eq_norm, &ineq_norm);
+    feasible = eq_norm < v.constraint_tolerance && ineq_norm < v.constraint_tolerance;
+  }
+  if (improvement < v.tolerance && feasible) {
     v.status[p] = STATUS_CONVERGED;
     return false;
   }

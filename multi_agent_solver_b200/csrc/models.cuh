@@ -38,6 +38,15 @@ enum DerivBits : unsigned {
 
 // Column-major helpers: A is NX x NX (A[r + c*NX]), B is NX x NU, l_ux is NU x NX.
 
+// Path constraints (OCP::equality_constraints / inequality_constraints, ocp.hpp:59-66): none of the reference's
+// examples sets them; models without them inherit these empty hooks and the augmented-Lagrangian code of the
+// kernels (ilqr.hpp:121-170,236-260,380-407) compiles away.
+struct NoConstraints {
+  static constexpr int NEQ = 0, NINEQ = 0;
+  MAS_HD static void eq(const double*, const double*, const double*, double*) {}
+  MAS_HD static void ineq(const double*, const double*, const double*, double*) {}
+};
+
 // ---- single-track kinematic bicycle, shared by StLane and StCirc ---------------------------------
 struct SingleTrackDyn {
   // The control enters only through tan(delta); RK4 evaluates f four times with the same control
@@ -81,7 +90,7 @@ struct SingleTrackDyn {
   }
 };
 
-struct StLane {
+struct StLane : NoConstraints {
   static constexpr int ID = 0;
   static constexpr int NX = 4, NU = 2, NP = 5;
   static constexpr unsigned AVAILABLE = D_A | D_B | D_LX | D_LU | D_LXX | D_LUU;
@@ -125,7 +134,22 @@ struct StLane {
   MAS_HD static void v_xx(const double*, const double*, double*) {}
 };
 
-struct StCirc {
+// Lane following with path constraints -- NOT one of the reference's examples (none of them has constraints):
+// the registered vehicle for the augmented-Lagrangian part of iLQR::solve.  Same dynamics, cost, bounds and
+// derivative mode as StLane, plus
+//   equality   c(x,u) = a - k_gain * (v_des - v) = 0      (acceleration follows a proportional speed law)
+//   inequality g(x,u) = v - v_max <= 0                     (speed limit)
+// with finite-difference constraint Jacobians (the defaults of ocp.hpp:137-171).
+// p = {desired_velocity, w_lane, w_speed, w_delta, w_acc, v_max, k_gain}
+struct StLaneCon : StLane {
+  static constexpr int ID = 5;
+  static constexpr int NP = 7;
+  static constexpr int NEQ = 1, NINEQ = 1;
+  MAS_HD static void eq(const double* x, const double* u, const double* p, double* c) { c[0] = u[1] - p[6] * (p[0] - x[3]); }
+  MAS_HD static void ineq(const double* x, const double*, const double* p, double* g) { g[0] = x[3] - p[5]; }
+};
+
+struct StCirc : NoConstraints {
   static constexpr int ID = 1;
   static constexpr int NX = 4, NU = 2, NP = 6;
   static constexpr unsigned AVAILABLE = D_A | D_B;
@@ -157,7 +181,7 @@ struct StCirc {
 // create_linear_lqr_ocp(4, 4, dt, T): A = I, B = I, Q = R = Qf = I.  The reference evaluates the dense
 // products; with identity matrices every skipped term is an exact +0, so the shortcuts below return
 // the same bits for finite inputs (x^T Q x = sum of squares accumulated left to right from 0.0).
-struct Lqr4 {
+struct Lqr4 : NoConstraints {
   static constexpr int ID = 2;
   static constexpr int NX = 4, NU = 4, NP = 0;
   static constexpr unsigned AVAILABLE = D_ALL;
@@ -214,7 +238,7 @@ struct Lqr4 {
   }
 };
 
-struct Pendulum {
+struct Pendulum : NoConstraints {
   static constexpr int ID = 3;
   static constexpr int NX = 2, NU = 1, NP = 1;
   static constexpr unsigned AVAILABLE = D_A | D_B;
@@ -273,7 +297,7 @@ struct Pendulum {
   MAS_HD static void v_xx(const double*, const double*, double*) {}
 };
 
-struct Rocket {
+struct Rocket : NoConstraints {
   static constexpr int ID = 4;
   static constexpr int NX = 3, NU = 1, NP = 6;
   static constexpr unsigned AVAILABLE = D_A | D_B | D_LX | D_LU | D_LXX | D_LUU | D_VX | D_VXX;

@@ -16,7 +16,7 @@ using namespace oracle;
 
 namespace {
 
-enum Model { MODEL_ST_LANE = 0, MODEL_ST_CIRC = 1, MODEL_LQR = 2, MODEL_PENDULUM = 3, MODEL_ROCKET = 4 };
+enum Model { MODEL_ST_LANE = 0, MODEL_ST_CIRC = 1, MODEL_LQR = 2, MODEL_PENDULUM = 3, MODEL_ROCKET = 4, MODEL_ST_LANE_CON = 5 };
 
 // params layout per model (all optional, NULL -> example constants):
 //   ST_LANE : desired_velocity, w_lane, w_speed, w_delta, w_acc
@@ -47,6 +47,17 @@ OCP build_ocp(int model, const double* x0, const double* params, int np, int hor
       Vec s(x0, x0 + 3);
       return create_max_altitude_rocket_ocp(&s);
     }
+    case MODEL_ST_LANE_CON: {  // params: desired_velocity, w_lane, w_speed, w_delta, w_acc, v_max, k_gain
+      Vec s(x0, x0 + 4);
+      LaneParams lp;
+      double v_max = 0.8, k_gain = 0.5;
+      if (params && np >= 7) {
+        lp = LaneParams{params[0], params[1], params[2], params[3], params[4]};
+        v_max = params[5];
+        k_gain = params[6];
+      }
+      return create_single_track_lane_constrained_ocp(&s, lp, v_max, k_gain);
+    }
   }
   throw std::invalid_argument("oracle: unknown model id");
 }
@@ -58,6 +69,7 @@ void model_dims(int model, int horizon, int* n, int* m, int* T, double* dt) {
     case MODEL_LQR: *n = 4; *m = 4; *T = horizon > 0 ? horizon : 10; *dt = 0.1; break;
     case MODEL_PENDULUM: *n = 2; *m = 1; *T = 60; *dt = 0.05; break;
     case MODEL_ROCKET: *n = 3; *m = 1; *T = 50; *dt = 0.1; break;
+    case MODEL_ST_LANE_CON: *n = 4; *m = 2; *T = 80; *dt = 0.1; break;
     default: throw std::invalid_argument("oracle: unknown model id");
   }
 }
@@ -162,6 +174,37 @@ int oracle_ilqr_solve_batch(int model, int batch, const double* x0, const double
     }
   }
   return err;
+}
+
+// The same solver object solving the same OCP n_repeat times in a row (warm start from best_controls; the
+// penalty parameter and the multipliers persist across calls, ilqr.hpp:331-338,415).  Outputs after every solve.
+int oracle_ilqr_solve_repeat(int model, const double* x0, const double* params, int np, int horizon, double* U_inout, int n_repeat,
+                             int max_iterations, double tolerance, double penalty, int trig, double* X_out, double* cost_out, int* iters_out,
+                             int* status_out) {
+  try {
+    int n, m, T;
+    double dt;
+    model_dims(model, horizon, &n, &m, &T, &dt);
+    trig_mode() = trig;
+    OCP p = build_ocp(model, x0, params, np, horizon);
+    std::memcpy(p.initial_controls.d.data(), U_inout, sizeof(double) * m * T);
+    p.initialize_problem();
+    iLQR solver;
+    SolverParams sp = make_params(max_iterations, tolerance, std::numeric_limits<double>::infinity());
+    sp["penalty"] = penalty;
+    solver.set_params(sp);
+    for (int r = 0; r < n_repeat; ++r) {
+      solver.solve(p);
+      cost_out[r] = p.best_cost;
+      iters_out[r] = solver.stats.iterations;
+      status_out[r] = solver.stats.status;
+      std::memcpy(X_out + static_cast<std::size_t>(r) * n * (T + 1), p.best_states.d.data(), sizeof(double) * n * (T + 1));
+    }
+    std::memcpy(U_inout, p.best_controls.d.data(), sizeof(double) * m * T);
+  } catch (...) {
+    return 1;
+  }
+  return 0;
 }
 
 // Single-problem solve with the per-iteration trace (cost after each iteration, accepted alpha index).

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 
-MODEL_ST_LANE, MODEL_ST_CIRC, MODEL_LQR, MODEL_PENDULUM, MODEL_ROCKET = range(5)
+MODEL_ST_LANE, MODEL_ST_CIRC, MODEL_LQR, MODEL_PENDULUM, MODEL_ROCKET, MODEL_ST_LANE_CON = range(6)
 STRATEGY_CENTRALIZED, STRATEGY_SEQUENTIAL, STRATEGY_LINESEARCH, STRATEGY_TRUSTREGION = range(4)
 TRIG_GLIBC, TRIG_PORTABLE = 0, 1
 STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_TIME_LIMIT = 0, 1, 2
@@ -106,6 +106,26 @@ def ilqr_solve_batch(model, x0, U_init=None, params=None, horizon=0, max_iterati
     if rc:
         raise RuntimeError("oracle_ilqr_solve_batch failed")
     return dict(X=X, U=U, cost=cost, iterations=iters, status=status, rollouts=stats[:, 0], alpha_trials=stats[:, 1], reg_retries=stats[:, 2])
+
+
+def ilqr_solve_repeat(model, x0, n_repeat, U_init=None, params=None, horizon=0, max_iterations=10, tolerance=1e-5, penalty=10.0,
+                      trig=TRIG_GLIBC):
+    """One solver object, n_repeat solve() calls on the same OCP (multipliers / penalty persist).  Per-solve outputs."""
+    x0 = _f64(x0).reshape(-1)
+    n, m, T, _ = model_dims(model, horizon)
+    U = default_controls(model, horizon) if U_init is None else np.array(U_init, dtype=np.float64).reshape(T, m).copy()
+    params = _f64(params)
+    np_ = 0 if params is None else params.size
+    X = np.zeros((n_repeat, T + 1, n))
+    cost = np.zeros(n_repeat)
+    iters = np.zeros(n_repeat, dtype=np.int32)
+    status = np.zeros(n_repeat, dtype=np.int32)
+    rc = lib().oracle_ilqr_solve_repeat(model, _p(x0), _p(params), np_, horizon, _p(U), int(n_repeat), int(max_iterations),
+                                        ctypes.c_double(tolerance), ctypes.c_double(penalty), int(trig), _p(X), _p(cost), _p(iters, ctypes.c_int),
+                                        _p(status, ctypes.c_int))
+    if rc:
+        raise RuntimeError("oracle_ilqr_solve_repeat failed")
+    return dict(X=X, U=U, cost=cost, iterations=iters, status=status)
 
 
 def ilqr_solve_trace(model, x0, U_init=None, params=None, horizon=0, max_iterations=10, tolerance=1e-5, trig=TRIG_GLIBC, aliased_sym=True):

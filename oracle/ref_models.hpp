@@ -113,6 +113,20 @@ inline OCP create_single_track_lane_following_ocp(const Vec* x0 = nullptr, const
   return p;
 }
 
+// ---- lane following with path constraints ------------------------------------------------------------------
+// NOT a reference example (none sets equality_constraints / inequality_constraints): the single-track lane problem
+// plus  c(x,u) = a - k_gain (v_des - v) = 0  and  g(x,u) = v - v_max <= 0, used to exercise the augmented-Lagrangian
+// part of iLQR::solve (ilqr.hpp:121-170,236-260,380-407).  Constraint Jacobians are the FD defaults that
+// initialize_problem installs (ocp.hpp:137-171).
+inline OCP create_single_track_lane_constrained_ocp(const Vec* x0, const LaneParams& lp, double v_max, double k_gain) {
+  OCP p = create_single_track_lane_following_ocp(x0, lp);
+  const double v_des = lp.desired_velocity;
+  p.equality_constraints = [=](const State& s, const Control& c) { return Vec{c[1] - k_gain * (v_des - s[3])}; };
+  p.inequality_constraints = [=](const State& s, const Control&) { return Vec{s[3] - v_max}; };
+  p.initialize_problem();
+  return p;
+}
+
 // ---- multi_agent_single_track.cpp:31-72 -------------------------------------------------------------
 // The example derives x0 from (theta, R); a caller may pass x0 directly (batched / jittered runs).
 inline Vec single_track_circular_x0(double initial_theta, double track_radius) {

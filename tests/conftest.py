@@ -64,6 +64,9 @@ MODEL_TABLE = {
     2: (4, 4, 10, 0.1, 0x1FF, 0, [0.0] * 4, [0.0] * 4, []),
     3: (2, 1, 60, 0.05, 0x0, 1, [-5.0], [5.0], [60.0]),
     4: (3, 1, 50, 0.1, 0x1BF, 1, [0.0], [20.0], [9.81, 50.0, 5e-3, 15.0, 2.0, 0.0]),
+    # lane following + path constraints (equality a = k (v_des - v), inequality v <= v_max): not a reference example,
+    # exercises the augmented-Lagrangian branch of iLQR::solve
+    5: (4, 2, 80, 0.1, 0x3F, 1, [-0.7, -1.0], [0.7, 1.0], [1.0, 10.0, 1.0, 0.1, 0.1, 0.8, 0.5]),
 }
 
 
@@ -71,7 +74,9 @@ class HostEmulation:
     def __init__(self):
         self.lib = ctypes.CDLL(_build_emulation())
 
-    def solve(self, model, x0, U, max_iterations, tolerance, L=1, C=2, mask=None, per_problem_params=None):
+    def solve(self, model, x0, U, max_iterations, tolerance, L=1, C=2, mask=None, per_problem_params=None, penalty=10.0, repeats=1):
+        """repeats > 1: the same solver state (multipliers, penalty) and warm start solving again; adds cost_history /
+        iterations_history [repeats, B]."""
         n, m, T, dt, emask, hb, lo, hi, prm = MODEL_TABLE[model]
         mask = emask if mask is None else mask
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
@@ -92,12 +97,17 @@ class HostEmulation:
         if per_problem_params is not None:
             ppa = np.ascontiguousarray(per_problem_params, dtype=np.float64)
             pp = ppa.ctypes.data_as(P)
+        hc = np.zeros((repeats, B))
+        hi_ = np.zeros((repeats, B), np.int32)
+        self.lib.emu_set_al_options(ctypes.c_double(penalty), ctypes.c_double(5.0), ctypes.c_double(1e-4), ctypes.c_double(1e-6), int(repeats),
+                                    hc.ctypes.data_as(P), hi_.ctypes.data_as(PI))
         rc = self.lib.emu_ilqr_solve_batch(model, B, T, ctypes.c_double(dt), ctypes.c_uint(mask), hb, lo.ctypes.data_as(P), hi.ctypes.data_as(P),
                                            sp.ctypes.data_as(P), pp, x0.ctypes.data_as(P), U.ctypes.data_as(P), X.ctypes.data_as(P),
                                            cost.ctypes.data_as(P), it.ctypes.data_as(PI), st.ctypes.data_as(PI), tr.ctypes.data_as(PI),
                                            rg.ctypes.data_as(PI), int(max_iterations), ctypes.c_double(tolerance), int(L), int(C))
+        self.lib.emu_set_al_options(ctypes.c_double(10.0), ctypes.c_double(5.0), ctypes.c_double(1e-4), ctypes.c_double(1e-6), 1, None, None)
         assert rc == 0
-        return dict(X=X, U=U, cost=cost, iterations=it, status=st, alpha_trials=tr, reg_retries=rg)
+        return dict(X=X, U=U, cost=cost, iterations=it, status=st, alpha_trials=tr, reg_retries=rg, cost_history=hc, iterations_history=hi_)
 
 
     def solve_centralized(self, model, x0, max_iterations=100, tolerance=1e-5):
@@ -136,7 +146,7 @@ def circle_x0(n_agents: int, radius: float = 20.0) -> np.ndarray:
 # ---- synthetic inputs ------------------------------------------------------------------------------
 def random_x0(model: int, batch: int, seed: int) -> np.ndarray:
     rng = np.random.default_rng(seed)
-    if model == 0:  # config 3 ranges
+    if model in (0, 5):  # config 3 ranges
         return np.stack([np.zeros(batch), rng.uniform(-2, 2, batch), rng.uniform(-0.5, 0.5, batch), rng.uniform(0, 2, batch)], -1)
     if model == 1:  # agents on the circle, tangential heading (multi_agent_single_track.cpp:41-44)
         th = rng.uniform(0, 2 * np.pi, batch)

@@ -17,6 +17,16 @@ using namespace mas_b200;
 
 namespace {
 
+// Constrained models: solver-object state that outlives a solve (BatchBase::prepare_constraint_state) and the
+// repeat count for "the same solver solving again"; hist_* receive [repeats][batch] when non-null.
+struct ALOptions {
+  double penalty = 10.0, penalty_increase = 5.0, constraint_tolerance = 1e-4, activation_tolerance = 1e-6;
+  int repeats = 1;
+  double* hist_cost = nullptr;
+  int* hist_iters = nullptr;
+};
+ALOptions g_al;
+
 template <class M>
 int emulate(int batch, int T, double dt, unsigned mask, int has_bounds, const double* lo, const double* hi, const double* shared_p,
             const double* per_problem_p, const double* x0, double* U, double* X, double* cost, int* iters, int* status, int* trials, int* reg,
@@ -58,12 +68,28 @@ int emulate(int batch, int T, double dt, unsigned mask, int has_bounds, const do
   v.reg_retries = srg.data();
   v.tolerance = tolerance;
   v.max_iterations = max_iterations;
+  constexpr int NEQs = M::NEQ > 0 ? M::NEQ : 1, NINEQs = M::NINEQ > 0 ? M::NINEQ : 1;
+  std::vector<double> slam_eq(static_cast<size_t>(NEQs) * T * ld, 0.0), slam_ineq(static_cast<size_t>(NINEQs) * T * ld, 0.0), spen(ld, g_al.penalty);
+  v.lam_eq = slam_eq.data();
+  v.lam_ineq = slam_ineq.data();
+  v.penalty = spen.data();
+  v.penalty_increase = g_al.penalty_increase;
+  v.constraint_tolerance = g_al.constraint_tolerance;
+  v.activation_tolerance = g_al.activation_tolerance;
+  if (HasConstraints<M>::value && T > kMaxALHorizon) return 2;
 
+ for (int rep = 0; rep < g_al.repeats; ++rep) {
   std::vector<int> list(batch), next;
   for (int p = 0; p < batch; ++p) {  // prologue_kernel
     const double c = rollout_thread<M>(v, p);
     v.cost[p] = c;
-    v.merit[p] = c;
+    if (HasConstraints<M>::value) {
+      double prm[M::NP > 0 ? M::NP : 1];
+      load_params<M>(v, p, prm);
+      v.merit[p] = al_merit_of_stored<M>(v, p, prm, c);
+    } else {
+      v.merit[p] = c;
+    }
     v.iters[p] = 0;
     v.trials[p] = 0;
     v.reg_retries[p] = 0;
@@ -146,6 +172,11 @@ int emulate(int batch, int T, double dt, unsigned mask, int has_bounds, const do
     list.swap(next);
   }
   for (int b = 0; b < batch; ++b) {
+    if (g_al.hist_cost) g_al.hist_cost[static_cast<size_t>(rep) * batch + b] = scost[b];
+    if (g_al.hist_iters) g_al.hist_iters[static_cast<size_t>(rep) * batch + b] = sit[b];
+  }
+ }
+  for (int b = 0; b < batch; ++b) {
     for (int r = 0; r < NX * (T + 1); ++r) X[static_cast<size_t>(b) * NX * (T + 1) + r] = sX[static_cast<size_t>(r) * ld + b];
     for (int r = 0; r < NU * T; ++r) U[static_cast<size_t>(b) * NU * T + r] = sU[static_cast<size_t>(r) * ld + b];
     cost[b] = scost[b];
@@ -168,8 +199,21 @@ extern "C" int emu_ilqr_solve_batch(int model, int batch, int T, double dt, unsi
     case 2: return emulate<Lqr4>(batch, T, dt, mask, has_bounds, lo, hi, shared_p, per_problem_p, x0, U, X, cost, iters, status, trials, reg, max_iterations, tolerance, L, C);
     case 3: return emulate<Pendulum>(batch, T, dt, mask, has_bounds, lo, hi, shared_p, per_problem_p, x0, U, X, cost, iters, status, trials, reg, max_iterations, tolerance, L, C);
     case 4: return emulate<Rocket>(batch, T, dt, mask, has_bounds, lo, hi, shared_p, per_problem_p, x0, U, X, cost, iters, status, trials, reg, max_iterations, tolerance, L, C);
+    case 5: return emulate<StLaneCon>(batch, T, dt, mask, has_bounds, lo, hi, shared_p, per_problem_p, x0, U, X, cost, iters, status, trials, reg, max_iterations, tolerance, L, C);
   }
   return 1;
+}
+
+// Settings for the next emu_ilqr_solve_batch calls on constrained models (pass repeats = 1 and nulls to reset).
+extern "C" void emu_set_al_options(double penalty, double penalty_increase, double constraint_tolerance, double activation_tolerance, int repeats,
+                                   double* hist_cost, int* hist_iters) {
+  g_al.penalty = penalty;
+  g_al.penalty_increase = penalty_increase;
+  g_al.constraint_tolerance = constraint_tolerance;
+  g_al.activation_tolerance = activation_tolerance;
+  g_al.repeats = repeats < 1 ? 1 : repeats;
+  g_al.hist_cost = hist_cost;
+  g_al.hist_iters = hist_iters;
 }
 
 // ---- centralized (stacked) solve, run with tid = 0, nthr = 1 -----------------------------------------------

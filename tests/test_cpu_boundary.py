@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(mas):
 
 
 def test_host_only_entry_points(mas):
-    for model in range(5):
+    for model in range(6):
         info = mas.model_info(model)
         d = mas.example_desc(model)
         assert d.state_dim == info["state_dim"] and d.control_dim == info["control_dim"]
@@ -44,7 +44,7 @@ def test_host_only_entry_points(mas):
 
 
 def test_example_controls_match_oracle(mas, oracle):
-    for model in range(5):
+    for model in range(6):
         d = mas.example_desc(model)
         assert np.array_equal(mas.example_controls(model, d.horizon_steps), oracle.default_controls(model))
 

@@ -208,3 +208,56 @@ def test_full_size_batch_properties(mas, ctx, oracle):
         np.testing.assert_array_equal(h["X"], full["X"][lo:hi])
         np.testing.assert_array_equal(h["cost"], full["cost"][lo:hi])
         np.testing.assert_array_equal(h["iterations"], full["iterations"][lo:hi])
+
+
+# ---- augmented-Lagrangian path constraints (ilqr.hpp:121-170,236-260,380-407) ------------------------------
+@pytest.mark.parametrize("mode", [0, 1, 3])
+def test_constrained_model_matches_oracle(mas, ctx, oracle, mode):
+    """Model 5 (lane following + equality and inequality path constraints) through the C ABI."""
+    B = 200
+    x0 = random_x0(5, B, seed=301)
+    desc = mas.example_desc(5)
+    assert (desc.state_dim, desc.control_dim, desc.horizon_steps) == (4, 2, 80)
+    U0 = np.zeros((B, 80, 2))
+    ref = oracle.ilqr_solve_batch(5, x0, U_init=U0, max_iterations=6, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    b = mas.Batch(ctx, desc, B)
+    b.set_line_search_mode(mode)
+    b.set_initial_states(x0)
+    b.set_controls(U0)
+    b.solve(mas.IlqrParams.make(6, 1e-5))
+    got = b.get_solution()
+    st = b.stats()
+    b.close()
+    assert_parity(got, ref)
+    assert is_bit_exact(got, ref)
+    assert st["alpha_trials"] == int(ref["alpha_trials"].sum())
+
+
+def test_constraint_state_persists_and_resets(mas, ctx, oracle):
+    """Multipliers and the penalty parameter live in the batch like the members of a reference solver object: a second
+    and third solve continue from them (ilqr.hpp:331-338); mas_b200_batch_reset_solver_state gives a fresh solver."""
+    B = 12
+    x0 = random_x0(5, B, seed=302)
+    U0 = np.zeros((B, 80, 2))
+    prm = mas.IlqrParams.make(5, 1e-5)
+    prm.penalty = 2.0
+    b = mas.Batch(ctx, mas.example_desc(5), B)
+    b.set_initial_states(x0)
+    b.set_controls(U0)
+    hist = []
+    for _ in range(3):
+        b.solve(prm)
+        hist.append(b.get_solution())
+    for i in range(B):
+        ref = oracle.ilqr_solve_repeat(5, x0[i], 3, U_init=U0[i], max_iterations=5, tolerance=1e-5, penalty=2.0, trig=oracle.TRIG_PORTABLE)
+        for r in range(3):
+            assert hist[r]["cost"][i] == ref["cost"][r] and hist[r]["iterations"][i] == ref["iterations"][r]
+            assert np.array_equal(hist[r]["X"][i], ref["X"][r])
+        assert np.array_equal(hist[2]["U"][i], ref["U"])
+    # fresh solver state + the original controls reproduce the first solve
+    b.reset_solver_state()
+    b.set_controls(U0)
+    b.solve(prm)
+    again = b.get_solution()
+    b.close()
+    assert np.array_equal(again["cost"], hist[0]["cost"]) and np.array_equal(again["X"], hist[0]["X"])

@@ -100,3 +100,46 @@ def test_nan_initial_state_matches_oracle(emu, oracle):
     assert got["iterations"][0] == ref["iterations"][0]
     assert got["status"][0] == ref["status"][0]
     assert np.isnan(got["cost"][0]) and np.isnan(ref["cost"][0])
+
+
+# ---- augmented-Lagrangian path constraints (ilqr.hpp:121-170,236-260,380-407) ------------------------------
+def test_constrained_model_bit_exact(emu, oracle):
+    """Model 5 = lane following + one equality and one inequality path constraint: constraint Jacobians by finite
+    differences, multiplier / penalty updates and the merit line search against the oracle."""
+    B = 24
+    x0 = random_x0(5, B, seed=77)
+    U0 = _defaults(oracle, 5, B)
+    ref = oracle.ilqr_solve_batch(5, x0, U_init=U0, max_iterations=6, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    got = emu.solve(5, x0, U0, 6, 1e-5)
+    assert_parity(got, ref)
+    assert is_bit_exact(got, ref)
+    assert np.array_equal(got["alpha_trials"], ref["alpha_trials"])
+    # the constraints matter: the unconstrained problem from the same inputs ends elsewhere
+    free = oracle.ilqr_solve_batch(0, x0, U_init=U0, max_iterations=6, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    assert np.mean(np.abs(free["cost"] - ref["cost"]) > 1e-6) > 0.5
+
+
+@pytest.mark.parametrize("L", [1, 4, 32])
+def test_constrained_model_lane_mappings(emu, oracle, L):
+    x0 = random_x0(5, 40, seed=78)
+    U0 = np.zeros((40, 80, 2))
+    ref = oracle.ilqr_solve_batch(5, x0, U_init=U0, max_iterations=4, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    got = emu.solve(5, x0, U0, 4, 1e-5, L=L, C=1)
+    assert is_bit_exact(got, ref)
+    assert np.array_equal(got["alpha_trials"], ref["alpha_trials"])
+
+
+@pytest.mark.parametrize("penalty", [10.0, 0.5])
+def test_multipliers_and_penalty_persist_across_solves(emu, oracle, penalty):
+    """The same solver object solving again starts from its multipliers and its grown penalty (ilqr.hpp:331-338)."""
+    x0 = random_x0(5, 6, seed=79)
+    U0 = np.zeros((6, 80, 2))
+    got = emu.solve(5, x0, U0, 5, 1e-5, penalty=penalty, repeats=3)
+    changed = 0
+    for b in range(6):
+        ref = oracle.ilqr_solve_repeat(5, x0[b], 3, U_init=U0[b], max_iterations=5, tolerance=1e-5, penalty=penalty, trig=oracle.TRIG_PORTABLE)
+        assert np.array_equal(got["cost_history"][:, b], ref["cost"])
+        assert np.array_equal(got["iterations_history"][:, b], ref["iterations"])
+        assert np.array_equal(got["U"][b], ref["U"]) and np.array_equal(got["X"][b], ref["X"][-1])
+        changed += int(ref["cost"][1] != ref["cost"][0])
+    assert changed > 0  # later solves do move: the persistent state is really in play
