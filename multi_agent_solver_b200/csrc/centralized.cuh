@@ -190,7 +190,7 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
       const int a = idx / NX, il = idx % NX;
       const double fp = stacked_sum1(cb, pref, A, a, S6[(a * NX + il) * 2 + 0]);
       const double fm = stacked_sum1(cb, pref, A, a, S6[(a * NX + il) * 2 + 1]);
-      Vx[idx] = (fp - fm) / (2 * e6);
+      Vx[idx] = MAS_DIV_CONST(fp - fm, 2 * e6);
     } else {
       const int e = idx - ns, i = e % ns, j = e / ns;
       const int a = i / NX, il = i % NX, b = j / NX, jl = j % NX;
@@ -199,7 +199,7 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
         const double fp = finite_or_zero(stacked_sum1(cb, pref, A, a, S5[(a * NX + il) * 2 + 0]));
         const double f0 = finite_or_zero(pref[A]);
         const double fm = finite_or_zero(stacked_sum1(cb, pref, A, a, S5[(a * NX + il) * 2 + 1]));
-        h = (fp - 2 * f0 + fm) / (e5 * e5);
+        h = MAS_DIV_CONST(fp - 2 * f0 + fm, e5 * e5);
       } else if (a == b) {
         const double* xa = xT + a * NX;
         const double* pa = P.prm + a * NPs;
@@ -211,12 +211,12 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
           xp[jl] = (q & 1) ? xa[jl] - e5 : xa[jl] + e5;
           v[q] = finite_or_zero(stacked_sum1(cb, pref, A, a, M::terminal(xp, pa)));
         }
-        h = (v[0] - v[1] - v[2] + v[3]) / (4 * e5 * e5);
+        h = MAS_DIV_CONST(v[0] - v[1] - v[2] + v[3], 4 * e5 * e5);
       } else {
         double v[4];
         for (int q = 0; q < 4; ++q)
           v[q] = finite_or_zero(stacked_sum2(cb, pref, A, a, S5[(a * NX + il) * 2 + ((q >> 1) & 1)], b, S5[(b * NX + jl) * 2 + (q & 1)]));
-        h = (v[0] - v[1] - v[2] + v[3]) / (4 * e5 * e5);
+        h = MAS_DIV_CONST(v[0] - v[1] - v[2] + v[3], 4 * e5 * e5);
       }
       Vxx[i + static_cast<size_t>(j) * ns] = h;
     }
@@ -278,7 +278,7 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
         const int a = e / NX, il = e % NX;
         const double fp = stacked_sum1(cb, pref, A, a, S6[(a * NX + il) * 2 + 0]);
         const double fm = stacked_sum1(cb, pref, A, a, S6[(a * NX + il) * 2 + 1]);
-        lx[e] = (fp - fm) / (2 * e6);
+        lx[e] = MAS_DIV_CONST(fp - fm, 2 * e6);
         continue;
       }
       e -= n_lx;
@@ -286,7 +286,7 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
         const int a = e / NU, il = e % NU;
         const double fp = stacked_sum1(cb, pref, A, a, R6[(a * NU + il) * 2 + 0]);
         const double fm = stacked_sum1(cb, pref, A, a, R6[(a * NU + il) * 2 + 1]);
-        lu[e] = (fp - fm) / (2 * e6);
+        lu[e] = MAS_DIV_CONST(fp - fm, 2 * e6);
         continue;
       }
       e -= n_lu;
@@ -302,7 +302,7 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
           const double fp = finite_or_zero(stacked_sum1(cb, pref, A, a, tab[(a * per + il) * 2 + 0]));
           const double f0 = finite_or_zero(pref[A]);
           const double fm = finite_or_zero(stacked_sum1(cb, pref, A, a, tab[(a * per + il) * 2 + 1]));
-          h = (fp - 2 * f0 + fm) / (e5 * e5);
+          h = MAS_DIV_CONST(fp - 2 * f0 + fm, e5 * e5);
         } else if (a == b) {
           const double* xa = xt + a * NX;
           const double* ua = ut + a * NU;
@@ -314,12 +314,12 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
                                   : agent_stage_pert<M>(xa, ua, t, pa, -1, 0, -1, 0, il, di, jl, dj);
             v[q] = finite_or_zero(stacked_sum1(cb, pref, A, a, c));
           }
-          h = (v[0] - v[1] - v[2] + v[3]) / (4 * e5 * e5);
+          h = MAS_DIV_CONST(v[0] - v[1] - v[2] + v[3], 4 * e5 * e5);
         } else {
           double v[4];
           for (int q = 0; q < 4; ++q)
             v[q] = finite_or_zero(stacked_sum2(cb, pref, A, a, tab[(a * per + il) * 2 + ((q >> 1) & 1)], b, tab[(b * per + jl) * 2 + (q & 1)]));
-          h = (v[0] - v[1] - v[2] + v[3]) / (4 * e5 * e5);
+          h = MAS_DIV_CONST(v[0] - v[1] - v[2] + v[3], 4 * e5 * e5);
         }
         (is_x ? lxx : luu)[i + static_cast<size_t>(j) * dim] = h;
         continue;
@@ -338,7 +338,7 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
             v[q] = finite_or_zero(stacked_sum2(cb, pref, A, a, R6[(a * NU + il) * 2 + su], b, S6[(b * NX + jl) * 2 + sx]));
           }
         }
-        lux[i + static_cast<size_t>(j) * ms] = (v[0] - v[1] - v[2] + v[3]) / (4 * e6 * e6);
+        lux[i + static_cast<size_t>(j) * ms] = MAS_DIV_CONST(v[0] - v[1] - v[2] + v[3], 4 * e6 * e6);
       }
     }
     MAS_CTA_SYNC();

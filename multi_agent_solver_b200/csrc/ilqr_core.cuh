@@ -138,7 +138,7 @@ MAS_HD void rk4_step(const double* x, const double* u, const double* prm, double
 #pragma unroll
   for (int i = 0; i < NX; ++i) xs[i] = x[i] + dt * k3[i];
   M::dynamics_c(xs, u, cu, prm, k4);
-  const double sixth = dt / 6.0;
+  const double sixth = MAS_DIV_CONST(dt, 6.0);
 #pragma unroll
   for (int i = 0; i < NX; ++i) xn[i] = x[i] + sixth * (((k1[i] + 2.0 * k2[i]) + 2.0 * k3[i]) + k4[i]);
 }
@@ -190,7 +190,7 @@ MAS_HD void fd_jac_x(const double* x, const double* u, const double* prm, double
     xp[i] = x[i] - eps;
     M::dynamics_c(xp, u, cu, prm, fm);
 #pragma unroll
-    for (int r = 0; r < NX; ++r) A[r + i * NX] = (fp[r] - fm[r]) / (2 * eps);
+    for (int r = 0; r < NX; ++r) A[r + i * NX] = MAS_DIV_CONST(fp[r] - fm[r], 2 * eps);
   }
 }
 template <class M>
@@ -207,7 +207,7 @@ MAS_HD void fd_jac_u(const double* x, const double* u, const double* prm, double
     up[i] = u[i] - eps;
     M::dynamics(x, up, prm, fm);
 #pragma unroll
-    for (int r = 0; r < NX; ++r) B[r + i * NX] = (fp[r] - fm[r]) / (2 * eps);
+    for (int r = 0; r < NX; ++r) B[r + i * NX] = MAS_DIV_CONST(fp[r] - fm[r], 2 * eps);
   }
 }
 template <class M>
@@ -223,7 +223,7 @@ MAS_HD void fd_l_x(const double* x, const double* u, int t, const double* prm, d
     const double fp = M::stage(xp, u, t, prm);
     xp[i] = x[i] - eps;
     const double fm = M::stage(xp, u, t, prm);
-    g[i] = (fp - fm) / (2 * eps);
+    g[i] = MAS_DIV_CONST(fp - fm, 2 * eps);
   }
 }
 template <class M>
@@ -239,7 +239,7 @@ MAS_HD void fd_l_u(const double* x, const double* u, int t, const double* prm, d
     const double fp = M::stage(x, up, t, prm);
     up[i] = u[i] - eps;
     const double fm = M::stage(x, up, t, prm);
-    g[i] = (fp - fm) / (2 * eps);
+    g[i] = MAS_DIV_CONST(fp - fm, 2 * eps);
   }
 }
 // Hessian of F(z) in z (either the state or the control slot), :138-210 and :229-261.
@@ -257,7 +257,7 @@ MAS_HD void fd_hessian(const double* z, const F& f, double* H) {
     const double f0 = finite_or_zero(f(z));
     zp[i] = z[i] - eps;
     const double fm = finite_or_zero(f(zp));
-    H[i + i * N] = (fp - 2 * f0 + fm) / (eps * eps);
+    H[i + i * N] = MAS_DIV_CONST(fp - 2 * f0 + fm, eps * eps);
   }
 #pragma unroll
   for (int i = 0; i < N; ++i)
@@ -276,7 +276,7 @@ MAS_HD void fd_hessian(const double* z, const F& f, double* H) {
         const double fmp = finite_or_zero(f(zp));
         zp[j] = z[j] - eps;
         const double fmm = finite_or_zero(f(zp));
-        H[i + j * N] = (fpp - fpm - fmp + fmm) / (4 * eps * eps);
+        H[i + j * N] = MAS_DIV_CONST(fpp - fpm - fmp + fmm, 4 * eps * eps);
       }
 }
 template <class M>
@@ -302,7 +302,7 @@ MAS_HD void fd_l_ux(const double* x, const double* u, int t, const double* prm, 
       const double fmp = finite_or_zero(M::stage(xp, up, t, prm));
       xp[j] = x[j] - eps;
       const double fmm = finite_or_zero(M::stage(xp, up, t, prm));
-      H[i + j * NU] = (fpp - fpm - fmp + fmm) / (4 * eps * eps);
+      H[i + j * NU] = MAS_DIV_CONST(fpp - fpm - fmp + fmm, 4 * eps * eps);
     }
 }
 template <class M>
@@ -337,7 +337,7 @@ MAS_HD void fd_v_x(const double* x, const double* prm, double* g) {  // :212-225
     const double fp = M::terminal(xp, prm);
     xp[i] = x[i] - eps;
     const double fm = M::terminal(xp, prm);
-    g[i] = (fp - fm) / (2 * eps);
+    g[i] = MAS_DIV_CONST(fp - fm, 2 * eps);
   }
 }
 
@@ -431,7 +431,7 @@ MAS_HD void fd_constraint_jacobians(const double* x, const double* u, const doub
     if (EQ) M::eq(xp, u, prm, fm);
     else M::ineq(xp, u, prm, fm);
 #pragma unroll
-    for (int r = 0; r < NC; ++r) Jx[r + i * NC] = (fp[r] - fm[r]) / (2 * eps);
+    for (int r = 0; r < NC; ++r) Jx[r + i * NC] = MAS_DIV_CONST(fp[r] - fm[r], 2 * eps);
   }
 #pragma unroll
   for (int i = 0; i < NU; ++i) {
@@ -444,7 +444,7 @@ MAS_HD void fd_constraint_jacobians(const double* x, const double* u, const doub
     if (EQ) M::eq(x, up, prm, fm);
     else M::ineq(x, up, prm, fm);
 #pragma unroll
-    for (int r = 0; r < NC; ++r) Ju[r + i * NC] = (fp[r] - fm[r]) / (2 * eps);
+    for (int r = 0; r < NC; ++r) Ju[r + i * NC] = MAS_DIV_CONST(fp[r] - fm[r], 2 * eps);
   }
 }
 

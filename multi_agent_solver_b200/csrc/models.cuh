@@ -60,7 +60,7 @@ struct SingleTrackDyn {
     pm::sincos_(psi, &s, &c);
     d[0] = v * c;
     d[1] = v * s;
-    d[2] = v * cu[0] / L;
+    d[2] = MAS_DIV_CONST(v * cu[0], L);
     d[3] = a;
   }
   MAS_HD static void f(const double* x, const double* u, double* d) {
@@ -78,7 +78,7 @@ struct SingleTrackDyn {
     A[0 + 3 * 4] = c;
     A[1 + 2 * 4] = v * c;
     A[1 + 3 * 4] = s;
-    A[2 + 3 * 4] = pm::tan_(delta) / L;
+    A[2 + 3 * 4] = MAS_DIV_CONST(pm::tan_(delta), L);
   }
   MAS_HD static void jac_u(const double* x, const double* u, double* B) {
     const double v = x[3], delta = u[0];

@@ -85,3 +85,37 @@ def test_close_to_glibc(pm):
     s, c, _ = pm(xs)
     assert np.max(np.abs(s - np.sin(xs)) / np.spacing(np.abs(np.sin(xs)))) <= 1.0
     assert np.max(np.abs(c - np.cos(xs)) / np.spacing(np.abs(np.cos(xs)))) <= 1.0
+
+
+# ---- div_const: division by a compile-time constant through its reciprocal, correctly rounded ---------------------
+DIVISORS = [2.5, 6.0, 2 * 1e-6, 1e-5 * 1e-5, 4 * 1e-5 * 1e-5, 4 * 1e-6 * 1e-6, 1e-6 * 1e-6]
+
+
+def test_div_const_reciprocals_meet_the_error_condition():
+    """Markstein's correction needs |RN(1/b) * b - 1| <= 2^-54 for q0 = RN(a * y) to be a faithful quotient."""
+    from fractions import Fraction
+
+    for b in DIVISORS:
+        assert abs(Fraction(1.0 / b) * Fraction(b) - 1) <= Fraction(1, 2**54), b
+
+
+@pytest.mark.parametrize("which", range(7))
+def test_div_const_equals_division_bit_for_bit(pm, which):
+    lib = ctypes.CDLL(LIB)
+    lib.pm_div_const_mismatches.restype = ctypes.c_long
+    rng = np.random.default_rng(100 + which)
+    n = 2_000_000
+    mant = rng.integers(0, 2**52, n, dtype=np.uint64)
+    expo = rng.integers(1, 2047, n, dtype=np.uint64)  # every normal binade
+    sign = rng.integers(0, 2, n, dtype=np.uint64)
+    wide = ((sign << np.uint64(63)) | (expo << np.uint64(52)) | mant).view(np.float64)
+    # mantissas of all ones / all zeros and their neighbours: the classic hard cases for reciprocal-based division
+    edge_m = np.array([0, 1, 2, 2**52 - 1, 2**52 - 2, 2**51, 2**51 - 1, 2**51 + 1], dtype=np.uint64)
+    edge = ((np.arange(900, 1150, dtype=np.uint64)[:, None] << np.uint64(52)) | edge_m[None, :]).reshape(-1).view(np.float64)
+    near = rng.uniform(-4, 4, n)  # the magnitudes the dynamics and the finite differences see
+    diff = rng.uniform(-1, 1, n) * 10.0 ** rng.uniform(-14, 2, n)
+    special = np.array([0.0, -0.0, 5e-324, -5e-324, 2.2e-308, 1.7e308, -1.7e308, np.inf, -np.inf, np.nan, 1e-290, 1e290])
+    P = ctypes.POINTER(ctypes.c_double)
+    for arr in (wide, edge, near, diff, special):
+        arr = np.ascontiguousarray(arr)
+        assert lib.pm_div_const_mismatches(which, arr.ctypes.data_as(P), ctypes.c_long(arr.size)) == 0
