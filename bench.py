@@ -202,7 +202,7 @@ def run_b200(args):
 
     desc = mas.example_desc(mas.Model.SINGLE_TRACK_LANE)
     prm = mas.IlqrParams.make(MAX_ITER, TOL)
-    depth = max(1, args.depth)
+    depth = args.depth if args.depth > 0 else (3 if args.steps < 8 else 4 if args.steps < 40 else 6)
     lanes = [Lane(torch, mas, local_rank, desc, per_rank, args, with_host_buffers=not args.resident_only) for _ in range(depth)]
     for ln in lanes:
         ln.batch.set_initial_states(x0_host)  # resident input of the `value` measurement
@@ -220,9 +220,15 @@ def run_b200(args):
         ln.batch.set_initial_states(x0_host)  # H2D from pinned memory
         ln.batch.set_controls(None)
         ln.batch.solve(prm)
-        ln.batch.get_solution(ln.out)  # D2H of X, U, cost, iterations, status into pinned memory; synchronises
+        # D2H of X, U, cost, iterations, status into pinned memory: staged in HBM on the solve stream, copied on the
+        # batch's copy stream while this lane's next solve starts; e2e_finish() waits for the last one inside the
+        # timed region, and every begin waits for the previous download of the lane
+        ln.batch.begin_get_solution(ln.out)
 
-    def timed(fn, steps, use_lanes, stagger_ms):
+    def e2e_finish(ln):
+        ln.batch.wait_solution()
+
+    def timed(fn, steps, use_lanes, stagger_ms, finish=None):
         """Runs exactly `steps` steps spread over `use_lanes` pipelines, each driven by its own host thread and
         started stagger_ms/len(use_lanes) apart so one solve's latency-bound tail overlaps another's bulk.
         Device time = latest end event - earliest start event over the lanes' streams (then max over ranks)."""
@@ -243,6 +249,8 @@ def run_b200(args):
                 e0[i].record(ln.stream)
                 for _ in range(counts[i]):
                     fn(ln)
+                if finish is not None:
+                    finish(ln)  # host-blocking: the lane's last results are in host memory before the end event
                 e1[i].record(ln.stream)
                 e1[i].synchronize()
             except Exception as exc:  # surfaced after join
@@ -300,7 +308,8 @@ def run_b200(args):
     # ---- e2e: host buffers in, host buffers out, every step ---------------------------------------------------------
     for ln in lanes:
         e2e_step(ln)
-    e2e_ms, e2e_wall = timed(e2e_step, args.steps, lanes, single_ms)
+        e2e_finish(ln)
+    e2e_ms, e2e_wall = timed(e2e_step, args.steps, lanes, single_ms, finish=e2e_finish)
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = total / (max(e2e_ms * 1e-3, e2e_wall))
     h2d = per_rank * NX * 8
@@ -387,7 +396,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--depth", type=int, default=6, help="independent solves in flight per GPU (1 = one at a time)")
+    ap.add_argument("--depth", type=int, default=0, help="independent solves in flight per GPU (1 = one at a time; 0 = by step count: "
+                    "3 below 8 steps, 4 below 40, else 6 -- fewer pipelines fill and drain faster when K is small)")
     ap.add_argument("--cpu-sample", type=int, default=8192, help="problems per CPU-baseline pass")
     ap.add_argument("--resident-only", action="store_true", help="run only warm-up + timed resident steps (for ncu)")
     ap.add_argument("--ls-mode", type=int, default=0, help="line search scheduling: 0 auto, 1 concurrent lanes, 2 compacted rounds")

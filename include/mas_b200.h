@@ -171,6 +171,12 @@ int mas_b200_batch_solve(mas_b200_batch_t b, const mas_b200_ilqr_params* params)
 /* OCP::best_states [batch][T+1][n], best_controls [batch][T][m], best_cost [batch], plus the
  * counters the reference lacks.  Any pointer may be NULL.  Synchronises. */
 int mas_b200_batch_get_solution(mas_b200_batch_t b, double* X, double* U, double* cost, int* iterations, int* status);
+/* The same results without holding up the context stream for the PCIe transfer: the solution is staged in HBM on
+ * the context stream, the device-to-host copies run on a second stream, and the call returns at once -- the next
+ * mas_b200_batch_set_* / mas_b200_batch_solve may follow immediately.  The host buffers (pinned memory for a truly
+ * asynchronous copy) are valid after mas_b200_batch_wait_solution; a second begin waits for the first. */
+int mas_b200_batch_begin_get_solution(mas_b200_batch_t b, double* X, double* U, double* cost, int* iterations, int* status);
+int mas_b200_batch_wait_solution(mas_b200_batch_t b);
 int mas_b200_batch_get_device_view(mas_b200_batch_t b, mas_b200_device_view* out);
 /* Constrained models only: the multipliers and the penalty parameter persist from solve to solve like the members
  * of a reference solver object (ilqr.hpp:331-338,415); this makes the next solve start from a fresh solver

@@ -265,6 +265,15 @@ class Batch:
                                                            _iptr(out.get("iterations")), _iptr(out.get("status"))))
         return out
 
+    def begin_get_solution(self, out) -> None:
+        """mas_b200_batch_begin_get_solution: asynchronous download into `out` (pinned arrays); pair with wait_solution()."""
+        self._out_keep = out
+        _check(load_library().mas_b200_batch_begin_get_solution(self._h, _dptr(out.get("X")), _dptr(out.get("U")), _dptr(out.get("cost")),
+                                                                 _iptr(out.get("iterations")), _iptr(out.get("status"))))
+
+    def wait_solution(self) -> None:
+        _check(load_library().mas_b200_batch_wait_solution(self._h))
+
     def device_view(self) -> DeviceView:
         v = DeviceView()
         _check(load_library().mas_b200_batch_get_device_view(self._h, ctypes.byref(v)))

@@ -344,6 +344,16 @@ int mas_b200_batch_get_solution(mas_b200_batch_t h, double* X, double* U, double
   return MAS_B200_OK;
 }
 
+int mas_b200_batch_begin_get_solution(mas_b200_batch_t h, double* X, double* U, double* cost, int* iterations, int* status) {
+  MAS_BATCH_GUARD(h);
+  return b->begin_download(X, U, cost, iterations, status);
+}
+
+int mas_b200_batch_wait_solution(mas_b200_batch_t h) {
+  MAS_BATCH_GUARD(h);
+  return b->wait_download();
+}
+
 int mas_b200_batch_get_device_view(mas_b200_batch_t h, mas_b200_device_view* out) {
   MAS_BATCH_GUARD(h);
   if (!out) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "out is NULL");

@@ -38,6 +38,8 @@ __global__ void soa_to_aos_kernel(const double* __restrict__ src, double* __rest
   }
 }
 
+__global__ void publish_count_kernel(const int* __restrict__ count, int* mapped_host_word) { *mapped_host_word = *count; }
+
 __global__ void time_limit_kernel(const int* __restrict__ list, const int* __restrict__ count, int* status) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < *count) status[list[i]] = STATUS_TIME_LIMIT;
@@ -70,6 +72,11 @@ BatchBase::~BatchBase() {
     if (p) cudaFree(p);
   if (h_counts) cudaFreeHost(h_counts);
   if (d_count_hist) cudaFree(d_count_hist);
+  if (download_pending) cudaEventSynchronize(ev_downloaded);
+  if (d_out_stage) cudaFree(d_out_stage);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
+  if (ev_staged) cudaEventDestroy(ev_staged);
+  if (ev_downloaded) cudaEventDestroy(ev_downloaded);
   for (auto& tl : timed) {
     cudaEventDestroy(tl.e0);
     cudaEventDestroy(tl.e1);
@@ -116,7 +123,8 @@ int BatchBase::allocate() {
   MAS_CUDA_CHECK(ialloc(&d_accept_idx, L));
   MAS_CUDA_CHECK(cudaMemsetAsync(d_accept_idx, 0xFF, L * sizeof(int), ctx->stream));  // -1: no accepted step size
   MAS_CUDA_CHECK(dalloc(&d_accept_merit, L));
-  MAS_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&h_counts), 4 * sizeof(int)));
+  MAS_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&h_counts), 4 * sizeof(int), cudaHostAllocMapped));
+  MAS_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h_counts_dev), h_counts, 0));
   MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
   MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
   return allocate_constraint_state();
@@ -220,6 +228,56 @@ int BatchBase::download_rows(const double* dev, double* host, int rows) {
   stats.kernel_launches++;
   MAS_CUDA_CHECK(cudaGetLastError());
   MAS_CUDA_CHECK(cudaMemcpyAsync(host, d_stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return MAS_B200_OK;
+}
+
+// Results to the host without holding up the solve stream for the PCIe transfer: transposes (HBM to HBM, fast) on
+// the solve stream into a staging area of their own, the device-to-host copies on `copy_stream`.  The caller may
+// start the next solve right away; wait_download() (or the next begin_download) fences the host buffers.
+int BatchBase::begin_download(double* X, double* U, double* cost, int* iterations, int* status) {
+  const size_t nX = static_cast<size_t>(batch) * nx * (T + 1), nU = static_cast<size_t>(batch) * nu * T;
+  if (!d_out_stage) {
+    MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_out_stage), (nX + nU + batch) * sizeof(double) + 2 * static_cast<size_t>(batch) * sizeof(int)));
+    MAS_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev_staged, cudaEventDisableTiming));
+    MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev_downloaded, cudaEventDisableTiming));
+  }
+  int rc = wait_download();  // the staging area and the previous host buffers are free again
+  if (rc) return rc;
+  double* sX = d_out_stage;
+  double* sU = sX + nX;
+  double* sc = sU + nU;
+  int* si = reinterpret_cast<int*>(sc + batch);
+  int* ss = si + batch;
+  dim3 block(32, 8);
+  if (X) {
+    soa_to_aos_kernel<<<dim3(div_up(batch, 32), div_up(nx * (T + 1), 32)), block, 0, ctx->stream>>>(d_X, sX, batch, nx * (T + 1), ld);
+    stats.kernel_launches++;
+  }
+  if (U) {
+    soa_to_aos_kernel<<<dim3(div_up(batch, 32), div_up(nu * T, 32)), block, 0, ctx->stream>>>(d_U, sU, batch, nu * T, ld);
+    stats.kernel_launches++;
+  }
+  MAS_CUDA_CHECK(cudaGetLastError());
+  if (cost) MAS_CUDA_CHECK(cudaMemcpyAsync(sc, d_cost, batch * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (iterations) MAS_CUDA_CHECK(cudaMemcpyAsync(si, d_iters, batch * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (status) MAS_CUDA_CHECK(cudaMemcpyAsync(ss, d_status, batch * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+  MAS_CUDA_CHECK(cudaEventRecord(ev_staged, ctx->stream));
+  MAS_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, ev_staged, 0));
+  if (X) MAS_CUDA_CHECK(cudaMemcpyAsync(X, sX, nX * sizeof(double), cudaMemcpyDeviceToHost, copy_stream));
+  if (U) MAS_CUDA_CHECK(cudaMemcpyAsync(U, sU, nU * sizeof(double), cudaMemcpyDeviceToHost, copy_stream));
+  if (cost) MAS_CUDA_CHECK(cudaMemcpyAsync(cost, sc, batch * sizeof(double), cudaMemcpyDeviceToHost, copy_stream));
+  if (iterations) MAS_CUDA_CHECK(cudaMemcpyAsync(iterations, si, batch * sizeof(int), cudaMemcpyDeviceToHost, copy_stream));
+  if (status) MAS_CUDA_CHECK(cudaMemcpyAsync(status, ss, batch * sizeof(int), cudaMemcpyDeviceToHost, copy_stream));
+  MAS_CUDA_CHECK(cudaEventRecord(ev_downloaded, copy_stream));
+  download_pending = true;
+  return MAS_B200_OK;
+}
+
+int BatchBase::wait_download() {
+  if (!download_pending) return MAS_B200_OK;
+  MAS_CUDA_CHECK(cudaEventSynchronize(ev_downloaded));
+  download_pending = false;
   return MAS_B200_OK;
 }
 

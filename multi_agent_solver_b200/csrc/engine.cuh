@@ -57,6 +57,7 @@ struct Context {
 __global__ void aos_to_soa_kernel(const double* __restrict__ src, double* __restrict__ dst, int batch, int rows, int ld);
 __global__ void soa_to_aos_kernel(const double* __restrict__ src, double* __restrict__ dst, int batch, int rows, int ld);
 __global__ void dfma_probe_kernel(double* out, int iters);
+__global__ void publish_count_kernel(const int* __restrict__ count, int* mapped_host_word);
 
 // OCP::initialize_problem / iLQR prologue: rollout + cost, reset of the per-solve counters and of
 // the active list (identity).  ilqr.hpp:75-78, ocp.hpp:110-113,182.
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(kBlock, 7) forward_kernel(BatchView<M::NX, M::
 // the owner takes its first improving candidate in index order -- the reference's sequential semantics
 // (ilqr.hpp:206-228) -- and lanes of finished problems take over candidates of the ones that need many.  A warp's
 // search costs about (candidates actually needed)/32 rollout times instead of 10.  Then owners commit / stop-test.
-template <class M>
+template <class M, int C>
 __global__ void __launch_bounds__(kBlock, 7) forward_coop_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
                                                                 int* next_list, int* next_count) {
   constexpr int kWarps = kBlock / 32;
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(kBlock, 7) forward_coop_kernel(BatchView<M::NX
   __syncwarp();
   if (n_valid > 0) {
     for (int round = 0; round < kNumAlphas; ++round) {  // at most ten rounds: every searching problem advances by >= 1
-      if (lane == 0) coop_assign(s_done[w], s_next[w], n_valid, &s_plan[w]);
+      if (lane == 0) coop_assign(s_done[w], s_next[w], n_valid, &s_plan[w], C);
       __syncwarp();
       bool any = false;
       for (int i = 0; i < n_valid; ++i) any = any || s_plan[w].quota[i] > 0;
@@ -177,15 +178,18 @@ __global__ void __launch_bounds__(kBlock, 7) forward_coop_kernel(BatchView<M::NX
         const int po = s_p[w][o], j = s_plan[w].cand[lane];
         double prm[M::NP > 0 ? M::NP : 1];
         load_params<M>(v, po, prm);
-        const double alpha = alpha_of(j);
-        double merit;
-        trial_rollout<M, 1>(v, po, prm, &alpha, &merit);
-        s_merit[w][o][j] = merit;
+        double alpha[C], merit[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) alpha[c] = alpha_of(j + c < kNumAlphas ? j + c : kNumAlphas - 1);
+        trial_rollout<M, C>(v, po, prm, alpha, merit);
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          if (j + c < kNumAlphas) s_merit[w][o][j + c] = merit[c];
       }
       __syncwarp();
       if (owner && !s_done[w][lane]) {
         int nx = s_next[w][lane];
-        const bool fin = coop_owner_update(s_merit[w][lane], current_merit, s_plan[w].quota[lane], &nx, &accepted, &accepted_merit);
+        const bool fin = coop_owner_update(s_merit[w][lane], current_merit, s_plan[w].quota[lane], &nx, &accepted, &accepted_merit, C);
         s_next[w][lane] = nx;
         s_done[w][lane] = fin ? 1 : 0;
       }
@@ -401,10 +405,19 @@ struct BatchBase {
   int* d_list[2] = {nullptr, nullptr};
   int* d_count = nullptr;  // [2]
   double* d_stage = nullptr;  // staging for AoS<->SoA transposes (max(nx*(T+1), nu*T) * batch doubles)
+  // asynchronous result download (begin_download / wait_download): the solution is transposed into its own staging
+  // area on the solve stream, then copied to the host on a second stream while the next solve already runs
+  double* d_out_stage = nullptr;  // [batch * (nx*(T+1) + nu*T + 1)] doubles, then 2 * batch ints
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_staged = nullptr, ev_downloaded = nullptr;
+  bool download_pending = false;
+  int begin_download(double* X, double* U, double* cost, int* iterations, int* status);
+  int wait_download();
   // strategy scratch (allocated on demand)
   double *d_U_old = nullptr, *d_X_old = nullptr, *d_cost_old = nullptr, *d_radius = nullptr;
   int* d_accepted = nullptr;
-  int* h_counts = nullptr;  // pinned, [4]
+  int* h_counts = nullptr;      // pinned + mapped, [4]: active counts published by publish_count_kernel
+  int* h_counts_dev = nullptr;  // the device-side address of the same words
   cudaEvent_t ev[2] = {nullptr, nullptr};
   bool per_problem_params = false;
   int tune_L = 0, tune_C = 0;
@@ -693,11 +706,16 @@ struct BatchImpl : BatchBase {
         last_C = 2;
       } else if (ls_mode == 3 || (ls_mode == 0 && tune_L == 0 && L == 1)) {
         // more problems than the device holds lanes: warp-cooperative search (32 problems per warp)
-        forward_coop_kernel<M><<<div_up(n_upper, kBlock), kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1],
-                                                                                  d_count + (cur ^ 1));
+        // two step sizes per lane by default: +3% with several solves in flight, neutral alone (B200, 65,536 problems)
+        if (tune_C != 1)
+          forward_coop_kernel<M, 2><<<div_up(n_upper, kBlock), kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1],
+                                                                                       d_count + (cur ^ 1));
+        else
+          forward_coop_kernel<M, 1><<<div_up(n_upper, kBlock), kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1],
+                                                                                       d_count + (cur ^ 1));
         stats.kernel_launches++;
         last_L = 32;
-        last_C = 1;
+        last_C = tune_C != 1 ? 2 : 1;
       } else {
         launch_forward(n_upper, cur, L, C);
       }
@@ -705,7 +723,11 @@ struct BatchImpl : BatchBase {
       MAS_CUDA_CHECK(cudaGetLastError());
       if (profiling)
         MAS_CUDA_CHECK(cudaMemcpyAsync(d_count_hist + it, d_count + cur, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
-      MAS_CUDA_CHECK(cudaMemcpyAsync(h_counts + (it & 1), d_count + (cur ^ 1), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      // the new active count goes to the host as a store into mapped pinned memory, not as a 4-byte D2H copy: the
+      // copy engine is a FIFO shared with other contexts' result downloads, and a count queued behind a 170 MB
+      // transfer stalls this loop for milliseconds (measured: 2x on the solve throughput of four contexts)
+      publish_count_kernel<<<1, 1, 0, ctx->stream>>>(d_count + (cur ^ 1), h_counts_dev + (it & 1));
+      stats.kernel_launches++;
       MAS_CUDA_CHECK(cudaEventRecord(ev[it & 1], ctx->stream));
       if (it >= 1) {
         // active count after iteration it-1: an upper bound for iteration it+1 (the list only shrinks)

@@ -935,7 +935,9 @@ struct CoopPlan {
   int cand[32];    // lane -> step-size index
   int quota[32];   // slot -> candidates evaluated this round
 };
-MAS_HD void coop_assign(const int* done, const int* next, int n_valid, CoopPlan* plan) {
+// With `chains` > 1 a lane's task is `chains` consecutive step sizes of one problem, rolled out by one thread as
+// independent instruction streams (they share the nominal trajectory and the gains it loads): quota stays in lanes.
+MAS_HD void coop_assign(const int* done, const int* next, int n_valid, CoopPlan* plan, int chains = 1) {
   int n_act = 0;
   for (int i = 0; i < n_valid; ++i) n_act += done[i] ? 0 : 1;
   for (int l = 0; l < 32; ++l) {
@@ -949,12 +951,12 @@ MAS_HD void coop_assign(const int* done, const int* next, int n_valid, CoopPlan*
   for (int i = 0; i < n_valid; ++i) {
     if (done[i]) continue;
     int q = base + (rank < rem ? 1 : 0);
-    const int left = kNumAlphas - next[i];
+    const int left = (kNumAlphas - next[i] + chains - 1) / chains;
     if (q > left) q = left;
     plan->quota[i] = q;
     for (int k = 0; k < q; ++k) {
       plan->owner[lane] = i;
-      plan->cand[lane] = next[i] + k;
+      plan->cand[lane] = next[i] + k * chains;
       ++lane;
     }
     ++rank;
@@ -964,15 +966,17 @@ MAS_HD void coop_assign(const int* done, const int* next, int n_valid, CoopPlan*
 // Owner's verdict after a round: first improving candidate among those just evaluated (strict <, ilqr.hpp:220).
 // Returns true when the problem's search is over (accepted, or all ten tried); *accepted = index or -1.
 MAS_HD bool coop_owner_update(const double* merits /* [kNumAlphas] of this problem */, double current_merit, int quota, int* next, int* accepted,
-                              double* accepted_merit) {
-  for (int j = *next; j < *next + quota; ++j)
+                              double* accepted_merit, int chains = 1) {
+  int end = *next + quota * chains;
+  if (end > kNumAlphas) end = kNumAlphas;
+  for (int j = *next; j < end; ++j)
     if (merits[j] < current_merit) {
       *accepted = j;
       *accepted_merit = merits[j];
       return true;
     }
-  *next += quota;
-  return *next >= kNumAlphas;
+  *next = end;
+  return end >= kNumAlphas;
 }
 
 // Accept / bookkeeping / stop test for one problem (ilqr.hpp:230-234,269-271).  Returns true when

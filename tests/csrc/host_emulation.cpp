@@ -120,7 +120,7 @@ int emulate(int batch, int T, double dt, unsigned mask, int has_bounds, const do
           cur[i] = i < n_valid ? v.merit[list[first + i]] : 0.0;
         }
         for (int round = 0; round < kNumAlphas; ++round) {
-          coop_assign(done, nxt, n_valid, &plan);
+          coop_assign(done, nxt, n_valid, &plan, C == 2 ? 2 : 1);
           bool any = false;
           for (int i = 0; i < n_valid; ++i) any = any || plan.quota[i] > 0;
           if (!any) break;
@@ -130,11 +130,19 @@ int emulate(int batch, int T, double dt, unsigned mask, int has_bounds, const do
             const int po = list[first + o];
             double prm[M::NP > 0 ? M::NP : 1];
             load_params<M>(v, po, prm);
-            const double alpha = alpha_of(plan.cand[lane]);
-            trial_rollout<M, 1>(v, po, prm, &alpha, &merits[o][plan.cand[lane]]);
+            const int j = plan.cand[lane];
+            if (C == 2) {
+              double alpha[2] = {alpha_of(j), alpha_of(j + 1 < kNumAlphas ? j + 1 : kNumAlphas - 1)}, m2[2];
+              trial_rollout<M, 2>(v, po, prm, alpha, m2);
+              merits[o][j] = m2[0];
+              if (j + 1 < kNumAlphas) merits[o][j + 1] = m2[1];
+            } else {
+              const double alpha = alpha_of(j);
+              trial_rollout<M, 1>(v, po, prm, &alpha, &merits[o][j]);
+            }
           }
           for (int i = 0; i < n_valid; ++i)
-            if (!done[i]) done[i] = coop_owner_update(merits[i], cur[i], plan.quota[i], &nxt[i], &acc[i], &accm[i]) ? 1 : 0;
+            if (!done[i]) done[i] = coop_owner_update(merits[i], cur[i], plan.quota[i], &nxt[i], &acc[i], &accm[i], C == 2 ? 2 : 1) ? 1 : 0;
         }
         for (int i = 0; i < n_valid; ++i) {
           const int p = list[first + i];

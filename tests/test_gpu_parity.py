@@ -261,3 +261,34 @@ def test_constraint_state_persists_and_resets(mas, ctx, oracle):
     again = b.get_solution()
     b.close()
     assert np.array_equal(again["cost"], hist[0]["cost"]) and np.array_equal(again["X"], hist[0]["X"])
+
+
+def test_asynchronous_download_survives_the_next_solve(mas, ctx, oracle):
+    """begin_get_solution stages the results in HBM; a following solve on other inputs must not disturb them."""
+    import torch
+
+    B = 300
+    xa, xb = random_x0(0, B, seed=401), random_x0(0, B, seed=402)
+    prm = mas.IlqrParams.make(10, 1e-5)
+    b = mas.Batch(ctx, mas.example_desc(0), B)
+
+    def pinned():
+        return dict(X=torch.empty((B, 81, 4), dtype=torch.float64).pin_memory().numpy(), U=torch.empty((B, 80, 2), dtype=torch.float64).pin_memory().numpy(),
+                    cost=torch.empty(B, dtype=torch.float64).pin_memory().numpy(), iterations=torch.empty(B, dtype=torch.int32).pin_memory().numpy(),
+                    status=torch.empty(B, dtype=torch.int32).pin_memory().numpy())
+
+    oa, ob = pinned(), pinned()
+    b.set_initial_states(xa)
+    b.set_controls(None)
+    b.solve(prm)
+    b.begin_get_solution(oa)
+    b.set_initial_states(xb)  # no wait in between
+    b.set_controls(None)
+    b.solve(prm)
+    b.begin_get_solution(ob)  # waits for the first download, then stages the second
+    b.wait_solution()
+    b.close()
+    for x0, got in ((xa, oa), (xb, ob)):
+        ref = oracle.ilqr_solve_batch(0, x0, max_iterations=10, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+        assert_parity(got, ref)
+        assert is_bit_exact(got, ref)

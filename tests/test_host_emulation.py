@@ -28,7 +28,7 @@ def test_models_bit_exact(emu, oracle, model, batch, cap):
     assert np.array_equal(got["reg_retries"], ref["reg_retries"])
 
 
-@pytest.mark.parametrize("L,C", [(1, 1), (1, 2), (2, 1), (4, 1), (8, 1), (16, 1), (32, 1)])
+@pytest.mark.parametrize("L,C", [(1, 1), (1, 2), (2, 1), (4, 1), (8, 1), (16, 1), (32, 1), (32, 2)])
 def test_lane_mappings_pick_the_first_improving_step(emu, oracle, L, C):
     x0 = random_x0(0, 24, seed=9)
     U0 = np.zeros((24, 80, 2))
