@@ -449,7 +449,7 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
             for (int j = 1; j < k; ++j) acc = acc + Lm[i + static_cast<size_t>(j) * ms] * Lm[k + static_cast<size_t>(j) * ms];
             s -= acc;
           }
-          Lm[i + static_cast<size_t>(k) * ms] = s / x;
+          Lm[i + static_cast<size_t>(k) * ms] = pm::div_(s, x);
         }
         MAS_CTA_SYNC();
       }
@@ -471,12 +471,12 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
       for (int i = 0; i < ms; ++i) {
         double s = x[i];
         for (int j = 0; j < i; ++j) s -= Lm[i + static_cast<size_t>(j) * ms] * x[j];
-        x[i] = s / Lm[i + static_cast<size_t>(i) * ms];
+        x[i] = pm::div_(s, Lm[i + static_cast<size_t>(i) * ms]);
       }
       for (int i = ms - 1; i >= 0; --i) {
         double s = x[i];
         for (int j = i + 1; j < ms; ++j) s -= Lm[j + static_cast<size_t>(i) * ms] * x[j];
-        x[i] = s / Lm[i + static_cast<size_t>(i) * ms];
+        x[i] = pm::div_(s, Lm[i + static_cast<size_t>(i) * ms]);
       }
     }
     MAS_CTA_SYNC();

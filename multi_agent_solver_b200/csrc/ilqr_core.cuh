@@ -110,6 +110,47 @@ MAS_HD void mat_nn(const double* A, const double* B, double* C) {
     }
 }
 
+// The same two products when one factor is a Jacobian with known structural zeros (models.cuh: A_NZ / B_NZ): terms
+// whose Jacobian entry is structurally zero are left out, the rest keep the k-ascending order.
+// C[R x CC] = A^T * B, A stored KD x R with sparsity NZ (bit k + i*KD)
+template <int KD, int R, int CC, unsigned long long NZ>
+MAS_HD void mat_tn_sa(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int j = 0; j < CC; ++j)
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      double s = 0.0;
+      bool first = true;
+#pragma unroll
+      for (int k = 0; k < KD; ++k)
+        if ((NZ >> (k + i * KD)) & 1ull) {
+          const double prod = A[k + i * KD] * B[k + j * KD];
+          s = first ? prod : s + prod;
+          first = false;
+        }
+      C[i + j * R] = s;
+    }
+}
+// C[R x CC] = A * B, B stored KD x CC with sparsity NZ (bit k + j*KD)
+template <int R, int KD, int CC, unsigned long long NZ>
+MAS_HD void mat_nn_sb(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int j = 0; j < CC; ++j)
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      double s = 0.0;
+      bool first = true;
+#pragma unroll
+      for (int k = 0; k < KD; ++k)
+        if ((NZ >> (k + j * KD)) & 1ull) {
+          const double prod = A[i + k * R] * B[k + j * KD];
+          s = first ? prod : s + prod;
+          first = false;
+        }
+      C[i + j * R] = s;
+    }
+}
+
 // `m = 0.5 * (m + m.transpose())` evaluated in place, columns outer / rows inner, as the reference's
 // aliased Eigen expression does (ilqr.hpp:102,192).
 template <int N>
@@ -173,7 +214,8 @@ MAS_HD double rollout_thread(const BatchView<M::NX, M::NU>& v, int p) {
 }
 
 // ---- finite-difference defaults (finite_differences.hpp) ------------------------------------------
-MAS_HD double finite_or_zero(double v) { return isfinite(v) ? v : 0.0; }  // safe_eval, :95-107
+// safe_eval, :95-107 (exponent field all ones = inf or nan; tested with integer instructions, off the fp64 pipe)
+MAS_HD double finite_or_zero(double v) { return ((pm::high_word(v) & 0x7ff00000u) != 0x7ff00000u) ? v : 0.0; }
 
 template <class M>
 MAS_HD void fd_jac_x(const double* x, const double* u, const double* prm, double* A) {  // :53-72
@@ -373,7 +415,7 @@ MAS_HD bool llt_factor(const double* a, double* L) {
             for (int j = 1; j < k; ++j) acc = acc + L[i + j * N] * L[k + j * N];
             s -= acc;
           }
-          L[i + k * N] = s / x;
+          L[i + k * N] = pm::div_(s, x);
         }
       }
     }
@@ -393,14 +435,14 @@ MAS_HD void llt_inverse(const double* L, double* inv) {
       double s = x[i];
 #pragma unroll
       for (int j = 0; j < i; ++j) s -= L[i + j * N] * x[j];
-      x[i] = s / L[i + i * N];
+      x[i] = pm::div_(s, L[i + i * N]);
     }
 #pragma unroll
     for (int i = N - 1; i >= 0; --i) {
       double s = x[i];
 #pragma unroll
       for (int j = i + 1; j < N; ++j) s -= L[j + i * N] * x[j];
-      x[i] = s / L[i + i * N];
+      x[i] = pm::div_(s, L[i + i * N]);
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) inv[i + c * N] = x[i];
@@ -693,21 +735,26 @@ MAS_HD int backward_thread(const BatchView<M::NX, M::NU>& v, int p) {
     double q_x[NX], q_u[NU], q_xx[NX * NX], q_ux[NU * NX], q_uu[NU * NU];
     constexpr int TMPN = (NX > NU ? NX : NU) * (NX > NU ? NX : NU);
     double AtV[NX * NX], BtV[NU * NX], tmp[TMPN];
-    mat_tn<NX, NX, 1>(A, v_x, tmp);
+    // structural zeros are only known for the analytic Jacobians of a compile-time derivative mode
+    constexpr unsigned long long kDense = ~0ull;
+    static_assert(NX * NX <= 64 && NX * NU <= 64, "sparsity masks are 64-bit");
+    constexpr unsigned long long a_nz = (MASK_CT >= 0 && (MASK_CT & D_A)) ? M::A_NZ : kDense;
+    constexpr unsigned long long b_nz = (MASK_CT >= 0 && (MASK_CT & D_B)) ? M::B_NZ : kDense;
+    mat_tn_sa<NX, NX, 1, a_nz>(A, v_x, tmp);
 #pragma unroll
     for (int i = 0; i < NX; ++i) q_x[i] = l_x[i] + tmp[i];
-    mat_tn<NX, NU, 1>(B, v_x, tmp);
+    mat_tn_sa<NX, NU, 1, b_nz>(B, v_x, tmp);
 #pragma unroll
     for (int i = 0; i < NU; ++i) q_u[i] = l_u[i] + tmp[i];
-    mat_tn<NX, NX, NX>(A, v_xx, AtV);
-    mat_tn<NX, NU, NX>(B, v_xx, BtV);
-    mat_nn<NX, NX, NX>(AtV, A, tmp);
+    mat_tn_sa<NX, NX, NX, a_nz>(A, v_xx, AtV);
+    mat_tn_sa<NX, NU, NX, b_nz>(B, v_xx, BtV);
+    mat_nn_sb<NX, NX, NX, a_nz>(AtV, A, tmp);
 #pragma unroll
     for (int i = 0; i < NX * NX; ++i) q_xx[i] = l_xx[i] + tmp[i];
-    mat_nn<NU, NX, NX>(BtV, A, tmp);
+    mat_nn_sb<NU, NX, NX, a_nz>(BtV, A, tmp);
 #pragma unroll
     for (int i = 0; i < NU * NX; ++i) q_ux[i] = l_ux[i] + tmp[i];
-    mat_nn<NU, NX, NU>(BtV, B, tmp);
+    mat_nn_sb<NU, NX, NU, b_nz>(BtV, B, tmp);
 #pragma unroll
     for (int i = 0; i < NU * NU; ++i) q_uu[i] = l_uu[i] + tmp[i];
 

@@ -41,7 +41,12 @@ enum DerivBits : unsigned {
 // Path constraints (OCP::equality_constraints / inequality_constraints, ocp.hpp:59-66): none of the reference's
 // examples sets them; models without them inherit these empty hooks and the augmented-Lagrangian code of the
 // kernels (ilqr.hpp:121-170,236-260,380-407) compiles away.
+//
+// A_NZ / B_NZ: structural sparsity of the analytic Jacobians, bit (r + c*NX) set when entry (r, c) can be nonzero.
+// The Riccati products skip the terms whose Jacobian factor is structurally zero (x + 0*y == x for finite y, so
+// only the sign of an exact zero can differ).  Default: dense.
 struct NoConstraints {
+  static constexpr unsigned long long A_NZ = ~0ull, B_NZ = ~0ull;
   static constexpr int NEQ = 0, NINEQ = 0;
   MAS_HD static void eq(const double*, const double*, const double*, double*) {}
   MAS_HD static void ineq(const double*, const double*, const double*, double*) {}
@@ -49,6 +54,9 @@ struct NoConstraints {
 
 // ---- single-track kinematic bicycle, shared by StLane and StCirc ---------------------------------
 struct SingleTrackDyn {
+  // A: (0,2) (1,2) (0,3) (1,3) (2,3);  B: (2,0) (3,1)
+  static constexpr unsigned long long A_NZ = (1ull << 8) | (1ull << 9) | (1ull << 12) | (1ull << 13) | (1ull << 14);
+  static constexpr unsigned long long B_NZ = (1ull << 2) | (1ull << 7);
   // The control enters only through tan(delta); RK4 evaluates f four times with the same control
   // (integrator.hpp:22-25), so the tangent is computed once per step and reused: same bits, a
   // quarter of the work.
@@ -91,6 +99,7 @@ struct SingleTrackDyn {
 };
 
 struct StLane : NoConstraints {
+  static constexpr unsigned long long A_NZ = SingleTrackDyn::A_NZ, B_NZ = SingleTrackDyn::B_NZ;
   static constexpr int ID = 0;
   static constexpr int NX = 4, NU = 2, NP = 5;
   static constexpr unsigned AVAILABLE = D_A | D_B | D_LX | D_LU | D_LXX | D_LUU;
@@ -150,6 +159,7 @@ struct StLaneCon : StLane {
 };
 
 struct StCirc : NoConstraints {
+  static constexpr unsigned long long A_NZ = SingleTrackDyn::A_NZ, B_NZ = SingleTrackDyn::B_NZ;
   static constexpr int ID = 1;
   static constexpr int NX = 4, NU = 2, NP = 6;
   static constexpr unsigned AVAILABLE = D_A | D_B;
@@ -182,6 +192,7 @@ struct StCirc : NoConstraints {
 // products; with identity matrices every skipped term is an exact +0, so the shortcuts below return
 // the same bits for finite inputs (x^T Q x = sum of squares accumulated left to right from 0.0).
 struct Lqr4 : NoConstraints {
+  static constexpr unsigned long long A_NZ = 0x8421ull, B_NZ = 0x8421ull;  // identity matrices
   static constexpr int ID = 2;
   static constexpr int NX = 4, NU = 4, NP = 0;
   static constexpr unsigned AVAILABLE = D_ALL;
