@@ -188,6 +188,12 @@ int mas_b200_batch_get_profile(mas_b200_batch_t b, mas_b200_profile* out);
 /* Tuning of the line-search kernel: lanes per problem (1,2,4,8,16; 0 = auto from batch size) and
  * step sizes rolled out together per lane (1 or 2; 0 = auto). */
 int mas_b200_batch_set_tuning(mas_b200_batch_t b, int forward_lanes, int forward_chains);
+/* The line search can keep the trajectories of its trial rollouts in HBM ((n + m) * T doubles per resident lane, about
+ * 0.3 GB) so that the accepted step is a copy, not a second pass over T dependent steps.  enable = 1 (default): in
+ * the launches over small active sets (4..16 lanes per problem), where it cuts 35 % off the line search; 2: also in
+ * the warp-cooperative kernel of large active sets (measured slower on B200: the extra HBM writes cost more than the
+ * second rollout); 0: off.  Dropped silently when the allocation fails.  Results are identical in every mode. */
+int mas_b200_batch_set_trial_store(mas_b200_batch_t b, int enable);
 /* How the line search (solvers/ilqr.hpp:195-228) is scheduled: 0 = auto (by active-set size),
  * 1 = all step sizes concurrently on `forward_lanes` lanes per problem, 2 = compacted rounds of two
  * step sizes over the problems still searching, 3 = warp-cooperative (a warp owns 32 problems and deals

@@ -239,6 +239,9 @@ class Batch:
     def solve(self, params: IlqrParams) -> None:
         _check(load_library().mas_b200_batch_solve(self._h, ctypes.byref(params)))
 
+    def set_trial_store(self, enable: bool) -> None:
+        _check(load_library().mas_b200_batch_set_trial_store(self._h, int(enable)))
+
     def reset_solver_state(self) -> None:
         _check(load_library().mas_b200_batch_reset_solver_state(self._h))
 

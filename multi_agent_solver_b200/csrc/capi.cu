@@ -411,6 +411,13 @@ int mas_b200_batch_set_tuning(mas_b200_batch_t h, int forward_lanes, int forward
   return MAS_B200_OK;
 }
 
+int mas_b200_batch_set_trial_store(mas_b200_batch_t h, int enable) {
+  MAS_BATCH_GUARD(h);
+  b->trial_store = enable != 0;
+  b->coop_store = enable == 2;
+  return MAS_B200_OK;
+}
+
 int mas_b200_batch_set_line_search_mode(mas_b200_batch_t h, int mode) {
   MAS_BATCH_GUARD(h);
   if (mode < 0 || mode > 3) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "line search mode must be 0 (auto), 1 (lanes), 2 (rounds) or 3 (warp-cooperative)");

@@ -74,6 +74,8 @@ BatchBase::~BatchBase() {
   if (d_count_hist) cudaFree(d_count_hist);
   if (download_pending) cudaEventSynchronize(ev_downloaded);
   if (d_out_stage) cudaFree(d_out_stage);
+  if (d_trial_X) cudaFree(d_trial_X);
+  if (d_trial_U) cudaFree(d_trial_U);
   if (copy_stream) cudaStreamDestroy(copy_stream);
   if (ev_staged) cudaEventDestroy(ev_staged);
   if (ev_downloaded) cudaEventDestroy(ev_downloaded);
@@ -271,6 +273,28 @@ int BatchBase::begin_download(double* X, double* U, double* cost, int* iteration
   if (status) MAS_CUDA_CHECK(cudaMemcpyAsync(status, ss, batch * sizeof(int), cudaMemcpyDeviceToHost, copy_stream));
   MAS_CUDA_CHECK(cudaEventRecord(ev_downloaded, copy_stream));
   download_pending = true;
+  return MAS_B200_OK;
+}
+
+// Scratch for the line search's trial trajectories.  Optional: when the device cannot spare it the kernels fall back to
+// rolling the accepted step out a second time (same results).
+int BatchBase::ensure_trial_store(long long min_slots) {
+  if (trial_store_tried && trial_slots >= min_slots) return MAS_B200_OK;
+  if (trial_store_tried && trial_slots == 0) return MAS_B200_OK;  // allocation failed before: stay on the fallback
+  trial_store_tried = true;
+  if (d_trial_X) cudaFree(d_trial_X);
+  if (d_trial_U) cudaFree(d_trial_U);
+  d_trial_X = d_trial_U = nullptr;
+  trial_slots = 0;
+  const size_t n = static_cast<size_t>(min_slots) * T;
+  if (cudaMalloc(reinterpret_cast<void**>(&d_trial_X), n * nx * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&d_trial_U), n * nu * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();  // clear the out-of-memory error; the solve proceeds without the store
+    if (d_trial_X) cudaFree(d_trial_X);
+    d_trial_X = d_trial_U = nullptr;
+    return MAS_B200_OK;
+  }
+  trial_slots = static_cast<int>(min_slots);
   return MAS_B200_OK;
 }
 

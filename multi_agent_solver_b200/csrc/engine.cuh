@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -105,12 +106,21 @@ __global__ void __launch_bounds__(kBlock, 7) forward_kernel(BatchView<M::NX, M::
   const int p = valid ? list[i] : 0;
   bool again = false;
   double prm[M::NP > 0 ? M::NP : 1];
-  int best_j = kNumAlphas;
-  double best_merit = 0.0, current_merit = 0.0;
+  int best_j = kNumAlphas, best_slot = -1;
+  double best_merit = 0.0, current_merit = 0.0, best_objective = 0.0;
+  // Wide mappings (L >= 4: small active sets, where a launch costs the latency of its sequential passes and nothing
+  // else) keep their trial trajectories: chain c of thread gid -> slot c * (threads of the grid) + gid, and the
+  // accepted step becomes a copy instead of one more pass over T dependent steps.  Large active sets do not: there
+  // the extra 48 B per step and rollout cost more HBM time than the second rollout (measured, 65,536 problems).
+  const int n_threads = gridDim.x * blockDim.x;
+  const bool store = L >= 4 && v.trial_X != nullptr && static_cast<long long>(n_threads) * C <= v.trial_slots;
   if (valid) {
     load_params<M>(v, p, prm);
     current_merit = v.merit[p];
-    lane_line_search<M, L, C>(v, p, prm, lane, current_merit, &best_j, &best_merit);
+    if (L >= 4 && store)
+      lane_line_search<M, L, C, (L >= 4)>(v, p, prm, lane, current_merit, &best_j, &best_merit, gid, n_threads, &best_slot, &best_objective);
+    else
+      lane_line_search<M, L, C, false>(v, p, prm, lane, current_merit, &best_j, &best_merit);
   }
   if (L > 1) {
     // first improving candidate of the group = minimum index; its merit travels with it.
@@ -119,13 +129,18 @@ __global__ void __launch_bounds__(kBlock, 7) forward_kernel(BatchView<M::NX, M::
     for (int off = L / 2; off > 0; off >>= 1) {
       const int oj = __shfl_xor_sync(0xffffffffu, best_j, off, L);
       const double om = __shfl_xor_sync(0xffffffffu, best_merit, off, L);
+      const int os = __shfl_xor_sync(0xffffffffu, best_slot, off, L);
+      const double oo = __shfl_xor_sync(0xffffffffu, best_objective, off, L);
       if (oj < best_j) {
         best_j = oj;
         best_merit = om;
+        best_slot = os;
+        best_objective = oo;
       }
     }
   }
-  if (valid && lane == 0) again = finish_iteration<M>(v, p, prm, current_merit, best_j, best_merit);
+  if (L >= 4) __syncwarp();  // the winner's trial trajectory was written by another lane of this warp
+  if (valid && lane == 0) again = finish_iteration<M>(v, p, prm, current_merit, best_j, best_merit, best_slot, best_objective);
   // warp-aggregated append to the next active list
   const unsigned vote = __ballot_sync(0xffffffffu, again);
   if (vote) {
@@ -143,11 +158,15 @@ __global__ void __launch_bounds__(kBlock, 7) forward_kernel(BatchView<M::NX, M::
 // the owner takes its first improving candidate in index order -- the reference's sequential semantics
 // (ilqr.hpp:206-228) -- and lanes of finished problems take over candidates of the ones that need many.  A warp's
 // search costs about (candidates actually needed)/32 rollout times instead of 10.  Then owners commit / stop-test.
-template <class M, int C>
+// STORE: lanes keep their trial trajectories (BatchView::trial_*) and an owner copies its accepted candidate right
+// after the round that produced it, instead of rolling it out again at the end.
+template <class M, int C, bool STORE>
 __global__ void __launch_bounds__(kBlock, 7) forward_coop_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
                                                                 int* next_list, int* next_count) {
   constexpr int kWarps = kBlock / 32;
   __shared__ double s_merit[kWarps][32][kNumAlphas];
+  __shared__ double s_obj[STORE ? kWarps : 1][STORE ? 32 : 1][kNumAlphas];  // plain cost per candidate (!= merit with constraints)
+  __shared__ int s_slot[STORE ? kWarps : 1][STORE ? 32 : 1][kNumAlphas];    // trial slot holding each candidate's trajectory
   __shared__ double s_cur[kWarps][32];
   __shared__ int s_p[kWarps][32], s_done[kWarps][32], s_next[kWarps][32];
   __shared__ CoopPlan s_plan[kWarps];
@@ -160,7 +179,9 @@ __global__ void __launch_bounds__(kBlock, 7) forward_coop_kernel(BatchView<M::NX
   const int p = owner ? list[first + lane] : 0;
   const double current_merit = owner ? v.merit[p] : 0.0;
   int accepted = -1;
-  double accepted_merit = 0.0;
+  double accepted_merit = 0.0, accepted_objective = 0.0;
+  bool committed = false;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
   s_p[w][lane] = p;
   s_cur[w][lane] = current_merit;
   s_done[w][lane] = owner ? 0 : 1;
@@ -181,10 +202,17 @@ __global__ void __launch_bounds__(kBlock, 7) forward_coop_kernel(BatchView<M::NX
         double alpha[C], merit[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) alpha[c] = alpha_of(j + c < kNumAlphas ? j + c : kNumAlphas - 1);
-        trial_rollout<M, C>(v, po, prm, alpha, merit);
+        double objective[C];
+        trial_rollout<M, C, STORE>(v, po, prm, alpha, merit, gid, n_threads, objective);
 #pragma unroll
         for (int c = 0; c < C; ++c)
-          if (j + c < kNumAlphas) s_merit[w][o][j + c] = merit[c];
+          if (j + c < kNumAlphas) {
+            s_merit[w][o][j + c] = merit[c];
+            if (STORE) {
+              s_obj[w][o][j + c] = objective[c];
+              s_slot[w][o][j + c] = gid + c * n_threads;
+            }
+          }
       }
       __syncwarp();
       if (owner && !s_done[w][lane]) {
@@ -192,6 +220,13 @@ __global__ void __launch_bounds__(kBlock, 7) forward_coop_kernel(BatchView<M::NX
         const bool fin = coop_owner_update(s_merit[w][lane], current_merit, s_plan[w].quota[lane], &nx, &accepted, &accepted_merit, C);
         s_next[w][lane] = nx;
         s_done[w][lane] = fin ? 1 : 0;
+        if (STORE && accepted >= 0) {
+          // take the stored trajectory now: the lane that produced it reuses its slot in the next round, and nothing
+          // reads this problem's nominal trajectory any more
+          accepted_objective = s_obj[w][lane][accepted];
+          accept_stored<M>(v, p, s_slot[w][lane][accepted]);
+          committed = true;
+        }
       }
       __syncwarp();
     }
@@ -200,7 +235,8 @@ __global__ void __launch_bounds__(kBlock, 7) forward_coop_kernel(BatchView<M::NX
   if (owner) {
     double prm[M::NP > 0 ? M::NP : 1];
     load_params<M>(v, p, prm);
-    again = finish_iteration<M>(v, p, prm, current_merit, accepted >= 0 ? accepted : kNumAlphas, accepted >= 0 ? accepted_merit : current_merit);
+    again = finish_iteration<M>(v, p, prm, current_merit, accepted >= 0 ? accepted : kNumAlphas, accepted >= 0 ? accepted_merit : current_merit,
+                                committed ? kSlotCommitted : -1, accepted_objective);
   }
   const unsigned vote = __ballot_sync(0xffffffffu, again);
   if (vote) {
@@ -231,7 +267,7 @@ __global__ void __launch_bounds__(kBlock, 7) trial_round_kernel(BatchView<M::NX,
     double alpha[C], merit[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) alpha[c] = alpha_of(base_j + c < kNumAlphas ? base_j + c : kNumAlphas - 1);
-    trial_rollout<M, C>(v, p, prm, alpha, merit);
+    trial_rollout<M, C, false>(v, p, prm, alpha, merit);
     int found = -1;
 #pragma unroll
     for (int c = 0; c < C; ++c)
@@ -411,6 +447,12 @@ struct BatchBase {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_staged = nullptr, ev_downloaded = nullptr;
   bool download_pending = false;
+  // trial trajectories of the line search (BatchView::trial_*), allocated at the first solve; 0 slots = recompute
+  double *d_trial_X = nullptr, *d_trial_U = nullptr;
+  int trial_slots = 0;
+  bool trial_store = true, trial_store_tried = false;
+  bool coop_store = false;  // mas_b200_batch_set_trial_store(b, 2): trial store in the cooperative kernel too
+  int ensure_trial_store(long long min_slots);
   int begin_download(double* X, double* U, double* cost, int* iterations, int* status);
   int wait_download();
   // strategy scratch (allocated on demand)
@@ -513,6 +555,9 @@ struct BatchImpl : BatchBase {
     view.penalty_increase = 5.0;
     view.constraint_tolerance = 1e-4;
     view.activation_tolerance = 1e-6;
+    view.trial_X = trial_store ? d_trial_X : nullptr;
+    view.trial_U = trial_store ? d_trial_U : nullptr;
+    view.trial_slots = trial_store ? trial_slots : 0;
   }
 
   void apply_al_params(const mas_b200_ilqr_params& prm) {
@@ -656,6 +701,15 @@ struct BatchImpl : BatchBase {
     const auto start = clock::now();
     int rc = prepare_constraint_state(prm);
     if (rc) return rc;
+    if (trial_store && prm.max_iterations > 0) {
+      query_occupancy();
+      // the widest launches that use the store: forward_kernel<L >= 4> with all lanes resident, or 16 lanes per problem
+      long long need = 0;
+      for (int k = 2; k <= 4; ++k) need = std::max(need, resident_lanes[k] + kBlock);
+      need = std::min(need, 16ll * div_up(batch, kBlock) * kBlock);
+      if (coop_store) need = std::max(need, 2ll * div_up(batch, kBlock) * kBlock);
+      ensure_trial_store(need);
+    }
     prof_begin(0);
     rc = launch_prologue(prm.max_iterations, &prm);
     prof_end();
@@ -707,12 +761,14 @@ struct BatchImpl : BatchBase {
       } else if (ls_mode == 3 || (ls_mode == 0 && tune_L == 0 && L == 1)) {
         // more problems than the device holds lanes: warp-cooperative search (32 problems per warp)
         // two step sizes per lane by default: +3% with several solves in flight, neutral alone (B200, 65,536 problems)
-        if (tune_C != 1)
-          forward_coop_kernel<M, 2><<<div_up(n_upper, kBlock), kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1],
-                                                                                       d_count + (cur ^ 1));
+        const int cgrid = div_up(n_upper, kBlock);
+        const bool cstore = coop_store && view.trial_X != nullptr && 2ll * cgrid * kBlock <= view.trial_slots;
+        if (tune_C != 1 && cstore)
+          forward_coop_kernel<M, 2, true><<<cgrid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1], d_count + (cur ^ 1));
+        else if (tune_C != 1)
+          forward_coop_kernel<M, 2, false><<<cgrid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1], d_count + (cur ^ 1));
         else
-          forward_coop_kernel<M, 1><<<div_up(n_upper, kBlock), kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1],
-                                                                                       d_count + (cur ^ 1));
+          forward_coop_kernel<M, 1, false><<<cgrid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1], d_count + (cur ^ 1));
         stats.kernel_launches++;
         last_L = 32;
         last_C = tune_C != 1 ? 2 : 1;

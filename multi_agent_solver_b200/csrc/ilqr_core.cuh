@@ -54,9 +54,32 @@ struct BatchView {
   double* lam_ineq;  // [T][NINEQ][ld]
   double* penalty;   // [ld]
   double penalty_increase, constraint_tolerance, activation_tolerance;
+  // Trial trajectories of the line search, one slot per (thread, chain) of the launch: [T][NX][trial_slots] for
+  // x_1..x_T and [T][NU][trial_slots].  The accepted candidate is then copied instead of being rolled out again
+  // (a second pass over T dependent RK4 steps).  Null / 0 = not available: the accepted step is recomputed.
+  double* trial_X;
+  double* trial_U;
+  int trial_slots;
 };
 
 constexpr int kMaxALHorizon = 128;  // horizon bound of constrained models (merit addends are kept per step)
+
+// Streaming (evict-first) store / load for data touched once: the trial store must not push the prefetched lines of
+// the nominal trajectory out of L1.
+MAS_HD void store_streaming(double* p, double v) {
+#if defined(__CUDA_ARCH__)
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+MAS_HD double load_streaming(const double* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
 
 // Pulls the line holding *p into L1 ahead of use.  Every kernel below walks the trajectory one time
 // step at a time with a long dependent fp64 chain per step; asking for step t+1's lines while step
@@ -809,10 +832,14 @@ MAS_HD int backward_thread(const BatchView<M::NX, M::NU>& v, int p) {
 // ---- forward pass (ilqr.hpp:206-217) for C step sizes at once, merit only ------------------------
 // The C rollouts share the loads of the nominal trajectory and gains and give the fp64 pipe C
 // independent dependency chains.  merit[c] = sum_t stage + terminal, accumulated in t order.
-template <class M, int C>
-MAS_HD void trial_rollout(const BatchView<M::NX, M::NU>& v, int p, const double* prm, const double* alpha, double* merit) {
+// STORE: chain c also writes its controls and states to trial slot slot0 + c * slot_stride (BatchView::trial_*).
+// objective (optional) receives the plain cost of each chain (== merit for models without constraints).
+template <class M, int C, bool STORE = false>
+MAS_HD void trial_rollout(const BatchView<M::NX, M::NU>& v, int p, const double* prm, const double* alpha, double* merit, int slot0 = -1,
+                          int slot_stride = 0, double* objective = nullptr) {
   constexpr int NX = M::NX, NU = M::NU;
   constexpr bool kAL = HasConstraints<M>::value;
+  const size_t n_slots = static_cast<size_t>(v.trial_slots);
   double xt[C][NX], cost[C];
   double al_terms[kAL ? C : 1][kAL ? 3 * kMaxALHorizon : 1];  // merit addends per step (local memory, constrained models only)
   const double al_rho = kAL ? v.penalty[p] : 0.0;
@@ -864,12 +891,50 @@ MAS_HD void trial_rollout(const BatchView<M::NX, M::NU>& v, int p, const double*
       rk4_step<M>(xt[c], u, prm, v.dt, xnext);
 #pragma unroll
       for (int i = 0; i < NX; ++i) xt[c][i] = xnext[i];
+      if (STORE) {
+        const size_t slot = static_cast<size_t>(slot0 + c * slot_stride);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) store_streaming(&v.trial_U[(static_cast<size_t>(t) * NU + i) * n_slots + slot], u[i]);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) store_streaming(&v.trial_X[(static_cast<size_t>(t) * NX + i) * n_slots + slot], xnext[i]);
+      }
     }
   }
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     cost[c] += M::terminal(xt[c], prm);
+    if (objective) objective[c] = cost[c];
     merit[c] = kAL ? al_finish_merit<M>(cost[c], al_terms[c], v.T) : cost[c];
+  }
+}
+
+// Accepted step taken from a trial slot: U[t] and X[t+1] of problem p are overwritten with the stored candidate.
+template <class M>
+MAS_HD void accept_stored(const BatchView<M::NX, M::NU>& v, int p, int slot) {
+  constexpr int NX = M::NX, NU = M::NU, kChunk = 8;
+  const size_t n_slots = static_cast<size_t>(v.trial_slots), s = static_cast<size_t>(slot);
+  // all loads of a chunk of steps are issued before its first store: the pointers may alias as far as the compiler
+  // knows, and a store waiting for its operand would hold back every load behind it (one DRAM latency per element)
+  for (int t0 = 0; t0 < v.T; t0 += kChunk) {
+    double bu[kChunk][NU], bx[kChunk][NX];
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k) {
+      const int t = t0 + k < v.T ? t0 + k : v.T - 1;
+#pragma unroll
+      for (int i = 0; i < NU; ++i) bu[k][i] = load_streaming(&v.trial_U[(static_cast<size_t>(t) * NU + i) * n_slots + s]);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) bx[k][i] = load_streaming(&v.trial_X[(static_cast<size_t>(t) * NX + i) * n_slots + s]);
+    }
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k) {
+      const int t = t0 + k;
+      if (t < v.T) {
+#pragma unroll
+        for (int i = 0; i < NU; ++i) v.U[soa_index<NU>(t, i, v.ld, p)] = bu[k][i];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) v.X[soa_index<NX>(t + 1, i, v.ld, p)] = bx[k][i];
+      }
+    }
   }
 }
 
@@ -944,19 +1009,22 @@ MAS_HD double alpha_of(int j) {
 // One lane's share of the line search: candidates j = lane, lane + L, ... in chunks of C, stopping
 // after the first chunk that holds an improving candidate (later candidates of this lane cannot win).
 // Returns the lane's first improving candidate (kNumAlphas if none) and its merit.
-template <class M, int L, int C>
+// slot0 >= 0: the lane's chains write their trajectories to trial slots slot0 + c * slot_stride (each pass overwrites
+// the previous one, which held no improving candidate); *best_slot / *best_objective describe the winner.
+template <class M, int L, int C, bool STORE = false>
 MAS_HD void lane_line_search(const BatchView<M::NX, M::NU>& v, int p, const double* prm, int lane, double current_merit, int* best_j,
-                             double* best_merit) {
+                             double* best_merit, int slot0 = -1, int slot_stride = 0, int* best_slot = nullptr, double* best_objective = nullptr) {
   *best_j = kNumAlphas;
   *best_merit = current_merit;
+  if (best_slot) *best_slot = -1;
   for (int base = lane; base < kNumAlphas; base += L * C) {
-    double alpha[C], merit[C];
+    double alpha[C], merit[C], objective[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const int j = base + c * L;
       alpha[c] = alpha_of(j < kNumAlphas ? j : kNumAlphas - 1);
     }
-    trial_rollout<M, C>(v, p, prm, alpha, merit);
+    trial_rollout<M, C, STORE>(v, p, prm, alpha, merit, slot0, slot_stride, objective);
     bool found = false;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -965,6 +1033,8 @@ MAS_HD void lane_line_search(const BatchView<M::NX, M::NU>& v, int p, const doub
         found = true;
         *best_j = j;
         *best_merit = merit[c];
+        if (best_slot) *best_slot = STORE ? slot0 + c * slot_stride : -1;
+        if (best_objective) *best_objective = objective[c];
       }
     }
     if (found) break;
@@ -1028,11 +1098,21 @@ MAS_HD bool coop_owner_update(const double* merits /* [kNumAlphas] of this probl
 
 // Accept / bookkeeping / stop test for one problem (ilqr.hpp:230-234,269-271).  Returns true when
 // the problem needs another iteration.
+// best_slot >= 0: the accepted candidate's trajectory is in that trial slot and its cost is best_objective;
+// kSlotCommitted: the caller has already copied it into X, U; otherwise (-1) it is rolled out again.
+constexpr int kSlotCommitted = -2;
 template <class M>
-MAS_HD bool finish_iteration(const BatchView<M::NX, M::NU>& v, int p, const double* prm, double current_merit, int best_j, double best_merit) {
+MAS_HD bool finish_iteration(const BatchView<M::NX, M::NU>& v, int p, const double* prm, double current_merit, int best_j, double best_merit,
+                             int best_slot = -1, double best_objective = 0.0) {
   if (best_j < kNumAlphas) {
-    const double c = commit_rollout<M>(v, p, prm, alpha_of(best_j));
-    v.cost[p] = c;  // objective(x,u) recomputed on the accepted trajectory: same arithmetic as the trial merit
+    double c;
+    if (best_slot >= 0 || best_slot == kSlotCommitted) {
+      if (best_slot >= 0) accept_stored<M>(v, p, best_slot);
+      c = best_objective;
+    } else {
+      c = commit_rollout<M>(v, p, prm, alpha_of(best_j));
+    }
+    v.cost[p] = c;  // objective(x,u) on the accepted trajectory: the trial's own sum, or the same arithmetic again
     v.merit[p] = best_merit;
   }
   const double improvement = current_merit - best_merit;

@@ -74,7 +74,8 @@ class HostEmulation:
     def __init__(self):
         self.lib = ctypes.CDLL(_build_emulation())
 
-    def solve(self, model, x0, U, max_iterations, tolerance, L=1, C=2, mask=None, per_problem_params=None, penalty=10.0, repeats=1):
+    def solve(self, model, x0, U, max_iterations, tolerance, L=1, C=2, mask=None, per_problem_params=None, penalty=10.0, repeats=1,
+              trial_store=True):
         """repeats > 1: the same solver state (multipliers, penalty) and warm start solving again; adds cost_history /
         iterations_history [repeats, B]."""
         n, m, T, dt, emask, hb, lo, hi, prm = MODEL_TABLE[model]
@@ -97,6 +98,7 @@ class HostEmulation:
         if per_problem_params is not None:
             ppa = np.ascontiguousarray(per_problem_params, dtype=np.float64)
             pp = ppa.ctypes.data_as(P)
+        self.lib.emu_set_trial_store(int(trial_store))
         hc = np.zeros((repeats, B))
         hi_ = np.zeros((repeats, B), np.int32)
         self.lib.emu_set_al_options(ctypes.c_double(penalty), ctypes.c_double(5.0), ctypes.c_double(1e-4), ctypes.c_double(1e-6), int(repeats),

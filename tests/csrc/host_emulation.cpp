@@ -22,6 +22,7 @@ namespace {
 struct ALOptions {
   double penalty = 10.0, penalty_increase = 5.0, constraint_tolerance = 1e-4, activation_tolerance = 1e-6;
   int repeats = 1;
+  bool trial_store = true;
   double* hist_cost = nullptr;
   int* hist_iters = nullptr;
 };
@@ -77,6 +78,12 @@ int emulate(int batch, int T, double dt, unsigned mask, int has_bounds, const do
   v.constraint_tolerance = g_al.constraint_tolerance;
   v.activation_tolerance = g_al.activation_tolerance;
   if (HasConstraints<M>::value && T > kMaxALHorizon) return 2;
+  // trial store (BatchView::trial_*): 64 slots, reused by every emulated warp / lane group in turn
+  std::vector<double> strial_X(static_cast<size_t>(NX) * T * 64), strial_U(static_cast<size_t>(NU) * T * 64);
+  v.trial_X = g_al.trial_store ? strial_X.data() : nullptr;
+  v.trial_U = g_al.trial_store ? strial_U.data() : nullptr;
+  v.trial_slots = g_al.trial_store ? 64 : 0;
+  const bool store = g_al.trial_store;
 
  for (int rep = 0; rep < g_al.repeats; ++rep) {
   std::vector<int> list(batch), next;
@@ -134,8 +141,8 @@ int emulate(int batch, int T, double dt, unsigned mask, int has_bounds, const do
             if (C == 2) {
               double alpha[2] = {alpha_of(j), alpha_of(j + 1 < kNumAlphas ? j + 1 : kNumAlphas - 1)}, m2[2];
               trial_rollout<M, 2>(v, po, prm, alpha, m2);
-              merits[o][j] = m2[0];
-              if (j + 1 < kNumAlphas) merits[o][j + 1] = m2[1];
+              for (int c = 0; c < 2; ++c)
+                if (j + c < kNumAlphas) merits[o][j + c] = m2[c];
             } else {
               const double alpha = alpha_of(j);
               trial_rollout<M, 1>(v, po, prm, &alpha, &merits[o][j]);
@@ -158,24 +165,30 @@ int emulate(int batch, int T, double dt, unsigned mask, int has_bounds, const do
       double prm[M::NP > 0 ? M::NP : 1];
       load_params<M>(v, p, prm);
       const double current_merit = v.merit[p];
-      int best_j = kNumAlphas;
-      double best_merit = 0.0;
+      int best_j = kNumAlphas, best_slot = -1;
+      double best_merit = 0.0, best_obj = 0.0;
       for (int lane = 0; lane < L; ++lane) {
-        int bj;
-        double bm;
+        int bj, bs;
+        double bm, bo = 0.0;
+        bs = -1;  // forward_kernel keeps trial trajectories for L >= 4 only: lane l -> slot l
         if (L == 1 && C == 2) lane_line_search<M, 1, 2>(v, p, prm, lane, current_merit, &bj, &bm);
         else if (L == 1) lane_line_search<M, 1, 1>(v, p, prm, lane, current_merit, &bj, &bm);
         else if (L == 2) lane_line_search<M, 2, 1>(v, p, prm, lane, current_merit, &bj, &bm);
+        else if (L == 4 && store) lane_line_search<M, 4, 1, true>(v, p, prm, lane, current_merit, &bj, &bm, lane, 16, &bs, &bo);
         else if (L == 4) lane_line_search<M, 4, 1>(v, p, prm, lane, current_merit, &bj, &bm);
+        else if (L == 8 && store) lane_line_search<M, 8, 1, true>(v, p, prm, lane, current_merit, &bj, &bm, lane, 16, &bs, &bo);
         else if (L == 8) lane_line_search<M, 8, 1>(v, p, prm, lane, current_merit, &bj, &bm);
+        else if (store) lane_line_search<M, 16, 1, true>(v, p, prm, lane, current_merit, &bj, &bm, lane, 16, &bs, &bo);
         else lane_line_search<M, 16, 1>(v, p, prm, lane, current_merit, &bj, &bm);
         if (bj < best_j) {
           best_j = bj;
           best_merit = bm;
+          best_slot = bs;
+          best_obj = bo;
         }
       }
       if (best_j == kNumAlphas) best_merit = current_merit;
-      if (finish_iteration<M>(v, p, prm, current_merit, best_j, best_merit)) next.push_back(p);
+      if (finish_iteration<M>(v, p, prm, current_merit, best_j, best_merit, best_slot, best_obj)) next.push_back(p);
     }
     list.swap(next);
   }
@@ -213,6 +226,8 @@ extern "C" int emu_ilqr_solve_batch(int model, int batch, int T, double dt, unsi
 }
 
 // Settings for the next emu_ilqr_solve_batch calls on constrained models (pass repeats = 1 and nulls to reset).
+extern "C" void emu_set_trial_store(int enable) { g_al.trial_store = enable != 0; }
+
 extern "C" void emu_set_al_options(double penalty, double penalty_increase, double constraint_tolerance, double activation_tolerance, int repeats,
                                    double* hist_cost, int* hist_iters) {
   g_al.penalty = penalty;

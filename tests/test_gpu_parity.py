@@ -292,3 +292,23 @@ def test_asynchronous_download_survives_the_next_solve(mas, ctx, oracle):
         ref = oracle.ilqr_solve_batch(0, x0, max_iterations=10, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
         assert_parity(got, ref)
         assert is_bit_exact(got, ref)
+
+
+@pytest.mark.parametrize("mode,lanes", [(0, 0), (1, 4), (1, 16), (3, 0)])
+def test_trial_store_on_and_off_agree(mas, ctx, oracle, mode, lanes):
+    """Accepted steps copied from the trial store vs rolled out again: identical results, and both equal the oracle."""
+    x0 = random_x0(0, 500, seed=610)
+    ref = oracle.ilqr_solve_batch(0, x0, max_iterations=10, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    outs = []
+    for store in (1, 0, 2):
+        b = mas.Batch(ctx, mas.example_desc(0), 500)
+        b.set_trial_store(store)
+        b.set_line_search_mode(mode)
+        b.set_tuning(lanes, 0)
+        b.set_initial_states(x0)
+        b.set_controls(None)
+        b.solve(mas.IlqrParams.make(10, 1e-5))
+        outs.append(b.get_solution())
+        b.close()
+    assert is_bit_exact(outs[0], ref) and is_bit_exact(outs[1], ref) and is_bit_exact(outs[2], ref)
+    assert_parity(outs[0], ref)

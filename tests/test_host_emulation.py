@@ -143,3 +143,15 @@ def test_multipliers_and_penalty_persist_across_solves(emu, oracle, penalty):
         assert np.array_equal(got["U"][b], ref["U"]) and np.array_equal(got["X"][b], ref["X"][-1])
         changed += int(ref["cost"][1] != ref["cost"][0])
     assert changed > 0  # later solves do move: the persistent state is really in play
+
+
+@pytest.mark.parametrize("model,L,C", [(0, 4, 1), (0, 8, 1), (0, 16, 1), (5, 4, 1), (5, 16, 1), (1, 8, 1), (4, 16, 1)])
+def test_stored_trials_equal_recomputed_steps(emu, model, L, C):
+    """The accepted step copied from the trial store is the rollout the commit pass would repeat: same bits."""
+    x0 = random_x0(model, 40, seed=90 + model)
+    T, m = MODEL_TABLE[model][2], MODEL_TABLE[model][1]
+    U0 = np.zeros((40, T, m))
+    a = emu.solve(model, x0, U0, 6, 1e-5, L=L, C=C, trial_store=True)
+    b = emu.solve(model, x0, U0, 6, 1e-5, L=L, C=C, trial_store=False)
+    for k in ("X", "U", "cost", "iterations", "status", "alpha_trials"):
+        assert np.array_equal(a[k], b[k]), k
