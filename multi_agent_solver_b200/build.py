@@ -24,7 +24,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
     "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
-]
+] + os.environ.get("MAS_B200_EXTRA_NVCC_FLAGS", "").split()  # tuning experiments, e.g. -DMAS_MIN_CTAS=9
 
 
 def _newest_input() -> float:

@@ -43,6 +43,10 @@ void set_last_error(const std::string& msg);
 // register file of an SM (64K) divides into more resident CTAs than with 4-warp ones (e.g. 7 x 64
 // instead of 3 x 128 threads at 134 registers), which turns the 65,536-problem batch into one wave.
 constexpr int kBlock = 64;
+// minimum resident CTAs per SM asked of the compiler for the iLQR kernels (7 -> 128 registers, in practice 8 CTAs)
+#ifndef MAS_MIN_CTAS
+#define MAS_MIN_CTAS 7
+#endif
 
 struct Context {
   int device = 0;
@@ -84,7 +88,7 @@ __global__ void __launch_bounds__(kBlock) prologue_kernel(BatchView<M::NX, M::NU
 }
 
 template <class M, int MASK_CT>
-__global__ void __launch_bounds__(kBlock, 7) backward_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
+__global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) backward_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
                                                        int* next_count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) *next_count = 0;
@@ -97,7 +101,7 @@ __global__ void __launch_bounds__(kBlock, 7) backward_kernel(BatchView<M::NX, M:
 // L lanes per problem (a power of two <= 16, aligned inside the warp); lane l rolls out step sizes
 // l, l+L, ...; the group picks the first improving candidate with shuffles; lane 0 commits.
 template <class M, int L, int C>
-__global__ void __launch_bounds__(kBlock, 7) forward_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
+__global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) forward_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
                                                       int* next_list, int* next_count) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = gid / L;
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(kBlock, 7) forward_kernel(BatchView<M::NX, M::
 // STORE: lanes keep their trial trajectories (BatchView::trial_*) and an owner copies its accepted candidate right
 // after the round that produced it, instead of rolling it out again at the end.
 template <class M, int C, bool STORE>
-__global__ void __launch_bounds__(kBlock, 7) forward_coop_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
+__global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) forward_coop_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
                                                                 int* next_list, int* next_count) {
   constexpr int kWarps = kBlock / 32;
   __shared__ double s_merit[kWarps][32][kNumAlphas];
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(kBlock, 7) forward_coop_kernel(BatchView<M::NX
 // of every round is full, and a problem stops costing rollouts at its first improving step size, as
 // in the reference's sequential loop (ilqr.hpp:206-228).  counts[r] holds the size of round r's list.
 template <class M, int C>
-__global__ void __launch_bounds__(kBlock, 7) trial_round_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
+__global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) trial_round_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
                                                                int* next_list, int* next_count, int base_j, int* accept_idx,
                                                                double* accept_merit) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(kBlock, 7) trial_round_kernel(BatchView<M::NX,
 
 // After the rounds: commit the accepted step (if any), bookkeeping, stop test, next active list.
 template <class M>
-__global__ void __launch_bounds__(kBlock, 7) finish_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
+__global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) finish_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
                                                           int* next_list, int* next_count, int* accept_idx, const double* __restrict__ accept_merit) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < *count;

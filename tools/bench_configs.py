@@ -106,6 +106,32 @@ def main():
     out.append({"config": 5, "what": "same, 296 scenarios with the track radius jittered in [15, 25]", "gpu_ms": t_gpu * 1e3,
                 "gpu_scenarios_per_s": 296 / t_gpu, "iterations_mean": float(its.mean()), "iterations_max": int(its.max())})
 
+    # the pendulum swing-up (all-FD, time-varying cost, up to 1000 iterations) and the rocket
+    # (analytic, mass clamp, 25 iterations) at batch scale, initial states jittered around the examples' own
+    rng = np.random.default_rng(11)
+    for model, name, B, x0 in (
+            (3, "pendulum_swing_up", 4096, np.stack([np.pi - 0.05 + rng.uniform(-0.1, 0.1, 4096), rng.uniform(-0.1, 0.1, 4096)], -1)),
+            (4, "rocket_max_altitude", 16384, np.stack([rng.uniform(0, 1, 16384), rng.uniform(-1, 1, 16384), 50.0 + rng.uniform(-2, 2, 16384)], -1))):
+        max_it, tol = {3: (1000, 1e-4), 4: (25, 1e-6)}[model]
+        dm = mas.example_desc(model)
+        pm_ = mas.IlqrParams.make(max_it, tol)
+        bb = mas.Batch(ctx, dm, B)
+
+        def solve_b():
+            bb.set_initial_states(x0)
+            bb.set_controls(mas.example_controls(model, dm.horizon_steps)[None].repeat(B, 0))
+            bb.solve(pm_)
+            return bb.get_solution()
+
+        t_gpu = best_of(solve_b, 2)
+        rb = solve_b()
+        ns = 128 if model == 3 else 2048
+        t_cpu = best_of(lambda: o.ilqr_solve_batch(model, x0[:ns], max_iterations=max_it, tolerance=tol, threads=threads), 1)
+        out.append({"config": name, "what": f"{name} x {B} problems, iLQR {max_it} / {tol:g}", "gpu_ms": t_gpu * 1e3, "gpu_solves_per_s": B / t_gpu,
+                    "cpu_oracle_solves_per_s": ns / t_cpu, "cpu_threads": threads, "cpu_sample": ns,
+                    "iterations_mean": float(rb["iterations"].mean()), "iterations_max": int(rb["iterations"].max())})
+        bb.close()
+
     for rec in out:
         print(json.dumps(rec), flush=True)
 
