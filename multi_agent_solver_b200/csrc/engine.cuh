@@ -19,6 +19,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -785,9 +786,15 @@ struct BatchImpl : BatchBase {
         MAS_CUDA_CHECK(cudaMemcpyAsync(d_count_hist + it, d_count + cur, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
       // the new active count goes to the host as a store into mapped pinned memory, not as a 4-byte D2H copy: the
       // copy engine is a FIFO shared with other contexts' result downloads, and a count queued behind a 170 MB
-      // transfer stalls this loop for milliseconds (measured: 2x on the solve throughput of four contexts)
-      publish_count_kernel<<<1, 1, 0, ctx->stream>>>(d_count + (cur ^ 1), h_counts_dev + (it & 1));
-      stats.kernel_launches++;
+      // transfer stalls this loop for milliseconds (measured: -23 % solve throughput of four contexts next to one D2H stream)
+      // (MAS_B200_COUNT_VIA_MEMCPY=1 restores the copy, for tools/copy_interference2.py)
+      static const bool count_via_memcpy = std::getenv("MAS_B200_COUNT_VIA_MEMCPY") != nullptr;
+      if (count_via_memcpy) {
+        MAS_CUDA_CHECK(cudaMemcpyAsync(h_counts + (it & 1), d_count + (cur ^ 1), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      } else {
+        publish_count_kernel<<<1, 1, 0, ctx->stream>>>(d_count + (cur ^ 1), h_counts_dev + (it & 1));
+        stats.kernel_launches++;
+      }
       MAS_CUDA_CHECK(cudaEventRecord(ev[it & 1], ctx->stream));
       if (it >= 1) {
         // active count after iteration it-1: an upper bound for iteration it+1 (the list only shrinks)
