@@ -372,7 +372,8 @@ def run_b200(args):
                        "single_solve_ms": single_ms,
                        "l2": "working set 670 MB per solve (X,U,K,k) > 126 MB L2, no flush needed",
                        "forward_lanes": st["forward_lanes"], "forward_chains": st["forward_chains"],
-                       "mean_iterations": iters_total / per_rank},
+                       "mean_iterations": iters_total / per_rank,
+                       "problem_iterations_per_s": value * iters_total / per_rank},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                     "wall_ms_per_step": e2e_wall * 1e3},
             "gpu_launches": int(launches),
