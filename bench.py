@@ -245,7 +245,7 @@ def run_b200(args):
                 ln = use_lanes[i]
                 go.wait()
                 if i:
-                    time.sleep(i * stagger_ms * 1e-3 / n)
+                    time.sleep(i * stagger_ms * args.stagger * 1e-3 / n)
                 e0[i].record(ln.stream)
                 for _ in range(counts[i]):
                     fn(ln)
@@ -399,6 +399,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--depth", type=int, default=0, help="independent solves in flight per GPU (1 = one at a time; 0 = by step count: "
                     "3 below 8 steps, 4 below 40, else 6 -- fewer pipelines fill and drain faster when K is small)")
+    ap.add_argument("--stagger", type=float, default=1.0, help="start offset between pipelines, in units of single_solve_ms / depth")
     ap.add_argument("--cpu-sample", type=int, default=8192, help="problems per CPU-baseline pass")
     ap.add_argument("--resident-only", action="store_true", help="run only warm-up + timed resident steps (for ncu)")
     ap.add_argument("--ls-mode", type=int, default=0, help="line search scheduling: 0 auto, 1 concurrent lanes, 2 compacted rounds")
