@@ -45,6 +45,8 @@ void set_last_error(const std::string& msg);
 // instead of 3 x 128 threads at 134 registers), which turns the 65,536-problem batch into one wave.
 constexpr int kBlock = 64;
 // minimum resident CTAs per SM asked of the compiler for the iLQR kernels (7 -> 128 registers, in practice 8 CTAs)
+// launches of at most this many threads (under a quarter of the device) stage their operands in shared memory
+constexpr int kStageMaxThreads = 16384;
 #ifndef MAS_MIN_CTAS
 #define MAS_MIN_CTAS 7
 #endif
@@ -91,11 +93,13 @@ __global__ void __launch_bounds__(kBlock) prologue_kernel(BatchView<M::NX, M::NU
 template <class M, int MASK_CT>
 __global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) backward_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
                                                        int* next_count) {
+  extern __shared__ double s_stage[];  // dynamic: 2 * (NX + NU) * kStageStride doubles for small (latency-bound) launches
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) *next_count = 0;
   if (i >= *count) return;
   const int p = list[i];
-  const int r = backward_thread<M, MASK_CT>(v, p);
+  double* stage = static_cast<int>(gridDim.x * blockDim.x) <= kStageMaxThreads ? s_stage + threadIdx.x : nullptr;
+  const int r = backward_thread<M, MASK_CT>(v, p, stage);
   if (r) v.reg_retries[p] += r;
 }
 
@@ -104,6 +108,13 @@ __global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) backward_kernel(BatchVie
 template <class M, int L, int C>
 __global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) forward_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
                                                       int* next_list, int* next_count) {
+  static_assert(kBlock == kStageStride, "the staging layout assumes kBlock threads per CTA");
+  // Wide mappings (small active sets, latency-bound launches) stage the next step's operands in shared memory with
+  // cp.async: -19 % on those launches.  Saturating launches do not: there the extra LDGSTS + LDS traffic through the
+  // memory-instruction queue costs more than the exposed load latency that other warps cover anyway (measured).
+  constexpr bool kStage = L >= 4;
+  extern __shared__ double s_stage[];  // dynamic: 2 * NV * kStageStride doubles when the launch stages, nothing otherwise
+  double* stage = (kStage && static_cast<int>(gridDim.x * blockDim.x) <= kStageMaxThreads) ? s_stage + threadIdx.x : nullptr;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = gid / L;
   const int lane = gid % L;
@@ -123,9 +134,9 @@ __global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) forward_kernel(BatchView
     load_params<M>(v, p, prm);
     current_merit = v.merit[p];
     if (L >= 4 && store)
-      lane_line_search<M, L, C, (L >= 4)>(v, p, prm, lane, current_merit, &best_j, &best_merit, gid, n_threads, &best_slot, &best_objective);
+      lane_line_search<M, L, C, (L >= 4)>(v, p, prm, lane, current_merit, &best_j, &best_merit, gid, n_threads, &best_slot, &best_objective, stage);
     else
-      lane_line_search<M, L, C, false>(v, p, prm, lane, current_merit, &best_j, &best_merit);
+      lane_line_search<M, L, C, false>(v, p, prm, lane, current_merit, &best_j, &best_merit, -1, 0, nullptr, nullptr, stage);
   }
   if (L > 1) {
     // first improving candidate of the group = minimum index; its merit travels with it.
@@ -617,12 +628,13 @@ struct BatchImpl : BatchBase {
   void launch_backward(int n_upper, int cur) {
     const int grid = div_up(n_upper, kBlock);
     const unsigned mask = desc.deriv_mask;
+    const size_t smem = static_cast<long long>(grid) * kBlock <= kStageMaxThreads ? 2 * (M::NX + M::NU) * kStageStride * sizeof(double) : 0;
     if (mask == M::EXAMPLE_MASK)
-      backward_kernel<M, static_cast<int>(M::EXAMPLE_MASK)><<<grid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
+      backward_kernel<M, static_cast<int>(M::EXAMPLE_MASK)><<<grid, kBlock, smem, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
     else if (mask == 0u)
-      backward_kernel<M, 0><<<grid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
+      backward_kernel<M, 0><<<grid, kBlock, smem, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
     else
-      backward_kernel<M, -1><<<grid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
+      backward_kernel<M, -1><<<grid, kBlock, smem, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
     stats.kernel_launches++;
   }
 
@@ -630,7 +642,9 @@ struct BatchImpl : BatchBase {
   void launch_forward_lc(int n_upper, int cur) {
     const long long threads = static_cast<long long>(n_upper) * L;
     const int grid = static_cast<int>((threads + kBlock - 1) / kBlock);
-    forward_kernel<M, L, C><<<grid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1], d_count + (cur ^ 1));
+    const bool stage = L >= 4 && static_cast<long long>(grid) * kBlock <= kStageMaxThreads;
+    const size_t smem = stage ? 2 * StepOperands<M::NX, M::NU>::NV * kStageStride * sizeof(double) : 0;
+    forward_kernel<M, L, C><<<grid, kBlock, smem, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1], d_count + (cur ^ 1));
     stats.kernel_launches++;
   }
 
@@ -673,6 +687,7 @@ struct BatchImpl : BatchBase {
   }
   void query_occupancy() {
     if (resident_lanes[0]) return;
+
     resident_lanes[0] = query_resident<1, 2>();
     resident_lanes[1] = query_resident<2, 1>();
     resident_lanes[2] = query_resident<4, 1>();

@@ -97,6 +97,65 @@ MAS_HD size_t soa_index(int t, int d, int ld, int p) {
   return (static_cast<size_t>(t) * DIM + d) * static_cast<size_t>(ld) + p;
 }
 
+// ---- asynchronous staging of the next time step's operands in shared memory -----------------------------------
+// `prefetch.global.L1` does not make the demand loads of the next step hit (ncu: 0.003 % L1 hits, 14 % of the line
+// search's stall samples on the long scoreboard), so the kernels that walk a trajectory copy step t+1's operands
+// into a per-thread shared-memory slot with cp.async while step t computes, and read them back with LDS.
+// Layout: stage[(buffer * NV + k) * kStageStride + thread]; a thread only ever touches its own column, so no
+// barrier is needed -- cp.async.wait_group orders the thread's own copies.  stage == nullptr (host build, kernels
+// without a staging area): plain loads + L1 prefetch.
+constexpr int kStageStride = 64;  // threads per CTA of the kernels that stage (engine.cuh: kBlock)
+MAS_HD void stage_copy8(double* smem_dst, const double* gmem_src) {
+#if defined(__CUDA_ARCH__)
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem_src));
+#else
+  *smem_dst = *gmem_src;
+#endif
+}
+MAS_HD void stage_commit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;");
+#endif
+}
+MAS_HD void stage_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+// Operands of one step of a trial / commit rollout: x_t (or x_{t+1} for the commit pass), u_t, k_t, K_t.
+template <int NX, int NU>
+struct StepOperands {
+  static constexpr int NV = NX + 2 * NU + NU * NX;
+};
+template <int NX, int NU>
+MAS_HD void stage_issue_step(const BatchView<NX, NU>& v, int p, int t, int t_state, double* stage, int buf) {
+  constexpr int NV = StepOperands<NX, NU>::NV;
+  double* dst = stage + static_cast<size_t>(buf) * NV * kStageStride;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) stage_copy8(dst + i * kStageStride, &v.X[soa_index<NX>(t_state, i, v.ld, p)]);
+#pragma unroll
+  for (int i = 0; i < NU; ++i) stage_copy8(dst + (NX + i) * kStageStride, &v.U[soa_index<NU>(t, i, v.ld, p)]);
+#pragma unroll
+  for (int i = 0; i < NU; ++i) stage_copy8(dst + (NX + NU + i) * kStageStride, &v.kff[soa_index<NU>(t, i, v.ld, p)]);
+#pragma unroll
+  for (int i = 0; i < NU * NX; ++i) stage_copy8(dst + (NX + 2 * NU + i) * kStageStride, &v.K[soa_index<NU * NX>(t, i, v.ld, p)]);
+  stage_commit();
+}
+template <int NX, int NU>
+MAS_HD void stage_read_step(const double* stage, int buf, double* xn, double* un, double* kv, double* Km) {
+  constexpr int NV = StepOperands<NX, NU>::NV;
+  const double* src = stage + static_cast<size_t>(buf) * NV * kStageStride;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) xn[i] = src[i * kStageStride];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) un[i] = src[(NX + i) * kStageStride];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) kv[i] = src[(NX + NU + i) * kStageStride];
+#pragma unroll
+  for (int i = 0; i < NU * NX; ++i) Km[i] = src[(NX + 2 * NU + i) * kStageStride];
+}
+
 template <class M, int NX, int NU>
 MAS_HD void load_params(const BatchView<NX, NU>& v, int p, double* prm) {
 #pragma unroll
@@ -704,8 +763,9 @@ MAS_HD void al_update(const BatchView<M::NX, M::NU>& v, int p, const double* prm
 // ---- backward pass for one problem (ilqr.hpp:92-193) --------------------------------------------
 // MASK_CT >= 0 fixes the derivative mode at compile time (dead branches vanish); -1 reads it from
 // the view.  Writes K, k for every t.  Returns the number of regularisation retries.
+// stage != nullptr: x_{t-1}, u_{t-1} are copied to shared memory with cp.async while step t computes.
 template <class M, int MASK_CT>
-MAS_HD int backward_thread(const BatchView<M::NX, M::NU>& v, int p) {
+MAS_HD int backward_thread(const BatchView<M::NX, M::NU>& v, int p, double* stage = nullptr) {
   constexpr int NX = M::NX, NU = M::NU;
   const unsigned mask = (MASK_CT >= 0) ? static_cast<unsigned>(MASK_CT) : v.deriv_mask;
   double prm[M::NP > 0 ? M::NP : 1];
@@ -725,16 +785,36 @@ MAS_HD int backward_thread(const BatchView<M::NX, M::NU>& v, int p) {
   else fd_hessian<NX>(x, TerminalInX<M>{prm}, v_xx);
   symmetrize_aliased<NX>(v_xx);
 
+  constexpr int NVB = NX + NU;  // staged operands per step
+  auto issue_xu = [&](int t, int buf) {
+    double* dst = stage + static_cast<size_t>(buf) * NVB * kStageStride;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) stage_copy8(dst + i * kStageStride, &v.X[soa_index<NX>(t, i, v.ld, p)]);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) stage_copy8(dst + (NX + i) * kStageStride, &v.U[soa_index<NU>(t, i, v.ld, p)]);
+    stage_commit();
+  };
+  if (stage) issue_xu(T - 1, (T - 1) & 1);
   for (int t = T - 1; t >= 0; --t) {
+    if (stage) {
+      stage_wait();
+      const double* src = stage + static_cast<size_t>(t & 1) * NVB * kStageStride;
 #pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] = v.X[soa_index<NX>(t, i, v.ld, p)];
+      for (int i = 0; i < NX; ++i) x[i] = src[i * kStageStride];
 #pragma unroll
-    for (int i = 0; i < NU; ++i) u[i] = v.U[soa_index<NU>(t, i, v.ld, p)];
-    if (t > 0) {
+      for (int i = 0; i < NU; ++i) u[i] = src[(NX + i) * kStageStride];
+      if (t > 0) issue_xu(t - 1, (t - 1) & 1);
+    } else {
 #pragma unroll
-      for (int i = 0; i < NX; ++i) prefetch_l1(&v.X[soa_index<NX>(t - 1, i, v.ld, p)]);
+      for (int i = 0; i < NX; ++i) x[i] = v.X[soa_index<NX>(t, i, v.ld, p)];
 #pragma unroll
-      for (int i = 0; i < NU; ++i) prefetch_l1(&v.U[soa_index<NU>(t - 1, i, v.ld, p)]);
+      for (int i = 0; i < NU; ++i) u[i] = v.U[soa_index<NU>(t, i, v.ld, p)];
+      if (t > 0) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) prefetch_l1(&v.X[soa_index<NX>(t - 1, i, v.ld, p)]);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) prefetch_l1(&v.U[soa_index<NU>(t - 1, i, v.ld, p)]);
+      }
     }
 
     // :106-113
@@ -836,10 +916,11 @@ MAS_HD int backward_thread(const BatchView<M::NX, M::NU>& v, int p) {
 // objective (optional) receives the plain cost of each chain (== merit for models without constraints).
 template <class M, int C, bool STORE = false>
 MAS_HD void trial_rollout(const BatchView<M::NX, M::NU>& v, int p, const double* prm, const double* alpha, double* merit, int slot0 = -1,
-                          int slot_stride = 0, double* objective = nullptr) {
+                          int slot_stride = 0, double* objective = nullptr, double* stage = nullptr) {
   constexpr int NX = M::NX, NU = M::NU;
   constexpr bool kAL = HasConstraints<M>::value;
   const size_t n_slots = static_cast<size_t>(v.trial_slots);
+  if (stage) stage_issue_step<NX, NU>(v, p, 0, 0, stage, 0);
   double xt[C][NX], cost[C];
   double al_terms[kAL ? C : 1][kAL ? 3 * kMaxALHorizon : 1];  // merit addends per step (local memory, constrained models only)
   const double al_rho = kAL ? v.penalty[p] : 0.0;
@@ -851,23 +932,29 @@ MAS_HD void trial_rollout(const BatchView<M::NX, M::NU>& v, int p, const double*
   }
   for (int t = 0; t < v.T; ++t) {
     double xn[NX], un[NU], kv[NU], Km[NU * NX];
+    if (stage) {
+      stage_wait();
+      stage_read_step<NX, NU>(stage, t & 1, xn, un, kv, Km);
+      if (t + 1 < v.T) stage_issue_step<NX, NU>(v, p, t + 1, t + 1, stage, (t + 1) & 1);
+    } else {
 #pragma unroll
-    for (int i = 0; i < NX; ++i) xn[i] = v.X[soa_index<NX>(t, i, v.ld, p)];
+      for (int i = 0; i < NX; ++i) xn[i] = v.X[soa_index<NX>(t, i, v.ld, p)];
 #pragma unroll
-    for (int i = 0; i < NU; ++i) un[i] = v.U[soa_index<NU>(t, i, v.ld, p)];
+      for (int i = 0; i < NU; ++i) un[i] = v.U[soa_index<NU>(t, i, v.ld, p)];
 #pragma unroll
-    for (int i = 0; i < NU; ++i) kv[i] = v.kff[soa_index<NU>(t, i, v.ld, p)];
+      for (int i = 0; i < NU; ++i) kv[i] = v.kff[soa_index<NU>(t, i, v.ld, p)];
 #pragma unroll
-    for (int i = 0; i < NU * NX; ++i) Km[i] = v.K[soa_index<NU * NX>(t, i, v.ld, p)];
-    if (t + 1 < v.T) {
+      for (int i = 0; i < NU * NX; ++i) Km[i] = v.K[soa_index<NU * NX>(t, i, v.ld, p)];
+      if (t + 1 < v.T) {
 #pragma unroll
-      for (int i = 0; i < NX; ++i) prefetch_l1(&v.X[soa_index<NX>(t + 1, i, v.ld, p)]);
+        for (int i = 0; i < NX; ++i) prefetch_l1(&v.X[soa_index<NX>(t + 1, i, v.ld, p)]);
 #pragma unroll
-      for (int i = 0; i < NU; ++i) prefetch_l1(&v.U[soa_index<NU>(t + 1, i, v.ld, p)]);
+        for (int i = 0; i < NU; ++i) prefetch_l1(&v.U[soa_index<NU>(t + 1, i, v.ld, p)]);
 #pragma unroll
-      for (int i = 0; i < NU; ++i) prefetch_l1(&v.kff[soa_index<NU>(t + 1, i, v.ld, p)]);
+        for (int i = 0; i < NU; ++i) prefetch_l1(&v.kff[soa_index<NU>(t + 1, i, v.ld, p)]);
 #pragma unroll
-      for (int i = 0; i < NU * NX; ++i) prefetch_l1(&v.K[soa_index<NU * NX>(t + 1, i, v.ld, p)]);
+        for (int i = 0; i < NU * NX; ++i) prefetch_l1(&v.K[soa_index<NU * NX>(t + 1, i, v.ld, p)]);
+      }
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -1013,7 +1100,8 @@ MAS_HD double alpha_of(int j) {
 // the previous one, which held no improving candidate); *best_slot / *best_objective describe the winner.
 template <class M, int L, int C, bool STORE = false>
 MAS_HD void lane_line_search(const BatchView<M::NX, M::NU>& v, int p, const double* prm, int lane, double current_merit, int* best_j,
-                             double* best_merit, int slot0 = -1, int slot_stride = 0, int* best_slot = nullptr, double* best_objective = nullptr) {
+                             double* best_merit, int slot0 = -1, int slot_stride = 0, int* best_slot = nullptr, double* best_objective = nullptr,
+                             double* stage = nullptr) {
   *best_j = kNumAlphas;
   *best_merit = current_merit;
   if (best_slot) *best_slot = -1;
@@ -1024,7 +1112,7 @@ MAS_HD void lane_line_search(const BatchView<M::NX, M::NU>& v, int p, const doub
       const int j = base + c * L;
       alpha[c] = alpha_of(j < kNumAlphas ? j : kNumAlphas - 1);
     }
-    trial_rollout<M, C, STORE>(v, p, prm, alpha, merit, slot0, slot_stride, objective);
+    trial_rollout<M, C, STORE>(v, p, prm, alpha, merit, slot0, slot_stride, objective, stage);
     bool found = false;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
