@@ -315,6 +315,21 @@ def run_b200(args):
     h2d = per_rank * NX * 8
     d2h = per_rank * (((T + 1) * NX + T * NU + 1) * 8 + 2 * 4)
 
+    # the same loop for a caller that only wants the controls (best_controls, best_cost, iterations, status; X = NULL):
+    # a third of the download, reported next to the headline e2e because at N > 1 the host's D2H bandwidth sets e2e
+    def e2e_step_u(ln):
+        ln.batch.set_initial_states(x0_host)
+        ln.batch.set_controls(None)
+        ln.batch.solve(prm)
+        ln.batch.begin_get_solution({k: v for k, v in ln.out.items() if k != "X"})
+
+    for ln in lanes:
+        e2e_step_u(ln)
+        e2e_finish(ln)
+    e2e_u_ms, e2e_u_wall = timed(e2e_step_u, args.steps, lanes, single_ms, finish=e2e_finish)
+    e2e_u_value = total / (max(e2e_u_ms * 1e-3, e2e_u_wall))
+    d2h_u = per_rank * ((T * NU + 1) * 8 + 2 * 4)
+
     # ---- per-kernel timing for the roofline: one solve at a time, CUDA events around every launch inside the engine
     batch = lanes[0].batch
     batch.set_profiling(True)
@@ -374,6 +389,8 @@ def run_b200(args):
                        "forward_lanes": st["forward_lanes"], "forward_chains": st["forward_chains"],
                        "mean_iterations": iters_total / per_rank,
                        "problem_iterations_per_s": value * iters_total / per_rank},
+            "e2e_controls_only": {"value": e2e_u_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_u, "ms_per_step": e2e_u_ms,
+                                  "note": "same loop without downloading the state trajectories (X = NULL in the C ABI); not the headline"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                     "wall_ms_per_step": e2e_wall * 1e3},
             "gpu_launches": int(launches),
