@@ -202,7 +202,7 @@ def run_b200(args):
 
     desc = mas.example_desc(mas.Model.SINGLE_TRACK_LANE)
     prm = mas.IlqrParams.make(MAX_ITER, TOL)
-    depth = args.depth if args.depth > 0 else (3 if args.steps < 8 else 4 if args.steps < 40 else 6)
+    depth = args.depth if args.depth > 0 else (3 if args.steps < 8 else 4)
     lanes = [Lane(torch, mas, local_rank, desc, per_rank, args, with_host_buffers=not args.resident_only) for _ in range(depth)]
     for ln in lanes:
         ln.batch.set_initial_states(x0_host)  # resident input of the `value` measurement
@@ -410,12 +410,12 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--steps", type=int, default=48, help="timed steps (one step = one solve of the 65,536-problem batch, 6-7 ms)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--depth", type=int, default=0, help="independent solves in flight per GPU (1 = one at a time; 0 = by step count: "
-                    "3 below 8 steps, 4 below 40, else 6 -- fewer pipelines fill and drain faster when K is small)")
+                    "3 below 8 steps, else 4 -- fewer pipelines fill and drain faster when K is small)")
     ap.add_argument("--stagger", type=float, default=1.0, help="start offset between pipelines, in units of single_solve_ms / depth")
     ap.add_argument("--cpu-sample", type=int, default=8192, help="problems per CPU-baseline pass")
     ap.add_argument("--resident-only", action="store_true", help="run only warm-up + timed resident steps (for ncu)")
