@@ -651,8 +651,11 @@ struct BatchImpl : BatchBase {
   void launch_forward(int n_upper, int cur, int L, int C) {
     if (L == 1 && C == 2) launch_forward_lc<1, 2>(n_upper, cur);
     else if (L == 1) launch_forward_lc<1, 1>(n_upper, cur);
+    else if (L == 2 && C == 2) launch_forward_lc<2, 2>(n_upper, cur);
     else if (L == 2) launch_forward_lc<2, 1>(n_upper, cur);
+    else if (L == 4 && C == 2) launch_forward_lc<4, 2>(n_upper, cur);
     else if (L == 4) launch_forward_lc<4, 1>(n_upper, cur);
+    else if (L == 8 && C == 2) launch_forward_lc<8, 2>(n_upper, cur);
     else if (L == 8) launch_forward_lc<8, 1>(n_upper, cur);
     else launch_forward_lc<16, 1>(n_upper, cur);
   }
@@ -689,9 +692,9 @@ struct BatchImpl : BatchBase {
     if (resident_lanes[0]) return;
 
     resident_lanes[0] = query_resident<1, 2>();
-    resident_lanes[1] = query_resident<2, 1>();
-    resident_lanes[2] = query_resident<4, 1>();
-    resident_lanes[3] = query_resident<8, 1>();
+    resident_lanes[1] = query_resident<2, 2>();
+    resident_lanes[2] = query_resident<4, 2>();
+    resident_lanes[3] = query_resident<8, 2>();
     resident_lanes[4] = query_resident<16, 1>();
   }
 
@@ -710,8 +713,10 @@ struct BatchImpl : BatchBase {
           break;
         }
     }
-    if (c == 0) c = (l == 1) ? 2 : 1;
-    if (l != 1) c = 1;
+    // two step sizes per lane wherever ten candidates do not fit in one pass of L lanes: 2 lanes need 3 passes
+    // instead of 5, 4 lanes 2 instead of 3, 8 lanes 1 instead of 2, and a two-chain pass costs about 1.3 single ones
+    if (c == 0) c = (l == 16) ? 1 : 2;
+    if (l == 16) c = 1;
     *L = l;
     *C = c;
   }
@@ -725,7 +730,7 @@ struct BatchImpl : BatchBase {
       query_occupancy();
       // the widest launches that use the store: forward_kernel<L >= 4> with all lanes resident, or 16 lanes per problem
       long long need = 0;
-      for (int k = 2; k <= 4; ++k) need = std::max(need, resident_lanes[k] + kBlock);
+      for (int k = 2; k <= 4; ++k) need = std::max(need, (k == 4 ? 1 : 2) * (resident_lanes[k] + kBlock));  // two chains for L = 4, 8
       need = std::min(need, 16ll * div_up(batch, kBlock) * kBlock);
       if (coop_store) need = std::max(need, 2ll * div_up(batch, kBlock) * kBlock);
       ensure_trial_store(need);

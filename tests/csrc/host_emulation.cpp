@@ -173,9 +173,14 @@ int emulate(int batch, int T, double dt, unsigned mask, int has_bounds, const do
         bs = -1;  // forward_kernel keeps trial trajectories for L >= 4 only: lane l -> slot l
         if (L == 1 && C == 2) lane_line_search<M, 1, 2>(v, p, prm, lane, current_merit, &bj, &bm);
         else if (L == 1) lane_line_search<M, 1, 1>(v, p, prm, lane, current_merit, &bj, &bm);
+        else if (L == 2 && C == 2) lane_line_search<M, 2, 2>(v, p, prm, lane, current_merit, &bj, &bm);
         else if (L == 2) lane_line_search<M, 2, 1>(v, p, prm, lane, current_merit, &bj, &bm);
+        else if (L == 4 && C == 2 && store) lane_line_search<M, 4, 2, true>(v, p, prm, lane, current_merit, &bj, &bm, lane, 16, &bs, &bo);
+        else if (L == 4 && C == 2) lane_line_search<M, 4, 2>(v, p, prm, lane, current_merit, &bj, &bm);
         else if (L == 4 && store) lane_line_search<M, 4, 1, true>(v, p, prm, lane, current_merit, &bj, &bm, lane, 16, &bs, &bo);
         else if (L == 4) lane_line_search<M, 4, 1>(v, p, prm, lane, current_merit, &bj, &bm);
+        else if (L == 8 && C == 2 && store) lane_line_search<M, 8, 2, true>(v, p, prm, lane, current_merit, &bj, &bm, lane, 16, &bs, &bo);
+        else if (L == 8 && C == 2) lane_line_search<M, 8, 2>(v, p, prm, lane, current_merit, &bj, &bm);
         else if (L == 8 && store) lane_line_search<M, 8, 1, true>(v, p, prm, lane, current_merit, &bj, &bm, lane, 16, &bs, &bo);
         else if (L == 8) lane_line_search<M, 8, 1>(v, p, prm, lane, current_merit, &bj, &bm);
         else if (store) lane_line_search<M, 16, 1, true>(v, p, prm, lane, current_merit, &bj, &bm, lane, 16, &bs, &bo);

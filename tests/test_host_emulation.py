@@ -28,7 +28,7 @@ def test_models_bit_exact(emu, oracle, model, batch, cap):
     assert np.array_equal(got["reg_retries"], ref["reg_retries"])
 
 
-@pytest.mark.parametrize("L,C", [(1, 1), (1, 2), (2, 1), (4, 1), (8, 1), (16, 1), (32, 1), (32, 2)])
+@pytest.mark.parametrize("L,C", [(1, 1), (1, 2), (2, 1), (2, 2), (4, 1), (4, 2), (8, 1), (8, 2), (16, 1), (32, 1), (32, 2)])
 def test_lane_mappings_pick_the_first_improving_step(emu, oracle, L, C):
     x0 = random_x0(0, 24, seed=9)
     U0 = np.zeros((24, 80, 2))
@@ -145,7 +145,7 @@ def test_multipliers_and_penalty_persist_across_solves(emu, oracle, penalty):
     assert changed > 0  # later solves do move: the persistent state is really in play
 
 
-@pytest.mark.parametrize("model,L,C", [(0, 4, 1), (0, 8, 1), (0, 16, 1), (5, 4, 1), (5, 16, 1), (1, 8, 1), (4, 16, 1)])
+@pytest.mark.parametrize("model,L,C", [(0, 4, 1), (0, 4, 2), (0, 8, 2), (0, 16, 1), (5, 4, 2), (5, 16, 1), (1, 8, 1), (4, 16, 1)])
 def test_stored_trials_equal_recomputed_steps(emu, model, L, C):
     """The accepted step copied from the trial store is the rollout the commit pass would repeat: same bits."""
     x0 = random_x0(model, 40, seed=90 + model)
