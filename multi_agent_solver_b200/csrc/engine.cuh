@@ -8,7 +8,8 @@
 //                          deals its lanes out to the (problem, step size) rollouts still needed
 //   forward_kernel       : the line search for small active sets: L lanes per problem roll out all step sizes
 //                          concurrently, warp-shuffle selection of the first improving one
-//   both then write the accepted step in place, apply the stop test and compact the active list.
+//   both then take the accepted step (re-rolled in place, or copied from the trial store in the wide lane mappings),
+//   apply the stop test and compact the active list.
 // Problems leave the active list as they converge, so later iterations only pay for what is left.
 // The strategy layer's kernels (trust region, joint line search) and the timing hooks are here too; the
 // centralized strategy lives in centralized.cuh.
@@ -776,7 +777,7 @@ struct BatchImpl : BatchBase {
       // Large active sets: compacted rounds (full warps, work stops at the first improving step size).
       // Small ones, where a pass is pure latency: all step sizes at once on L lanes per problem.
       // (measured on B200, 65,536 ST-lane problems: every round pays the latency of T sequential steps,
-      //  0.4 ms, so rounds lose to the lane mapping, 26.6 vs 16.9 ms per solve; auto therefore = lanes)
+      //  so rounds lost to the lane mapping by 57 % per solve when both were measured; auto therefore = lanes)
       const bool rounds = ls_mode == 2;
       if (rounds) {
         rc = launch_rounds(n_upper, cur);
