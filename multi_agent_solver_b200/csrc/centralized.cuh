@@ -45,7 +45,25 @@ struct StackedProblem {
   double* fast;                // K, Q_ux (padded columns) and L | inv | K^T Q_uu: shared memory when it fits, else in `work`
   double* out_cost;            // [1 + A]: stacked best_cost, then per-agent costs
   int* out_int;                // iterations, status, reg_retries, alpha_trials
+  long long* phase_cycles;     // optional [kNumPhases]: SM cycles per phase of this scenario (diagnostics), or null
 };
+
+// Phases timed by MAS_PHASE (thread 0 of the scenario's CTA, clock64 between barriers).
+enum StackedPhase { PH_TERMINAL = 0, PH_FD, PH_QASM, PH_LLT, PH_INVERSE, PH_GAINS, PH_VALUE, PH_ROLLOUT, kNumPhases };
+#if defined(__CUDA_ARCH__)
+#define MAS_PHASE_BEGIN() long long mas_phase_t0 = (P.phase_cycles && tid == 0) ? clock64() : 0
+#define MAS_PHASE(k)                                              \
+  do {                                                            \
+    if (P.phase_cycles && tid == 0) {                             \
+      const long long now = clock64();                            \
+      P.phase_cycles[k] += now - mas_phase_t0;                    \
+      mas_phase_t0 = now;                                         \
+    }                                                             \
+  } while (0)
+#else
+#define MAS_PHASE_BEGIN() ((void)0)
+#define MAS_PHASE(k) ((void)0)
+#endif
 
 // Offsets into the double workspace of one scenario.
 struct StackedWork {
@@ -80,7 +98,10 @@ struct StackedWork {
     // fast scratch (offsets below are relative to StackedProblem::fast): K and Q_ux with columns padded to ms + 1
     // (conflict-free column reads from shared memory), a region that holds L and Q_uu_inv during the
     // factorisation and K^T Q_uu afterwards, then the per-agent cost tables of the FD stencils and the scalars
-    const size_t region = static_cast<size_t>(ns) * ms > 2 * static_cast<size_t>(ms) * ms ? static_cast<size_t>(ns) * ms : 2 * static_cast<size_t>(ms) * ms;
+    // (the inverse's columns are padded to ms + 1 as well: one thread owns a column, and an unpadded stride of
+    //  ms doubles would put all 32 columns of a warp in the same bank)
+    const size_t lu_inv = static_cast<size_t>(ms) * ms + static_cast<size_t>(ms) * (ms + 1);
+    const size_t region = static_cast<size_t>(ns) * ms > lu_inv ? static_cast<size_t>(ns) * ms : lu_inv;
     size_t fo = 2 * static_cast<size_t>(ns) * (ms + 1) + region;
     auto ftake = [&](size_t n) {
       const size_t r = fo;
@@ -159,6 +180,7 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
   double* fC = fQ + static_cast<size_t>(ns) * ldk;
   double *Lm = fC, *inv = fC + static_cast<size_t>(ms) * ms, *KtQ = fC;  // K^T Q_uu reuses the space of L and inv
 
+  MAS_PHASE_BEGIN();
   // ---- terminal value (ilqr.hpp:92-102): FD gradient (eps 1e-6) and Hessian (eps 1e-5) of the stacked terminal cost
   const double* xT = P.X + static_cast<size_t>(T) * ns;
   for (int a = tid; a < A; a += nthr) {
@@ -237,6 +259,7 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
   for (int t = T - 1; t >= 0; --t) {
     const double* xt = P.X + static_cast<size_t>(t) * ns;
     const double* ut = P.U + static_cast<size_t>(t) * ms;
+    if (t == T - 1) MAS_PHASE(PH_TERMINAL);
     // ---- per-agent pieces: FD Jacobian blocks, base stage cost, singly perturbed stage costs
     for (int a = tid; a < A; a += nthr) {
       const double* xa = xt + a * NX;
@@ -342,6 +365,7 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
       }
     }
     MAS_CTA_SYNC();
+    MAS_PHASE(PH_FD);
     // ---- Q_x, Q_u, A^T V_xx, B^T V_xx (ilqr.hpp:115-119); A, B block diagonal
     for (int idx = tid; idx < ns + ms + ns * ns + ms * ns; idx += nthr) {
       int e = idx;
@@ -414,6 +438,7 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
     }
     if (tid == 0) scal[SC_REG] = 1e-6;
     MAS_CTA_SYNC();
+    MAS_PHASE(PH_QASM);
     // ---- LLT of Q_uu_reg with the cumulative-shift retry loop (ilqr.hpp:172-182); unblocked, lower
     for (;;) {
       for (int e = tid; e < ms * ms; e += nthr) Lm[e] = Qreg[e];
@@ -464,13 +489,16 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
       MAS_CTA_SYNC();
       if (!(reg < 1e300)) break;
     }
-    // ---- Q_uu_inv = llt.solve(I), one column per thread, the column is its own work vector
+    MAS_PHASE(PH_LLT);
+    // ---- Q_uu_inv = llt.solve(I), one column per thread, the column (stride ldk, conflict-free) is its own work
+    // vector.  Forward substitution on e_c: rows above c stay exactly zero, and their products are left out of the
+    // later rows' sums (s - L*0 == s).
     for (int c = tid; c < ms; c += nthr) {
-      double* x = inv + static_cast<size_t>(c) * ms;
+      double* x = inv + static_cast<size_t>(c) * ldk;
       for (int i = 0; i < ms; ++i) x[i] = (i == c) ? 1.0 : 0.0;
-      for (int i = 0; i < ms; ++i) {
+      for (int i = c; i < ms; ++i) {
         double s = x[i];
-        for (int j = 0; j < i; ++j) s -= Lm[i + static_cast<size_t>(j) * ms] * x[j];
+        for (int j = c; j < i; ++j) s -= Lm[i + static_cast<size_t>(j) * ms] * x[j];
         x[i] = pm::div_(s, Lm[i + static_cast<size_t>(i) * ms]);
       }
       for (int i = ms - 1; i >= 0; --i) {
@@ -480,24 +508,26 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
       }
     }
     MAS_CTA_SYNC();
+    MAS_PHASE(PH_INVERSE);
     // ---- gains k = (-inv) Q_u, K = (-inv) Q_ux (ilqr.hpp:185-186)
     double* Kt = P.K + static_cast<size_t>(t) * ms * ns;
     double* kt = P.kff + static_cast<size_t>(t) * ms;
     for (int idx = tid; idx < ms + ms * ns; idx += nthr) {
       if (idx < ms) {
         const int i = idx;
-        double s = (-inv[i + 0 * static_cast<size_t>(ms)]) * Qu[0];
-        for (int k = 1; k < ms; ++k) s = s + (-inv[i + static_cast<size_t>(k) * ms]) * Qu[k];
+        double s = (-inv[i + 0 * static_cast<size_t>(ldk)]) * Qu[0];
+        for (int k = 1; k < ms; ++k) s = s + (-inv[i + static_cast<size_t>(k) * ldk]) * Qu[k];
         kt[i] = s;
       } else {
         const int e = idx - ms, i = e % ms, j = e / ms;
-        double s = (-inv[i + 0 * static_cast<size_t>(ms)]) * fQ[0 + static_cast<size_t>(j) * ldk];
-        for (int k = 1; k < ms; ++k) s = s + (-inv[i + static_cast<size_t>(k) * ms]) * fQ[k + static_cast<size_t>(j) * ldk];
+        double s = (-inv[i + 0 * static_cast<size_t>(ldk)]) * fQ[0 + static_cast<size_t>(j) * ldk];
+        for (int k = 1; k < ms; ++k) s = s + (-inv[i + static_cast<size_t>(k) * ldk]) * fQ[k + static_cast<size_t>(j) * ldk];
         Kt[i + static_cast<size_t>(j) * ms] = s;
         fK[i + static_cast<size_t>(j) * ldk] = s;
       }
     }
     MAS_CTA_SYNC();
+    MAS_PHASE(PH_GAINS);
     // ---- K^T Q_uu (unregularised), then the value update (ilqr.hpp:188-192)
     for (int e = tid; e < ns * ms; e += nthr) {
       const int i = e % ns, j = e / ns;
@@ -506,8 +536,8 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
       KtQ[i + static_cast<size_t>(j) * ns] = s;
     }
     MAS_CTA_SYNC();
-    for (int idx = tid; idx < ns + ns * ns; idx += nthr) {
-      if (idx < ns) {
+    for (int idx = tid; idx < ns; idx += nthr) {
+      {
         const int i = idx;
         double t1 = fK[0 + static_cast<size_t>(i) * ldk] * Qu[0];
         for (int k = 1; k < ms; ++k) t1 = t1 + fK[k + static_cast<size_t>(i) * ldk] * Qu[k];
@@ -516,16 +546,42 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
         double t3 = KtQ[i + 0 * static_cast<size_t>(ns)] * kt[0];
         for (int k = 1; k < ms; ++k) t3 = t3 + KtQ[i + static_cast<size_t>(k) * ns] * kt[k];
         Vx[i] = ((Qx[i] + t1) + t2) + t3;
-      } else {
-        const int e = idx - ns, i = e % ns, j = e / ns;
-        double m1 = fK[0 + static_cast<size_t>(i) * ldk] * fQ[0 + static_cast<size_t>(j) * ldk];
-        for (int k = 1; k < ms; ++k) m1 = m1 + fK[k + static_cast<size_t>(i) * ldk] * fQ[k + static_cast<size_t>(j) * ldk];
-        double m2 = fQ[0 + static_cast<size_t>(i) * ldk] * fK[0 + static_cast<size_t>(j) * ldk];
-        for (int k = 1; k < ms; ++k) m2 = m2 + fQ[k + static_cast<size_t>(i) * ldk] * fK[k + static_cast<size_t>(j) * ldk];
-        double m3 = KtQ[i + 0 * static_cast<size_t>(ns)] * fK[0 + static_cast<size_t>(j) * ldk];
-        for (int k = 1; k < ms; ++k) m3 = m3 + KtQ[i + static_cast<size_t>(k) * ns] * fK[k + static_cast<size_t>(j) * ldk];
-        Vxx[i + static_cast<size_t>(j) * ns] = ((Qxx[i + static_cast<size_t>(j) * ns] + m1) + m2) + m3;
       }
+    }
+    // V_xx: each thread owns one row index i and four consecutive columns, so that every operand it loads feeds four
+    // (K, Q_ux of column i) or three (K, Q_ux of column j) of its twelve independent k-ascending sums
+    for (int e = tid; e < ns * ((ns + 3) / 4); e += nthr) {
+      const int i = e % ns, j0 = (e / ns) * 4;
+      int jc[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) jc[r] = j0 + r < ns ? j0 + r : ns - 1;
+      double m1[4], m2[4], m3[4];
+      {
+        const double a1 = fK[static_cast<size_t>(i) * ldk], a2 = fQ[static_cast<size_t>(i) * ldk], a3 = KtQ[i];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const double b1 = fQ[static_cast<size_t>(jc[r]) * ldk], b2 = fK[static_cast<size_t>(jc[r]) * ldk];
+          m1[r] = a1 * b1;
+          m2[r] = a2 * b2;
+          m3[r] = a3 * b2;
+        }
+      }
+      for (int k = 1; k < ms; ++k) {
+        const double a1 = fK[k + static_cast<size_t>(i) * ldk], a2 = fQ[k + static_cast<size_t>(i) * ldk], a3 = KtQ[i + static_cast<size_t>(k) * ns];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const double b1 = fQ[k + static_cast<size_t>(jc[r]) * ldk], b2 = fK[k + static_cast<size_t>(jc[r]) * ldk];
+          m1[r] = m1[r] + a1 * b1;
+          m2[r] = m2[r] + a2 * b2;
+          m3[r] = m3[r] + a3 * b2;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (j0 + r < ns) {
+          const size_t o = i + static_cast<size_t>(j0 + r) * ns;
+          Vxx[o] = ((Qxx[o] + m1[r]) + m2[r]) + m3[r];
+        }
     }
     MAS_CTA_SYNC();
     for (int e = tid; e < ns * ns; e += nthr) {
@@ -538,6 +594,7 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
       if (i <= j) Vxx[i + static_cast<size_t>(j) * ns] = 0.5 * (Vxx[i + static_cast<size_t>(j) * ns] + Vxx[j + static_cast<size_t>(i) * ns]);
     }
     MAS_CTA_SYNC();
+    MAS_PHASE(PH_VALUE);
   }
 }
 
@@ -615,7 +672,9 @@ MAS_HD void stacked_solve(const StackedProblem<M>& P, int tid, int nthr) {
     P.out_int[2] = 0;
     P.out_int[3] = 0;
   }
+  MAS_PHASE_BEGIN();
   stacked_rollout<M>(P, W, -1.0, P.X, P.U, tid, nthr);
+  MAS_PHASE(PH_ROLLOUT);
   if (tid == 0) {
     scal[SC_COST] = scal[SC_TRIAL];
     scal[SC_MERIT] = scal[SC_TRIAL];
@@ -624,6 +683,9 @@ MAS_HD void stacked_solve(const StackedProblem<M>& P, int tid, int nthr) {
   for (int iter = 0; iter < P.max_iterations; ++iter) {
     if (tid == 0) P.out_int[0] = iter + 1;
     stacked_backward<M>(P, W, tid, nthr);
+#if defined(__CUDA_ARCH__)
+    if (P.phase_cycles && tid == 0) mas_phase_t0 = clock64();  // the backward pass accounted for its own phases
+#endif
     const double current_merit = scal[SC_MERIT];
     int accepted = -1;
     double best_merit = current_merit;
@@ -632,6 +694,7 @@ MAS_HD void stacked_solve(const StackedProblem<M>& P, int tid, int nthr) {
       stacked_rollout<M>(P, W, alpha, P.Xt, P.Ut, tid, nthr);
       const double trial = scal[SC_TRIAL];
       MAS_CTA_SYNC();
+      MAS_PHASE(PH_ROLLOUT);
       if (tid == 0) P.out_int[3] += 1;
       if (trial < best_merit) {
         best_merit = trial;

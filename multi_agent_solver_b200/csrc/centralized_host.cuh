@@ -1,5 +1,7 @@
 // centralized_host.cuh -- kernel wrapper and host launcher of the stacked (centralized) solve.
 #pragma once
+#include <cstdio>
+#include <cstdlib>
 #include "centralized.cuh"
 #include "engine.cuh"
 
@@ -29,6 +31,7 @@ __global__ void __launch_bounds__(kCentralizedThreads) centralized_kernel(Stacke
   P.fast = fast_in_shared ? mas_fast_scratch : P.work + fast_offset;
   P.out_cost = base.out_cost + static_cast<size_t>(s) * (1 + base.A);
   P.out_int = base.out_int + static_cast<size_t>(s) * 4;
+  if (s != 0) P.phase_cycles = nullptr;  // diagnostics: scenario 0 only
   stacked_solve<M>(P, threadIdx.x, blockDim.x);
 }
 
@@ -63,9 +66,18 @@ int run_centralized(Context* ctx, const mas_b200_ocp_desc& d, const mas_b200_ilq
         if (p) cudaFree(p);
       if (oi) cudaFree(oi);
     }
-  } b;
+  };
+  const long long key[4] = {S, A, T, M::ID};
+  const bool reuse = ctx->centralized_workspace && std::equal(key, key + 4, ctx->centralized_key);
+  if (!reuse) {
+    ctx->centralized_workspace.reset();  // free the old shape first
+    ctx->centralized_workspace = std::make_shared<Buffers>();
+    std::fill(ctx->centralized_key, ctx->centralized_key + 4, 0LL);  // valid only once every allocation succeeded
+  }
+  Buffers& b = *static_cast<Buffers*>(ctx->centralized_workspace.get());
   auto dalloc = [&](double** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(double)); };
   const size_t Ss = static_cast<size_t>(S);
+  if (!reuse) {
   MAS_CUDA_CHECK(dalloc(&b.x0, Ss * ns));
   MAS_CUDA_CHECK(dalloc(&b.prm, Ss * A * NPs));
   MAS_CUDA_CHECK(dalloc(&b.X, Ss * (T + 1) * ns));
@@ -77,6 +89,8 @@ int run_centralized(Context* ctx, const mas_b200_ocp_desc& d, const mas_b200_ilq
   MAS_CUDA_CHECK(dalloc(&b.work, Ss * W.total));
   MAS_CUDA_CHECK(dalloc(&b.oc, Ss * (1 + A)));
   MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&b.oi), Ss * 4 * sizeof(int)));
+  std::copy(key, key + 4, ctx->centralized_key);
+  }
   MAS_CUDA_CHECK(cudaMemcpyAsync(b.x0, x0, Ss * ns * sizeof(double), cudaMemcpyHostToDevice, st));  // [S][A][NX] is already [S][ns]
   MAS_CUDA_CHECK(cudaMemcpyAsync(b.prm, hP.data(), hP.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   MAS_CUDA_CHECK(cudaMemcpyAsync(b.U, hU.data(), hU.size() * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -103,6 +117,14 @@ int run_centralized(Context* ctx, const mas_b200_ocp_desc& d, const mas_b200_ilq
   P.work = b.work;
   P.out_cost = b.oc;
   P.out_int = b.oi;
+  // MAS_B200_CENTRALIZED_PHASES=1: SM cycles per phase of scenario 0 to stderr (how the time of a stacked solve splits
+  // between finite differences, the dense Riccati algebra and the line-search rollouts)
+  long long* d_phase = nullptr;
+  if (std::getenv("MAS_B200_CENTRALIZED_PHASES")) {
+    MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_phase), kNumPhases * sizeof(long long)));
+    MAS_CUDA_CHECK(cudaMemsetAsync(d_phase, 0, kNumPhases * sizeof(long long), st));
+  }
+  P.phase_cycles = d_phase;
   // K, Q_ux and the factorisation scratch live in shared memory when they fit (A = 32 single-track agents: 199 KB)
   const size_t fast_bytes = W.fast_doubles * sizeof(double);
   int max_optin = 0;
@@ -121,6 +143,17 @@ int run_centralized(Context* ctx, const mas_b200_ocp_desc& d, const mas_b200_ilq
   MAS_CUDA_CHECK(cudaMemcpyAsync(hc.data(), b.oc, hc.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
   MAS_CUDA_CHECK(cudaMemcpyAsync(hi.data(), b.oi, hi.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
   MAS_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (d_phase) {
+    long long h[kNumPhases];
+    MAS_CUDA_CHECK(cudaMemcpy(h, d_phase, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(d_phase);
+    static const char* names[kNumPhases] = {"terminal FD", "stage FD tables + derivatives", "Q assembly (A^T V A ...)", "LLT of Q_uu", "Q_uu inverse",
+                                            "gains", "value update", "rollouts (prologue + line search)"};
+    long long tot = 0;
+    for (long long c : h) tot += c;
+    std::fprintf(stderr, "[mas_b200] centralized scenario 0: %lld cycles\n", tot);
+    for (int i = 0; i < kNumPhases; ++i) std::fprintf(stderr, "[mas_b200]   %-36s %12lld  %5.1f %%\n", names[i], h[i], 100.0 * h[i] / (tot ? tot : 1));
+  }
   // scatter the stacked trajectories back to the agents' blocks (centralized.hpp:30-31)
   for (int s = 0; s < S; ++s) {
     for (int a = 0; a < A; ++a) {

@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -59,6 +60,10 @@ struct Context {
   int sm_count = 148;
   void* nccl_comm = nullptr;  // ncclComm_t when multi-GPU is initialised
   int rank = 0, world = 1;
+  // device workspace of the last centralized strategy call, kept for the next call of the same shape (a 592-scenario
+  // config-5 run needs 1.3 GB: allocating and freeing it per call cost up to 100 ms); freed with the context
+  std::shared_ptr<void> centralized_workspace;
+  long long centralized_key[4] = {0, 0, 0, 0};
 };
 
 // ---- kernels ------------------------------------------------------------------------------------

@@ -282,6 +282,7 @@ int emulate_centralized(int A, int T, double dt, int has_bounds, const double* l
   P.fast = work.data() + W.fast;
   P.out_cost = out_cost;
   P.out_int = out_int;
+  P.phase_cycles = nullptr;
   stacked_solve<M>(P, 0, 1);
   return 0;
 }

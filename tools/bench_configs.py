@@ -90,7 +90,7 @@ def main():
     xe = np.stack([20 * np.cos(th), 20 * np.sin(th), 1.57 + th, np.full(32, 4.0)], -1)[None]
     for S5 in (1, 148, 592):
         x5 = np.repeat(xe, S5, axis=0)
-        t_gpu = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, d1, p100, 1, x5, trace=False), 2)
+        t_gpu = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, d1, p100, 1, x5, trace=False), 5)
         rec = {"config": 5, "what": f"multi_agent_single_track --agents 32 --strategy centralized, the example scenario x {S5} replicas "
                                     "(stacked n=128, m=64, all-FD, 4 iterations each)", "gpu_ms": t_gpu * 1e3, "gpu_scenarios_per_s": S5 / t_gpu}
         if S5 == 1:
@@ -101,7 +101,7 @@ def main():
     # (b) track radius jittered per scenario: iteration counts spread widely and the slowest scenario sets the time
     x5, gp5, _ = circle(296, 32, seed=5)
     r5 = mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, d1, p100, 1, x5, model_params=gp5)
-    t_gpu = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, d1, p100, 1, x5, model_params=gp5, trace=False), 1)
+    t_gpu = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, d1, p100, 1, x5, model_params=gp5, trace=False), 2)
     its = r5["trace_iters"][:, 0, 0]
     out.append({"config": 5, "what": "same, 296 scenarios with the track radius jittered in [15, 25]", "gpu_ms": t_gpu * 1e3,
                 "gpu_scenarios_per_s": 296 / t_gpu, "iterations_mean": float(its.mean()), "iterations_max": int(its.max())})
