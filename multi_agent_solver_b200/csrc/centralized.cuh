@@ -147,6 +147,38 @@ MAS_HD double stacked_sum2(const double* c, const double* pref, int A, int a, do
   return s;
 }
 
+// The four stencil points of a mixed second difference at once: agent a's term takes va[(q >> 1) & 1], agent b's term
+// vb[q & 1] (a != b), v[q] = the stacked value.  Every sum performs exactly the additions of stacked_sum2 in the same
+// order; computing them side by side gives the fp64 pipe four independent chains instead of one (two before the
+// second replaced term, where the pairs still coincide) and loads each c[k] once.
+MAS_HD void stacked_sum2x4(const double* c, const double* pref, int A, int a, const double* va, int b, const double* vb, double* v) {
+  const bool a_first = a < b;
+  const int lo_i = a_first ? a : b, hi_i = a_first ? b : a;
+  const double* first = a_first ? va : vb;
+  const double* second = a_first ? vb : va;
+  double p0 = pref[lo_i] + first[0], p1 = pref[lo_i] + first[1];
+  for (int k = lo_i + 1; k < hi_i; ++k) {
+    const double ck = c[k];
+    p0 += ck;
+    p1 += ck;
+  }
+  // q = 2*ia + ib with ia the variant of agent a and ib the variant of agent b
+  double s[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int ia = (q >> 1) & 1, ib = q & 1;
+    const int f = a_first ? ia : ib, g = a_first ? ib : ia;
+    s[q] = (f ? p1 : p0) + second[g];
+  }
+  for (int k = hi_i + 1; k < A; ++k) {
+    const double ck = c[k];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s[q] += ck;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) v[q] = s[q];
+}
+
 // cost of one agent at (x + sx*eps*e_i + ..., u + ...) helpers
 template <class M>
 MAS_HD double agent_stage_pert(const double* x, const double* u, int t, const double* prm, int ix, double dxv, int jx, double djv, int iu, double duv,
@@ -340,8 +372,8 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
           h = MAS_DIV_CONST(v[0] - v[1] - v[2] + v[3], 4 * e5 * e5);
         } else {
           double v[4];
-          for (int q = 0; q < 4; ++q)
-            v[q] = finite_or_zero(stacked_sum2(cb, pref, A, a, tab[(a * per + il) * 2 + ((q >> 1) & 1)], b, tab[(b * per + jl) * 2 + (q & 1)]));
+          stacked_sum2x4(cb, pref, A, a, &tab[(a * per + il) * 2], b, &tab[(b * per + jl) * 2], v);
+          for (int q = 0; q < 4; ++q) v[q] = finite_or_zero(v[q]);
           h = MAS_DIV_CONST(v[0] - v[1] - v[2] + v[3], 4 * e5 * e5);
         }
         (is_x ? lxx : luu)[i + static_cast<size_t>(j) * dim] = h;
@@ -352,14 +384,15 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
         const int i = e % ms, j = e / ms;
         const int a = i / NU, il = i % NU, b = j / NX, jl = j % NX;
         double v[4];
-        for (int q = 0; q < 4; ++q) {
-          const int sx = q & 1, su = (q >> 1) & 1;  // q: 0 pp, 1 pm (x-), 2 mp (u-), 3 mm
-          if (a == b) {
+        if (a == b) {
+          for (int q = 0; q < 4; ++q) {
+            const int sx = q & 1, su = (q >> 1) & 1;  // q: 0 pp, 1 pm (x-), 2 mp (u-), 3 mm
             const double c = agent_stage_pert<M>(xt + a * NX, ut + a * NU, t, P.prm + a * NPs, jl, sx ? -e6 : e6, -1, 0, il, su ? -e6 : e6, -1, 0);
             v[q] = finite_or_zero(stacked_sum1(cb, pref, A, a, c));
-          } else {
-            v[q] = finite_or_zero(stacked_sum2(cb, pref, A, a, R6[(a * NU + il) * 2 + su], b, S6[(b * NX + jl) * 2 + sx]));
           }
+        } else {  // agent a (control, variant su = bit 1 of q), agent b (state, variant sx = bit 0 of q)
+          stacked_sum2x4(cb, pref, A, a, &R6[(a * NU + il) * 2], b, &S6[(b * NX + jl) * 2], v);
+          for (int q = 0; q < 4; ++q) v[q] = finite_or_zero(v[q]);
         }
         lux[i + static_cast<size_t>(j) * ms] = MAS_DIV_CONST(v[0] - v[1] - v[2] + v[3], 4 * e6 * e6);
       }
