@@ -474,32 +474,23 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
     MAS_PHASE(PH_QASM);
     // ---- LLT of Q_uu_reg with the cumulative-shift retry loop (ilqr.hpp:172-182); unblocked, lower
     for (;;) {
+      // Row i's running sum of squares sq[i] = L_i0^2 + ... (added as the columns are produced, i.e. in the order the
+      // reference's pivot computation adds them) makes the pivot of column k a single subtraction; every thread
+      // evaluates it redundantly from the untouched diagonal of Q_uu_reg, so a column costs one barrier.
+      double* sq = P.fast + W.dx;  // the rollout's scratch, free during the backward pass
       for (int e = tid; e < ms * ms; e += nthr) Lm[e] = Qreg[e];
-      if (tid == 0) scal[SC_FLAG] = 0.0;
+      for (int i = tid; i < ms; i += nthr) sq[i] = 0.0;
       MAS_CTA_SYNC();
       bool failed = false;
       for (int k = 0; k < ms; ++k) {
-        if (tid == 0) {
-          double x = Lm[k + static_cast<size_t>(k) * ms];
-          if (k > 0) {
-            double sq = 0.0;
-            for (int j = 0; j < k; ++j) sq += Lm[k + static_cast<size_t>(j) * ms] * Lm[k + static_cast<size_t>(j) * ms];
-            x -= sq;
-          }
-          if (x <= 0.0) {
-            scal[SC_FLAG] = 1.0;
-          } else {
-            x = sqrt(x);
-            Lm[k + static_cast<size_t>(k) * ms] = x;
-            scal[SC_PIVOT] = x;
-          }
-        }
-        MAS_CTA_SYNC();
-        if (scal[SC_FLAG] != 0.0) {
+        double x = Qreg[k + static_cast<size_t>(k) * ms];
+        if (k > 0) x -= sq[k];
+        if (x <= 0.0) {
           failed = true;
           break;
         }
-        const double x = scal[SC_PIVOT];
+        x = sqrt(x);
+        if (tid == 0) Lm[k + static_cast<size_t>(k) * ms] = x;
         for (int i = k + 1 + tid; i < ms; i += nthr) {
           double s = Lm[i + static_cast<size_t>(k) * ms];
           if (k > 0) {
@@ -507,7 +498,9 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
             for (int j = 1; j < k; ++j) acc = acc + Lm[i + static_cast<size_t>(j) * ms] * Lm[k + static_cast<size_t>(j) * ms];
             s -= acc;
           }
-          Lm[i + static_cast<size_t>(k) * ms] = pm::div_(s, x);
+          const double l = pm::div_(s, x);
+          Lm[i + static_cast<size_t>(k) * ms] = l;
+          sq[i] += l * l;
         }
         MAS_CTA_SYNC();
       }
@@ -545,28 +538,59 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
     // ---- gains k = (-inv) Q_u, K = (-inv) Q_ux (ilqr.hpp:185-186)
     double* Kt = P.K + static_cast<size_t>(t) * ms * ns;
     double* kt = P.kff + static_cast<size_t>(t) * ms;
-    for (int idx = tid; idx < ms + ms * ns; idx += nthr) {
-      if (idx < ms) {
+    for (int idx = tid; idx < ms; idx += nthr) {
+      {
         const int i = idx;
         double s = (-inv[i + 0 * static_cast<size_t>(ldk)]) * Qu[0];
         for (int k = 1; k < ms; ++k) s = s + (-inv[i + static_cast<size_t>(k) * ldk]) * Qu[k];
         kt[i] = s;
-      } else {
-        const int e = idx - ms, i = e % ms, j = e / ms;
-        double s = (-inv[i + 0 * static_cast<size_t>(ldk)]) * fQ[0 + static_cast<size_t>(j) * ldk];
-        for (int k = 1; k < ms; ++k) s = s + (-inv[i + static_cast<size_t>(k) * ldk]) * fQ[k + static_cast<size_t>(j) * ldk];
-        Kt[i + static_cast<size_t>(j) * ms] = s;
-        fK[i + static_cast<size_t>(j) * ldk] = s;
       }
+    }
+    for (int e = tid; e < ms * ((ns + 3) / 4); e += nthr) {  // K: row i, four columns per thread
+      const int i = e % ms, j0 = (e / ms) * 4;
+      int jc[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) jc[r] = j0 + r < ns ? j0 + r : ns - 1;
+      double acc[4];
+      {
+        const double a0 = -inv[i];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] = a0 * fQ[static_cast<size_t>(jc[r]) * ldk];
+      }
+      for (int k = 1; k < ms; ++k) {
+        const double a0 = -inv[i + static_cast<size_t>(k) * ldk];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] = acc[r] + a0 * fQ[k + static_cast<size_t>(jc[r]) * ldk];
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (j0 + r < ns) {
+          Kt[i + static_cast<size_t>(j0 + r) * ms] = acc[r];
+          fK[i + static_cast<size_t>(j0 + r) * ldk] = acc[r];
+        }
     }
     MAS_CTA_SYNC();
     MAS_PHASE(PH_GAINS);
     // ---- K^T Q_uu (unregularised), then the value update (ilqr.hpp:188-192)
-    for (int e = tid; e < ns * ms; e += nthr) {
-      const int i = e % ns, j = e / ns;
-      double s = fK[0 + static_cast<size_t>(i) * ldk] * Quu[0 + static_cast<size_t>(j) * ms];
-      for (int k = 1; k < ms; ++k) s = s + fK[k + static_cast<size_t>(i) * ldk] * Quu[k + static_cast<size_t>(j) * ms];
-      KtQ[i + static_cast<size_t>(j) * ns] = s;
+    for (int e = tid; e < ns * ((ms + 3) / 4); e += nthr) {  // four columns of K^T Q_uu per thread, as in V_xx below
+      const int i = e % ns, j0 = (e / ns) * 4;
+      int jc[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) jc[r] = j0 + r < ms ? j0 + r : ms - 1;
+      double acc[4];
+      {
+        const double a0 = fK[static_cast<size_t>(i) * ldk];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] = a0 * Quu[static_cast<size_t>(jc[r]) * ms];
+      }
+      for (int k = 1; k < ms; ++k) {
+        const double a0 = fK[k + static_cast<size_t>(i) * ldk];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] = acc[r] + a0 * Quu[k + static_cast<size_t>(jc[r]) * ms];
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (j0 + r < ms) KtQ[i + static_cast<size_t>(j0 + r) * ns] = acc[r];
     }
     MAS_CTA_SYNC();
     for (int idx = tid; idx < ns; idx += nthr) {
