@@ -583,7 +583,23 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
 #pragma unroll
         for (int r = 0; r < 4; ++r) acc[r] = a0 * Quu[static_cast<size_t>(jc[r]) * ms];
       }
-      for (int k = 1; k < ms; ++k) {
+      // Q_uu lives in global memory (L2 at best: L1 is 20 KB next to 207 KB of shared memory): fetch four rows of
+      // the four columns before using any, so that sixteen loads are in flight instead of four
+      int k = 1;
+      for (; k + 4 <= ms; k += 4) {
+        double q[4][4], a0[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          a0[kk] = fK[k + kk + static_cast<size_t>(i) * ldk];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) q[kk][r] = Quu[k + kk + static_cast<size_t>(jc[r]) * ms];
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) acc[r] = acc[r] + a0[kk] * q[kk][r];
+      }
+      for (; k < ms; ++k) {
         const double a0 = fK[k + static_cast<size_t>(i) * ldk];
 #pragma unroll
         for (int r = 0; r < 4; ++r) acc[r] = acc[r] + a0 * Quu[k + static_cast<size_t>(jc[r]) * ms];
@@ -641,16 +657,26 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
         }
     }
     MAS_CTA_SYNC();
-    for (int e = tid; e < ns * ns; e += nthr) {
-      const int i = e % ns, j = e / ns;
-      if (i > j) Vxx[i + static_cast<size_t>(j) * ns] = 0.5 * (Vxx[i + static_cast<size_t>(j) * ns] + Vxx[j + static_cast<size_t>(i) * ns]);
+    // aliased symmetrisation (see symmetrize_aliased): strict lower triangle first, then the rest with the new lower
+    // values.  Four entries per trip, all loads before the first store (the stores would otherwise hold back the
+    // loads queued behind them, one L2 latency per entry).
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int e0 = tid * 4; e0 < ns * ns; e0 += nthr * 4) {
+        double a[4], b[4];
+        bool on[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int e = e0 + r, i = e % ns, j = e / ns;
+          on[r] = e < ns * ns && (pass == 0 ? i > j : i <= j);
+          a[r] = on[r] ? Vxx[i + static_cast<size_t>(j) * ns] : 0.0;
+          b[r] = on[r] ? Vxx[j + static_cast<size_t>(i) * ns] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (on[r]) Vxx[e0 + r] = 0.5 * (a[r] + b[r]);
+      }
+      MAS_CTA_SYNC();
     }
-    MAS_CTA_SYNC();
-    for (int e = tid; e < ns * ns; e += nthr) {
-      const int i = e % ns, j = e / ns;
-      if (i <= j) Vxx[i + static_cast<size_t>(j) * ns] = 0.5 * (Vxx[i + static_cast<size_t>(j) * ns] + Vxx[j + static_cast<size_t>(i) * ns]);
-    }
-    MAS_CTA_SYNC();
     MAS_PHASE(PH_VALUE);
   }
 }
