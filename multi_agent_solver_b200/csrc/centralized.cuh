@@ -147,6 +147,21 @@ MAS_HD double stacked_sum2(const double* c, const double* pref, int A, int a, do
   return s;
 }
 
+// N stencil points that replace the same agent's term: N chains of the additions of stacked_sum1, side by side.
+template <int N>
+MAS_HD void stacked_sum1xN(const double* c, const double* pref, int A, int a, const double* va, double* v) {
+  double s[N];
+#pragma unroll
+  for (int q = 0; q < N; ++q) s[q] = pref[a] + va[q];
+  for (int k = a + 1; k < A; ++k) {
+    const double ck = c[k];
+#pragma unroll
+    for (int q = 0; q < N; ++q) s[q] += ck;
+  }
+#pragma unroll
+  for (int q = 0; q < N; ++q) v[q] = s[q];
+}
+
 // The four stencil points of a mixed second difference at once: agent a's term takes va[(q >> 1) & 1], agent b's term
 // vb[q & 1] (a != b), v[q] = the stacked value.  Every sum performs exactly the additions of stacked_sum2 in the same
 // order; computing them side by side gives the fp64 pipe four independent chains instead of one (two before the
@@ -257,19 +272,21 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
       } else if (a == b) {
         const double* xa = xT + a * NX;
         const double* pa = P.prm + a * NPs;
-        double v[4];
+        double v[4], cq[4];
         for (int q = 0; q < 4; ++q) {
           double xp[NX];
           for (int k = 0; k < NX; ++k) xp[k] = xa[k];
           xp[il] = (q & 2) ? xa[il] - e5 : xa[il] + e5;
           xp[jl] = (q & 1) ? xa[jl] - e5 : xa[jl] + e5;
-          v[q] = finite_or_zero(stacked_sum1(cb, pref, A, a, M::terminal(xp, pa)));
+          cq[q] = M::terminal(xp, pa);
         }
+        stacked_sum1xN<4>(cb, pref, A, a, cq, v);
+        for (int q = 0; q < 4; ++q) v[q] = finite_or_zero(v[q]);
         h = MAS_DIV_CONST(v[0] - v[1] - v[2] + v[3], 4 * e5 * e5);
       } else {
         double v[4];
-        for (int q = 0; q < 4; ++q)
-          v[q] = finite_or_zero(stacked_sum2(cb, pref, A, a, S5[(a * NX + il) * 2 + ((q >> 1) & 1)], b, S5[(b * NX + jl) * 2 + (q & 1)]));
+        stacked_sum2x4(cb, pref, A, a, &S5[(a * NX + il) * 2], b, &S5[(b * NX + jl) * 2], v);
+        for (int q = 0; q < 4; ++q) v[q] = finite_or_zero(v[q]);
         h = MAS_DIV_CONST(v[0] - v[1] - v[2] + v[3], 4 * e5 * e5);
       }
       Vxx[i + static_cast<size_t>(j) * ns] = h;
@@ -331,17 +348,17 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
       int e = idx;
       if (e < n_lx) {
         const int a = e / NX, il = e % NX;
-        const double fp = stacked_sum1(cb, pref, A, a, S6[(a * NX + il) * 2 + 0]);
-        const double fm = stacked_sum1(cb, pref, A, a, S6[(a * NX + il) * 2 + 1]);
-        lx[e] = MAS_DIV_CONST(fp - fm, 2 * e6);
+        double f2[2];
+        stacked_sum1xN<2>(cb, pref, A, a, &S6[(a * NX + il) * 2], f2);
+        lx[e] = MAS_DIV_CONST(f2[0] - f2[1], 2 * e6);
         continue;
       }
       e -= n_lx;
       if (e < n_lu) {
         const int a = e / NU, il = e % NU;
-        const double fp = stacked_sum1(cb, pref, A, a, R6[(a * NU + il) * 2 + 0]);
-        const double fm = stacked_sum1(cb, pref, A, a, R6[(a * NU + il) * 2 + 1]);
-        lu[e] = MAS_DIV_CONST(fp - fm, 2 * e6);
+        double f2[2];
+        stacked_sum1xN<2>(cb, pref, A, a, &R6[(a * NU + il) * 2], f2);
+        lu[e] = MAS_DIV_CONST(f2[0] - f2[1], 2 * e6);
         continue;
       }
       e -= n_lu;
@@ -354,21 +371,24 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
         const int a = i / per, il = i % per, b = j / per, jl = j % per;
         double h;
         if (i == j) {
-          const double fp = finite_or_zero(stacked_sum1(cb, pref, A, a, tab[(a * per + il) * 2 + 0]));
+          double f2[2];
+          stacked_sum1xN<2>(cb, pref, A, a, &tab[(a * per + il) * 2], f2);
+          const double fp = finite_or_zero(f2[0]);
           const double f0 = finite_or_zero(pref[A]);
-          const double fm = finite_or_zero(stacked_sum1(cb, pref, A, a, tab[(a * per + il) * 2 + 1]));
+          const double fm = finite_or_zero(f2[1]);
           h = MAS_DIV_CONST(fp - 2 * f0 + fm, e5 * e5);
         } else if (a == b) {
           const double* xa = xt + a * NX;
           const double* ua = ut + a * NU;
           const double* pa = P.prm + a * NPs;
-          double v[4];
+          double v[4], cq[4];
           for (int q = 0; q < 4; ++q) {
             const double di = (q & 2) ? -e5 : e5, dj = (q & 1) ? -e5 : e5;
-            const double c = is_x ? agent_stage_pert<M>(xa, ua, t, pa, il, di, jl, dj, -1, 0, -1, 0)
-                                  : agent_stage_pert<M>(xa, ua, t, pa, -1, 0, -1, 0, il, di, jl, dj);
-            v[q] = finite_or_zero(stacked_sum1(cb, pref, A, a, c));
+            cq[q] = is_x ? agent_stage_pert<M>(xa, ua, t, pa, il, di, jl, dj, -1, 0, -1, 0)
+                         : agent_stage_pert<M>(xa, ua, t, pa, -1, 0, -1, 0, il, di, jl, dj);
           }
+          stacked_sum1xN<4>(cb, pref, A, a, cq, v);
+          for (int q = 0; q < 4; ++q) v[q] = finite_or_zero(v[q]);
           h = MAS_DIV_CONST(v[0] - v[1] - v[2] + v[3], 4 * e5 * e5);
         } else {
           double v[4];
@@ -385,11 +405,13 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
         const int a = i / NU, il = i % NU, b = j / NX, jl = j % NX;
         double v[4];
         if (a == b) {
+          double cq[4];
           for (int q = 0; q < 4; ++q) {
             const int sx = q & 1, su = (q >> 1) & 1;  // q: 0 pp, 1 pm (x-), 2 mp (u-), 3 mm
-            const double c = agent_stage_pert<M>(xt + a * NX, ut + a * NU, t, P.prm + a * NPs, jl, sx ? -e6 : e6, -1, 0, il, su ? -e6 : e6, -1, 0);
-            v[q] = finite_or_zero(stacked_sum1(cb, pref, A, a, c));
+            cq[q] = agent_stage_pert<M>(xt + a * NX, ut + a * NU, t, P.prm + a * NPs, jl, sx ? -e6 : e6, -1, 0, il, su ? -e6 : e6, -1, 0);
           }
+          stacked_sum1xN<4>(cb, pref, A, a, cq, v);
+          for (int q = 0; q < 4; ++q) v[q] = finite_or_zero(v[q]);
         } else {  // agent a (control, variant su = bit 1 of q), agent b (state, variant sx = bit 0 of q)
           stacked_sum2x4(cb, pref, A, a, &R6[(a * NU + il) * 2], b, &S6[(b * NX + jl) * 2], v);
           for (int q = 0; q < 4; ++q) v[q] = finite_or_zero(v[q]);
