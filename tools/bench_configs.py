@@ -1,7 +1,8 @@
 """Secondary measurements: BASELINE.json configs 1, 2, 4, 5 (the headline config 3 is bench.py).
 
 Each config is run through the C ABI with host buffers (what a caller of the reference's API would see), timed
-with the wall clock around synchronous calls, best of a few repeats after a warm-up, next to the oracle (CPU
+with the wall clock around synchronous calls, best of several repeats after a warm-up (the shared boxes show sporadic
+10x outliers on these short host-driven loops), next to the oracle (CPU
 restatement of the reference) on a bounded sample with all host threads.  One JSON line per config.
 
     python tools/bench_configs.py > gpurun_out/other_configs.jsonl
@@ -68,7 +69,7 @@ def main():
     x0, gp, op = circle(S, A)
     d1 = mas.example_desc(1)
     p100 = mas.IlqrParams.make(100, 1e-5)
-    t_gpu = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.TRUSTREGION, d1, p100, 10, x0, model_params=gp, trace=False), 3)
+    t_gpu = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.TRUSTREGION, d1, p100, 10, x0, model_params=gp, trace=False), 6)
     ns = 256
     t_cpu = best_of(lambda: o.strategy_run_batch(o.STRATEGY_TRUSTREGION, 1, x0[:ns], params=op[:ns], max_outer=10, max_iterations=100, tolerance=1e-5,
                                                  threads=threads), 1)
@@ -79,7 +80,7 @@ def main():
     # config 4: 1,024 LQR agents, sequential, 10 outer rounds
     x4 = np.tile([1.0, 0.0, 0.0, 0.0], (1, 1024, 1))
     d2 = mas.example_desc(2)
-    t_gpu = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.SEQUENTIAL, d2, p100, 10, x4, trace=False), 3)
+    t_gpu = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.SEQUENTIAL, d2, p100, 10, x4, trace=False), 6)
     t_cpu = best_of(lambda: o.strategy_run_batch(o.STRATEGY_SEQUENTIAL, 2, x4, max_outer=10, max_iterations=100, tolerance=1e-5, threads=threads), 1)
     out.append({"config": 4, "what": "multi_agent_lqr --agents 1024 --strategy sequential, 10 outer rounds (one scenario)", "gpu_ms": t_gpu * 1e3,
                 "cpu_oracle_ms": t_cpu * 1e3, "cpu_threads": threads, "gpu_agent_solves_per_s": 1024 * 10 / t_gpu})
