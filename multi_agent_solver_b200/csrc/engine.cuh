@@ -698,7 +698,7 @@ struct BatchImpl : BatchBase {
     if (resident_lanes[0]) return;
 
     resident_lanes[0] = query_resident<1, 2>();
-    resident_lanes[1] = query_resident<2, 2>();
+    resident_lanes[1] = query_resident<2, 1>();
     resident_lanes[2] = query_resident<4, 2>();
     resident_lanes[3] = query_resident<8, 2>();
     resident_lanes[4] = query_resident<16, 1>();
@@ -719,9 +719,10 @@ struct BatchImpl : BatchBase {
           break;
         }
     }
-    // two step sizes per lane wherever ten candidates do not fit in one pass of L lanes: 2 lanes need 3 passes
-    // instead of 5, 4 lanes 2 instead of 3, 8 lanes 1 instead of 2, and a two-chain pass costs about 1.3 single ones
-    if (c == 0) c = (l == 16) ? 1 : 2;
+    // two step sizes per lane where that saves passes: 4 lanes need 2 passes instead of 3 (0.48 vs 0.54 ms on the
+    // launch list of the headline batch), 8 lanes 1 instead of 2 (0.25 vs 0.35 ms); with 2 lanes 3 two-chain passes
+    // cost as much as 5 single ones (0.89 vs 0.86 ms), so they stay single
+    if (c == 0) c = (l == 4 || l == 8 || l == 1) ? 2 : 1;
     if (l == 16) c = 1;
     *L = l;
     *C = c;
