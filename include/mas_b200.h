@@ -201,7 +201,11 @@ int mas_b200_batch_set_trial_store(mas_b200_batch_t b, int enable);
 int mas_b200_batch_set_line_search_mode(mas_b200_batch_t b, int mode);
 
 /* One-shot: set_initial_states + set_controls + initialize + solve + get_solution on host buffers.
- * U is in/out (initial_controls in, best_controls out; NULL = zero initial controls, not returned). */
+ * U is in/out (initial_controls in, best_controls out; NULL = zero initial controls, not returned).
+ * The device batch behind this call stays with the context and is reused by the next call with the same description
+ * and batch size (each call still starts from a fresh solver state); mas_b200_strategy_run shares it.  A call of
+ * another shape replaces it, mas_b200_context_destroy frees it.
+ */
 int mas_b200_ilqr_solve_batch(mas_b200_context_t ctx, const mas_b200_ocp_desc* desc, const mas_b200_ilqr_params* params, int batch,
                               const double* x0, const double* model_params, double* U, double* X, double* cost, int* iterations, int* status);
 

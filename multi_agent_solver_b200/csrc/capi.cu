@@ -96,11 +96,17 @@ static int validate_params(const mas_b200_ilqr_params* p) {
 
 using namespace mas_b200;
 
-struct mas_b200_context {
-  Context c;
-};
 struct mas_b200_batch {
   BatchBase* b;
+};
+struct mas_b200_context {
+  Context c;
+  // The batch behind the one-shot entry points (mas_b200_ilqr_solve_batch, mas_b200_strategy_run), kept for the next
+  // call of the same shape: creating and destroying it allocates up to 2 GB and cost 8-19 ms on a one-problem solve
+  // that itself takes 1 ms.  A call with another description or size replaces it; destroyed with the context.
+  mas_b200_batch* scratch_batch = nullptr;
+  mas_b200_ocp_desc scratch_desc{};
+  int scratch_size = 0;
 };
 
 extern "C" {
@@ -229,6 +235,8 @@ int mas_b200_context_create(int device_id, void* stream, mas_b200_context_t* out
 int mas_b200_context_destroy(mas_b200_context_t ctx) {
   if (!ctx) return MAS_B200_OK;
   cudaSetDevice(ctx->c.device);
+  if (ctx->scratch_batch) mas_b200_batch_destroy(ctx->scratch_batch);
+  ctx->c.centralized_workspace.reset();
   if (ctx->c.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(static_cast<ncclComm_t>(ctx->c.nccl_comm));
   if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
   delete ctx;
@@ -425,19 +433,44 @@ int mas_b200_batch_set_line_search_mode(mas_b200_batch_t h, int mode) {
   return MAS_B200_OK;
 }
 
+// One-shot calls borrow the context's scratch batch; every borrow starts from a fresh solver (no multipliers, default
+// tuning), as a newly constructed reference solver would.
+static int borrow_scratch_batch(mas_b200_context_t ctx, const mas_b200_ocp_desc* desc, int batch, mas_b200_batch_t* out) {
+  if (!ctx || !desc) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "ctx/desc is NULL");
+  if (ctx->scratch_batch && ctx->scratch_size == batch && std::memcmp(&ctx->scratch_desc, desc, sizeof(*desc)) == 0) {
+    BatchBase* b = ctx->scratch_batch->b;
+    b->al_fresh = true;
+    b->tune_L = b->tune_C = 0;
+    b->ls_mode = 0;
+    *out = ctx->scratch_batch;
+    return MAS_B200_OK;
+  }
+  if (ctx->scratch_batch) {
+    mas_b200_batch_destroy(ctx->scratch_batch);
+    ctx->scratch_batch = nullptr;
+  }
+  mas_b200_batch_t h = nullptr;
+  const int rc = mas_b200_batch_create(ctx, desc, batch, &h);
+  if (rc) return rc;
+  ctx->scratch_batch = h;
+  std::memcpy(&ctx->scratch_desc, desc, sizeof(*desc));
+  ctx->scratch_size = batch;
+  *out = h;
+  return MAS_B200_OK;
+}
+
 int mas_b200_ilqr_solve_batch(mas_b200_context_t ctx, const mas_b200_ocp_desc* desc, const mas_b200_ilqr_params* params, int batch,
                               const double* x0, const double* model_params, double* U, double* X, double* cost, int* iterations, int* status) {
   int rc = validate_params(params);
   if (rc) return rc;
   mas_b200_batch_t h = nullptr;
-  rc = mas_b200_batch_create(ctx, desc, batch, &h);
+  rc = borrow_scratch_batch(ctx, desc, batch, &h);
   if (rc) return rc;
   rc = mas_b200_batch_set_initial_states(h, x0);
   if (!rc) rc = mas_b200_batch_set_params(h, model_params);
   if (!rc) rc = mas_b200_batch_set_controls(h, U);
   if (!rc) rc = mas_b200_batch_solve(h, params);
   if (!rc) rc = mas_b200_batch_get_solution(h, X, U, cost, iterations, status);
-  mas_b200_batch_destroy(h);
   return rc;
 }
 
@@ -474,7 +507,7 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
   const bool keeps_old = strategy == MAS_B200_STRATEGY_TRUSTREGION || strategy == MAS_B200_STRATEGY_LINESEARCH;
   const int batch = n_scenarios * n_agents;
   mas_b200_batch_t h = nullptr;
-  rc = mas_b200_batch_create(ctx, agent_desc, batch, &h);
+  rc = borrow_scratch_batch(ctx, agent_desc, batch, &h);
   if (rc) return rc;
   BatchBase* b = h->b;
   cudaStream_t st = ctx->c.stream;
@@ -590,8 +623,7 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
     if (costs) std::memcpy(costs, c.data(), sizeof(double) * batch);
     return MAS_B200_OK;
   };
-  rc = run();
-  mas_b200_batch_destroy(h);
+  rc = run();  // the batch stays with the context (borrow_scratch_batch)
   return rc;
 }
 
