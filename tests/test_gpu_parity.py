@@ -312,3 +312,30 @@ def test_trial_store_on_and_off_agree(mas, ctx, oracle, mode, lanes):
         b.close()
     assert is_bit_exact(outs[0], ref) and is_bit_exact(outs[1], ref) and is_bit_exact(outs[2], ref)
     assert_parity(outs[0], ref)
+
+
+def test_one_shot_calls_reuse_the_context_batch_without_leaking_state(mas, ctx, oracle):
+    """mas_b200_ilqr_solve_batch keeps its device batch in the context between calls of the same shape; every call must
+    still behave like a fresh solver on a fresh problem (per-problem parameters, warm start, multipliers)."""
+    B = 64
+    desc = mas.example_desc(1)
+    prm = mas.IlqrParams.make(30, 1e-5)
+    rng = np.random.default_rng(77)
+    R = rng.uniform(15, 25, B)
+    th = rng.uniform(0, 2 * np.pi, B)
+    x0 = np.stack([R * np.cos(th), R * np.sin(th), 1.57 + th, np.full(B, 4.0)], -1)
+    gp = np.stack([R, np.full(B, 5.0), np.ones(B), np.ones(B), np.full(B, 1e-3), np.full(B, 1e-3)], -1)
+    a = mas.ilqr_solve_batch(ctx, desc, prm, x0, model_params=gp)       # per-problem radii
+    b = mas.ilqr_solve_batch(ctx, desc, prm, x0)                        # same shape, shared default parameters
+    c = mas.ilqr_solve_batch(ctx, desc, prm, x0, model_params=gp)       # and back
+    ref_a = oracle.ilqr_solve_batch(1, x0, params=gp[:, :2], max_iterations=30, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    ref_b = oracle.ilqr_solve_batch(1, x0, max_iterations=30, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    assert is_bit_exact(a, ref_a) and is_bit_exact(b, ref_b) and is_bit_exact(c, ref_a)
+    # constrained model: a second one-shot call is a fresh solver again (no multipliers carried over)
+    d5 = mas.example_desc(5)
+    x5 = random_x0(5, B, seed=78)
+    p5 = mas.IlqrParams.make(5, 1e-5)
+    r1 = mas.ilqr_solve_batch(ctx, d5, p5, x5)
+    r2 = mas.ilqr_solve_batch(ctx, d5, p5, x5)
+    ref5 = oracle.ilqr_solve_batch(5, x5, max_iterations=5, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    assert is_bit_exact(r1, ref5) and is_bit_exact(r2, ref5)
