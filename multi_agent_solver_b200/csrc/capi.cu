@@ -423,6 +423,7 @@ int mas_b200_batch_set_trial_store(mas_b200_batch_t h, int enable) {
   MAS_BATCH_GUARD(h);
   b->trial_store = enable != 0;
   b->coop_store = enable == 2;
+  b->backward_lanes_enabled = enable != 0;  // the same switch turns the lane-parallel backward pass off (A/B runs, tests)
   return MAS_B200_OK;
 }
 

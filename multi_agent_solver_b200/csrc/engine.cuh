@@ -109,6 +109,29 @@ __global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) backward_kernel(BatchVie
   if (r) v.reg_retries[p] += r;
 }
 
+// Backward pass with LB lanes per problem (backward_lanes): for derivative modes with many finite-difference
+// callbacks and active sets small enough for all lanes to be resident.  Launch with
+// (kBlock / LB) * DerivBlock<M>::size doubles of dynamic shared memory.
+struct GroupSync {
+  unsigned mask;
+  __device__ void operator()() const { __syncwarp(mask); }
+};
+template <class M, int MASK_CT, int LB>
+__global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) backward_lanes_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list,
+                                                                             const int* __restrict__ count, int* next_count) {
+  extern __shared__ double s_blk[];
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid == 0) *next_count = 0;
+  const int i = gid / LB, lane = gid % LB;
+  if (i >= *count) return;  // whole groups leave together: the group barrier below only names the group's lanes
+  const int p = list[i];
+  const unsigned first = (threadIdx.x & 31u) & ~static_cast<unsigned>(LB - 1);
+  const GroupSync sync{(LB == 32 ? 0xffffffffu : ((1u << LB) - 1u)) << first};
+  double* blk = s_blk + static_cast<size_t>(threadIdx.x / LB) * DerivBlock<M>::size;
+  const int r = backward_lanes<M, MASK_CT, LB>(v, p, lane, blk, sync);
+  if (lane == 0 && r) v.reg_retries[p] += r;
+}
+
 // L lanes per problem (a power of two <= 16, aligned inside the warp); lane l rolls out step sizes
 // l, l+L, ...; the group picks the first improving candidate with shuffles; lane 0 commits.
 template <class M, int L, int C>
@@ -473,6 +496,7 @@ struct BatchBase {
   double *d_trial_X = nullptr, *d_trial_U = nullptr;
   int trial_slots = 0;
   bool trial_store = true, trial_store_tried = false;
+  bool backward_lanes_enabled = true;  // lane-parallel backward pass for FD-heavy derivative modes (set_tuning lanes < 0 disables)
   bool coop_store = false;  // mas_b200_batch_set_trial_store(b, 2): trial store in the cooperative kernel too
   int ensure_trial_store(long long min_slots);
   int begin_download(double* X, double* U, double* cost, int* iterations, int* status);
@@ -632,8 +656,34 @@ struct BatchImpl : BatchBase {
   }
 
   void launch_backward(int n_upper, int cur) {
-    const int grid = div_up(n_upper, kBlock);
     const unsigned mask = desc.deriv_mask;
+    // many finite-difference callbacks and few enough problems for eight lanes each to be resident: deal the stencil
+    // points out to the lanes (backward_lanes_kernel)
+    // at least the n x n stage Hessian by FD, and enough tasks to keep eight lanes busy (n = 4: 40; the pendulum's 13
+    // and the rocket's 21 measured slower than one thread per problem)
+    const bool fd_heavy = !(mask & D_LXX) && (mask == 0u || mask != M::EXAMPLE_MASK) && DerivBlock<M>::n_tasks >= 32;
+    if (backward_lanes_enabled && fd_heavy && ls_mode == 0 && tune_L == 0) {
+      {
+        constexpr int LB = 8;
+        if (!resident_backward_lanes) {
+          int blocks = 0;
+          const size_t sm = (kBlock / LB) * DerivBlock<M>::size * sizeof(double);
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, backward_lanes_kernel<M, 0, LB>, kBlock, sm) != cudaSuccess || blocks <= 0) blocks = 4;
+          resident_backward_lanes = static_cast<long long>(blocks) * kBlock * ctx->sm_count;
+        }
+        if (static_cast<long long>(n_upper) * LB <= resident_backward_lanes) {
+          const int lgrid = static_cast<int>((static_cast<long long>(n_upper) * LB + kBlock - 1) / kBlock);
+          const size_t sm = (kBlock / LB) * DerivBlock<M>::size * sizeof(double);
+          if (mask == 0u)
+            backward_lanes_kernel<M, 0, LB><<<lgrid, kBlock, sm, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
+          else
+            backward_lanes_kernel<M, -1, LB><<<lgrid, kBlock, sm, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
+          stats.kernel_launches++;
+          return;
+        }
+      }
+    }
+    const int grid = div_up(n_upper, kBlock);
     const size_t smem = static_cast<long long>(grid) * kBlock <= kStageMaxThreads ? 2 * (M::NX + M::NU) * kStageStride * sizeof(double) : 0;
     if (mask == M::EXAMPLE_MASK)
       backward_kernel<M, static_cast<int>(M::EXAMPLE_MASK)><<<grid, kBlock, smem, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
@@ -686,6 +736,7 @@ struct BatchImpl : BatchBase {
     return MAS_B200_OK;
   }
 
+  long long resident_backward_lanes = 0;  // resident threads of backward_lanes_kernel, queried at first use
   // Resident lanes of every forward_kernel variant on this device (occupancy x SMs), queried once.
   long long resident_lanes[5] = {0, 0, 0, 0, 0};  // L = 1 (C=2), 2, 4, 8, 16
   template <int L, int C>

@@ -760,6 +760,256 @@ MAS_HD void al_update(const BatchView<M::NX, M::NU>& v, int p, const double* prm
   if (*eq_norm > v.constraint_tolerance || *ineq_norm > v.constraint_tolerance) v.penalty[p] = rho * v.penalty_increase;
 }
 
+// ---- finite-difference derivatives as independent tasks ------------------------------------------------------
+// For derivative modes that leave many callbacks to finite differences (all-FD: 118 stage-cost and 12 dynamics
+// evaluations per time step at n = 4, m = 2) one thread per problem spends almost all of a step on stencil points
+// that do not depend on each other.  The lane-parallel backward pass (engine.cuh: backward_lanes_kernel) deals them
+// out as tasks -- one column of A or B, one gradient entry, one Hessian entry -- to the lanes of a problem; each task
+// performs exactly the operations the whole-matrix routines above perform for that entry (x - eps is x + (-eps) bit
+// for bit), writes its result into the problem's derivative block in shared memory, and lane 0 then runs the
+// sequential Riccati step on the assembled block.
+template <class M>
+struct DerivBlock {  // offsets (doubles) inside a problem's block
+  static constexpr int NX = M::NX, NU = M::NU;
+  static constexpr int oA = 0, oB = oA + NX * NX, olx = oB + NX * NU, olu = olx + NX, olxx = olu + NU, oluu = olxx + NX * NX, olux = oluu + NU * NU,
+                       size = olux + NU * NX;
+  // task ranges in the order above: NX columns of A, NU columns of B, NX + NU gradient entries, then the Hessian entries
+  static constexpr int tA = 0, tB = tA + NX, tlx = tB + NU, tlu = tlx + NX, tlxx = tlu + NU, tluu = tlxx + NX * NX, tlux = tluu + NU * NU,
+                       n_tasks = tlux + NU * NX;
+  // terminal value: NX gradient entries and NX*NX Hessian entries, into the first NX + NX*NX doubles of the block
+  static constexpr int n_terminal_tasks = NX + NX * NX;
+};
+
+// zp = z with d added to component i (and e to component j): a select per component, so that i and j may be run-time
+template <int N>
+MAS_HD void perturbed(const double* z, int i, double d, int j, double e, double* zp) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) zp[k] = (k == i) ? z[k] + d : ((k == j) ? z[k] + e : z[k]);
+}
+// entry (i, j) of fd_hessian<N>(z, f, H)
+template <int N, class F>
+MAS_HD double fd_hessian_entry(const double* z, const F& f, int i, int j) {
+  const double eps = 1e-5;
+  double zp[N];
+  if (i == j) {
+    perturbed<N>(z, i, eps, -1, 0.0, zp);
+    const double fp = finite_or_zero(f(zp));
+    const double f0 = finite_or_zero(f(z));
+    perturbed<N>(z, i, -eps, -1, 0.0, zp);
+    const double fm = finite_or_zero(f(zp));
+    return MAS_DIV_CONST(fp - 2 * f0 + fm, eps * eps);
+  }
+  perturbed<N>(z, i, eps, j, eps, zp);
+  const double fpp = finite_or_zero(f(zp));
+  perturbed<N>(z, i, eps, j, -eps, zp);
+  const double fpm = finite_or_zero(f(zp));
+  perturbed<N>(z, i, -eps, j, eps, zp);
+  const double fmp = finite_or_zero(f(zp));
+  perturbed<N>(z, i, -eps, j, -eps, zp);
+  const double fmm = finite_or_zero(f(zp));
+  return MAS_DIV_CONST(fpp - fpm - fmp + fmm, 4 * eps * eps);
+}
+// One task of the stage derivatives; groups whose callback is analytic in `mask` are skipped (lane 0 fills them).
+template <class M>
+MAS_HD void fd_stage_task(unsigned mask, int task, const double* x, const double* u, int t, const double* prm, double* blk) {
+  constexpr int NX = M::NX, NU = M::NU;
+  using D = DerivBlock<M>;
+  const double e6 = 1e-6;
+  if (task < D::tB) {  // column i of A, fd_jac_x
+    if (mask & D_A) return;
+    const int i = task - D::tA;
+    double xp[NX], fp[NX], fm[NX], cu[M::NCU];
+    M::control_terms(u, prm, cu);
+    perturbed<NX>(x, i, e6, -1, 0.0, xp);
+    M::dynamics_c(xp, u, cu, prm, fp);
+    perturbed<NX>(x, i, -e6, -1, 0.0, xp);
+    M::dynamics_c(xp, u, cu, prm, fm);
+#pragma unroll
+    for (int r = 0; r < NX; ++r) blk[D::oA + r + i * NX] = MAS_DIV_CONST(fp[r] - fm[r], 2 * e6);
+  } else if (task < D::tlx) {  // column i of B, fd_jac_u
+    if (mask & D_B) return;
+    const int i = task - D::tB;
+    double up[NU], fp[NX], fm[NX];
+    perturbed<NU>(u, i, e6, -1, 0.0, up);
+    M::dynamics(x, up, prm, fp);
+    perturbed<NU>(u, i, -e6, -1, 0.0, up);
+    M::dynamics(x, up, prm, fm);
+#pragma unroll
+    for (int r = 0; r < NX; ++r) blk[D::oB + r + i * NX] = MAS_DIV_CONST(fp[r] - fm[r], 2 * e6);
+  } else if (task < D::tlu) {  // fd_l_x
+    if (mask & D_LX) return;
+    const int i = task - D::tlx;
+    double xp[NX];
+    perturbed<NX>(x, i, e6, -1, 0.0, xp);
+    const double fp = M::stage(xp, u, t, prm);
+    perturbed<NX>(x, i, -e6, -1, 0.0, xp);
+    const double fm = M::stage(xp, u, t, prm);
+    blk[D::olx + i] = MAS_DIV_CONST(fp - fm, 2 * e6);
+  } else if (task < D::tlxx) {  // fd_l_u
+    if (mask & D_LU) return;
+    const int i = task - D::tlu;
+    double up[NU];
+    perturbed<NU>(u, i, e6, -1, 0.0, up);
+    const double fp = M::stage(x, up, t, prm);
+    perturbed<NU>(u, i, -e6, -1, 0.0, up);
+    const double fm = M::stage(x, up, t, prm);
+    blk[D::olu + i] = MAS_DIV_CONST(fp - fm, 2 * e6);
+  } else if (task < D::tluu) {  // l_xx(i, j)
+    if (mask & D_LXX) return;
+    const int e = task - D::tlxx, i = e % NX, j = e / NX;
+    blk[D::olxx + i + j * NX] = fd_hessian_entry<NX>(x, StageInX<M>{u, prm, t}, i, j);
+  } else if (task < D::tlux) {  // l_uu(i, j)
+    if (mask & D_LUU) return;
+    const int e = task - D::tluu, i = e % NU, j = e / NU;
+    blk[D::oluu + i + j * NU] = fd_hessian_entry<NU>(u, StageInU<M>{x, prm, t}, i, j);
+  } else {  // l_ux(i, j): control i, state j, fd_l_ux
+    if (mask & D_LUX) return;
+    const int e = task - D::tlux, i = e % NU, j = e / NU;
+    double xp[NX], up[NU];
+    perturbed<NX>(x, j, e6, -1, 0.0, xp);
+    perturbed<NU>(u, i, e6, -1, 0.0, up);
+    const double fpp = finite_or_zero(M::stage(xp, up, t, prm));
+    perturbed<NX>(x, j, -e6, -1, 0.0, xp);
+    const double fpm = finite_or_zero(M::stage(xp, up, t, prm));
+    perturbed<NX>(x, j, e6, -1, 0.0, xp);
+    perturbed<NU>(u, i, -e6, -1, 0.0, up);
+    const double fmp = finite_or_zero(M::stage(xp, up, t, prm));
+    perturbed<NX>(x, j, -e6, -1, 0.0, xp);
+    const double fmm = finite_or_zero(M::stage(xp, up, t, prm));
+    blk[D::olux + i + j * NU] = MAS_DIV_CONST(fpp - fpm - fmp + fmm, 4 * e6 * e6);
+  }
+}
+// One task of the terminal value: v_x(i) for task < NX, else v_xx(i, j); blk = [v_x | v_xx].
+template <class M>
+MAS_HD void fd_terminal_task(unsigned mask, int task, const double* x, const double* prm, double* blk) {
+  constexpr int NX = M::NX;
+  const double e6 = 1e-6;
+  if (task < NX) {
+    if (mask & D_VX) return;
+    double xp[NX];
+    perturbed<NX>(x, task, e6, -1, 0.0, xp);
+    const double fp = M::terminal(xp, prm);
+    perturbed<NX>(x, task, -e6, -1, 0.0, xp);
+    const double fm = M::terminal(xp, prm);
+    blk[task] = MAS_DIV_CONST(fp - fm, 2 * e6);
+  } else {
+    if (mask & D_VXX) return;
+    const int e = task - NX, i = e % NX, j = e / NX;
+    blk[NX + i + j * NX] = fd_hessian_entry<NX>(x, TerminalInX<M>{prm}, i, j);
+  }
+}
+// Lane 0 after the tasks: the derivative arrays of the step, analytic where `mask` says so, else from the block.
+template <class M>
+MAS_HD void gather_stage_derivatives(unsigned mask, const double* blk, const double* x, const double* u, int t, const double* prm, double* A, double* B,
+                                     double* l_x, double* l_u, double* l_xx, double* l_uu, double* l_ux) {
+  constexpr int NX = M::NX, NU = M::NU;
+  using D = DerivBlock<M>;
+  if (mask & D_A) M::jac_x(x, u, prm, A);
+  else
+    for (int i = 0; i < NX * NX; ++i) A[i] = blk[D::oA + i];
+  if (mask & D_B) M::jac_u(x, u, prm, B);
+  else
+    for (int i = 0; i < NX * NU; ++i) B[i] = blk[D::oB + i];
+  if (mask & D_LX) M::l_x(x, u, t, prm, l_x);
+  else
+    for (int i = 0; i < NX; ++i) l_x[i] = blk[D::olx + i];
+  if (mask & D_LU) M::l_u(x, u, t, prm, l_u);
+  else
+    for (int i = 0; i < NU; ++i) l_u[i] = blk[D::olu + i];
+  if (mask & D_LXX) M::l_xx(x, u, t, prm, l_xx);
+  else
+    for (int i = 0; i < NX * NX; ++i) l_xx[i] = blk[D::olxx + i];
+  if (mask & D_LUU) M::l_uu(x, u, t, prm, l_uu);
+  else
+    for (int i = 0; i < NU * NU; ++i) l_uu[i] = blk[D::oluu + i];
+  if (mask & D_LUX) M::l_ux(x, u, t, prm, l_ux);
+  else
+    for (int i = 0; i < NU * NX; ++i) l_ux[i] = blk[D::olux + i];
+}
+
+// ---- one time step of the Riccati recursion (ilqr.hpp:115-193) given the derivatives at (x_t, u_t) --------------
+// Q assembly, constraint terms, Q_uu regularisation + LLT + inverse, gains (stored), value update in place.
+// Returns the number of regularisation retries of this step.
+template <class M, int MASK_CT>
+MAS_HD int riccati_step(const BatchView<M::NX, M::NU>& v, int p, int t, const double* x, const double* u, const double* prm, double al_rho,
+                        const double* A, const double* B, const double* l_x, const double* l_u, const double* l_xx, const double* l_uu,
+                        const double* l_ux, double* v_x, double* v_xx) {
+  constexpr int NX = M::NX, NU = M::NU;
+  int retries = 0;
+  // :115-119
+  double q_x[NX], q_u[NU], q_xx[NX * NX], q_ux[NU * NX], q_uu[NU * NU];
+  constexpr int TMPN = (NX > NU ? NX : NU) * (NX > NU ? NX : NU);
+  double AtV[NX * NX], BtV[NU * NX], tmp[TMPN];
+  // structural zeros are only known for the analytic Jacobians of a compile-time derivative mode
+  constexpr unsigned long long kDense = ~0ull;
+  static_assert(NX * NX <= 64 && NX * NU <= 64, "sparsity masks are 64-bit");
+  constexpr unsigned long long a_nz = (MASK_CT >= 0 && (MASK_CT & D_A)) ? M::A_NZ : kDense;
+  constexpr unsigned long long b_nz = (MASK_CT >= 0 && (MASK_CT & D_B)) ? M::B_NZ : kDense;
+  mat_tn_sa<NX, NX, 1, a_nz>(A, v_x, tmp);
+#pragma unroll
+  for (int i = 0; i < NX; ++i) q_x[i] = l_x[i] + tmp[i];
+  mat_tn_sa<NX, NU, 1, b_nz>(B, v_x, tmp);
+#pragma unroll
+  for (int i = 0; i < NU; ++i) q_u[i] = l_u[i] + tmp[i];
+  mat_tn_sa<NX, NX, NX, a_nz>(A, v_xx, AtV);
+  mat_tn_sa<NX, NU, NX, b_nz>(B, v_xx, BtV);
+  mat_nn_sb<NX, NX, NX, a_nz>(AtV, A, tmp);
+#pragma unroll
+  for (int i = 0; i < NX * NX; ++i) q_xx[i] = l_xx[i] + tmp[i];
+  mat_nn_sb<NU, NX, NX, a_nz>(BtV, A, tmp);
+#pragma unroll
+  for (int i = 0; i < NU * NX; ++i) q_ux[i] = l_ux[i] + tmp[i];
+  mat_nn_sb<NU, NX, NU, b_nz>(BtV, B, tmp);
+#pragma unroll
+  for (int i = 0; i < NU * NU; ++i) q_uu[i] = l_uu[i] + tmp[i];
+
+  // :121-170 constraint terms (models with path constraints only)
+  if (HasConstraints<M>::value) al_backward_terms<M>(v, p, t, x, u, prm, al_rho, q_x, q_u, q_xx, q_ux, q_uu);
+
+  // :172-183
+  double q_reg[NU * NU], L[NU * NU], inv[NU * NU];
+#pragma unroll
+  for (int i = 0; i < NU * NU; ++i) q_reg[i] = q_uu[i];
+  double reg = 1e-6;
+  while (!llt_factor<NU>(q_reg, L)) {
+#pragma unroll
+    for (int i = 0; i < NU; ++i) q_reg[i + i * NU] += reg;
+    reg *= 10.0;
+    ++retries;
+    if (!(reg < 1e300)) break;  // reference loops forever on NaN-free garbage; bail out instead
+  }
+  llt_inverse<NU>(L, inv);
+
+  // :185-186  k = (-Q_uu_inv) q_u,  K = (-Q_uu_inv) Q_ux
+  double ninv[NU * NU], kv[NU], Km[NU * NX];
+#pragma unroll
+  for (int i = 0; i < NU * NU; ++i) ninv[i] = -inv[i];
+  mat_nn<NU, NU, 1>(ninv, q_u, kv);
+  mat_nn<NU, NU, NX>(ninv, q_ux, Km);
+
+#pragma unroll
+  for (int i = 0; i < NU; ++i) v.kff[soa_index<NU>(t, i, v.ld, p)] = kv[i];
+#pragma unroll
+  for (int i = 0; i < NU * NX; ++i) v.K[soa_index<NU * NX>(t, i, v.ld, p)] = Km[i];
+
+  // :188-192 value update with the unregularised Q_uu
+  double KtQuu[NX * NU], t1[NX], t2[NX], t3[NX];
+  mat_tn<NU, NX, NU>(Km, q_uu, KtQuu);
+  mat_tn<NU, NX, 1>(Km, q_u, t1);
+  mat_tn<NU, NX, 1>(q_ux, kv, t2);
+  mat_nn<NX, NU, 1>(KtQuu, kv, t3);
+#pragma unroll
+  for (int i = 0; i < NX; ++i) v_x[i] = ((q_x[i] + t1[i]) + t2[i]) + t3[i];
+  double m1[NX * NX], m2[NX * NX], m3[NX * NX];
+  mat_tn<NU, NX, NX>(Km, q_ux, m1);
+  mat_tn<NU, NX, NX>(q_ux, Km, m2);
+  mat_nn<NX, NU, NX>(KtQuu, Km, m3);
+#pragma unroll
+  for (int i = 0; i < NX * NX; ++i) v_xx[i] = ((q_xx[i] + m1[i]) + m2[i]) + m3[i];
+  symmetrize_aliased<NX>(v_xx);
+  return retries;
+}
+
 // ---- backward pass for one problem (ilqr.hpp:92-193) --------------------------------------------
 // MASK_CT >= 0 fixes the derivative mode at compile time (dead branches vanish); -1 reads it from
 // the view.  Writes K, k for every t.  Returns the number of regularisation retries.
@@ -834,77 +1084,61 @@ MAS_HD int backward_thread(const BatchView<M::NX, M::NU>& v, int p, double* stag
     if (mask & D_LUX) M::l_ux(x, u, t, prm, l_ux);
     else fd_l_ux<M>(x, u, t, prm, l_ux);
 
-    // :115-119
-    double q_x[NX], q_u[NU], q_xx[NX * NX], q_ux[NU * NX], q_uu[NU * NU];
-    constexpr int TMPN = (NX > NU ? NX : NU) * (NX > NU ? NX : NU);
-    double AtV[NX * NX], BtV[NU * NX], tmp[TMPN];
-    // structural zeros are only known for the analytic Jacobians of a compile-time derivative mode
-    constexpr unsigned long long kDense = ~0ull;
-    static_assert(NX * NX <= 64 && NX * NU <= 64, "sparsity masks are 64-bit");
-    constexpr unsigned long long a_nz = (MASK_CT >= 0 && (MASK_CT & D_A)) ? M::A_NZ : kDense;
-    constexpr unsigned long long b_nz = (MASK_CT >= 0 && (MASK_CT & D_B)) ? M::B_NZ : kDense;
-    mat_tn_sa<NX, NX, 1, a_nz>(A, v_x, tmp);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) q_x[i] = l_x[i] + tmp[i];
-    mat_tn_sa<NX, NU, 1, b_nz>(B, v_x, tmp);
-#pragma unroll
-    for (int i = 0; i < NU; ++i) q_u[i] = l_u[i] + tmp[i];
-    mat_tn_sa<NX, NX, NX, a_nz>(A, v_xx, AtV);
-    mat_tn_sa<NX, NU, NX, b_nz>(B, v_xx, BtV);
-    mat_nn_sb<NX, NX, NX, a_nz>(AtV, A, tmp);
-#pragma unroll
-    for (int i = 0; i < NX * NX; ++i) q_xx[i] = l_xx[i] + tmp[i];
-    mat_nn_sb<NU, NX, NX, a_nz>(BtV, A, tmp);
-#pragma unroll
-    for (int i = 0; i < NU * NX; ++i) q_ux[i] = l_ux[i] + tmp[i];
-    mat_nn_sb<NU, NX, NU, b_nz>(BtV, B, tmp);
-#pragma unroll
-    for (int i = 0; i < NU * NU; ++i) q_uu[i] = l_uu[i] + tmp[i];
+    retries += riccati_step<M, MASK_CT>(v, p, t, x, u, prm, al_rho, A, B, l_x, l_u, l_xx, l_uu, l_ux, v_x, v_xx);
+  }
+  return retries;
+}
 
-    // :121-170 constraint terms (models with path constraints only)
-    if (HasConstraints<M>::value) al_backward_terms<M>(v, p, t, x, u, prm, al_rho, q_x, q_u, q_xx, q_ux, q_uu);
-
-    // :172-183
-    double q_reg[NU * NU], L[NU * NU], inv[NU * NU];
+// ---- lane-parallel backward pass: LB lanes per problem --------------------------------------------------------
+// Every lane of the group walks the time loop; per step the lanes take the FD tasks lane, lane + LB, ... and write the
+// problem's derivative block `blk` (shared memory); after a group barrier lane 0 assembles the derivatives and runs
+// riccati_step (V_x, V_xx live in its registers).  `group_sync` is __syncwarp over the group's lanes on the device and
+// a no-op in the sequential host emulation, which calls this function once per lane *phase* instead (see
+// tests/csrc/host_emulation.cpp).  Returns the regularisation retries (lane 0).
+template <class M, int MASK_CT, int LB, class Sync>
+MAS_HD int backward_lanes(const BatchView<M::NX, M::NU>& v, int p, int lane, double* blk, const Sync& group_sync) {
+  constexpr int NX = M::NX, NU = M::NU;
+  using D = DerivBlock<M>;
+  const unsigned mask = (MASK_CT >= 0) ? static_cast<unsigned>(MASK_CT) : v.deriv_mask;
+  double prm[M::NP > 0 ? M::NP : 1];
+  load_params<M>(v, p, prm);
+  const int T = v.T;
+  int retries = 0;
+  const double al_rho = HasConstraints<M>::value ? v.penalty[p] : 0.0;
+  double x[NX], u[NU], v_x[NX], v_xx[NX * NX];
 #pragma unroll
-    for (int i = 0; i < NU * NU; ++i) q_reg[i] = q_uu[i];
-    double reg = 1e-6;
-    while (!llt_factor<NU>(q_reg, L)) {
-#pragma unroll
-      for (int i = 0; i < NU; ++i) q_reg[i + i * NU] += reg;
-      reg *= 10.0;
-      ++retries;
-      if (!(reg < 1e300)) break;  // reference loops forever on NaN-free garbage; bail out instead
-    }
-    llt_inverse<NU>(L, inv);
-
-    // :185-186  k = (-Q_uu_inv) q_u,  K = (-Q_uu_inv) Q_ux
-    double ninv[NU * NU], kv[NU], Km[NU * NX];
-#pragma unroll
-    for (int i = 0; i < NU * NU; ++i) ninv[i] = -inv[i];
-    mat_nn<NU, NU, 1>(ninv, q_u, kv);
-    mat_nn<NU, NU, NX>(ninv, q_ux, Km);
-
-#pragma unroll
-    for (int i = 0; i < NU; ++i) v.kff[soa_index<NU>(t, i, v.ld, p)] = kv[i];
-#pragma unroll
-    for (int i = 0; i < NU * NX; ++i) v.K[soa_index<NU * NX>(t, i, v.ld, p)] = Km[i];
-
-    // :188-192 value update with the unregularised Q_uu
-    double KtQuu[NX * NU], t1[NX], t2[NX], t3[NX];
-    mat_tn<NU, NX, NU>(Km, q_uu, KtQuu);
-    mat_tn<NU, NX, 1>(Km, q_u, t1);
-    mat_tn<NU, NX, 1>(q_ux, kv, t2);
-    mat_nn<NX, NU, 1>(KtQuu, kv, t3);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) v_x[i] = ((q_x[i] + t1[i]) + t2[i]) + t3[i];
-    double m1[NX * NX], m2[NX * NX], m3[NX * NX];
-    mat_tn<NU, NX, NX>(Km, q_ux, m1);
-    mat_tn<NU, NX, NX>(q_ux, Km, m2);
-    mat_nn<NX, NU, NX>(KtQuu, Km, m3);
-#pragma unroll
-    for (int i = 0; i < NX * NX; ++i) v_xx[i] = ((q_xx[i] + m1[i]) + m2[i]) + m3[i];
+  for (int i = 0; i < NX; ++i) x[i] = v.X[soa_index<NX>(T, i, v.ld, p)];
+  for (int task = lane; task < D::n_terminal_tasks; task += LB) fd_terminal_task<M>(mask, task, x, prm, blk);
+  group_sync();
+  if (lane == 0) {
+    if (mask & D_VX) M::v_x(x, prm, v_x);
+    else
+      for (int i = 0; i < NX; ++i) v_x[i] = blk[i];
+    if (mask & D_VXX) M::v_xx(x, prm, v_xx);
+    else
+      for (int i = 0; i < NX * NX; ++i) v_xx[i] = blk[NX + i];
     symmetrize_aliased<NX>(v_xx);
+  }
+  group_sync();
+  for (int t = T - 1; t >= 0; --t) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = v.X[soa_index<NX>(t, i, v.ld, p)];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) u[i] = v.U[soa_index<NU>(t, i, v.ld, p)];
+    if (t > 0) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) prefetch_l1(&v.X[soa_index<NX>(t - 1, i, v.ld, p)]);
+#pragma unroll
+      for (int i = 0; i < NU; ++i) prefetch_l1(&v.U[soa_index<NU>(t - 1, i, v.ld, p)]);
+    }
+    for (int task = lane; task < D::n_tasks; task += LB) fd_stage_task<M>(mask, task, x, u, t, prm, blk);
+    group_sync();
+    if (lane == 0) {
+      double A[NX * NX], B[NX * NU], l_x[NX], l_u[NU], l_xx[NX * NX], l_uu[NU * NU], l_ux[NU * NX];
+      gather_stage_derivatives<M>(mask, blk, x, u, t, prm, A, B, l_x, l_u, l_xx, l_uu, l_ux);
+      retries += riccati_step<M, MASK_CT>(v, p, t, x, u, prm, al_rho, A, B, l_x, l_u, l_xx, l_uu, l_ux, v_x, v_xx);
+    }
+    group_sync();
   }
   return retries;
 }

@@ -23,10 +23,47 @@ struct ALOptions {
   double penalty = 10.0, penalty_increase = 5.0, constraint_tolerance = 1e-4, activation_tolerance = 1e-6;
   int repeats = 1;
   bool trial_store = true;
+  int backward_lanes = 0;  // > 0: lane-parallel backward pass with that many lanes per problem
   double* hist_cost = nullptr;
   int* hist_iters = nullptr;
 };
 ALOptions g_al;
+
+// backward_lanes (ilqr_core.cuh) with the lanes of a group run one after the other inside every phase: the FD tasks of
+// a step by "lane" 0..LB-1, then lane 0's gather + riccati_step.  Same task functions, same block layout.
+template <class M, int MASK_CT>
+int emulate_backward_lanes(const BatchView<M::NX, M::NU>& v, int p, int LB) {
+  constexpr int NX = M::NX, NU = M::NU;
+  using D = DerivBlock<M>;
+  const unsigned mask = (MASK_CT >= 0) ? static_cast<unsigned>(MASK_CT) : v.deriv_mask;
+  double prm[M::NP > 0 ? M::NP : 1];
+  load_params<M>(v, p, prm);
+  const int T = v.T;
+  int retries = 0;
+  const double al_rho = HasConstraints<M>::value ? v.penalty[p] : 0.0;
+  std::vector<double> blk(D::size > D::n_terminal_tasks ? D::size : D::n_terminal_tasks, 0.0);
+  double x[NX], u[NU], v_x[NX], v_xx[NX * NX];
+  for (int i = 0; i < NX; ++i) x[i] = v.X[soa_index<NX>(T, i, v.ld, p)];
+  for (int lane = 0; lane < LB; ++lane)
+    for (int task = lane; task < D::n_terminal_tasks; task += LB) fd_terminal_task<M>(mask, task, x, prm, blk.data());
+  if (mask & D_VX) M::v_x(x, prm, v_x);
+  else
+    for (int i = 0; i < NX; ++i) v_x[i] = blk[i];
+  if (mask & D_VXX) M::v_xx(x, prm, v_xx);
+  else
+    for (int i = 0; i < NX * NX; ++i) v_xx[i] = blk[NX + i];
+  symmetrize_aliased<NX>(v_xx);
+  for (int t = T - 1; t >= 0; --t) {
+    for (int i = 0; i < NX; ++i) x[i] = v.X[soa_index<NX>(t, i, v.ld, p)];
+    for (int i = 0; i < NU; ++i) u[i] = v.U[soa_index<NU>(t, i, v.ld, p)];
+    for (int lane = 0; lane < LB; ++lane)
+      for (int task = lane; task < D::n_tasks; task += LB) fd_stage_task<M>(mask, task, x, u, t, prm, blk.data());
+    double A[NX * NX], B[NX * NU], l_x[NX], l_u[NU], l_xx[NX * NX], l_uu[NU * NU], l_ux[NU * NX];
+    gather_stage_derivatives<M>(mask, blk.data(), x, u, t, prm, A, B, l_x, l_u, l_xx, l_uu, l_ux);
+    retries += riccati_step<M, MASK_CT>(v, p, t, x, u, prm, al_rho, A, B, l_x, l_u, l_xx, l_uu, l_ux, v_x, v_xx);
+  }
+  return retries;
+}
 
 template <class M>
 int emulate(int batch, int T, double dt, unsigned mask, int has_bounds, const double* lo, const double* hi, const double* shared_p,
@@ -107,7 +144,9 @@ int emulate(int batch, int T, double dt, unsigned mask, int has_bounds, const do
   for (int it = 0; it < max_iterations && !list.empty(); ++it) {
     for (int p : list) {  // backward_kernel
       int r;
-      if (mask == M::EXAMPLE_MASK) r = backward_thread<M, static_cast<int>(M::EXAMPLE_MASK)>(v, p);
+      if (g_al.backward_lanes > 0 && mask == 0u) r = emulate_backward_lanes<M, 0>(v, p, g_al.backward_lanes);
+      else if (g_al.backward_lanes > 0) r = emulate_backward_lanes<M, -1>(v, p, g_al.backward_lanes);
+      else if (mask == M::EXAMPLE_MASK) r = backward_thread<M, static_cast<int>(M::EXAMPLE_MASK)>(v, p);
       else if (mask == 0u) r = backward_thread<M, 0>(v, p);
       else r = backward_thread<M, -1>(v, p);
       v.reg_retries[p] += r;
@@ -232,6 +271,7 @@ extern "C" int emu_ilqr_solve_batch(int model, int batch, int T, double dt, unsi
 
 // Settings for the next emu_ilqr_solve_batch calls on constrained models (pass repeats = 1 and nulls to reset).
 extern "C" void emu_set_trial_store(int enable) { g_al.trial_store = enable != 0; }
+extern "C" void emu_set_backward_lanes(int lanes) { g_al.backward_lanes = lanes; }
 
 extern "C" void emu_set_al_options(double penalty, double penalty_increase, double constraint_tolerance, double activation_tolerance, int repeats,
                                    double* hist_cost, int* hist_iters) {

@@ -339,3 +339,27 @@ def test_one_shot_calls_reuse_the_context_batch_without_leaking_state(mas, ctx, 
     r2 = mas.ilqr_solve_batch(ctx, d5, p5, x5)
     ref5 = oracle.ilqr_solve_batch(5, x5, max_iterations=5, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
     assert is_bit_exact(r1, ref5) and is_bit_exact(r2, ref5)
+
+
+@pytest.mark.parametrize("model,mask", [(1, 0), (0, 0), (0, 0x0F)])
+def test_lane_parallel_backward_pass_matches_the_one_thread_pass(mas, ctx, emu, model, mask):
+    """backward_lanes_kernel (FD stencil points over eight lanes per problem) against backward_kernel on the same inputs."""
+    B = 200
+    x0 = random_x0(model, B, seed=520 + model)
+    desc = mas.example_desc(model)
+    desc.deriv_mask = mask
+    outs = []
+    for lanes_on in (1, 0):
+        b = mas.Batch(ctx, desc, B)
+        b.set_trial_store(lanes_on)  # 0 also switches the lane-parallel backward pass off
+        b.set_initial_states(x0)
+        b.set_controls(None)
+        b.solve(mas.IlqrParams.make(8, 1e-5))
+        outs.append(b.get_solution())
+        outs[-1]["stats"] = b.stats()
+        b.close()
+    assert is_bit_exact(outs[0], outs[1])
+    assert outs[0]["stats"]["reg_retries"] == outs[1]["stats"]["reg_retries"]
+    T, m = desc.horizon_steps, desc.control_dim
+    exp = emu.solve(model, x0, np.zeros((B, T, m)), 8, 1e-5, mask=mask)
+    assert is_bit_exact(outs[0], exp)

@@ -155,3 +155,22 @@ def test_stored_trials_equal_recomputed_steps(emu, model, L, C):
     b = emu.solve(model, x0, U0, 6, 1e-5, L=L, C=C, trial_store=False)
     for k in ("X", "U", "cost", "iterations", "status", "alpha_trials"):
         assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("model,mask,lanes", [(1, 0, 8), (3, 0, 8), (0, 0, 8), (0, 0x3F & ~0x30, 4), (4, 0, 3), (5, 0, 8)])
+def test_lane_parallel_backward_pass_is_bit_identical(emu, oracle, model, mask, lanes):
+    """backward_lanes: FD stencil points dealt out as tasks to the lanes of a problem, Riccati on lane 0.  Every task
+    repeats the arithmetic of the whole-matrix FD routines, so the one-thread backward pass is reproduced bit for bit
+    (and with it the oracle where the oracle has the same derivative mode)."""
+    max_it, tol = EXAMPLE_SOLVER_PARAMS.get(model, (6, 1e-5))
+    max_it = min(max_it, 12)
+    x0 = random_x0(model, 10, seed=300 + model)
+    n, m, T = MODEL_TABLE[model][:3]
+    U0 = np.zeros((10, T, m))
+    one = emu.solve(model, x0, U0, max_it, tol, mask=mask)
+    par = emu.solve(model, x0, U0, max_it, tol, mask=mask, backward_lanes=lanes)
+    for k in ("X", "U", "cost", "iterations", "status", "alpha_trials", "reg_retries"):
+        assert np.array_equal(one[k], par[k]), k
+    if mask == MODEL_TABLE[model][4]:  # the example's own derivative mode: the oracle applies
+        ref = oracle.ilqr_solve_batch(model, x0, U_init=U0, max_iterations=max_it, tolerance=tol, trig=oracle.TRIG_PORTABLE)
+        assert is_bit_exact(par, ref)
