@@ -657,30 +657,26 @@ struct BatchImpl : BatchBase {
 
   void launch_backward(int n_upper, int cur) {
     const unsigned mask = desc.deriv_mask;
-    // many finite-difference callbacks and few enough problems for eight lanes each to be resident: deal the stencil
-    // points out to the lanes (backward_lanes_kernel)
-    // at least the n x n stage Hessian by FD, and enough tasks to keep eight lanes busy (n = 4: 40; the pendulum's 13
-    // and the rocket's 21 measured slower than one thread per problem)
+    // Many finite-difference callbacks (at least the n x n stage Hessian) and enough tasks to keep eight lanes busy
+    // (n = 4: 40; the pendulum's 13 and the rocket's 21 measured slower than one thread per problem), and few enough
+    // problems for eight lanes each to be resident: deal the stencil points out to the lanes (backward_lanes_kernel).
     const bool fd_heavy = !(mask & D_LXX) && (mask == 0u || mask != M::EXAMPLE_MASK) && DerivBlock<M>::n_tasks >= 32;
     if (backward_lanes_enabled && fd_heavy && ls_mode == 0 && tune_L == 0) {
-      {
-        constexpr int LB = 8;
-        if (!resident_backward_lanes) {
-          int blocks = 0;
-          const size_t sm = (kBlock / LB) * DerivBlock<M>::size * sizeof(double);
-          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, backward_lanes_kernel<M, 0, LB>, kBlock, sm) != cudaSuccess || blocks <= 0) blocks = 4;
-          resident_backward_lanes = static_cast<long long>(blocks) * kBlock * ctx->sm_count;
-        }
-        if (static_cast<long long>(n_upper) * LB <= resident_backward_lanes) {
-          const int lgrid = static_cast<int>((static_cast<long long>(n_upper) * LB + kBlock - 1) / kBlock);
-          const size_t sm = (kBlock / LB) * DerivBlock<M>::size * sizeof(double);
-          if (mask == 0u)
-            backward_lanes_kernel<M, 0, LB><<<lgrid, kBlock, sm, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
-          else
-            backward_lanes_kernel<M, -1, LB><<<lgrid, kBlock, sm, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
-          stats.kernel_launches++;
-          return;
-        }
+      constexpr int LB = 8;
+      const size_t sm = (kBlock / LB) * DerivBlock<M>::size * sizeof(double);
+      if (!resident_backward_lanes) {
+        int blocks = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, backward_lanes_kernel<M, 0, LB>, kBlock, sm) != cudaSuccess || blocks <= 0) blocks = 4;
+        resident_backward_lanes = static_cast<long long>(blocks) * kBlock * ctx->sm_count;
+      }
+      if (static_cast<long long>(n_upper) * LB <= resident_backward_lanes) {
+        const int lgrid = static_cast<int>((static_cast<long long>(n_upper) * LB + kBlock - 1) / kBlock);
+        if (mask == 0u)
+          backward_lanes_kernel<M, 0, LB><<<lgrid, kBlock, sm, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
+        else
+          backward_lanes_kernel<M, -1, LB><<<lgrid, kBlock, sm, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));
+        stats.kernel_launches++;
+        return;
       }
     }
     const int grid = div_up(n_upper, kBlock);
