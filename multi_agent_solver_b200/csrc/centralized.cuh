@@ -68,7 +68,7 @@ enum StackedPhase { PH_TERMINAL = 0, PH_FD, PH_QASM, PH_LLT, PH_INVERSE, PH_GAIN
 // Offsets into the double workspace of one scenario.
 struct StackedWork {
   int ns, ms, A, NX, NU;
-  size_t Vx, Vxx, Ab, Bb, lx, lu, lxx, luu, lux, Qx, Qu, Qxx, Qux, Quu, Qreg, AtV, BtV, cb, pref, S5, R5, S6, R6, dx, scal, fast, fast_doubles, total;
+  size_t Vx, Vxx, Ab, Bb, lx, lu, lxx, luu, lux, fd_set, fd2, Qx, Qu, Qxx, Qux, Quu, Qreg, AtV, BtV, cb, pref, S5, R5, S6, R6, dx, scal, fast, fast_doubles, total;
   MAS_HD StackedWork(int A_, int NX_, int NU_) : A(A_), NX(NX_), NU(NU_) {
     ns = A * NX;
     ms = A * NU;
@@ -87,6 +87,8 @@ struct StackedWork {
     lxx = take(static_cast<size_t>(ns) * ns);
     luu = take(static_cast<size_t>(ms) * ms);
     lux = take(static_cast<size_t>(ms) * ns);
+    fd_set = o - Ab;      // Ab .. lux are contiguous: the derivative arrays of one time step
+    fd2 = take(fd_set);   // second copy: step t-1's derivatives are produced while step t is factorised
     Qx = take(ns);
     Qu = take(ms);
     Qxx = take(static_cast<size_t>(ns) * ns);
@@ -121,6 +123,19 @@ struct StackedWork {
     total = o;
   }
 };
+
+// Barrier over a warp-aligned group of `count` threads of the CTA (named barrier `id`, 1..15); the whole CTA when
+// count == all.  Sequential host emulation: nothing.
+MAS_HD void stacked_group_sync(int id, int count, int all) {
+#if defined(__CUDA_ARCH__)
+  if (count == all) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#else
+  (void)id;
+  (void)count;
+  (void)all;
+#endif
+}
 
 enum StackedScalar { SC_COST = 0, SC_MERIT = 1, SC_TRIAL = 2, SC_REG = 3, SC_PIVOT = 4, SC_FLAG = 5, SC_INNER = 6 };
 
@@ -222,6 +237,7 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
          *R5 = P.fast + W.R5, *S6 = P.fast + W.S6, *R6 = P.fast + W.R6, *scal = P.fast + W.scal;
   const double e5 = 1e-5, e6 = 1e-6;
   const int ldk = ms + 1;
+  const int nthr_all = nthr;
   double* fK = P.fast;                                   // K of the current step, column i at i*ldk
   double* fQ = fK + static_cast<size_t>(ns) * ldk;       // Q_ux, same layout
   double* fC = fQ + static_cast<size_t>(ns) * ldk;
@@ -305,122 +321,203 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
   }
   MAS_CTA_SYNC();
 
-  for (int t = T - 1; t >= 0; --t) {
+  // Two bodies that do not depend on each other inside a step: the finite-difference derivatives of a time step (they
+  // need x_t, u_t only) and the factorisation + inverse of Q_uu (64 of the CTA's threads at most, the rest used to wait
+  // at its barriers).  With at least four warps, warps 0-1 factorise step t while the other warps already produce
+  // step t-1's derivatives into the second set of arrays; otherwise, and in the host emulation, they run in turn.
+  const size_t fd_stride = W.fd2 - W.Ab;
+  auto fd_phase = [&](int t, int tid, int nthr, int bar_id) {
     const double* xt = P.X + static_cast<size_t>(t) * ns;
     const double* ut = P.U + static_cast<size_t>(t) * ms;
-    if (t == T - 1) MAS_PHASE(PH_TERMINAL);
-    // ---- per-agent pieces: FD Jacobian blocks, base stage cost, singly perturbed stage costs
-    for (int a = tid; a < A; a += nthr) {
-      const double* xa = xt + a * NX;
-      const double* ua = ut + a * NU;
-      const double* pa = P.prm + a * NPs;
-      fd_jac_x<M>(xa, ua, pa, Ab + static_cast<size_t>(a) * NX * NX);
-      fd_jac_u<M>(xa, ua, pa, Bb + static_cast<size_t>(a) * NX * NU);
-      cb[a] = M::stage(xa, ua, t, pa);
-    }
-    for (int e = tid; e < A * (NX + NU) * 2; e += nthr) {
-      const int a = e / ((NX + NU) * 2), r = e % ((NX + NU) * 2), v = r / 2, sgn = r % 2;
-      const double* xa = xt + a * NX;
-      const double* ua = ut + a * NU;
-      const double* pa = P.prm + a * NPs;
-      if (v < NX) {
-        S5[(a * NX + v) * 2 + sgn] = agent_stage_pert<M>(xa, ua, t, pa, v, sgn ? -e5 : e5, -1, 0, -1, 0, -1, 0);
-        S6[(a * NX + v) * 2 + sgn] = agent_stage_pert<M>(xa, ua, t, pa, v, sgn ? -e6 : e6, -1, 0, -1, 0, -1, 0);
-      } else {
-        const int iu = v - NX;
-        R5[(a * NU + iu) * 2 + sgn] = agent_stage_pert<M>(xa, ua, t, pa, -1, 0, -1, 0, iu, sgn ? -e5 : e5, -1, 0);
-        R6[(a * NU + iu) * 2 + sgn] = agent_stage_pert<M>(xa, ua, t, pa, -1, 0, -1, 0, iu, sgn ? -e6 : e6, -1, 0);
+    const size_t off = (t & 1) ? fd_stride : 0;
+    double *Ab = w + W.Ab + off, *Bb = w + W.Bb + off, *lx = w + W.lx + off, *lu = w + W.lu + off, *lxx = w + W.lxx + off, *luu = w + W.luu + off,
+           *lux = w + W.lux + off;
+    auto fsync = [&]() { stacked_group_sync(bar_id, nthr, nthr_all); };
+      // ---- per-agent pieces: FD Jacobian blocks, base stage cost, singly perturbed stage costs
+      for (int a = tid; a < A; a += nthr) {
+        const double* xa = xt + a * NX;
+        const double* ua = ut + a * NU;
+        const double* pa = P.prm + a * NPs;
+        fd_jac_x<M>(xa, ua, pa, Ab + static_cast<size_t>(a) * NX * NX);
+        fd_jac_u<M>(xa, ua, pa, Bb + static_cast<size_t>(a) * NX * NU);
+        cb[a] = M::stage(xa, ua, t, pa);
       }
-    }
-    MAS_CTA_SYNC();
-    if (tid == 0) {
-      double s = 0.0;
-      pref[0] = s;
-      for (int a = 0; a < A; ++a) {
-        s += cb[a];
-        pref[a + 1] = s;
-      }
-    }
-    MAS_CTA_SYNC();
-    // ---- FD derivatives of the stacked stage cost (finite_differences.hpp:110-210,263-287)
-    const int n_lx = ns, n_lu = ms, n_lxx = ns * ns, n_luu = ms * ms, n_lux = ms * ns;
-    for (int idx = tid; idx < n_lx + n_lu + n_lxx + n_luu + n_lux; idx += nthr) {
-      int e = idx;
-      if (e < n_lx) {
-        const int a = e / NX, il = e % NX;
-        double f2[2];
-        stacked_sum1xN<2>(cb, pref, A, a, &S6[(a * NX + il) * 2], f2);
-        lx[e] = MAS_DIV_CONST(f2[0] - f2[1], 2 * e6);
-        continue;
-      }
-      e -= n_lx;
-      if (e < n_lu) {
-        const int a = e / NU, il = e % NU;
-        double f2[2];
-        stacked_sum1xN<2>(cb, pref, A, a, &R6[(a * NU + il) * 2], f2);
-        lu[e] = MAS_DIV_CONST(f2[0] - f2[1], 2 * e6);
-        continue;
-      }
-      e -= n_lu;
-      if (e < n_lxx + n_luu) {
-        const bool is_x = e < n_lxx;
-        if (!is_x) e -= n_lxx;
-        const int dim = is_x ? ns : ms, per = is_x ? NX : NU;
-        const double* tab = is_x ? S5 : R5;
-        const int i = e % dim, j = e / dim;
-        const int a = i / per, il = i % per, b = j / per, jl = j % per;
-        double h;
-        if (i == j) {
-          double f2[2];
-          stacked_sum1xN<2>(cb, pref, A, a, &tab[(a * per + il) * 2], f2);
-          const double fp = finite_or_zero(f2[0]);
-          const double f0 = finite_or_zero(pref[A]);
-          const double fm = finite_or_zero(f2[1]);
-          h = MAS_DIV_CONST(fp - 2 * f0 + fm, e5 * e5);
-        } else if (a == b) {
-          const double* xa = xt + a * NX;
-          const double* ua = ut + a * NU;
-          const double* pa = P.prm + a * NPs;
-          double v[4], cq[4];
-          for (int q = 0; q < 4; ++q) {
-            const double di = (q & 2) ? -e5 : e5, dj = (q & 1) ? -e5 : e5;
-            cq[q] = is_x ? agent_stage_pert<M>(xa, ua, t, pa, il, di, jl, dj, -1, 0, -1, 0)
-                         : agent_stage_pert<M>(xa, ua, t, pa, -1, 0, -1, 0, il, di, jl, dj);
-          }
-          stacked_sum1xN<4>(cb, pref, A, a, cq, v);
-          for (int q = 0; q < 4; ++q) v[q] = finite_or_zero(v[q]);
-          h = MAS_DIV_CONST(v[0] - v[1] - v[2] + v[3], 4 * e5 * e5);
+      for (int e = tid; e < A * (NX + NU) * 2; e += nthr) {
+        const int a = e / ((NX + NU) * 2), r = e % ((NX + NU) * 2), v = r / 2, sgn = r % 2;
+        const double* xa = xt + a * NX;
+        const double* ua = ut + a * NU;
+        const double* pa = P.prm + a * NPs;
+        if (v < NX) {
+          S5[(a * NX + v) * 2 + sgn] = agent_stage_pert<M>(xa, ua, t, pa, v, sgn ? -e5 : e5, -1, 0, -1, 0, -1, 0);
+          S6[(a * NX + v) * 2 + sgn] = agent_stage_pert<M>(xa, ua, t, pa, v, sgn ? -e6 : e6, -1, 0, -1, 0, -1, 0);
         } else {
-          double v[4];
-          stacked_sum2x4(cb, pref, A, a, &tab[(a * per + il) * 2], b, &tab[(b * per + jl) * 2], v);
-          for (int q = 0; q < 4; ++q) v[q] = finite_or_zero(v[q]);
-          h = MAS_DIV_CONST(v[0] - v[1] - v[2] + v[3], 4 * e5 * e5);
+          const int iu = v - NX;
+          R5[(a * NU + iu) * 2 + sgn] = agent_stage_pert<M>(xa, ua, t, pa, -1, 0, -1, 0, iu, sgn ? -e5 : e5, -1, 0);
+          R6[(a * NU + iu) * 2 + sgn] = agent_stage_pert<M>(xa, ua, t, pa, -1, 0, -1, 0, iu, sgn ? -e6 : e6, -1, 0);
         }
-        (is_x ? lxx : luu)[i + static_cast<size_t>(j) * dim] = h;
-        continue;
       }
-      e -= n_lxx + n_luu;
-      {  // cross term H(i,j): control i, state j; f_pp=(x+,u+) f_pm=(x-,u+) f_mp=(x+,u-) f_mm=(x-,u-)
-        const int i = e % ms, j = e / ms;
-        const int a = i / NU, il = i % NU, b = j / NX, jl = j % NX;
-        double v[4];
-        if (a == b) {
-          double cq[4];
-          for (int q = 0; q < 4; ++q) {
-            const int sx = q & 1, su = (q >> 1) & 1;  // q: 0 pp, 1 pm (x-), 2 mp (u-), 3 mm
-            cq[q] = agent_stage_pert<M>(xt + a * NX, ut + a * NU, t, P.prm + a * NPs, jl, sx ? -e6 : e6, -1, 0, il, su ? -e6 : e6, -1, 0);
+      fsync();
+      if (tid == 0) {
+        double s = 0.0;
+        pref[0] = s;
+        for (int a = 0; a < A; ++a) {
+          s += cb[a];
+          pref[a + 1] = s;
+        }
+      }
+      fsync();
+      // ---- FD derivatives of the stacked stage cost (finite_differences.hpp:110-210,263-287)
+      const int n_lx = ns, n_lu = ms, n_lxx = ns * ns, n_luu = ms * ms, n_lux = ms * ns;
+      for (int idx = tid; idx < n_lx + n_lu + n_lxx + n_luu + n_lux; idx += nthr) {
+        int e = idx;
+        if (e < n_lx) {
+          const int a = e / NX, il = e % NX;
+          double f2[2];
+          stacked_sum1xN<2>(cb, pref, A, a, &S6[(a * NX + il) * 2], f2);
+          lx[e] = MAS_DIV_CONST(f2[0] - f2[1], 2 * e6);
+          continue;
+        }
+        e -= n_lx;
+        if (e < n_lu) {
+          const int a = e / NU, il = e % NU;
+          double f2[2];
+          stacked_sum1xN<2>(cb, pref, A, a, &R6[(a * NU + il) * 2], f2);
+          lu[e] = MAS_DIV_CONST(f2[0] - f2[1], 2 * e6);
+          continue;
+        }
+        e -= n_lu;
+        if (e < n_lxx + n_luu) {
+          const bool is_x = e < n_lxx;
+          if (!is_x) e -= n_lxx;
+          const int dim = is_x ? ns : ms, per = is_x ? NX : NU;
+          const double* tab = is_x ? S5 : R5;
+          const int i = e % dim, j = e / dim;
+          const int a = i / per, il = i % per, b = j / per, jl = j % per;
+          double h;
+          if (i == j) {
+            double f2[2];
+            stacked_sum1xN<2>(cb, pref, A, a, &tab[(a * per + il) * 2], f2);
+            const double fp = finite_or_zero(f2[0]);
+            const double f0 = finite_or_zero(pref[A]);
+            const double fm = finite_or_zero(f2[1]);
+            h = MAS_DIV_CONST(fp - 2 * f0 + fm, e5 * e5);
+          } else if (a == b) {
+            const double* xa = xt + a * NX;
+            const double* ua = ut + a * NU;
+            const double* pa = P.prm + a * NPs;
+            double v[4], cq[4];
+            for (int q = 0; q < 4; ++q) {
+              const double di = (q & 2) ? -e5 : e5, dj = (q & 1) ? -e5 : e5;
+              cq[q] = is_x ? agent_stage_pert<M>(xa, ua, t, pa, il, di, jl, dj, -1, 0, -1, 0)
+                           : agent_stage_pert<M>(xa, ua, t, pa, -1, 0, -1, 0, il, di, jl, dj);
+            }
+            stacked_sum1xN<4>(cb, pref, A, a, cq, v);
+            for (int q = 0; q < 4; ++q) v[q] = finite_or_zero(v[q]);
+            h = MAS_DIV_CONST(v[0] - v[1] - v[2] + v[3], 4 * e5 * e5);
+          } else {
+            double v[4];
+            stacked_sum2x4(cb, pref, A, a, &tab[(a * per + il) * 2], b, &tab[(b * per + jl) * 2], v);
+            for (int q = 0; q < 4; ++q) v[q] = finite_or_zero(v[q]);
+            h = MAS_DIV_CONST(v[0] - v[1] - v[2] + v[3], 4 * e5 * e5);
           }
-          stacked_sum1xN<4>(cb, pref, A, a, cq, v);
-          for (int q = 0; q < 4; ++q) v[q] = finite_or_zero(v[q]);
-        } else {  // agent a (control, variant su = bit 1 of q), agent b (state, variant sx = bit 0 of q)
-          stacked_sum2x4(cb, pref, A, a, &R6[(a * NU + il) * 2], b, &S6[(b * NX + jl) * 2], v);
-          for (int q = 0; q < 4; ++q) v[q] = finite_or_zero(v[q]);
+          (is_x ? lxx : luu)[i + static_cast<size_t>(j) * dim] = h;
+          continue;
         }
-        lux[i + static_cast<size_t>(j) * ms] = MAS_DIV_CONST(v[0] - v[1] - v[2] + v[3], 4 * e6 * e6);
+        e -= n_lxx + n_luu;
+        {  // cross term H(i,j): control i, state j; f_pp=(x+,u+) f_pm=(x-,u+) f_mp=(x+,u-) f_mm=(x-,u-)
+          const int i = e % ms, j = e / ms;
+          const int a = i / NU, il = i % NU, b = j / NX, jl = j % NX;
+          double v[4];
+          if (a == b) {
+            double cq[4];
+            for (int q = 0; q < 4; ++q) {
+              const int sx = q & 1, su = (q >> 1) & 1;  // q: 0 pp, 1 pm (x-), 2 mp (u-), 3 mm
+              cq[q] = agent_stage_pert<M>(xt + a * NX, ut + a * NU, t, P.prm + a * NPs, jl, sx ? -e6 : e6, -1, 0, il, su ? -e6 : e6, -1, 0);
+            }
+            stacked_sum1xN<4>(cb, pref, A, a, cq, v);
+            for (int q = 0; q < 4; ++q) v[q] = finite_or_zero(v[q]);
+          } else {  // agent a (control, variant su = bit 1 of q), agent b (state, variant sx = bit 0 of q)
+            stacked_sum2x4(cb, pref, A, a, &R6[(a * NU + il) * 2], b, &S6[(b * NX + jl) * 2], v);
+            for (int q = 0; q < 4; ++q) v[q] = finite_or_zero(v[q]);
+          }
+          lux[i + static_cast<size_t>(j) * ms] = MAS_DIV_CONST(v[0] - v[1] - v[2] + v[3], 4 * e6 * e6);
+        }
       }
-    }
-    MAS_CTA_SYNC();
-    MAS_PHASE(PH_FD);
+    fsync();
+  };
+  auto llt_inverse_phase = [&](int tid, int nthr, int bar_id) {
+    auto lsync = [&]() { stacked_group_sync(bar_id, nthr, nthr_all); };
+      // ---- LLT of Q_uu_reg with the cumulative-shift retry loop (ilqr.hpp:172-182); unblocked, lower
+      for (;;) {
+        // Row i's running sum of squares sq[i] = L_i0^2 + ... (added as the columns are produced, i.e. in the order the
+        // reference's pivot computation adds them) makes the pivot of column k a single subtraction; every thread
+        // evaluates it redundantly from the untouched diagonal of Q_uu_reg, so a column costs one barrier.
+        double* sq = P.fast + W.dx;  // the rollout's scratch, free during the backward pass
+        for (int e = tid; e < ms * ms; e += nthr) Lm[e] = Qreg[e];
+        for (int i = tid; i < ms; i += nthr) sq[i] = 0.0;
+        lsync();
+        bool failed = false;
+        for (int k = 0; k < ms; ++k) {
+          double x = Qreg[k + static_cast<size_t>(k) * ms];
+          if (k > 0) x -= sq[k];
+          if (x <= 0.0) {
+            failed = true;
+            break;
+          }
+          x = sqrt(x);
+          if (tid == 0) Lm[k + static_cast<size_t>(k) * ms] = x;
+          for (int i = k + 1 + tid; i < ms; i += nthr) {
+            double s = Lm[i + static_cast<size_t>(k) * ms];
+            if (k > 0) {
+              double acc = Lm[i + 0 * static_cast<size_t>(ms)] * Lm[k + 0 * static_cast<size_t>(ms)];
+              for (int j = 1; j < k; ++j) acc = acc + Lm[i + static_cast<size_t>(j) * ms] * Lm[k + static_cast<size_t>(j) * ms];
+              s -= acc;
+            }
+            const double l = pm::div_(s, x);
+            Lm[i + static_cast<size_t>(k) * ms] = l;
+            sq[i] += l * l;
+          }
+          lsync();
+        }
+        if (!failed) break;
+        const double reg = scal[SC_REG];
+        lsync();
+        for (int i = tid; i < ms; i += nthr) Qreg[i + static_cast<size_t>(i) * ms] += reg;
+        if (tid == 0) {
+          scal[SC_REG] = reg * 10.0;
+          P.out_int[2] += 1;
+        }
+        lsync();
+        if (!(reg < 1e300)) break;
+      }
+      // ---- Q_uu_inv = llt.solve(I), one column per thread, the column (stride ldk, conflict-free) is its own work
+      // vector.  Forward substitution on e_c: rows above c stay exactly zero, and their products are left out of the
+      // later rows' sums (s - L*0 == s).
+      for (int c = tid; c < ms; c += nthr) {
+        double* x = inv + static_cast<size_t>(c) * ldk;
+        for (int i = 0; i < ms; ++i) x[i] = (i == c) ? 1.0 : 0.0;
+        for (int i = c; i < ms; ++i) {
+          double s = x[i];
+          for (int j = c; j < i; ++j) s -= Lm[i + static_cast<size_t>(j) * ms] * x[j];
+          x[i] = pm::div_(s, Lm[i + static_cast<size_t>(i) * ms]);
+        }
+        for (int i = ms - 1; i >= 0; --i) {
+          double s = x[i];
+          for (int j = i + 1; j < ms; ++j) s -= Lm[j + static_cast<size_t>(i) * ms] * x[j];
+          x[i] = pm::div_(s, Lm[i + static_cast<size_t>(i) * ms]);
+        }
+      }
+      lsync();
+    lsync();
+  };
+  const bool overlap = nthr_all >= 128 && (nthr_all % 32) == 0;
+  MAS_PHASE(PH_TERMINAL);
+  fd_phase(T - 1, tid, nthr, 0);
+  MAS_PHASE(PH_FD);
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t off = (t & 1) ? fd_stride : 0;
+    double *Ab = w + W.Ab + off, *Bb = w + W.Bb + off, *lx = w + W.lx + off, *lu = w + W.lu + off, *lxx = w + W.lxx + off, *luu = w + W.luu + off,
+           *lux = w + W.lux + off;
     // ---- Q_x, Q_u, A^T V_xx, B^T V_xx (ilqr.hpp:115-119); A, B block diagonal
     for (int idx = tid; idx < ns + ms + ns * ns + ms * ns; idx += nthr) {
       int e = idx;
@@ -494,69 +591,17 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
     if (tid == 0) scal[SC_REG] = 1e-6;
     MAS_CTA_SYNC();
     MAS_PHASE(PH_QASM);
-    // ---- LLT of Q_uu_reg with the cumulative-shift retry loop (ilqr.hpp:172-182); unblocked, lower
-    for (;;) {
-      // Row i's running sum of squares sq[i] = L_i0^2 + ... (added as the columns are produced, i.e. in the order the
-      // reference's pivot computation adds them) makes the pivot of column k a single subtraction; every thread
-      // evaluates it redundantly from the untouched diagonal of Q_uu_reg, so a column costs one barrier.
-      double* sq = P.fast + W.dx;  // the rollout's scratch, free during the backward pass
-      for (int e = tid; e < ms * ms; e += nthr) Lm[e] = Qreg[e];
-      for (int i = tid; i < ms; i += nthr) sq[i] = 0.0;
+    if (overlap && t > 0) {
+      if (tid < 64) llt_inverse_phase(tid, 64, 1);
+      else fd_phase(t - 1, tid - 64, nthr_all - 64, 2);
       MAS_CTA_SYNC();
-      bool failed = false;
-      for (int k = 0; k < ms; ++k) {
-        double x = Qreg[k + static_cast<size_t>(k) * ms];
-        if (k > 0) x -= sq[k];
-        if (x <= 0.0) {
-          failed = true;
-          break;
-        }
-        x = sqrt(x);
-        if (tid == 0) Lm[k + static_cast<size_t>(k) * ms] = x;
-        for (int i = k + 1 + tid; i < ms; i += nthr) {
-          double s = Lm[i + static_cast<size_t>(k) * ms];
-          if (k > 0) {
-            double acc = Lm[i + 0 * static_cast<size_t>(ms)] * Lm[k + 0 * static_cast<size_t>(ms)];
-            for (int j = 1; j < k; ++j) acc = acc + Lm[i + static_cast<size_t>(j) * ms] * Lm[k + static_cast<size_t>(j) * ms];
-            s -= acc;
-          }
-          const double l = pm::div_(s, x);
-          Lm[i + static_cast<size_t>(k) * ms] = l;
-          sq[i] += l * l;
-        }
-        MAS_CTA_SYNC();
-      }
-      if (!failed) break;
-      const double reg = scal[SC_REG];
-      MAS_CTA_SYNC();
-      for (int i = tid; i < ms; i += nthr) Qreg[i + static_cast<size_t>(i) * ms] += reg;
-      if (tid == 0) {
-        scal[SC_REG] = reg * 10.0;
-        P.out_int[2] += 1;
-      }
-      MAS_CTA_SYNC();
-      if (!(reg < 1e300)) break;
+      MAS_PHASE(PH_LLT);  // with the overlap this slot holds max(LLT + inverse, FD of the next step)
+    } else {
+      llt_inverse_phase(tid, nthr, 0);
+      MAS_PHASE(PH_LLT);
+      if (t > 0) fd_phase(t - 1, tid, nthr, 0);
+      MAS_PHASE(PH_FD);
     }
-    MAS_PHASE(PH_LLT);
-    // ---- Q_uu_inv = llt.solve(I), one column per thread, the column (stride ldk, conflict-free) is its own work
-    // vector.  Forward substitution on e_c: rows above c stay exactly zero, and their products are left out of the
-    // later rows' sums (s - L*0 == s).
-    for (int c = tid; c < ms; c += nthr) {
-      double* x = inv + static_cast<size_t>(c) * ldk;
-      for (int i = 0; i < ms; ++i) x[i] = (i == c) ? 1.0 : 0.0;
-      for (int i = c; i < ms; ++i) {
-        double s = x[i];
-        for (int j = c; j < i; ++j) s -= Lm[i + static_cast<size_t>(j) * ms] * x[j];
-        x[i] = pm::div_(s, Lm[i + static_cast<size_t>(i) * ms]);
-      }
-      for (int i = ms - 1; i >= 0; --i) {
-        double s = x[i];
-        for (int j = i + 1; j < ms; ++j) s -= Lm[j + static_cast<size_t>(i) * ms] * x[j];
-        x[i] = pm::div_(s, Lm[i + static_cast<size_t>(i) * ms]);
-      }
-    }
-    MAS_CTA_SYNC();
-    MAS_PHASE(PH_INVERSE);
     // ---- gains k = (-inv) Q_u, K = (-inv) Q_ux (ilqr.hpp:185-186)
     double* Kt = P.K + static_cast<size_t>(t) * ms * ns;
     double* kt = P.kff + static_cast<size_t>(t) * ms;

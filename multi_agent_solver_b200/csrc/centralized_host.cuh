@@ -147,7 +147,7 @@ int run_centralized(Context* ctx, const mas_b200_ocp_desc& d, const mas_b200_ilq
     long long h[kNumPhases];
     MAS_CUDA_CHECK(cudaMemcpy(h, d_phase, sizeof(h), cudaMemcpyDeviceToHost));
     cudaFree(d_phase);
-    static const char* names[kNumPhases] = {"terminal FD", "stage FD tables + derivatives", "Q assembly (A^T V A ...)", "LLT of Q_uu", "Q_uu inverse",
+    static const char* names[kNumPhases] = {"terminal FD", "stage FD tables + derivatives (not overlapped)", "Q assembly (A^T V A ...)", "LLT + inverse || FD of the next step", "(unused)",
                                             "gains", "value update", "rollouts (prologue + line search)"};
     long long tot = 0;
     for (long long c : h) tot += c;
