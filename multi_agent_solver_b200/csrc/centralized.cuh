@@ -226,8 +226,20 @@ MAS_HD double agent_stage_pert(const double* x, const double* u, int t, const do
 }
 
 // One backward pass over the stacked problem (ilqr.hpp:92-193).  Returns nothing; retries are counted in out_int[2].
-template <class M>
+// FAST_SHARED: StackedProblem::fast is known to point into shared memory (the device kernel when the scratch fits);
+// told to the compiler so that it emits shared-memory loads instead of generic ones.
+#if defined(__CUDA_ARCH__)
+#define MAS_FAST_IS_SHARED(flag, ptr) \
+  do {                                \
+    if (flag) __builtin_assume(__isShared(ptr)); \
+  } while (0)
+#else
+#define MAS_FAST_IS_SHARED(flag, ptr) ((void)0)
+#endif
+
+template <class M, bool FAST_SHARED = false>
 MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, int tid, int nthr) {
+  MAS_FAST_IS_SHARED(FAST_SHARED, P.fast);
   constexpr int NX = M::NX, NU = M::NU, NPs = (M::NP > 0 ? M::NP : 1);
   const int A = P.A, ns = W.ns, ms = W.ms, T = P.T;
   double* w = P.work;
@@ -751,8 +763,9 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
 // Rollout of the stacked system.  alpha < 0: plain rollout of the controls in Uout (prologue, ilqr.hpp:75-76);
 // otherwise the line-search forward pass (ilqr.hpp:208-217) from the nominal (P.X, P.U) with gains.  The stacked
 // stage cost is the block-order sum of the agents' costs, accumulated over t.  Result in scal[SC_TRIAL].
-template <class M>
+template <class M, bool FAST_SHARED = false>
 MAS_HD void stacked_rollout(const StackedProblem<M>& P, const StackedWork& W, double alpha, double* Xout, double* Uout, int tid, int nthr) {
+  MAS_FAST_IS_SHARED(FAST_SHARED, P.fast);
   constexpr int NX = M::NX, NU = M::NU, NPs = (M::NP > 0 ? M::NP : 1);
   const int A = P.A, ns = W.ns, ms = W.ms, T = P.T;
   double* w = P.work;
@@ -810,8 +823,9 @@ MAS_HD void stacked_rollout(const StackedProblem<M>& P, const StackedWork& W, do
 
 // The whole centralized solve of one scenario: iLQR::solve on the stacked OCP, then the per-agent cost
 // re-evaluation of centralized.hpp:27-36.
-template <class M>
+template <class M, bool FAST_SHARED = false>
 MAS_HD void stacked_solve(const StackedProblem<M>& P, int tid, int nthr) {
+  MAS_FAST_IS_SHARED(FAST_SHARED, P.fast);
   constexpr int NX = M::NX, NU = M::NU, NPs = (M::NP > 0 ? M::NP : 1);
   const StackedWork W(P.A, NX, NU);
   const int ns = W.ns, ms = W.ms, T = P.T;
@@ -823,7 +837,7 @@ MAS_HD void stacked_solve(const StackedProblem<M>& P, int tid, int nthr) {
     P.out_int[3] = 0;
   }
   MAS_PHASE_BEGIN();
-  stacked_rollout<M>(P, W, -1.0, P.X, P.U, tid, nthr);
+  stacked_rollout<M, FAST_SHARED>(P, W, -1.0, P.X, P.U, tid, nthr);
   MAS_PHASE(PH_ROLLOUT);
   if (tid == 0) {
     scal[SC_COST] = scal[SC_TRIAL];
@@ -832,7 +846,7 @@ MAS_HD void stacked_solve(const StackedProblem<M>& P, int tid, int nthr) {
   MAS_CTA_SYNC();
   for (int iter = 0; iter < P.max_iterations; ++iter) {
     if (tid == 0) P.out_int[0] = iter + 1;
-    stacked_backward<M>(P, W, tid, nthr);
+    stacked_backward<M, FAST_SHARED>(P, W, tid, nthr);
 #if defined(__CUDA_ARCH__)
     if (P.phase_cycles && tid == 0) mas_phase_t0 = clock64();  // the backward pass accounted for its own phases
 #endif
@@ -841,7 +855,7 @@ MAS_HD void stacked_solve(const StackedProblem<M>& P, int tid, int nthr) {
     double best_merit = current_merit;
     double alpha = 1.0;
     for (int j = 0; j < kNumAlphas; ++j) {
-      stacked_rollout<M>(P, W, alpha, P.Xt, P.Ut, tid, nthr);
+      stacked_rollout<M, FAST_SHARED>(P, W, alpha, P.Xt, P.Ut, tid, nthr);
       const double trial = scal[SC_TRIAL];
       MAS_CTA_SYNC();
       MAS_PHASE(PH_ROLLOUT);

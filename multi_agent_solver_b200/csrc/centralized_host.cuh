@@ -28,11 +28,16 @@ __global__ void __launch_bounds__(kCentralizedThreads) centralized_kernel(Stacke
   P.K = base.K + static_cast<size_t>(s) * T * ms * ns;
   P.kff = base.kff + static_cast<size_t>(s) * T * ms;
   P.work = base.work + static_cast<size_t>(s) * work_stride;
-  P.fast = fast_in_shared ? mas_fast_scratch : P.work + fast_offset;
+  P.fast = mas_fast_scratch;
   P.out_cost = base.out_cost + static_cast<size_t>(s) * (1 + base.A);
   P.out_int = base.out_int + static_cast<size_t>(s) * 4;
   if (s != 0) P.phase_cycles = nullptr;  // diagnostics: scenario 0 only
-  stacked_solve<M>(P, threadIdx.x, blockDim.x);
+  if (fast_in_shared) {
+    stacked_solve<M, true>(P, threadIdx.x, blockDim.x);
+  } else {  // stacked problems too large for shared memory: the same scratch inside the global workspace
+    P.fast = P.work + fast_offset;
+    stacked_solve<M, false>(P, threadIdx.x, blockDim.x);
+  }
 }
 
 // CentralizedStrategy::operator() for n_scenarios scenarios of n_agents agents (host arrays as in
