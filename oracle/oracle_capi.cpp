@@ -101,6 +101,7 @@ int oracle_default_controls(int model, int horizon, double* U /* [T][m] */) {
     model_dims(model, horizon, &n, &m, &T, &dt);
     Vec x0(n, 0.0);
     if (model == MODEL_ROCKET) x0[2] = 1.0;
+    trig_mode() = TRIG_GLIBC;  // the example computes its initial guess with libm (pendulum_swing_up.cpp:110-113)
     OCP p = build_ocp(model, x0.data(), nullptr, 0, horizon);
     std::memcpy(U, p.initial_controls.d.data(), sizeof(double) * m * T);
   } catch (...) {

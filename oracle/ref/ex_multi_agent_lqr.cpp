@@ -1,0 +1,4 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.  The reference's examples/multi_agent_lqr.cpp, compiled as it is
+// (its main() renamed by the preprocessor so that the file can live in a shared library).
+#define main ref_example_main_multi_agent_lqr
+#include "multi_agent_lqr.cpp"
