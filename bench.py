@@ -4,21 +4,25 @@
 Workload (BASELINE.json configs[2], SURVEY 8d "config 3"): 65,536 independent single-track
 lane-following OCPs (n=4, m=2, T=80, dt=0.1, bounds as examples/single_track_ocp.cpp:105-109),
 x0 = (0, Y, psi, v) from std::mt19937_64(20240607), U_init = 0, iLQR params 10 / 1e-5 / max_ms=inf.
-A "step" is one solve of the whole batch.  With N > 1 every rank solves its own 65,536-problem shard
-(independent problems, no data-path collective): weak scaling; --scaling strong splits one 65,536
-batch across the ranks instead.  Throughput is measured with --depth (default 6) independent solves in
-flight per GPU -- each a whole step on its own stream, driven by its own host thread, starts staggered --
-because the last iterations of a solve are bound by the latency of T sequential time steps and leave
-the GPU nearly idle; the time of one solve alone is reported as config.single_solve_ms.
+A "step" is one solve of the whole batch.  With N > 1 the 65,536 problems are SHARDED over the ranks
+(contiguous ranges, independent problems, no data-path collective): strong scaling, as BASELINE names
+it; one full 65,536-problem shard per rank (weak scaling) is measured too and reported under "weak".
 
-  value : solves/s, inputs (x0) resident in HBM in the engine's layout when the timed region starts
-  e2e   : same metric through the C ABI with HOST buffers: x0 host->device, solve, and X, U, cost,
-          iterations, status device->host inside the timed region, every step
+  value    : solves/s, inputs (x0) resident in HBM in the engine's layout when the timed region starts
+  e2e      : same metric through the C ABI with HOST buffers: x0 host->device, solve, and X, U, cost,
+             iterations, status device->host inside the timed region, every step
+  parity   : the results of the timed batch against the CPU checkers, outside the timed region:
+             (i) bit for bit against the reference's own sources compiled with portable trig
+             (oracle/_ref, else the restated oracle), all problems of rank 0's shard;
+             (ii) against the reference in its own libm mode, next to the reference's own 1-ulp band
   roofline : the dominant kernel, timed per launch with CUDA events inside the engine
-  cpu_baseline : the oracle (CPU restatement of the reference, OpenMP over problems) on a bounded sample
+  cpu_baseline : the reference's CPU implementation (oracle/_ref = its unmodified sources; else the
+             restated oracle) on a bounded sample, all host threads
+  configs  : short runs of BASELINE configs 1, 2, 4 (with the library's per-round NCCL all-gather at N > 1), 5
 
---impl reference times the reference's own CPU path instead: the reference cannot be built here
-(needs Eigen 3.4, absent, no network), so this is the oracle port on all host threads.
+--impl reference times the reference's own CPU path instead (oracle/_ref/libref.so, built from
+/root/reference's unmodified headers and examples against oracle/eigen_shim); the product library is
+never loaded on that path.
 """
 from __future__ import annotations
 
@@ -40,12 +44,19 @@ UNIT = "solves/s"
 PROBLEMS = 65536
 T, NX, NU = 80, 4, 2
 MAX_ITER, TOL = 10, 1e-5
+WORKLOAD = "batched single-track iLQR, 65,536 independent OCPs with randomised initial states (BASELINE configs[2])"
 # algorithmic HBM bytes per problem-iteration: backward reads X,U and writes K,k; forward
 # reads X,U,K,k once and writes the accepted X,U once
 BWD_BYTES = 8 * ((T + 1) * NX + T * NU + T * NU * NX + T * NU)
 FWD_BYTES = 8 * ((T + 1) * NX + T * NU + T * NU * NX + T * NU) + 8 * ((T + 1) * NX + T * NU)
 # algorithmic flops per time step, SURVEY 8d convention (MAC = 2, one trig/div-heavy call = 32)
 BWD_FLOPS_STEP, FWD_FLOPS_STEP = 1764.0, 494.0 + 12.0
+
+
+def shared_config(n_gpus: int) -> dict:
+    """The part of `config` that both arms print identically (what is measured, not how)."""
+    return {"workload": WORKLOAD, "problems_total": PROBLEMS, "horizon": T, "state_dim": NX, "control_dim": NU, "max_iterations": MAX_ITER,
+            "tolerance": TOL, "max_ms": "inf", "n_gpus": n_gpus}
 
 
 def load_peaks():
@@ -58,18 +69,18 @@ def load_peaks():
 
 def load_traffic(kernel: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, averaged over the launches of one
-    solve, from the committed ncu capture of this same workload (profiles/r01_traffic.json)."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    # the engine's "forward" timing bucket is the line search whichever kernel ran it: the warp-cooperative kernel
-    # (large active sets) and the lane kernel (small ones); average over the launches of both
+    solve, from the committed ncu capture of this same workload (profiles/r02_traffic.json, else r01)."""
     names = ["forward_coop_kernel", "forward_kernel"] if kernel == "forward_kernel" else [kernel]
-    try:
-        with open(path) as f:
-            t = json.load(f)
-        launches = sum(t[n]["launches"] for n in names if n in t)
-        return sum(t[n]["launches"] * t[n]["dram_bytes_per_launch"] for n in names if n in t) / launches
-    except Exception:
-        return None
+    for fn in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                t = json.load(f)
+            launches = sum(t[n]["launches"] for n in names if n in t)
+            if launches:
+                return sum(t[n]["launches"] * t[n]["dram_bytes_per_launch"] for n in names if n in t) / launches, fn
+        except Exception:
+            continue
+    return None, None
 
 
 class ClockSampler:
@@ -115,46 +126,124 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(n_problems: int, steps: int, warmup: int, threads: int = 0):
-    """Times the oracle (the reference's CPU algorithm, OpenMP parallel-for over problems) on the
-    first n_problems problems of the workload.  Returns (solves/s, threads, ms/step)."""
-    from oracle import oracle_py as o
-    import multi_agent_solver_b200 as mas
+# ---- CPU arm: the reference's own implementation --------------------------------------------------------------
+def cpu_checker():
+    """(module, kind): oracle/_ref (the reference's unmodified sources) when its library is there or can be built,
+    else the restated oracle.  Neither loads the product library."""
+    from oracle import ref_py
 
-    x0 = mas.synthetic_single_track_x0(PROBLEMS)[:n_problems]
+    if ref_py.available():
+        try:
+            ref_py.build()
+            return ref_py, "reference"
+        except Exception:
+            pass
+    from oracle import oracle_py
+
+    oracle_py.build()
+    return oracle_py, "port"
+
+
+def cpu_solve(mod, kind, x0, trig, threads, instrument):
+    if kind == "reference":
+        return mod.ilqr_solve_batch(mod.MODEL_ST_LANE, x0, max_iterations=MAX_ITER, tolerance=TOL, trig=trig, threads=threads, instrument=instrument)
+    return mod.ilqr_solve_batch(mod.MODEL_ST_LANE, x0, max_iterations=MAX_ITER, tolerance=TOL, trig=trig, threads=threads)
+
+
+def cpu_describe(kind: str) -> str:
+    if kind == "reference":
+        return ("oracle/_ref/libref.so = the reference's unmodified headers + examples/single_track_ocp.cpp (g++ -O3 -DNDEBUG -fopenmp, "
+                "std::function callbacks and heap temporaries included) against oracle/eigen_shim; glibc libm; one fresh iLQR per problem, "
+                "`omp parallel for schedule(static)` over problems as in strategies/nash.hpp:59-64")
+    return "oracle/ (C++ restatement of the reference, glibc libm, -O3 -ffp-contract=off, OpenMP static over problems); oracle/_ref not available"
+
+
+def cpu_reference_run(n_problems: int, steps: int, warmup: int, threads: int = 0):
+    """Times the reference's CPU implementation on the first n_problems problems of the workload.
+    Returns (solves/s, threads, ms/step, kind)."""
+    mod, kind = cpu_checker()
+    x0 = mod.synthetic_single_track_x0(PROBLEMS)[:n_problems]
     # all host cores this process may use (torchrun sets OMP_NUM_THREADS=1; the num_threads clause overrides it)
     threads = threads or len(os.sched_getaffinity(0))
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        o.ilqr_solve_batch(o.MODEL_ST_LANE, x0, max_iterations=MAX_ITER, tolerance=TOL, trig=o.TRIG_GLIBC, threads=threads)
+        cpu_solve(mod, kind, x0, 0, threads, instrument=False)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     mean = float(np.mean(times))
-    return n_problems / mean, threads, mean * 1e3
+    return n_problems / mean, threads, mean * 1e3, kind
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.cpu_sample
-    value, threads, ms = cpu_reference_run(n, args.steps, max(args.warmup, 1))
+    mod, kind = cpu_checker()
+    threads = len(os.sched_getaffinity(0))
+    # size the per-step sample so that the whole --steps/--warmup run stays within ~2 minutes: probe the speed first
+    x_probe = mod.synthetic_single_track_x0(PROBLEMS)[:2048]
+    cpu_solve(mod, kind, x_probe[:256], 0, threads, instrument=False)
+    t0 = time.perf_counter()
+    cpu_solve(mod, kind, x_probe, 0, threads, instrument=False)
+    rate = 2048 / max(time.perf_counter() - t0, 1e-6)
+    warm = max(args.warmup, 1)
+    n = args.cpu_sample if args.cpu_sample > 0 else int(min(PROBLEMS, max(4096, (110.0 * rate / (args.steps + warm)) // 4096 * 4096)))
+    value, threads, ms, kind = cpu_reference_run(n, args.steps, warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "batched single-track iLQR, 65,536 independent OCPs (BASELINE configs[2]); each step solves a bounded sample",
-                   "problems_per_step": n, "horizon": T, "max_iterations": MAX_ITER, "tolerance": TOL},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"first {n} of the 65,536 problems per step; oracle/ (C++ restatement of the reference, glibc libm, "
-                                   f"-O3 -ffp-contract=off, OpenMP static over problems); the reference itself needs Eigen 3.4, absent here"},
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": shared_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"first {n} of the 65,536 problems per step (throughput per solve does not depend on the batch size); " + cpu_describe(kind)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ---- parity gate -------------------------------------------------------------------------------------------------
+def parity_gate(x0, got, threads):
+    """Results of the timed batch (rank 0's shard) against the CPU checkers.  Not timed."""
+    mod, kind = cpu_checker()
+    t0 = time.perf_counter()
+    ref = cpu_solve(mod, kind, x0, 1, threads, instrument=True)  # portable trig: the mode the kernels are bit-compatible with
+    n = x0.shape[0]
+    same = (np.all(got["X"] == ref["X"], axis=(1, 2)) & np.all(got["U"] == ref["U"], axis=(1, 2)) & (got["cost"] == ref["cost"]))
+    rel = np.abs(got["cost"] - ref["cost"]) / np.maximum(np.abs(ref["cost"]), 1e-300)
+    out = {
+        "checker": "oracle/_ref: the reference's unmodified sources, portable trig bound at link time" if kind == "reference"
+                   else "oracle/ restatement (oracle/_ref not available), portable trig",
+        "problems_checked": int(n), "bit_equal_problems": int(same.sum()),
+        "max_rel_cost": float(rel.max()), "max_abs_dX": float(np.abs(got["X"] - ref["X"]).max()), "max_abs_dU": float(np.abs(got["U"] - ref["U"]).max()),
+        "iterations_equal": bool(np.array_equal(got["iterations"], ref["iterations"])), "status_equal": bool(np.array_equal(got["status"], ref["status"])),
+        "tolerances": {"cost_rel": 1e-9, "traj_abs": 1e-7},
+    }
+    out["pass"] = bool(out["max_rel_cost"] <= 1e-9 and out["max_abs_dX"] <= 1e-7 and out["max_abs_dU"] <= 1e-7 and out["iterations_equal"]
+                       and out["status_equal"])
+    # (ii) against the reference in its own libm mode, and the reference against itself under a 1-ulp change of x0: the
+    # problem's finite-difference cross term (finite_differences.hpp:263-287) amplifies the last bit of libm
+    g = cpu_solve(mod, kind, x0, 0, threads, instrument=True)
+    relg = np.abs(got["cost"] - g["cost"]) / np.maximum(np.abs(g["cost"]), 1e-300)
+    dxg = np.maximum(np.abs(got["X"] - g["X"]).max(axis=(1, 2)), np.abs(got["U"] - g["U"]).max(axis=(1, 2)))
+    nb = min(n, 8192)
+    x0p = x0[:nb].copy()
+    x0p[:, 1] = np.nextafter(x0p[:, 1], np.inf)
+    gp = cpu_solve(mod, kind, x0p, 0, threads, instrument=False)
+    relb = np.abs(gp["cost"] - g["cost"][:nb]) / np.maximum(np.abs(g["cost"][:nb]), 1e-300)
+    dxb = np.maximum(np.abs(gp["X"] - g["X"][:nb]).max(axis=(1, 2)), np.abs(gp["U"] - g["U"][:nb]).max(axis=(1, 2)))
+    out["vs_reference_libm"] = {
+        "frac_cost_within_1e-9": float((relg <= 1e-9).mean()), "frac_traj_within_1e-7": float((dxg <= 1e-7).mean()),
+        "median_rel_cost": float(np.median(relg)), "max_rel_cost": float(relg.max()),
+        "iterations_equal_frac": float((got["iterations"] == g["iterations"]).mean()), "status_equal_frac": float((got["status"] == g["status"]).mean()),
+        "reference_own_1ulp_band": {"problems": int(nb), "frac_cost_within_1e-9": float((relb <= 1e-9).mean()),
+                                    "frac_traj_within_1e-7": float((dxb <= 1e-7).mean()), "median_rel_cost": float(np.median(relb)),
+                                    "max_rel_cost": float(relb.max()),
+                                    "what": "the reference (glibc libm) against itself with x0[1] moved by one ulp"},
+    }
+    out["seconds"] = time.perf_counter() - t0
+    return out
 
 
 class Lane:
@@ -176,6 +265,145 @@ class Lane:
                             iterations=torch.empty(per_rank, dtype=torch.int32).pin_memory().numpy(),
                             status=torch.empty(per_rank, dtype=torch.int32).pin_memory().numpy())
 
+    def close(self):
+        self.batch.close()
+
+
+def best_of(fn, repeats=3):
+    fn()
+    ts = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    return min(ts)
+
+
+def circle_scenarios(n_scen, n_agents, seed=0, jitter=True):
+    rng = np.random.default_rng(seed)
+    th = 2.0 * np.pi * np.arange(n_agents) / n_agents
+    R = rng.uniform(15, 25, (n_scen, 1)) if jitter else np.full((n_scen, 1), 20.0)
+    x0 = np.stack([R * np.cos(th), R * np.sin(th), np.broadcast_to(1.57 + th, (n_scen, n_agents)), np.full((n_scen, n_agents), 4.0)], -1)
+    gp = np.broadcast_to(np.stack([R[:, 0], np.full(n_scen, 5.0), np.ones(n_scen), np.ones(n_scen), np.full(n_scen, 1e-3), np.full(n_scen, 1e-3)],
+                                  -1)[:, None, :], (n_scen, n_agents, 6)).copy()
+    return x0, gp
+
+
+def run_other_configs(mas, torch, dist, rank, world, local_rank):
+    """Short runs of BASELINE configs 1, 2, 4, 5 through the C ABI with host buffers (wall clock around synchronous
+    calls, best of a few).  Every block is independent; a failure is recorded, never fatal for the headline line."""
+    out = {}
+    ctx = mas.Context(local_rank)
+    p10, p100 = mas.IlqrParams.make(10, 1e-5), mas.IlqrParams.make(100, 1e-5)
+
+    def guarded(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as exc:  # noqa: BLE001
+            out[name] = {"error": repr(exc)[:300]}
+
+    def config1():
+        b = mas.Batch(ctx, mas.example_desc(0), 1)
+        x1 = np.array([[0.0, 1.0, 0.0, 0.0]])
+
+        def solve1():
+            b.set_initial_states(x1)
+            b.set_controls(None)
+            b.solve(p10)
+            return b.get_solution()
+
+        t = best_of(solve1, 7)
+        r = solve1()
+        b.close()
+        return {"what": "single_track_ocp --solver ilqr, one problem, single-solve latency (host buffers)", "latency_us": t * 1e6,
+                "cost": float(r["cost"][0]), "iterations": int(r["iterations"][0])}
+
+    def config2():
+        S, A = 4096, 3
+        x0, gp = circle_scenarios(S, A)
+        d1 = mas.example_desc(1)
+        t = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.TRUSTREGION, d1, p100, 10, x0, model_params=gp, trace=False), 3)
+        return {"what": "multi_agent_single_track --agents 3 --strategy trustregion x 4,096 scenarios (radius jittered), 10 outer rounds, one GPU",
+                "scenarios_per_s": S / t, "ms": t * 1e3}
+
+    def config5():
+        d1 = mas.example_desc(1)
+        th = 2.0 * np.pi * np.arange(32) / 32
+        xe = np.stack([20 * np.cos(th), 20 * np.sin(th), 1.57 + th, np.full(32, 4.0)], -1)[None]
+        rec = {"what": "multi_agent_single_track --agents 32 --strategy centralized (stacked n=128, m=64, all-FD), one GPU"}
+        t1 = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, d1, p100, 1, xe, trace=False), 3)
+        rec["one_scenario_ms"] = t1 * 1e3
+        S5 = 592
+        x5 = np.repeat(xe, S5, axis=0)
+        t = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, d1, p100, 1, x5, trace=False), 2)
+        rec["replicas"] = S5
+        rec["scenarios_per_s"] = S5 / t
+        xj, gpj = circle_scenarios(296, 32, seed=5)
+        tj = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, d1, p100, 1, xj, model_params=gpj, trace=False), 1)
+        rec["jittered_radius_scenarios_per_s"] = 296 / tj
+        return rec
+
+    if rank == 0:
+        guarded("config1", config1)
+        guarded("config2", config2)
+        guarded("config5", config5)
+
+    # config 4: 1,024 LQR agents, sequential, 10 outer rounds; at N > 1 the agents are sharded over the ranks (1,024 / N
+    # each) and every round ends with the library's NCCL all-gather of all agents' (X, U, cost)
+    def config4():
+        A_total, outer = 1024, 10
+        A_loc = A_total // world
+        x4 = np.tile([1.0, 0.0, 0.0, 0.0], (1, A_total, 1))  # multi_agent_lqr.cpp:30-33: every agent starts at (1, 0, 0, 0)
+        d2 = mas.example_desc(2)
+        cctx = mas.Context(local_rank)
+        if world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid = torch.frombuffer(bytearray(mas.Context.nccl_unique_id()), dtype=torch.uint8).cuda()
+            dist.broadcast(uid, 0)
+            cctx.init_nccl(bytes(uid.cpu().numpy().tobytes()), rank, world)
+            cctx.set_agent_sharding(True)
+        mine = x4[:, rank * A_loc:(rank + 1) * A_loc]
+        res = {}
+
+        def run():
+            res["r"] = mas.strategy_run(cctx, mas.Strategy.SEQUENTIAL, d2, p100, outer, mine, trace=False)
+
+        run()
+        ts, cs = [], []
+        for _ in range(3):
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run()
+            ts.append(time.perf_counter() - t0)
+            cs.append(cctx.exchange_stats()["collective_ms"] if world > 1 else 0.0)
+        t = min(ts)
+        tt = torch.tensor([t], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        rec = {"what": f"multi_agent_lqr --agents 1024 --strategy sequential, 10 outer rounds, {A_loc} agents per GPU",
+               "ms": float(tt[0]) * 1e3, "agent_solves_per_s": A_total * outer / float(tt[0]), "total_cost": float(res["r"]["total_cost"][0])}
+        if world > 1:
+            st = cctx.exchange_stats()
+            rec["allgather"] = {"per_round_ms": min(cs) / max(st["rounds"], 1), "rounds": st["rounds"], "bytes_received_per_round": st["bytes_per_round"],
+                                "what": "ncclAllGather of every agent's (X, U, cost) after every outer round, CUDA events around the group"}
+            # the same agents on one GPU without a communicator: the joint total must be the same bits
+            if rank == 0:
+                full = mas.strategy_run(ctx, mas.Strategy.SEQUENTIAL, d2, p100, outer, x4, trace=False)
+                rec["bit_equal_to_one_gpu"] = bool(full["total_cost"][0] == res["r"]["total_cost"][0]
+                                                   and np.array_equal(full["costs"][0, :A_loc], res["r"]["costs"][0]))
+        cctx.close()
+        return rec
+
+    try:
+        out["config4_nash"] = config4()
+    except Exception as exc:  # noqa: BLE001
+        out["config4_nash"] = {"error": repr(exc)[:300]}
+    ctx.close()
+    return out
+
 
 def run_b200(args):
     import torch
@@ -194,158 +422,179 @@ def run_b200(args):
         dist = dist_mod
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     n_gpus = world
-    per_rank = PROBLEMS if args.scaling == "weak" else PROBLEMS // world
-    total = per_rank * world
-
+    scaling = args.scaling if args.scaling != "auto" else ("strong" if world > 1 else "weak")
     x0_all = mas.synthetic_single_track_x0(PROBLEMS)
-    if args.scaling == "weak":
-        # every rank gets the 65,536 problems, rotated so the ranks do not solve identical shards in the same order
-        x0 = np.roll(x0_all, -rank * 4099, axis=0).copy()
-    else:
-        x0 = x0_all[rank * per_rank:(rank + 1) * per_rank].copy()
-    x0_host = torch.from_numpy(x0).pin_memory().numpy()
-
     desc = mas.example_desc(mas.Model.SINGLE_TRACK_LANE)
     prm = mas.IlqrParams.make(MAX_ITER, TOL)
     depth = args.depth if args.depth > 0 else (3 if args.steps < 8 else 4)
-    lanes = [Lane(torch, mas, local_rank, desc, per_rank, args, with_host_buffers=not args.resident_only) for _ in range(depth)]
-    for ln in lanes:
-        ln.batch.set_initial_states(x0_host)  # resident input of the `value` measurement
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def resident_step(ln):
-        ln.batch.set_controls(None)  # U_init = 0 (device memset); x0 is already resident
-        ln.batch.solve(prm)
-
-    def e2e_step(ln):
-        ln.batch.set_initial_states(x0_host)  # H2D from pinned memory
-        ln.batch.set_controls(None)
-        ln.batch.solve(prm)
-        # D2H of X, U, cost, iterations, status into pinned memory: staged in HBM on the solve stream, copied on the
-        # batch's copy stream while this lane's next solve starts; e2e_finish() waits for the last one inside the
-        # timed region, and every begin waits for the previous download of the lane
-        ln.batch.begin_get_solution(ln.out)
-
-    def e2e_finish(ln):
-        ln.batch.wait_solution()
-
-    def timed(fn, steps, use_lanes, stagger_ms, finish=None):
-        """Runs exactly `steps` steps spread over `use_lanes` pipelines, each driven by its own host thread and
-        started stagger_ms/len(use_lanes) apart so one solve's latency-bound tail overlaps another's bulk.
-        Device time = latest end event - earliest start event over the lanes' streams (then max over ranks)."""
-        n = len(use_lanes)
-        counts = [steps // n + (1 if i < steps % n else 0) for i in range(n)]
-        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
-        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
-        go = threading.Barrier(n + 1)
-        errors = []
-
-        def work(i):
-            try:
-                torch.cuda.set_device(local_rank)  # the current device is per host thread
-                ln = use_lanes[i]
-                go.wait()
-                if i:
-                    time.sleep(i * stagger_ms * args.stagger * 1e-3 / n)
-                e0[i].record(ln.stream)
-                for _ in range(counts[i]):
-                    fn(ln)
-                if finish is not None:
-                    finish(ln)  # host-blocking: the lane's last results are in host memory before the end event
-                e1[i].record(ln.stream)
-                e1[i].synchronize()
-            except Exception as exc:  # surfaced after join
-                errors.append(exc)
-
-        threads = [threading.Thread(target=work, args=(i,)) for i in range(n)]
-        for t in threads:
-            t.start()
-        barrier()
-        w0 = time.perf_counter()
-        go.wait()
-        for t in threads:
-            t.join()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - w0
-        if errors:
-            raise errors[0]
-        active = [i for i in range(n) if counts[i] > 0]
-        starts = [e0[active[0]].elapsed_time(e0[i]) for i in active]
-        ends = [e0[active[0]].elapsed_time(e1[i]) for i in active]
-        ms = max(ends) - min(starts)
-        barrier()
-        if dist is not None:
-            t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms, wall = float(t[0]), float(t[1]) / 1e3
-        return ms / steps, wall / steps
-
-    # ---- one solve at a time: latency of a 65,536-problem solve, and the reference for kernel shares ------------
-    for _ in range(max(args.warmup, 3)):
+    def measure(mode: str, steps: int, full: bool):
+        """One scaling mode: strong = the 65,536 problems split over the ranks, weak = 65,536 per rank."""
+        per_rank = PROBLEMS if mode == "weak" else PROBLEMS // world
+        total = per_rank * world
+        if mode == "weak":
+            # every rank gets the 65,536 problems, rotated so the ranks do not solve identical shards in the same order
+            x0 = np.roll(x0_all, -rank * 4099, axis=0).copy()
+        else:
+            x0 = x0_all[rank * per_rank:(rank + 1) * per_rank].copy()
+        x0_host = torch.from_numpy(x0).pin_memory().numpy()
+        lanes = [Lane(torch, mas, local_rank, desc, per_rank, args, with_host_buffers=full and not args.resident_only) for _ in range(depth)]
         for ln in lanes:
-            resident_step(ln)
-    barrier()
-    single_ms, _ = timed(resident_step, max(3, min(args.steps, 6)), lanes[:1], 0.0)
+            ln.batch.set_initial_states(x0_host)  # resident input of the `value` measurement
 
-    # ---- resident throughput: `depth` solves in flight ----------------------------------------------------------
-    launches0 = sum(ln.batch.stats()["kernel_launches"] for ln in lanes)
+        def resident_step(ln):
+            ln.batch.set_controls(None)  # U_init = 0 (device memset); x0 is already resident
+            ln.batch.solve(prm)
+
+        def e2e_step(ln, keys=None):
+            ln.batch.set_initial_states(x0_host)  # H2D from pinned memory
+            ln.batch.set_controls(None)
+            ln.batch.solve(prm)
+            # D2H of X, U, cost, iterations, status into pinned memory: staged in HBM on the solve stream, copied on the
+            # batch's copy stream while this lane's next solve starts; e2e_finish() waits for the last one inside the
+            # timed region, and every begin waits for the previous download of the lane
+            ln.batch.begin_get_solution(ln.out if keys is None else {k: v for k, v in ln.out.items() if k in keys})
+
+        def e2e_finish(ln):
+            ln.batch.wait_solution()
+
+        def timed(fn, nsteps, use_lanes, stagger_ms, finish=None):
+            """Runs exactly `nsteps` steps spread over `use_lanes` pipelines, each driven by its own host thread and
+            started stagger_ms/len(use_lanes) apart so one solve's latency-bound tail overlaps another's bulk.
+            Device time = latest end event - earliest start event over the lanes' streams (then max over ranks)."""
+            n = len(use_lanes)
+            counts = [nsteps // n + (1 if i < nsteps % n else 0) for i in range(n)]
+            e0 = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+            e1 = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+            go = threading.Barrier(n + 1)
+            errors = []
+
+            def work(i):
+                try:
+                    torch.cuda.set_device(local_rank)  # the current device is per host thread
+                    ln = use_lanes[i]
+                    go.wait()
+                    if i:
+                        time.sleep(i * stagger_ms * args.stagger * 1e-3 / n)
+                    e0[i].record(ln.stream)
+                    for _ in range(counts[i]):
+                        fn(ln)
+                    if finish is not None:
+                        finish(ln)  # host-blocking: the lane's last results are in host memory before the end event
+                    e1[i].record(ln.stream)
+                    e1[i].synchronize()
+                except Exception as exc:  # surfaced after join
+                    errors.append(exc)
+
+            threads = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+            for t in threads:
+                t.start()
+            barrier()
+            w0 = time.perf_counter()
+            go.wait()
+            for t in threads:
+                t.join()
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - w0
+            if errors:
+                raise errors[0]
+            active = [i for i in range(n) if counts[i] > 0]
+            starts = [e0[active[0]].elapsed_time(e0[i]) for i in active]
+            ends = [e0[active[0]].elapsed_time(e1[i]) for i in active]
+            ms = max(ends) - min(starts)
+            barrier()
+            if dist is not None:
+                t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms, wall = float(t[0]), float(t[1]) / 1e3
+            return ms / nsteps, wall / nsteps
+
+        res = {"per_rank": per_rank, "total": total, "x0": x0, "lanes": lanes}
+        # ---- one solve at a time: latency of one solve of the shard, and the reference for kernel shares -----------
+        for _ in range(max(args.warmup, 3)):
+            for ln in lanes:
+                resident_step(ln)
+        barrier()
+        res["single_ms"], _ = timed(resident_step, max(3, min(steps, 6)), lanes[:1], 0.0)
+        # ---- resident throughput: `depth` solves in flight ------------------------------------------------------
+        launches0 = sum(ln.batch.stats()["kernel_launches"] for ln in lanes)
+        res["ms_step"], res["wall_step"] = timed(resident_step, steps, lanes, res["single_ms"])
+        res["launches"] = sum(ln.batch.stats()["kernel_launches"] for ln in lanes) - launches0
+        res["value"] = total / (res["ms_step"] * 1e-3)
+        res["stats"] = lanes[0].batch.stats()
+        if not full or args.resident_only:
+            return res
+        # ---- e2e: host buffers in, host buffers out, every step ---------------------------------------------------
+        for ln in lanes:
+            e2e_step(ln)
+            e2e_finish(ln)
+        e2e_ms, e2e_wall = timed(e2e_step, steps, lanes, res["single_ms"], finish=e2e_finish)
+        res["e2e"] = {"value": total / (max(e2e_ms * 1e-3, e2e_wall)), "unit": UNIT, "h2d_bytes_per_step": per_rank * NX * 8,
+                      "d2h_bytes_per_step": per_rank * (((T + 1) * NX + T * NU + 1) * 8 + 2 * 4), "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall * 1e3}
+        # what the timed batch produced (lane 0's last download): input of the parity gate
+        res["timed_output"] = {k: v.copy() for k, v in lanes[0].out.items()}
+        # the same loop for a caller that only wants the controls (X = NULL): a third of the download, reported next to the
+        # headline e2e because at N > 1 the host's D2H bandwidth sets e2e
+        ukeys = ("U", "cost", "iterations", "status")
+        for ln in lanes:
+            e2e_step(ln, ukeys)
+            e2e_finish(ln)
+        u_ms, u_wall = timed(lambda ln: e2e_step(ln, ukeys), steps, lanes, res["single_ms"], finish=e2e_finish)
+        res["e2e_controls_only"] = {"value": total / (max(u_ms * 1e-3, u_wall)), "unit": UNIT, "h2d_bytes_per_step": per_rank * NX * 8,
+                                    "d2h_bytes_per_step": per_rank * ((T * NU + 1) * 8 + 2 * 4), "ms_per_step": u_ms,
+                                    "note": "same loop without downloading the state trajectories (X = NULL in the C ABI); not the headline"}
+        # ---- per-kernel timing for the roofline: one solve at a time, CUDA events around every launch inside the engine
+        batch = lanes[0].batch
+        batch.set_profiling(True)
+        for _ in range(max(2, min(steps, 5))):
+            resident_step(lanes[0])
+        res["prof"] = batch.profile()
+        batch.set_profiling(False)
+        res["fp64_peak"] = lanes[0].ctx.probe_fp64_peak()
+        return res
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_step, wall_step = timed(resident_step, args.steps, lanes, single_ms)
-    launches = sum(ln.batch.stats()["kernel_launches"] for ln in lanes) - launches0
-    st = lanes[0].batch.stats()
-    value = total / (ms_step * 1e-3)
+    main = measure(scaling, args.steps, full=True)
+    clocks = sampler.stop() if rank == 0 else None
+    for ln in main["lanes"]:
+        ln.close()
 
     if args.resident_only:  # short form for ncu captures: only the resident steps above
         if rank == 0:
-            sampler.stop()
-            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_step, "single_solve_ms": single_ms,
-                              "gpu_launches": int(launches), "note": "resident-only run (profiling aid), not a bench line"}), flush=True)
-        for ln in lanes:
-            ln.batch.close()
+            print(json.dumps({"metric": METRIC, "value": main["value"], "unit": UNIT, "ms_per_step": main["ms_step"], "single_solve_ms": main["single_ms"],
+                              "gpu_launches": int(main["launches"]), "note": "resident-only run (profiling aid), not a bench line"}), flush=True)
         return
 
-    # ---- e2e: host buffers in, host buffers out, every step ---------------------------------------------------------
-    for ln in lanes:
-        e2e_step(ln)
-        e2e_finish(ln)
-    e2e_ms, e2e_wall = timed(e2e_step, args.steps, lanes, single_ms, finish=e2e_finish)
-    clocks = sampler.stop() if rank == 0 else None
-    e2e_value = total / (max(e2e_ms * 1e-3, e2e_wall))
-    h2d = per_rank * NX * 8
-    d2h = per_rank * (((T + 1) * NX + T * NU + 1) * 8 + 2 * 4)
+    weak = None
+    if world > 1 and scaling == "strong" and not args.no_weak:
+        w = measure("weak", max(8, args.steps // 2), full=False)
+        weak = {"value": w["value"], "unit": UNIT, "ms_per_step": w["ms_step"], "problems_per_gpu": w["per_rank"], "problems_total": w["total"],
+                "what": "one full 65,536-problem shard per rank, resident inputs (round 1's N > 1 headline)"}
+        for ln in w["lanes"]:
+            ln.close()
 
-    # the same loop for a caller that only wants the controls (best_controls, best_cost, iterations, status; X = NULL):
-    # a third of the download, reported next to the headline e2e because at N > 1 the host's D2H bandwidth sets e2e
-    def e2e_step_u(ln):
-        ln.batch.set_initial_states(x0_host)
-        ln.batch.set_controls(None)
-        ln.batch.solve(prm)
-        ln.batch.begin_get_solution({k: v for k, v in ln.out.items() if k != "X"})
-
-    for ln in lanes:
-        e2e_step_u(ln)
-        e2e_finish(ln)
-    e2e_u_ms, e2e_u_wall = timed(e2e_step_u, args.steps, lanes, single_ms, finish=e2e_finish)
-    e2e_u_value = total / (max(e2e_u_ms * 1e-3, e2e_u_wall))
-    d2h_u = per_rank * ((T * NU + 1) * 8 + 2 * 4)
-
-    # ---- per-kernel timing for the roofline: one solve at a time, CUDA events around every launch inside the engine
-    batch = lanes[0].batch
-    batch.set_profiling(True)
-    for _ in range(max(2, min(args.steps, 5))):
-        resident_step(lanes[0])
-    prof = batch.profile()
-    batch.set_profiling(False)
-    fp64_peak = lanes[0].ctx.probe_fp64_peak()
-    out = batch.get_solution()
+    other = None
+    if not args.no_configs:
+        other = run_other_configs(mas, torch, dist, rank, world, local_rank)
 
     if rank == 0:
+        per_rank, total = main["per_rank"], main["total"]
+        st, prof, single_ms, ms_step = main["stats"], main["prof"], main["single_ms"], main["ms_step"]
+        out = main["timed_output"]
+        threads = len(os.sched_getaffinity(0))
+        parity = None
+        if not args.no_parity:
+            try:
+                parity = parity_gate(main["x0"], out, threads)
+            except Exception as exc:  # noqa: BLE001
+                parity = {"error": repr(exc)[:300]}
         hbm_peak, peak_src = load_peaks()
         iters_total = int(out["iterations"].sum())
         n_solves = max(prof["solves"], 1)
@@ -361,52 +610,64 @@ def run_b200(args):
         dom = max(("forward_kernel", "backward_kernel"), key=lambda k: kernels[k]["ms_per_solve"])
         k = kernels[dom]
         n_launch = max(k["launches_per_solve"], 1)
-        achieved = (k["alg_bytes_per_solve"] / n_launch) / (k["ms_per_solve"] / n_launch * 1e-3) / 1e9
-        alg_flops = T * (st["iterations"] * BWD_FLOPS_STEP + (st["alpha_trials"] + per_rank) * FWD_FLOPS_STEP)
+        hbm_achieved = (k["alg_bytes_per_solve"] / n_launch) / (k["ms_per_solve"] / n_launch * 1e-3) / 1e9
+        # algorithmic flops of one solve of the shard (SURVEY 8d convention), split by kernel: trial rollouts + the accepted
+        # step's rollout for the line search, derivatives + Riccati for the backward pass
+        fwd_flops = T * (st["alpha_trials"] + st["iterations"]) * FWD_FLOPS_STEP
+        bwd_flops = T * st["iterations"] * BWD_FLOPS_STEP
+        alg_flops = fwd_flops + bwd_flops + T * per_rank * FWD_FLOPS_STEP
+        dom_flops = fwd_flops if dom == "forward_kernel" else bwd_flops
+        fp64_peak = main["fp64_peak"]
+        dom_tflops = dom_flops / (k["ms_per_solve"] * 1e-3) / 1e12
+        traffic, traffic_src = load_traffic(dom)
         roofline = {
-            "bound": "hbm", "kernel": "line search (forward_coop_kernel + forward_kernel)" if dom == "forward_kernel" else dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": load_traffic(dom), "peak_source": peak_src,
+            "bound": "fp64", "kernel": "line search (forward_coop_kernel + forward_kernel)" if dom == "forward_kernel" else dom,
+            "achieved": dom_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": dom_tflops / fp64_peak if fp64_peak else None,
+            "peak_source": "DFMA throughput probe on this GPU (mas_b200_probe_fp64_peak: 8 independent FMA chains per thread, 8 x 256 threads "
+                           "per SM, CUDA events); MEASURED_PEAKS.json holds no fp64 figure.  The kernels run -fmad=false (the reference build has no "
+                           "FMA contraction), so a multiply-add is two pipe slots: the ceiling of `frac` for unfused arithmetic is 0.5",
+            "achieved_what": "algorithmic flops of the sequential reference for this kernel's share of one solve (SURVEY 8d convention: "
+                             "MAC = 2, one trig / division = 32) / the kernel's summed launch time, one solve in flight",
+            "traffic": traffic, "traffic_source": traffic_src,
             "avg_launch_ms": k["ms_per_solve"] / n_launch, "alg_bytes_per_launch": k["alg_bytes_per_solve"] / n_launch,
+            "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak, "peak_source": peak_src,
+                    "note": "algorithmic bytes / launch time: HBM is not the bound of this kernel"},
             "kernel_share_of_single_solve": {name: v["ms_per_solve"] / single_ms for name, v in kernels.items()},
-            "note": "kernel durations: CUDA events around every launch on the engine's stream, one solve in flight; the kernels are bound by the "
-                    "fp64 pipe and by the latency of T sequential steps, not by HBM (profiles/README.md)",
-            "fp64": {"alg_tflops": alg_flops / (ms_step * 1e-3) / 1e12, "dfma_peak_tflops_measured": fp64_peak,
-                     "frac": alg_flops / (ms_step * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
-                     "note": "algorithmic flops of the sequential reference (SURVEY 8d convention) / step time"},
+            "whole_step_fp64": {"alg_tflops": alg_flops / (ms_step * 1e-3) / 1e12,
+                                "frac": alg_flops / (ms_step * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
+                                "note": f"all kernels of a step / ms_per_step with {depth} solves in flight"},
         }
         cpu_baseline = None
         if n_gpus == 1:  # reported on rank 0 at N=1 only
-            cpu_val, cpu_threads, cpu_ms = cpu_reference_run(args.cpu_sample, 1, 1)
-            cpu_baseline = {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": "port",
-                            "sample": f"first {args.cpu_sample} of the 65,536 problems, one pass ({cpu_ms:.0f} ms); oracle/ C++ restatement of the "
-                                      "reference (glibc libm, OpenMP static over problems); the reference needs Eigen 3.4, absent here"}
+            sample = args.cpu_sample if args.cpu_sample > 0 else 16384
+            cpu_val, cpu_threads, cpu_ms, kind = cpu_reference_run(sample, 1, 1)
+            cpu_baseline = {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": kind,
+                            "sample": f"first {sample} of the 65,536 problems, one pass ({cpu_ms:.0f} ms) after one warm-up pass; " + cpu_describe(kind)}
+        cfg = shared_config(n_gpus)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "batched single-track iLQR, 65,536 independent OCPs with randomised initial states (BASELINE configs[2])",
-                       "problems_per_gpu": per_rank, "problems_total": total, "horizon": T, "state_dim": NX, "control_dim": NU,
-                       "max_iterations": MAX_ITER, "tolerance": TOL, "max_ms": "inf", "parallelism": f"independent shards x{n_gpus}",
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": cfg,
+            "engine": {"problems_per_gpu": per_rank, "parallelism": f"contiguous shards of independent problems x{n_gpus}, no data-path collective",
                        "solves_in_flight": depth,
-                       "pipelining": f"{depth} independent 65,536-problem solves in flight per GPU, each a whole step on its own stream and host "
+                       "pipelining": f"{depth} independent solves of the shard in flight per GPU, each a whole step on its own stream and host "
                                      "thread, starts staggered; ms_per_step = device time of the K steps / K",
                        "single_solve_ms": single_ms,
-                       "l2": "working set 670 MB per solve (X,U,K,k) > 126 MB L2, no flush needed",
+                       "l2": f"working set {per_rank * 10272 / 1e6:.0f} MB per solve (X,U,K,k) x {depth} in flight"
+                             + (" > 126 MB L2, no flush needed" if per_rank * 10272 * depth > 126e6 else " (fits L2: flushed by the other lanes' traffic only)"),
                        "forward_lanes": st["forward_lanes"], "forward_chains": st["forward_chains"],
-                       "mean_iterations": iters_total / per_rank,
-                       "problem_iterations_per_s": value * iters_total / per_rank},
-            "e2e_controls_only": {"value": e2e_u_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_u, "ms_per_step": e2e_u_ms,
-                                  "note": "same loop without downloading the state trajectories (X = NULL in the C ABI); not the headline"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                    "wall_ms_per_step": e2e_wall * 1e3},
-            "gpu_launches": int(launches),
+                       "mean_iterations": iters_total / per_rank, "problem_iterations_per_s": main["value"] * iters_total / per_rank},
+            "e2e": main["e2e"], "e2e_controls_only": main["e2e_controls_only"],
+            "gpu_launches": int(main["launches"]),
+            "parity": parity,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "weak": weak,
+            "configs": other,
             "clocks": clocks,
-            "wall_ms_per_step": wall_step * 1e3,
+            "wall_ms_per_step": main["wall_step"] * 1e3,
         }
         print(json.dumps(line), flush=True)
-    for ln in lanes:
-        ln.batch.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -418,12 +679,15 @@ def main():
     ap.add_argument("--steps", type=int, default=48, help="timed steps (one step = one solve of the 65,536-problem batch, 6-7 ms)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"], help="auto = strong (65,536 split over the ranks) at N > 1")
     ap.add_argument("--depth", type=int, default=0, help="independent solves in flight per GPU (1 = one at a time; 0 = by step count: "
                     "3 below 8 steps, else 4 -- fewer pipelines fill and drain faster when K is small)")
     ap.add_argument("--stagger", type=float, default=1.0, help="start offset between pipelines, in units of single_solve_ms / depth")
-    ap.add_argument("--cpu-sample", type=int, default=8192, help="problems per CPU-baseline pass")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="problems per CPU-baseline pass (0 = sized automatically)")
     ap.add_argument("--resident-only", action="store_true", help="run only warm-up + timed resident steps (for ncu)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity gate (profiling runs)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the config 1/2/4/5 blocks")
+    ap.add_argument("--no-weak", action="store_true", help="skip the extra weak-scaling measurement at N > 1")
     ap.add_argument("--ls-mode", type=int, default=0, help="line search scheduling: 0 auto, 1 concurrent lanes, 2 compacted rounds")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--chains", type=int, default=0)

@@ -214,7 +214,10 @@ int mas_b200_ilqr_solve_batch(mas_b200_context_t ctx, const mas_b200_ocp_desc* d
  * array order (already the id-sorted block order of MultiAgentProblem::compute_offsets,
  * multi_agent_problem.hpp:37-50).  Arrays are [scenario][agent][...].  U_init: every agent's
  * initial_controls / best_controls before the first round, NULL = zeros.  trace_* may be NULL:
- * [scenario][outer][agent] inner iteration counts / accepted flags / best_cost after the round. */
+ * [scenario][outer][agent] inner iteration counts / accepted flags / best_cost after the round.
+ * MAS_B200_STRATEGY_CENTRALIZED: the stacked problem always starts from zero controls (build_global_ocp never sets
+ * initial_controls, multi_agent_problem.hpp:52-127) -- U_init is ignored; max_outer has no meaning, and the
+ * iteration count of the stacked solve is written to trace_iterations[scenario][0][0] only when max_outer >= 1. */
 int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_ocp_desc* agent_desc, const mas_b200_ilqr_params* params,
                           int max_outer, int n_scenarios, int n_agents, const double* x0, const double* model_params, const double* U_init,
                           double* X, double* U, double* costs, double* total_cost, int* trace_iterations, int* trace_accepted, double* trace_cost);
@@ -223,6 +226,22 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
  * distributed by the caller (torch.distributed / MPI / file). ------------------------------------- */
 int mas_b200_nccl_unique_id(void* id128);
 int mas_b200_context_init_nccl(mas_b200_context_t ctx, const void* id128, int rank, int world_size);
+/* On a context with a communicator, the Nash strategies of mas_b200_strategy_run end every outer round
+ * (strategies/nash.hpp:86-87,105-177,196-245) with an NCCL all-gather of every agent's (best_states, best_controls,
+ * best_cost), so that every rank holds the joint trajectory set of all ranks.  Every rank must pass the same
+ * n_scenarios, n_agents, max_outer, strategy and horizon (checked up front with a small all-gather; a mismatch is
+ * MAS_B200_ERR_INVALID_ARGUMENT on every rank, never a hang) -- pad the last shard when the units do not divide.
+ *   agents_sharded = 0 (default): the ranks hold different SCENARIOS; total_cost[s] is the local scenario's sum.
+ *   agents_sharded = 1: the ranks hold different AGENTS of the same n_scenarios scenarios (rank-major = id order,
+ *     e.g. 1,024 agents as 8 x 128); total_cost[s] is the sum over ALL ranks' agents in block order
+ *     (collect_solution, nash.hpp:23-37), formed from the gathered costs, identical on every rank. */
+int mas_b200_context_set_agent_sharding(mas_b200_context_t ctx, int agents_sharded);
+/* The joint set of the last Nash strategy run (after its last round): [world][n_scenarios][n_agents][...] with the
+ * per-agent shapes of mas_b200_strategy_run, rank-major.  Any pointer may be NULL.  Synchronises. */
+int mas_b200_strategy_get_joint(mas_b200_context_t ctx, double* X_all, double* U_all, double* costs_all);
+/* Device time spent in the per-round collectives of the last run (CUDA events around every exchange, summed),
+ * the number of rounds, and the bytes every rank received per round. */
+int mas_b200_strategy_get_exchange_stats(mas_b200_context_t ctx, double* collective_ms, int* rounds, long long* bytes_per_round);
 
 /* Synthetic inputs of the headline batch: x0_i = (0, Y, psi, v) with Y~U(-2,2),
  * psi~U(-0.5,0.5), v~U(0,2) from std::mt19937_64(seed), drawn in that order, problem-major.

@@ -339,7 +339,10 @@ inline Solution run_strategy(int kind, int max_outer, const mas_b200_ilqr_params
     std::copy(o.best_controls.data(), o.best_controls.data() + static_cast<std::size_t>(m) * T, U0.begin() + static_cast<std::size_t>(a) * m * T);
   }
   double total = 0.0;
-  check(mas_b200_strategy_run(Device::context(), kind, &d, &prm, max_outer, 1, A, x0.data(), np > 0 ? prms.data() : nullptr, U0.data(), X.data(),
+  // centralized: the stacked problem starts from zero controls in the reference (build_global_ocp never sets
+  // initial_controls), so the agents' best_controls are not passed
+  const double* u_init = kind == MAS_B200_STRATEGY_CENTRALIZED ? nullptr : U0.data();
+  check(mas_b200_strategy_run(Device::context(), kind, &d, &prm, max_outer, 1, A, x0.data(), np > 0 ? prms.data() : nullptr, u_init, X.data(),
                               U.data(), costs.data(), &total, nullptr, nullptr, nullptr));
   for (int a = 0; a < A; ++a) {
     OCP& o = *problem.blocks[a].agent->ocp;
@@ -348,7 +351,9 @@ inline Solution run_strategy(int kind, int max_outer, const mas_b200_ilqr_params
     std::copy(X.begin() + static_cast<std::size_t>(a) * n * (T + 1), X.begin() + static_cast<std::size_t>(a + 1) * n * (T + 1), o.best_states.data());
     std::copy(U.begin() + static_cast<std::size_t>(a) * m * T, U.begin() + static_cast<std::size_t>(a + 1) * m * T, o.best_controls.data());
     o.best_cost = costs[a];
-    o.update_initial_with_best();
+    // the Nash strategies end every accepted / restored round with update_initial_with_best (nash.hpp:66-71,232,241);
+    // CentralizedStrategy writes best_* only (centralized.hpp:29-36)
+    if (kind != MAS_B200_STRATEGY_CENTRALIZED) o.update_initial_with_best();
     sol.states.push_back(o.best_states);
     sol.controls.push_back(o.best_controls);
     sol.costs.push_back(o.best_cost);

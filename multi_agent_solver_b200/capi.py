@@ -187,6 +187,23 @@ class Context:
         _check(load_library().mas_b200_nccl_unique_id(buf))
         return buf.raw
 
+    def set_agent_sharding(self, agents_sharded: bool) -> None:
+        _check(load_library().mas_b200_context_set_agent_sharding(self._h, int(bool(agents_sharded))))
+
+    def strategy_joint(self, world: int, n_scenarios: int, n_agents: int, desc: "OcpDesc") -> dict:
+        """mas_b200_strategy_get_joint: every rank's agents after the last round, [world, scenarios, agents, ...]."""
+        T, nx, nu = desc.horizon_steps, desc.state_dim, desc.control_dim
+        X = np.empty((world, n_scenarios, n_agents, T + 1, nx))
+        U = np.empty((world, n_scenarios, n_agents, T, nu))
+        costs = np.empty((world, n_scenarios, n_agents))
+        _check(load_library().mas_b200_strategy_get_joint(self._h, _dptr(X), _dptr(U), _dptr(costs)))
+        return dict(X=X, U=U, costs=costs)
+
+    def exchange_stats(self) -> dict:
+        ms, rounds, nbytes = ctypes.c_double(), ctypes.c_int(), ctypes.c_longlong()
+        _check(load_library().mas_b200_strategy_get_exchange_stats(self._h, ctypes.byref(ms), ctypes.byref(rounds), ctypes.byref(nbytes)))
+        return dict(collective_ms=ms.value, rounds=rounds.value, bytes_per_round=nbytes.value)
+
     def probe_fp64_peak(self) -> float:
         tf = ctypes.c_double()
         _check(load_library().mas_b200_probe_fp64_peak(self._h, ctypes.byref(tf)))

@@ -107,7 +107,54 @@ struct mas_b200_context {
   mas_b200_batch* scratch_batch = nullptr;
   mas_b200_ocp_desc scratch_desc{};
   int scratch_size = 0;
+  // Per-round exchange of the Nash strategies (multi-GPU): after every outer round each rank all-gathers every
+  // agent's (X, U, cost) so that all ranks hold the joint trajectory set.  The gathered set of the LAST round stays
+  // here (device memory, rank-major, each rank's block in the engine's [rows][ld] layout) for
+  // mas_b200_strategy_get_joint; the buffers are reused by the next run of the same shape and freed with the context.
+  struct Joint {
+    double *X = nullptr, *U = nullptr, *cost = nullptr;
+    long long* check = nullptr;  // [world][kCheck] shape words of every rank
+    size_t nX = 0, nU = 0, L = 0;
+    int world = 0, batch = 0, n_scenarios = 0, n_agents = 0, valid = 0;
+    double collective_ms = 0.0;
+    int rounds = 0;
+    void release() {
+      if (X) cudaFree(X);
+      if (U) cudaFree(U);
+      if (cost) cudaFree(cost);
+      if (check) cudaFree(check);
+      X = U = cost = nullptr;
+      check = nullptr;
+      nX = nU = L = 0;
+      world = valid = 0;
+    }
+  } joint;
+  int agents_sharded = 0;  // 1: the ranks hold different AGENTS of the same scenarios (joint totals over all ranks)
 };
+
+namespace {
+// cudaEvent pairs around the per-round collectives, destroyed on every exit path
+struct EventPairs {
+  std::vector<cudaEvent_t> ev;
+  ~EventPairs() {
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  }
+  int record(cudaStream_t st) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return 1;
+    ev.push_back(e);
+    return cudaEventRecord(e, st) != cudaSuccess;
+  }
+  double total_ms() const {
+    double t = 0.0;
+    for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) t += ms;
+    }
+    return t;
+  }
+};
+}  // namespace
 
 extern "C" {
 
@@ -236,6 +283,7 @@ int mas_b200_context_destroy(mas_b200_context_t ctx) {
   if (!ctx) return MAS_B200_OK;
   cudaSetDevice(ctx->c.device);
   if (ctx->scratch_batch) mas_b200_batch_destroy(ctx->scratch_batch);
+  ctx->joint.release();
   ctx->c.centralized_workspace.reset();
   if (ctx->c.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(static_cast<ncclComm_t>(ctx->c.nccl_comm));
   if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
@@ -499,8 +547,10 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
     std::vector<int> its(n_scenarios);
     rc = fn(&ctx->c, d, *params, n_scenarios, n_agents, x0, model_params, U_init, X, U, costs, total_cost, its.data(), nullptr, nullptr);
     if (rc) return rc;
-    if (trace_iterations)
-      for (int s = 0; s < n_scenarios; ++s) trace_iterations[static_cast<size_t>(s) * (max_outer > 0 ? max_outer : 1) * n_agents] = its[s];
+    // the documented trace shape is [scenario][max_outer][agent]: with max_outer == 0 it has no elements, so nothing is
+    // written (max_outer has no meaning for the centralized strategy; pass 1 to receive the iteration count)
+    if (trace_iterations && max_outer >= 1)
+      for (int s = 0; s < n_scenarios; ++s) trace_iterations[static_cast<size_t>(s) * max_outer * n_agents] = its[s];
     return MAS_B200_OK;
   }
   if (strategy != MAS_B200_STRATEGY_SEQUENTIAL && strategy != MAS_B200_STRATEGY_TRUSTREGION && strategy != MAS_B200_STRATEGY_LINESEARCH)
@@ -534,13 +584,43 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
       MAS_CUDA_CHECK(cudaMemcpyAsync(b->d_radius, ones.data(), L * sizeof(double), cudaMemcpyHostToDevice, st));
       MAS_CUDA_CHECK(cudaStreamSynchronize(st));
     }
-    // joint buffers for the per-round exchange of every agent's (X, U, cost) across ranks
-    double *g_X = nullptr, *g_U = nullptr, *g_c = nullptr;
+    // joint buffers for the per-round exchange of every agent's (X, U, cost) across ranks (kept in the context)
     const size_t nX = L * b->nx * (b->T + 1), nU = L * b->nu * b->T;
+    mas_b200_context::Joint& J = ctx->joint;
+    EventPairs coll_events;
+    J.valid = 0;
     if (ctx->c.nccl_comm) {
-      MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&g_X), nX * ctx->c.world * sizeof(double)));
-      MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&g_U), nU * ctx->c.world * sizeof(double)));
-      MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&g_c), L * ctx->c.world * sizeof(double)));
+      const int world = ctx->c.world;
+      if (J.world != world || J.nX != nX || J.nU != nU || J.L != L) {
+        J.release();
+        MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&J.X), nX * world * sizeof(double)));
+        MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&J.U), nU * world * sizeof(double)));
+        MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&J.cost), L * world * sizeof(double)));
+        MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&J.check), static_cast<size_t>(world + 1) * 8 * sizeof(long long)));
+        J.world = world;
+        J.nX = nX;
+        J.nU = nU;
+        J.L = L;
+      }
+      J.batch = batch;
+      J.n_scenarios = n_scenarios;
+      J.n_agents = n_agents;
+      // every rank must bring the same shape to the collectives (equal counts are what ncclAllGather assumes): exchange
+      // the shape words first and fail on ALL ranks alike if they differ, instead of hanging or corrupting memory
+      const long long mine[8] = {static_cast<long long>(L), batch, max_outer, n_agents, static_cast<long long>(nX), static_cast<long long>(nU),
+                                 strategy, n_scenarios};
+      ncclComm_t comm = static_cast<ncclComm_t>(ctx->c.nccl_comm);
+      MAS_CUDA_CHECK(cudaMemcpyAsync(J.check + static_cast<size_t>(world) * 8, mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+      MAS_NCCL_CHECK(g_nccl.AllGather(J.check + static_cast<size_t>(world) * 8, J.check, 8, ncclInt64, comm, st));
+      std::vector<long long> all(static_cast<size_t>(world) * 8);
+      MAS_CUDA_CHECK(cudaMemcpyAsync(all.data(), J.check, all.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+      MAS_CUDA_CHECK(cudaStreamSynchronize(st));
+      for (int rk = 0; rk < world; ++rk)
+        for (int k = 0; k < 8; ++k)
+          if (all[static_cast<size_t>(rk) * 8 + k] != mine[k])
+            return fail(MAS_B200_ERR_INVALID_ARGUMENT,
+                        "multi-GPU strategy run: ranks disagree on the local shape (scenarios x agents, horizon, max_outer or strategy); "
+                        "give every rank the same number of scenarios and agents (pad the last shard)");
     }
     // per-round record: inner iteration counts, accept flags, costs ([scenario][outer][agent])
     auto record_trace = [&](int outer) -> int {
@@ -598,28 +678,46 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
       }
       if (ctx->c.nccl_comm) {  // every rank ends the round holding all agents' trajectories
         ncclComm_t comm = static_cast<ncclComm_t>(ctx->c.nccl_comm);
+        if (coll_events.record(st)) return fail(MAS_B200_ERR_CUDA, "cudaEventRecord failed");
         MAS_NCCL_CHECK(g_nccl.GroupStart());
-        MAS_NCCL_CHECK(g_nccl.AllGather(b->d_X, g_X, nX, ncclDouble, comm, st));
-        MAS_NCCL_CHECK(g_nccl.AllGather(b->d_U, g_U, nU, ncclDouble, comm, st));
-        MAS_NCCL_CHECK(g_nccl.AllGather(b->d_cost, g_c, L, ncclDouble, comm, st));
+        MAS_NCCL_CHECK(g_nccl.AllGather(b->d_X, J.X, nX, ncclDouble, comm, st));
+        MAS_NCCL_CHECK(g_nccl.AllGather(b->d_U, J.U, nU, ncclDouble, comm, st));
+        MAS_NCCL_CHECK(g_nccl.AllGather(b->d_cost, J.cost, L, ncclDouble, comm, st));
         MAS_NCCL_CHECK(g_nccl.GroupEnd());
+        if (coll_events.record(st)) return fail(MAS_B200_ERR_CUDA, "cudaEventRecord failed");
       }
       if (strategy != MAS_B200_STRATEGY_LINESEARCH) {
         r = record_trace(outer);
         if (r) return r;
       }
     }
-    if (g_X) cudaFree(g_X);
-    if (g_U) cudaFree(g_U);
-    if (g_c) cudaFree(g_c);
     // collect_solution (nash.hpp:23-37): per-agent trajectories and costs, total in block order
     std::vector<double> c(batch);
     r = mas_b200_batch_get_solution(h, X, U, c.data(), nullptr, nullptr);
     if (r) return r;
-    for (int s = 0; s < n_scenarios; ++s) {
-      double tot = 0.0;
-      for (int a = 0; a < n_agents; ++a) tot += c[static_cast<size_t>(s) * n_agents + a];
-      if (total_cost) total_cost[s] = tot;
+    if (ctx->c.nccl_comm) {
+      J.collective_ms = coll_events.total_ms();
+      J.rounds = max_outer;
+      J.valid = max_outer > 0 ? 1 : 0;
+    }
+    if (ctx->c.nccl_comm && ctx->agents_sharded && max_outer > 0) {
+      // the ranks hold different agents of the same scenarios: the scenario total runs over ALL ranks' agents, in block
+      // order (rank-major = id order), from the gathered costs of the last round -- the same sum on every rank
+      std::vector<double> all(static_cast<size_t>(ctx->c.world) * L);
+      MAS_CUDA_CHECK(cudaMemcpyAsync(all.data(), J.cost, all.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+      MAS_CUDA_CHECK(cudaStreamSynchronize(st));
+      for (int s = 0; s < n_scenarios; ++s) {
+        double tot = 0.0;
+        for (int rk = 0; rk < ctx->c.world; ++rk)
+          for (int a = 0; a < n_agents; ++a) tot += all[static_cast<size_t>(rk) * L + static_cast<size_t>(s) * n_agents + a];
+        if (total_cost) total_cost[s] = tot;
+      }
+    } else {
+      for (int s = 0; s < n_scenarios; ++s) {
+        double tot = 0.0;
+        for (int a = 0; a < n_agents; ++a) tot += c[static_cast<size_t>(s) * n_agents + a];
+        if (total_cost) total_cost[s] = tot;
+      }
     }
     if (costs) std::memcpy(costs, c.data(), sizeof(double) * batch);
     return MAS_B200_OK;
@@ -650,6 +748,42 @@ int mas_b200_context_init_nccl(mas_b200_context_t ctx, const void* id128, int ra
   ctx->c.nccl_comm = comm;
   ctx->c.rank = rank;
   ctx->c.world = world_size;
+  return MAS_B200_OK;
+}
+
+int mas_b200_context_set_agent_sharding(mas_b200_context_t ctx, int agents_sharded) {
+  if (!ctx) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  ctx->agents_sharded = agents_sharded != 0;
+  return MAS_B200_OK;
+}
+
+int mas_b200_strategy_get_joint(mas_b200_context_t ctx, double* X_all, double* U_all, double* costs_all) {
+  if (!ctx) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  mas_b200_context::Joint& J = ctx->joint;
+  if (!ctx->c.nccl_comm || !J.valid || !ctx->scratch_batch)
+    return fail(MAS_B200_ERR_INVALID_ARGUMENT, "no joint trajectory set: run a Nash strategy (max_outer >= 1) on a context with a communicator first");
+  BatchBase* b = ctx->scratch_batch->b;
+  if (b->batch != J.batch) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "the context's batch changed since the strategy run");
+  const size_t per_x = static_cast<size_t>(J.batch) * b->nx * (b->T + 1), per_u = static_cast<size_t>(J.batch) * b->nu * b->T;
+  for (int rk = 0; rk < J.world; ++rk) {
+    int rc = MAS_B200_OK;
+    if (X_all) rc = b->download_rows(J.X + static_cast<size_t>(rk) * J.nX, X_all + rk * per_x, b->nx * (b->T + 1));
+    if (!rc && U_all) rc = b->download_rows(J.U + static_cast<size_t>(rk) * J.nU, U_all + rk * per_u, b->nu * b->T);
+    if (rc) return rc;
+    if (costs_all)
+      MAS_CUDA_CHECK(cudaMemcpyAsync(costs_all + static_cast<size_t>(rk) * J.batch, J.cost + static_cast<size_t>(rk) * J.L, J.batch * sizeof(double),
+                                     cudaMemcpyDeviceToHost, ctx->c.stream));
+  }
+  MAS_CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+  return MAS_B200_OK;
+}
+
+int mas_b200_strategy_get_exchange_stats(mas_b200_context_t ctx, double* collective_ms, int* rounds, long long* bytes_per_round) {
+  if (!ctx) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  const mas_b200_context::Joint& J = ctx->joint;
+  if (collective_ms) *collective_ms = J.valid ? J.collective_ms : 0.0;
+  if (rounds) *rounds = J.valid ? J.rounds : 0;
+  if (bytes_per_round) *bytes_per_round = J.valid ? static_cast<long long>((J.nX + J.nU + J.L) * sizeof(double)) * J.world : 0;
   return MAS_B200_OK;
 }
 

@@ -57,11 +57,10 @@ int run_centralized(Context* ctx, const mas_b200_ocp_desc& d, const mas_b200_ilq
     for (int a = 0; a < A; ++a) {
       for (int i = 0; i < M::NP; ++i)
         hP[(static_cast<size_t>(s) * A + a) * NPs + i] = model_params ? model_params[(static_cast<size_t>(s) * A + a) * M::NP + i] : d.params[i];
-      if (U_init)
-        for (int t = 0; t < T; ++t)
-          for (int i = 0; i < NU; ++i)
-            hU[(static_cast<size_t>(s) * T + t) * ms + a * NU + i] = U_init[((static_cast<size_t>(s) * A + a) * T + t) * NU + i];
     }
+  // U_init is deliberately not used: build_global_ocp() never sets initial_controls, so initialize_problem() starts the
+  // stacked OCP from zero controls whatever the agents hold (multi_agent_problem.hpp:52-127, ocp.hpp:104-108)
+  (void)U_init;
   struct Buffers {
     double *x0 = nullptr, *prm = nullptr, *X = nullptr, *Xt = nullptr, *U = nullptr, *Ut = nullptr, *K = nullptr, *k = nullptr, *work = nullptr,
            *oc = nullptr;

@@ -7,6 +7,7 @@
 #include <omp.h>
 
 #include <cstring>
+#include <random>
 #include <stdexcept>
 
 #include "ref_multi_agent.hpp"
@@ -92,6 +93,21 @@ int oracle_model_dims(int model, int horizon, int* n, int* m, int* T, double* dt
 }
 
 int oracle_max_threads() { return omp_get_max_threads(); }
+
+// Config-3 initial states: x0 = (0, Y, psi, v), std::mt19937_64(seed), draws Y, psi, v per problem.
+// Same generator as the product's mas_b200_synthetic_single_track_x0, here so that the CPU arm of bench.py never
+// has to load the product library.
+int oracle_synthetic_single_track_x0(unsigned long long seed, int batch, double* x0) {
+  std::mt19937_64 rng(seed);
+  std::uniform_real_distribution<double> dy(-2.0, 2.0), dpsi(-0.5, 0.5), dv(0.0, 2.0);
+  for (int i = 0; i < batch; ++i) {
+    x0[4 * i + 0] = 0.0;
+    x0[4 * i + 1] = dy(rng);
+    x0[4 * i + 2] = dpsi(rng);
+    x0[4 * i + 3] = dv(rng);
+  }
+  return 0;
+}
 
 // Default initial controls of the example (pendulum sinusoid, rocket constant thrust, zeros otherwise).
 int oracle_default_controls(int model, int horizon, double* U /* [T][m] */) {

@@ -77,6 +77,13 @@ def max_threads() -> int:
     return lib().ref_max_threads()
 
 
+def synthetic_single_track_x0(batch: int, seed: int = 20240607) -> np.ndarray:
+    """Config-3 initial states (SURVEY 8d): std::mt19937_64(seed); Y, psi, v per problem."""
+    x0 = np.empty((batch, 4))
+    lib().ref_synthetic_single_track_x0(ctypes.c_ulonglong(seed), int(batch), _p(x0))
+    return x0
+
+
 def default_controls(model: int, horizon: int = 0) -> np.ndarray:
     n, m, T, _ = model_dims(model, horizon)
     U = np.zeros((T, m))
