@@ -85,3 +85,24 @@ def test_unsupported_strategies_fail_loudly(mas, ctx):
         with pytest.raises(mas.MasB200Error) as e:
             mas.strategy_run(ctx, kind, mas.example_desc(1), mas.IlqrParams.make(100, 1e-5), 2, x0)
         assert e.value.code == 1
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3])
+def test_constrained_agents_inside_strategies(mas, ctx, oracle, kind):
+    """Agents with path constraints (model 5) through sequential / line-search / trust-region Nash: the device batch keeps
+    every agent's multipliers and penalty from round to round like the reference's per-agent solver clones
+    (nash.hpp:17-21,76-84); bit-exact against the oracle, which tests/test_ref_pin.py pins to the reference's own code."""
+    from conftest import random_x0
+
+    x0 = random_x0(5, 24, seed=2).reshape(8, 3, 4)
+    desc = mas.example_desc(5)
+    strategy = {1: mas.Strategy.SEQUENTIAL, 2: mas.Strategy.LINESEARCH, 3: mas.Strategy.TRUSTREGION}[kind]
+    got = mas.strategy_run(ctx, strategy, desc, mas.IlqrParams.make(6, 1e-5), 3, x0)
+    prm = np.tile(np.array([1.0, 10.0, 1.0, 0.1, 0.1, 0.8, 0.5]), (8, 3, 1))
+    ref = oracle.strategy_run_batch(kind, 5, x0, params=prm, max_outer=3, max_iterations=6, trig=oracle.TRIG_PORTABLE)
+    for k in ("X", "U", "costs", "total_cost"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert np.array_equal(got["trace_iters"], ref["trace_iters"])
+    # a second run starts from fresh solvers again
+    again = mas.strategy_run(ctx, strategy, desc, mas.IlqrParams.make(6, 1e-5), 3, x0)
+    assert np.array_equal(again["U"], got["U"])

@@ -174,3 +174,35 @@ def test_lane_parallel_backward_pass_is_bit_identical(emu, oracle, model, mask, 
     if mask == MODEL_TABLE[model][4]:  # the example's own derivative mode: the oracle applies
         ref = oracle.ilqr_solve_batch(model, x0, U_init=U0, max_iterations=max_it, tolerance=tol, trig=oracle.TRIG_PORTABLE)
         assert is_bit_exact(par, ref)
+
+
+def test_nonfinite_trajectories(emu, oracle):
+    """NaN / inf trajectories and costs through the device source on the CPU: same bits (NaN-aware), iteration counts and
+    flags as the oracle and -- when its library is there -- as the reference's own sources (oracle/_ref)."""
+    from oracle import ref_py
+
+    x0 = random_x0(0, 24, seed=1)
+    x0[1] = [0, 1e160, 0.1, 1.0]
+    x0[2] = [0, 0.5, 1e7, 1.0]
+    x0[3] = [0, np.nan, 0.0, 1.0]
+    x0[4] = [0, 0.5, 0.0, np.inf]
+    x0[5] = [0, 0.5, 0.0, 1e200]
+    x0[6] = [0, 1e154, 0.0, 1.0]
+    x0[7] = [0, 0.5, 823549.4, 1.0]
+    x0[8] = [0, -0.3, 0.2, 1e100]
+    U = np.zeros((24, 80, 2))
+    refs = [oracle.ilqr_solve_batch(0, x0, U_init=U, trig=oracle.TRIG_PORTABLE)]
+    if ref_py.available():
+        refs.append(ref_py.ilqr_solve_batch(0, x0, U_init=U, trig=1))
+    for L, C in ((1, 2), (4, 1), (16, 1)):
+        got = emu.solve(0, x0, U, 10, 1e-5, L=L, C=C)
+        for ref in refs:
+            for k in ("X", "U", "cost", "iterations", "status"):
+                assert np.array_equal(got[k], ref[k], equal_nan=got[k].dtype.kind == "f"), (L, C, k)
+    assert not np.isfinite(refs[0]["cost"][1:7]).any() and (refs[0]["status"][1:7] == 1).all()
+    # all-FD circular-track model on the same initial states
+    Uc = np.zeros((24, 10, 2))
+    ref_fd = oracle.ilqr_solve_batch(1, x0, U_init=Uc, max_iterations=8, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    got_fd = emu.solve(1, x0, Uc, 8, 1e-5)
+    for k in ("X", "U", "cost", "iterations", "status"):
+        assert np.array_equal(got_fd[k], ref_fd[k], equal_nan=got_fd[k].dtype.kind == "f"), k

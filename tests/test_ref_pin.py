@@ -128,6 +128,18 @@ def test_strategies_lqr(oracle, ref, kind):
     assert np.array_equal(its, b["iterations_total"])
 
 
+@pytest.mark.parametrize("kind", [1, 2, 3])
+def test_strategies_with_constrained_agents(oracle, ref, kind):
+    """Path constraints inside the Nash strategies: every agent keeps its own solver for all outer rounds
+    (nash.hpp:17-21,76-84), so multipliers and penalty persist from round to round."""
+    x0 = random_x0(5, 6, seed=2).reshape(2, 3, 4)
+    prm = np.tile(np.array([1.0, 10.0, 1.0, 0.1, 0.1, 0.8, 0.5]), (2, 3, 1))
+    a = oracle.strategy_run_batch(kind, 5, x0, params=prm, max_outer=3, max_iterations=6, trig=1)
+    b = ref.strategy_run_batch(kind, 5, x0, params=prm, max_outer=3, max_iterations=6, trig=1)
+    assert_same(a, b, ("X", "U", "costs", "total_cost"))
+    assert np.array_equal(a["trace_iters"].sum(1), b["iterations_total"])
+
+
 def test_config5_centralized_32_agents(oracle, ref):
     """build_global_ocp (multi_agent_problem.hpp:52-127) + centralized.hpp:18-38 + the stacked all-FD solve at
     n = 128, m = 64 (about 20 s of CPU for the two runs)."""
