@@ -194,6 +194,13 @@ int mas_b200_batch_set_tuning(mas_b200_batch_t b, int forward_lanes, int forward
  * the warp-cooperative kernel of large active sets (measured slower on B200: the extra HBM writes cost more than the
  * second rollout); 0: off.  Dropped silently when the allocation fails.  Results are identical in every mode. */
 int mas_b200_batch_set_trial_store(mas_b200_batch_t b, int enable);
+/* How the backward pass (solvers/ilqr.hpp:92-193) is mapped: 0 = auto; 1 = one thread per problem, derivatives and
+ * Riccati step fused; 2 = the finite-difference stencil points of a step dealt out to eight lanes per problem;
+ * 3 = time-parallel: the derivatives of ALL time steps (ilqr.hpp:106-113 is independent across t) evaluated at once by
+ * one kernel, then the Riccati recursion alone as a second one.  Auto takes 3 for active sets of at most max_problems
+ * problems (default 8192; 0 = keep) and for finite-difference-heavy derivative modes whenever the derivative blocks
+ * fit 512 MB.  Results are bit-identical in every mode. */
+int mas_b200_batch_set_backward_mode(mas_b200_batch_t b, int mode, int max_problems);
 /* How the line search (solvers/ilqr.hpp:195-228) is scheduled: 0 = auto (by active-set size),
  * 1 = all step sizes concurrently on `forward_lanes` lanes per problem, 2 = compacted rounds of two
  * step sizes over the problems still searching, 3 = warp-cooperative (a warp owns 32 problems and deals

@@ -273,6 +273,10 @@ class Batch:
     def set_tuning(self, forward_lanes: int = 0, forward_chains: int = 0) -> None:
         _check(load_library().mas_b200_batch_set_tuning(self._h, int(forward_lanes), int(forward_chains)))
 
+    def set_backward_mode(self, mode: int, max_problems: int = 0) -> None:
+        """0 auto, 1 one thread per problem, 2 FD tasks over eight lanes, 3 time-parallel linearisation + Riccati sweep."""
+        _check(load_library().mas_b200_batch_set_backward_mode(self._h, int(mode), int(max_problems)))
+
     def set_line_search_mode(self, mode: int) -> None:
         """0 auto, 1 concurrent lanes, 2 compacted rounds."""
         _check(load_library().mas_b200_batch_set_line_search_mode(self._h, int(mode)))

@@ -475,6 +475,14 @@ int mas_b200_batch_set_trial_store(mas_b200_batch_t h, int enable) {
   return MAS_B200_OK;
 }
 
+int mas_b200_batch_set_backward_mode(mas_b200_batch_t h, int mode, int max_problems) {
+  MAS_BATCH_GUARD(h);
+  if (mode < 0 || mode > 3) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "backward mode must be 0 (auto), 1 (one thread), 2 (FD lanes) or 3 (time-parallel)");
+  b->backward_mode = mode;
+  if (max_problems > 0) b->tp_max_problems = max_problems;
+  return MAS_B200_OK;
+}
+
 int mas_b200_batch_set_line_search_mode(mas_b200_batch_t h, int mode) {
   MAS_BATCH_GUARD(h);
   if (mode < 0 || mode > 3) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "line search mode must be 0 (auto), 1 (lanes), 2 (rounds) or 3 (warp-cooperative)");
@@ -491,6 +499,7 @@ static int borrow_scratch_batch(mas_b200_context_t ctx, const mas_b200_ocp_desc*
     b->al_fresh = true;
     b->tune_L = b->tune_C = 0;
     b->ls_mode = 0;
+    b->backward_mode = 0;
     *out = ctx->scratch_batch;
     return MAS_B200_OK;
   }

@@ -74,6 +74,7 @@ BatchBase::~BatchBase() {
   if (d_count_hist) cudaFree(d_count_hist);
   if (download_pending) cudaEventSynchronize(ev_downloaded);
   if (d_out_stage) cudaFree(d_out_stage);
+  if (d_deriv) cudaFree(d_deriv);
   if (d_trial_X) cudaFree(d_trial_X);
   if (d_trial_U) cudaFree(d_trial_U);
   if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -163,6 +164,27 @@ int BatchBase::prepare_constraint_state(const mas_b200_ilqr_params& prm) {
   MAS_CUDA_CHECK(cudaMemcpyAsync(d_penalty, rho.data(), L * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   MAS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   al_fresh = false;
+  return MAS_B200_OK;
+}
+
+// Derivative blocks of the time-parallel backward pass: [T+1][block_doubles][deriv_cap] doubles.  As many slots as the
+// batch needs, within 512 MB (e.g. 13,600 problems at T = 80, the whole batch at T = 10); larger active sets take the
+// fused kernels.  A failed allocation disables the path for this batch.
+int BatchBase::ensure_deriv_store(int block_doubles) {
+  if (d_deriv) return MAS_B200_OK;
+  if (deriv_cap < 0) return MAS_B200_ERR_CUDA;
+  const size_t per_slot = static_cast<size_t>(T + 1) * block_doubles * sizeof(double);
+  long long cap = static_cast<long long>((512ull << 20) / per_slot);
+  cap = std::min<long long>(cap, ld);
+  cap = (cap / 32) * 32;
+  if (cap < 32) cap = 32;
+  if (cudaMalloc(reinterpret_cast<void**>(&d_deriv), per_slot * cap) != cudaSuccess) {
+    cudaGetLastError();
+    d_deriv = nullptr;
+    deriv_cap = -1;
+    return MAS_B200_ERR_CUDA;
+  }
+  deriv_cap = static_cast<int>(cap);
   return MAS_B200_OK;
 }
 

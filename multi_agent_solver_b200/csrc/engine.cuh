@@ -132,6 +132,61 @@ __global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) backward_lanes_kernel(Ba
   if (lane == 0 && r) v.reg_retries[p] += r;
 }
 
+// ---- time-parallel linearisation + Riccati sweep (ilqr_core.cuh: linearize_point / riccati_sweep_thread) ----------
+// Small active sets are bound by the latency of the T sequential backward steps; the derivative evaluations inside a
+// step do not depend on the value function, so they are taken out of that chain: linearize_kernel computes the
+// derivative blocks of ALL (problem, time step) pairs at once (thread -> (problem, FD task group, t); consecutive
+// threads = consecutive problems, so block entries are written as coalesced rows of D[t][entry][slot]), and
+// riccati_sweep_kernel then runs the recursion alone, one thread per problem, fetching block t-1 into shared memory
+// with cp.async while step t computes.  FD-heavy derivative modes gain the whole stencil (118 cost + 12 dynamics
+// evaluations per step at n = 4, m = 2) spread over T x G threads per problem.
+constexpr int kLinBlock = 128;
+constexpr int kSweepBlock = 32;
+template <class M, int MASK_CT>
+__global__ void __launch_bounds__(kLinBlock) linearize_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
+                                                             double* __restrict__ D, int cap, int n_pad, int G) {
+  using DB = DerivBlock<M>;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int i = static_cast<int>(gid % n_pad);
+  const long long rest = gid / n_pad;
+  const int g = static_cast<int>(rest % G), t = static_cast<int>(rest / G);
+  if (i >= *count || t > v.T) return;
+  const int p = list[i];
+  const unsigned mask = (MASK_CT >= 0) ? static_cast<unsigned>(MASK_CT) : v.deriv_mask;
+  double* base = D + static_cast<size_t>(t) * DB::size * cap + i;
+  linearize_point<M>(v, p, t, mask, g, G, [&](int off, double val) { base[static_cast<size_t>(off) * cap] = val; });
+}
+
+template <class M, int MASK_CT>
+__global__ void __launch_bounds__(kSweepBlock) riccati_sweep_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
+                                                                   int* next_count, const double* __restrict__ D, int cap) {
+  using DB = DerivBlock<M>;
+  __shared__ double s_blk[2 * DB::size * kSweepBlock];  // [buffer][entry][thread]
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *next_count = 0;
+  if (i >= *count) return;
+  const int p = list[i];
+  double* mine = s_blk + threadIdx.x;
+  auto issue = [&](int t) {
+    const double* src = D + static_cast<size_t>(t) * DB::size * cap + i;
+    double* dst = mine + static_cast<size_t>(t & 1) * DB::size * kSweepBlock;
+    const int n = t == v.T ? DB::n_terminal_tasks : DB::size;
+    for (int k = 0; k < n; ++k) stage_copy8(dst + k * kSweepBlock, src + static_cast<size_t>(k) * cap);
+    stage_commit();
+  };
+  issue(v.T);
+  const int r = riccati_sweep_thread<M, MASK_CT>(v, p, [&](int t, double* blk) {
+    stage_wait();
+    const double* src = mine + static_cast<size_t>(t & 1) * DB::size * kSweepBlock;
+    const int n = t == v.T ? DB::n_terminal_tasks : DB::size;
+#pragma unroll
+    for (int k = 0; k < DB::size; ++k)
+      if (k < n) blk[k] = src[k * kSweepBlock];
+    if (t > 0) issue(t - 1);
+  });
+  if (r) v.reg_retries[p] += r;
+}
+
 // L lanes per problem (a power of two <= 16, aligned inside the warp); lane l rolls out step sizes
 // l, l+L, ...; the group picks the first improving candidate with shuffles; lane 0 commits.
 template <class M, int L, int C>
@@ -497,6 +552,14 @@ struct BatchBase {
   int trial_slots = 0;
   bool trial_store = true, trial_store_tried = false;
   bool backward_lanes_enabled = true;  // lane-parallel backward pass for FD-heavy derivative modes (set_tuning lanes < 0 disables)
+  // time-parallel linearisation + Riccati sweep (linearize_kernel / riccati_sweep_kernel): derivative blocks
+  // D[T+1][DerivBlock::size][deriv_cap] in HBM, allocated at first use.  backward_mode: 0 auto, 1 one thread per problem
+  // (fused), 2 FD tasks over eight lanes (fused), 3 time-parallel whenever the active set fits deriv_cap.
+  double* d_deriv = nullptr;
+  int deriv_cap = 0;
+  int backward_mode = 0;
+  int tp_max_problems = 8192;  // auto: largest active set that takes the time-parallel path (analytic-heavy modes)
+  int ensure_deriv_store(int block_doubles);
   bool coop_store = false;  // mas_b200_batch_set_trial_store(b, 2): trial store in the cooperative kernel too
   int ensure_trial_store(long long min_slots);
   int begin_download(double* X, double* U, double* cost, int* iterations, int* status);
@@ -655,13 +718,40 @@ struct BatchImpl : BatchBase {
     return MAS_B200_OK;
   }
 
+  template <int MASK_CT>
+  void launch_time_parallel(int n_upper, int cur, int G) {
+    const int n_pad = div_up(n_upper, 32) * 32;
+    const long long threads = static_cast<long long>(n_pad) * G * (T + 1);
+    linearize_kernel<M, MASK_CT><<<static_cast<int>((threads + kLinBlock - 1) / kLinBlock), kLinBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur,
+                                                                                                                        d_deriv, deriv_cap, n_pad, G);
+    riccati_sweep_kernel<M, MASK_CT><<<div_up(n_upper, kSweepBlock), kSweepBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur,
+                                                                                                   d_count + (cur ^ 1), d_deriv, deriv_cap);
+    stats.kernel_launches += 2;
+  }
+
   void launch_backward(int n_upper, int cur) {
     const unsigned mask = desc.deriv_mask;
+    // MAS_B200_BACKWARD_MODE / MAS_B200_TP_MAX: A/B switches for the entry points that own their batch (strategies)
+    static const int env_mode = std::getenv("MAS_B200_BACKWARD_MODE") ? std::atoi(std::getenv("MAS_B200_BACKWARD_MODE")) : 0;
+    static const int env_tp_max = std::getenv("MAS_B200_TP_MAX") ? std::atoi(std::getenv("MAS_B200_TP_MAX")) : 0;
+    const int backward_mode = this->backward_mode ? this->backward_mode : env_mode;
+    const int tp_max_problems = env_tp_max > 0 ? env_tp_max : this->tp_max_problems;
+    {
+      const bool fd_heavy_tp = !(mask & D_LXX) && (mask == 0u || mask != M::EXAMPLE_MASK);
+      const bool want = backward_mode == 3 || (backward_mode == 0 && ls_mode == 0 && tune_L == 0 && (fd_heavy_tp || n_upper <= tp_max_problems));
+      if (want && ensure_deriv_store(DerivBlock<M>::size) == MAS_B200_OK && n_upper <= deriv_cap) {
+        const int G = fd_heavy_tp ? 8 : 2;
+        if (mask == M::EXAMPLE_MASK) launch_time_parallel<static_cast<int>(M::EXAMPLE_MASK)>(n_upper, cur, G);
+        else if (mask == 0u) launch_time_parallel<0>(n_upper, cur, G);
+        else launch_time_parallel<-1>(n_upper, cur, G);
+        return;
+      }
+    }
     // Many finite-difference callbacks (at least the n x n stage Hessian) and enough tasks to keep eight lanes busy
     // (n = 4: 40; the pendulum's 13 and the rocket's 21 measured slower than one thread per problem), and few enough
     // problems for eight lanes each to be resident: deal the stencil points out to the lanes (backward_lanes_kernel).
     const bool fd_heavy = !(mask & D_LXX) && (mask == 0u || mask != M::EXAMPLE_MASK) && DerivBlock<M>::n_tasks >= 32;
-    if (backward_lanes_enabled && fd_heavy && ls_mode == 0 && tune_L == 0) {
+    if (backward_mode != 1 && (backward_mode == 2 || (backward_lanes_enabled && fd_heavy && ls_mode == 0 && tune_L == 0))) {
       constexpr int LB = 8;
       const size_t sm = (kBlock / LB) * DerivBlock<M>::size * sizeof(double);
       if (!resident_backward_lanes) {
@@ -669,7 +759,7 @@ struct BatchImpl : BatchBase {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, backward_lanes_kernel<M, 0, LB>, kBlock, sm) != cudaSuccess || blocks <= 0) blocks = 4;
         resident_backward_lanes = static_cast<long long>(blocks) * kBlock * ctx->sm_count;
       }
-      if (static_cast<long long>(n_upper) * LB <= resident_backward_lanes) {
+      if (backward_mode == 2 || static_cast<long long>(n_upper) * LB <= resident_backward_lanes) {
         const int lgrid = static_cast<int>((static_cast<long long>(n_upper) * LB + kBlock - 1) / kBlock);
         if (mask == 0u)
           backward_lanes_kernel<M, 0, LB><<<lgrid, kBlock, sm, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1));

@@ -1143,6 +1143,173 @@ MAS_HD int backward_lanes(const BatchView<M::NX, M::NU>& v, int p, int lane, dou
   return retries;
 }
 
+// ---- time-parallel linearisation + Riccati sweep (small active sets) -------------------------------------------
+// The derivatives the backward pass needs at (x_t, u_t) -- A, B, l_x, l_u, l_xx, l_uu, l_ux, and V_x, V_xx at x_T
+// (ilqr.hpp:92-100,106-113) -- depend on the current trajectory only, not on the value function, so they are
+// independent across time steps.  `linearize_point` computes the derivative block of ONE (problem, time step) pair,
+// optionally split over G cooperating threads (FD stencil tasks g, g + G, ...; the analytic callbacks on g == 0), and
+// hands every entry to `put(offset, value)`; the engine runs it for all (problem, t) pairs of a small active set at
+// once (linearize_kernel) and stores the blocks in HBM.  `riccati_sweep_thread` is then the sequential part alone:
+// per step it fetches the block with `get(t, offset)` and runs the same riccati_step as the fused kernels.  Every
+// entry is produced by the very function the fused pass uses, so the results are bit-identical (tests: host emulation
+// and GPU).  t == T addresses the terminal block [V_x | V_xx].
+template <class M>
+MAS_HD void deriv_task_info(unsigned mask, int task, int* off, int* cnt, bool* analytic) {
+  constexpr int NX = M::NX, NU = M::NU;
+  using D = DerivBlock<M>;
+  if (task < D::tB) {
+    *off = D::oA + (task - D::tA) * NX;
+    *cnt = NX;
+    *analytic = (mask & D_A) != 0;
+  } else if (task < D::tlx) {
+    *off = D::oB + (task - D::tB) * NX;
+    *cnt = NX;
+    *analytic = (mask & D_B) != 0;
+  } else if (task < D::tlu) {
+    *off = D::olx + (task - D::tlx);
+    *cnt = 1;
+    *analytic = (mask & D_LX) != 0;
+  } else if (task < D::tlxx) {
+    *off = D::olu + (task - D::tlu);
+    *cnt = 1;
+    *analytic = (mask & D_LU) != 0;
+  } else if (task < D::tluu) {
+    *off = D::olxx + (task - D::tlxx);
+    *cnt = 1;
+    *analytic = (mask & D_LXX) != 0;
+  } else if (task < D::tlux) {
+    *off = D::oluu + (task - D::tluu);
+    *cnt = 1;
+    *analytic = (mask & D_LUU) != 0;
+  } else {
+    *off = D::olux + (task - D::tlux);
+    *cnt = 1;
+    *analytic = (mask & D_LUX) != 0;
+  }
+  (void)NU;
+}
+
+template <class M, class Put>
+MAS_HD void linearize_point(const BatchView<M::NX, M::NU>& v, int p, int t, unsigned mask, int g, int G, const Put& put) {
+  constexpr int NX = M::NX, NU = M::NU;
+  using D = DerivBlock<M>;
+  double prm[M::NP > 0 ? M::NP : 1];
+  load_params<M>(v, p, prm);
+  double x[NX], u[NU];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) x[i] = v.X[soa_index<NX>(t, i, v.ld, p)];
+  if (t == v.T) {  // terminal value (ilqr.hpp:92-100); the aliased symmetrisation (:102) belongs to the sweep
+    double blk[D::n_terminal_tasks];
+    for (int task = g; task < D::n_terminal_tasks; task += G) {
+      const bool analytic = task < NX ? (mask & D_VX) != 0 : (mask & D_VXX) != 0;
+      if (analytic) continue;
+      fd_terminal_task<M>(mask, task, x, prm, blk);
+      put(task, blk[task]);
+    }
+    if (g == 0) {
+      if (mask & D_VX) {
+        double vx[NX];
+        M::v_x(x, prm, vx);
+        for (int i = 0; i < NX; ++i) put(i, vx[i]);
+      }
+      if (mask & D_VXX) {
+        double vxx[NX * NX];
+        M::v_xx(x, prm, vxx);
+        for (int i = 0; i < NX * NX; ++i) put(NX + i, vxx[i]);
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < NU; ++i) u[i] = v.U[soa_index<NU>(t, i, v.ld, p)];
+  double blk[D::size];
+  for (int task = g; task < D::n_tasks; task += G) {
+    int off, cnt;
+    bool analytic;
+    deriv_task_info<M>(mask, task, &off, &cnt, &analytic);
+    if (analytic) continue;
+    fd_stage_task<M>(mask, task, x, u, t, prm, blk);
+    for (int k = 0; k < cnt; ++k) put(off + k, blk[off + k]);
+  }
+  if (g == 0) {  // analytic callbacks (:106-113)
+    if (mask & D_A) {
+      double A[NX * NX];
+      M::jac_x(x, u, prm, A);
+      for (int i = 0; i < NX * NX; ++i) put(D::oA + i, A[i]);
+    }
+    if (mask & D_B) {
+      double B[NX * NU];
+      M::jac_u(x, u, prm, B);
+      for (int i = 0; i < NX * NU; ++i) put(D::oB + i, B[i]);
+    }
+    if (mask & D_LX) {
+      double g1[NX];
+      M::l_x(x, u, t, prm, g1);
+      for (int i = 0; i < NX; ++i) put(D::olx + i, g1[i]);
+    }
+    if (mask & D_LU) {
+      double g2[NU];
+      M::l_u(x, u, t, prm, g2);
+      for (int i = 0; i < NU; ++i) put(D::olu + i, g2[i]);
+    }
+    if (mask & D_LXX) {
+      double H[NX * NX];
+      M::l_xx(x, u, t, prm, H);
+      for (int i = 0; i < NX * NX; ++i) put(D::olxx + i, H[i]);
+    }
+    if (mask & D_LUU) {
+      double H[NU * NU];
+      M::l_uu(x, u, t, prm, H);
+      for (int i = 0; i < NU * NU; ++i) put(D::oluu + i, H[i]);
+    }
+    if (mask & D_LUX) {
+      double H[NU * NX];
+      M::l_ux(x, u, t, prm, H);
+      for (int i = 0; i < NU * NX; ++i) put(D::olux + i, H[i]);
+    }
+  }
+}
+
+// The sequential half: terminal value, then T Riccati steps on stored derivative blocks.  `fetch(t, blk)` fills blk
+// (DerivBlock<M>::size doubles) with the block of step t (t == T: [V_x | V_xx]) -- the device stages the next block in
+// shared memory while the current step computes.  Returns the regularisation retries.
+template <class M, int MASK_CT, class Fetch>
+MAS_HD int riccati_sweep_thread(const BatchView<M::NX, M::NU>& v, int p, const Fetch& fetch) {
+  constexpr int NX = M::NX, NU = M::NU;
+  using D = DerivBlock<M>;
+  double prm[M::NP > 0 ? M::NP : 1];
+  load_params<M>(v, p, prm);
+  const int T = v.T;
+  int retries = 0;
+  const double al_rho = HasConstraints<M>::value ? v.penalty[p] : 0.0;
+  double blk[D::size];
+  double v_x[NX], v_xx[NX * NX];
+  fetch(T, blk);
+#pragma unroll
+  for (int i = 0; i < NX; ++i) v_x[i] = blk[i];
+#pragma unroll
+  for (int i = 0; i < NX * NX; ++i) v_xx[i] = blk[NX + i];
+  symmetrize_aliased<NX>(v_xx);
+  for (int t = T - 1; t >= 0; --t) {
+    double x[NX], u[NU];
+    if (HasConstraints<M>::value) {  // only the constraint terms of riccati_step look at (x_t, u_t)
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = v.X[soa_index<NX>(t, i, v.ld, p)];
+#pragma unroll
+      for (int i = 0; i < NU; ++i) u[i] = v.U[soa_index<NU>(t, i, v.ld, p)];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < NU; ++i) u[i] = 0.0;
+    }
+    fetch(t, blk);
+    retries += riccati_step<M, MASK_CT>(v, p, t, x, u, prm, al_rho, blk + D::oA, blk + D::oB, blk + D::olx, blk + D::olu, blk + D::olxx, blk + D::oluu,
+                                        blk + D::olux, v_x, v_xx);
+  }
+  return retries;
+}
+
 // ---- forward pass (ilqr.hpp:206-217) for C step sizes at once, merit only ------------------------
 // The C rollouts share the loads of the nominal trajectory and gains and give the fp64 pipe C
 // independent dependency chains.  merit[c] = sum_t stage + terminal, accumulated in t order.

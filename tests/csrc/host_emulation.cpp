@@ -23,7 +23,7 @@ struct ALOptions {
   double penalty = 10.0, penalty_increase = 5.0, constraint_tolerance = 1e-4, activation_tolerance = 1e-6;
   int repeats = 1;
   bool trial_store = true;
-  int backward_lanes = 0;  // > 0: lane-parallel backward pass with that many lanes per problem
+  int backward_lanes = 0;  // > 0: lane-parallel backward pass with that many lanes per problem; < 0: time-parallel with -n threads per point
   double* hist_cost = nullptr;
   int* hist_iters = nullptr;
 };
@@ -63,6 +63,21 @@ int emulate_backward_lanes(const BatchView<M::NX, M::NU>& v, int p, int LB) {
     retries += riccati_step<M, MASK_CT>(v, p, t, x, u, prm, al_rho, A, B, l_x, l_u, l_xx, l_uu, l_ux, v_x, v_xx);
   }
   return retries;
+}
+
+// Time-parallel backward pass (linearize_kernel + riccati_sweep_kernel): the derivative blocks of all T + 1 points are
+// produced first, each by G emulated threads, then the sweep consumes them.
+template <class M, int MASK_CT>
+int emulate_time_parallel(const BatchView<M::NX, M::NU>& v, int p, int G) {
+  using D = DerivBlock<M>;
+  const unsigned mask = (MASK_CT >= 0) ? static_cast<unsigned>(MASK_CT) : v.deriv_mask;
+  std::vector<double> store(static_cast<size_t>(v.T + 1) * D::size, 0.0);
+  for (int t = v.T; t >= 0; --t)
+    for (int g = G - 1; g >= 0; --g)
+      linearize_point<M>(v, p, t, mask, g, G, [&](int off, double val) { store[static_cast<size_t>(t) * D::size + off] = val; });
+  return riccati_sweep_thread<M, MASK_CT>(v, p, [&](int t, double* blk) {
+    for (int k = 0; k < D::size; ++k) blk[k] = store[static_cast<size_t>(t) * D::size + k];
+  });
 }
 
 template <class M>
@@ -144,7 +159,10 @@ int emulate(int batch, int T, double dt, unsigned mask, int has_bounds, const do
   for (int it = 0; it < max_iterations && !list.empty(); ++it) {
     for (int p : list) {  // backward_kernel
       int r;
-      if (g_al.backward_lanes > 0 && mask == 0u) r = emulate_backward_lanes<M, 0>(v, p, g_al.backward_lanes);
+      if (g_al.backward_lanes < 0 && mask == M::EXAMPLE_MASK) r = emulate_time_parallel<M, static_cast<int>(M::EXAMPLE_MASK)>(v, p, -g_al.backward_lanes);
+      else if (g_al.backward_lanes < 0 && mask == 0u) r = emulate_time_parallel<M, 0>(v, p, -g_al.backward_lanes);
+      else if (g_al.backward_lanes < 0) r = emulate_time_parallel<M, -1>(v, p, -g_al.backward_lanes);
+      else if (g_al.backward_lanes > 0 && mask == 0u) r = emulate_backward_lanes<M, 0>(v, p, g_al.backward_lanes);
       else if (g_al.backward_lanes > 0) r = emulate_backward_lanes<M, -1>(v, p, g_al.backward_lanes);
       else if (mask == M::EXAMPLE_MASK) r = backward_thread<M, static_cast<int>(M::EXAMPLE_MASK)>(v, p);
       else if (mask == 0u) r = backward_thread<M, 0>(v, p);

@@ -413,3 +413,36 @@ def test_lane_parallel_backward_pass_matches_the_one_thread_pass(mas, ctx, emu, 
     T, m = desc.horizon_steps, desc.control_dim
     exp = emu.solve(model, x0, np.zeros((B, T, m)), 8, 1e-5, mask=mask)
     assert is_bit_exact(outs[0], exp)
+
+
+@pytest.mark.parametrize("model,mask", [(0, None), (0, 0), (1, 0), (2, None), (3, 0), (4, None), (5, None)])
+def test_backward_modes_are_bit_identical(mas, ctx, oracle, model, mask):
+    """mas_b200_batch_set_backward_mode: one thread per problem (1), FD tasks over eight lanes (2) and the time-parallel
+    linearisation + Riccati sweep (3) give the same bits, and the oracle's where the derivative mode is the example's."""
+    max_it, tol = EXAMPLE_SOLVER_PARAMS.get(model, (6, 1e-5))
+    max_it = min(max_it, 12)
+    B = 200
+    x0 = random_x0(model, B, seed=500 + model)
+    desc = mas.example_desc(model)
+    example_mask = desc.deriv_mask
+    if mask is not None:
+        desc.deriv_mask = mask
+    U0 = np.zeros((B, desc.horizon_steps, desc.control_dim))
+    outs = []
+    for mode in (1, 2, 3):
+        b = mas.Batch(ctx, desc, B)
+        b.set_backward_mode(mode)
+        b.set_initial_states(x0)
+        b.set_controls(U0)
+        b.solve(mas.IlqrParams.make(max_it, tol))
+        o = b.get_solution()
+        o["stats"] = b.stats()
+        outs.append(o)
+        b.close()
+    for o in outs[1:]:
+        for k in ("X", "U", "cost", "iterations", "status"):
+            assert np.array_equal(o[k], outs[0][k], equal_nan=o[k].dtype.kind == "f"), k
+        assert o["stats"]["reg_retries"] == outs[0]["stats"]["reg_retries"]
+    if desc.deriv_mask == example_mask:
+        ref = oracle.ilqr_solve_batch(model, x0, U_init=U0, max_iterations=max_it, tolerance=tol, trig=oracle.TRIG_PORTABLE)
+        assert is_bit_exact(outs[2], ref)

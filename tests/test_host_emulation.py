@@ -206,3 +206,23 @@ def test_nonfinite_trajectories(emu, oracle):
     got_fd = emu.solve(1, x0, Uc, 8, 1e-5)
     for k in ("X", "U", "cost", "iterations", "status"):
         assert np.array_equal(got_fd[k], ref_fd[k], equal_nan=got_fd[k].dtype.kind == "f"), k
+
+
+@pytest.mark.parametrize("model,mask,threads", [(0, None, 2), (0, 0, 8), (1, 0, 8), (2, None, 1), (3, 0, 3), (4, None, 2), (5, None, 2), (0, 0x3F & ~0x30, 5)])
+def test_time_parallel_backward_pass_is_bit_identical(emu, oracle, model, mask, threads):
+    """linearize_point for all (problem, t) pairs first -- each by `threads` cooperating threads --, then the Riccati
+    recursion alone (riccati_sweep_thread): the derivative evaluation leaves the sequential chain (ilqr.hpp:106-113 is
+    independent across t).  Same bits as the fused one-thread pass, and as the oracle in the example's derivative mode."""
+    max_it, tol = EXAMPLE_SOLVER_PARAMS.get(model, (6, 1e-5))
+    max_it = min(max_it, 12)
+    x0 = random_x0(model, 10, seed=400 + model)
+    n, m, T = MODEL_TABLE[model][:3]
+    mask = MODEL_TABLE[model][4] if mask is None else mask
+    U0 = np.zeros((10, T, m))
+    one = emu.solve(model, x0, U0, max_it, tol, mask=mask)
+    par = emu.solve(model, x0, U0, max_it, tol, mask=mask, backward_lanes=-threads)
+    for k in ("X", "U", "cost", "iterations", "status", "alpha_trials", "reg_retries"):
+        assert np.array_equal(one[k], par[k]), k
+    if mask == MODEL_TABLE[model][4]:
+        ref = oracle.ilqr_solve_batch(model, x0, U_init=U0, max_iterations=max_it, tolerance=tol, trig=oracle.TRIG_PORTABLE)
+        assert is_bit_exact(par, ref)
