@@ -257,6 +257,8 @@ class Lane:
             self.batch.set_tuning(args.lanes, args.chains)
         if args.ls_mode:
             self.batch.set_line_search_mode(args.ls_mode)
+        if args.hint:
+            self.batch.set_concurrency_hint(args.hint)
         self.out = None
         if with_host_buffers:
             self.out = dict(X=torch.empty((per_rank, T + 1, NX), dtype=torch.float64).pin_memory().numpy(),
@@ -426,7 +428,14 @@ def run_b200(args):
     x0_all = mas.synthetic_single_track_x0(PROBLEMS)
     desc = mas.example_desc(mas.Model.SINGLE_TRACK_LANE)
     prm = mas.IlqrParams.make(MAX_ITER, TOL)
-    depth = args.depth if args.depth > 0 else (3 if args.steps < 8 else 4)
+    # solves in flight per GPU: a full 65,536-problem shard fills the device in its first iterations (4 pipelines hide the
+    # latency-bound tail); the smaller shards of strong scaling are latency-bound from the start, so more of them are kept
+    # in flight, and every batch is told that it shares the device (mas_b200_batch_set_concurrency_hint: narrower lane
+    # mappings, i.e. less speculative work).  Measured on one B200 (profiles/r02_strong_scaling_tuning.txt).
+    shard = args.shard or (PROBLEMS if scaling == "weak" else PROBLEMS // world)
+    depth = args.depth if args.depth > 0 else (3 if args.steps < 8 else (4 if shard >= PROBLEMS else (6 if shard >= PROBLEMS // 2 else 8)))
+    if args.hint == 0 and shard < PROBLEMS:
+        args.hint = 4
 
     def barrier():
         if dist is not None:
@@ -436,12 +445,14 @@ def run_b200(args):
     def measure(mode: str, steps: int, full: bool):
         """One scaling mode: strong = the 65,536 problems split over the ranks, weak = 65,536 per rank."""
         per_rank = PROBLEMS if mode == "weak" else PROBLEMS // world
+        if args.shard:  # profiling aid: the shard a rank would hold at N = 65,536 / shard GPUs, on this GPU alone
+            per_rank = args.shard
         total = per_rank * world
         if mode == "weak":
             # every rank gets the 65,536 problems, rotated so the ranks do not solve identical shards in the same order
             x0 = np.roll(x0_all, -rank * 4099, axis=0).copy()
         else:
-            x0 = x0_all[rank * per_rank:(rank + 1) * per_rank].copy()
+            x0 = x0_all[(rank * per_rank) % PROBLEMS:(rank * per_rank) % PROBLEMS + per_rank].copy()
         x0_host = torch.from_numpy(x0).pin_memory().numpy()
         lanes = [Lane(torch, mas, local_rank, desc, per_rank, args, with_host_buffers=full and not args.resident_only) for _ in range(depth)]
         for ln in lanes:
@@ -582,7 +593,16 @@ def run_b200(args):
 
     other = None
     if not args.no_configs:
-        other = run_other_configs(mas, torch, dist, rank, world, local_rank)
+        # the library's own NCCL communicator may announce its version on stdout: keep stdout clean for the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            other = run_other_configs(mas, torch, dist, rank, world, local_rank)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     if rank == 0:
         per_rank, total = main["per_rank"], main["total"]
@@ -649,7 +669,7 @@ def run_b200(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg,
             "engine": {"problems_per_gpu": per_rank, "parallelism": f"contiguous shards of independent problems x{n_gpus}, no data-path collective",
-                       "solves_in_flight": depth,
+                       "solves_in_flight": depth, "concurrency_hint": args.hint or 1,
                        "pipelining": f"{depth} independent solves of the shard in flight per GPU, each a whole step on its own stream and host "
                                      "thread, starts staggered; ms_per_step = device time of the K steps / K",
                        "single_solve_ms": single_ms,
@@ -689,6 +709,8 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the config 1/2/4/5 blocks")
     ap.add_argument("--no-weak", action="store_true", help="skip the extra weak-scaling measurement at N > 1")
     ap.add_argument("--ls-mode", type=int, default=0, help="line search scheduling: 0 auto, 1 concurrent lanes, 2 compacted rounds")
+    ap.add_argument("--shard", type=int, default=0, help="profiling aid (with --resident-only): problems per rank, overriding 65,536 / N")
+    ap.add_argument("--hint", type=int, default=0, help="mas_b200_batch_set_concurrency_hint of every pipeline (0 = leave at 1)")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--chains", type=int, default=0)
     args = ap.parse_args()

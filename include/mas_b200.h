@@ -201,6 +201,11 @@ int mas_b200_batch_set_trial_store(mas_b200_batch_t b, int enable);
  * problems (default 8192; 0 = keep) and for finite-difference-heavy derivative modes whenever the derivative blocks
  * fit 512 MB.  Results are bit-identical in every mode. */
 int mas_b200_batch_set_backward_mode(mas_b200_batch_t b, int mode, int max_problems);
+/* How many independent solves the caller keeps in flight on this device (other batches on other streams; default 1).
+ * The automatic lane mappings trade work for latency: a small active set evaluates all ten step sizes of the line
+ * search at once on up to 16 lanes per problem when the device would otherwise idle.  With n solves in flight the
+ * device is not idle, and each batch sizes its mappings for 1/n of it.  Results do not depend on the hint. */
+int mas_b200_batch_set_concurrency_hint(mas_b200_batch_t b, int solves_in_flight);
 /* How the line search (solvers/ilqr.hpp:195-228) is scheduled: 0 = auto (by active-set size),
  * 1 = all step sizes concurrently on `forward_lanes` lanes per problem, 2 = compacted rounds of two
  * step sizes over the problems still searching, 3 = warp-cooperative (a warp owns 32 problems and deals

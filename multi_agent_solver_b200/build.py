@@ -15,8 +15,11 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
-OBJ_DIR = os.path.join(PKG_DIR, "_obj")
-LIB_PATH = os.path.join(PKG_DIR, "libmas_b200.so")
+# MAS_B200_VARIANT=<name>: a tuning build next to the product library (tools/_variants/libmas_b200_<name>.so, own object
+# directory), selected at run time with MAS_B200_LIB=<path>; used for A/B measurements only.
+VARIANT = os.environ.get("MAS_B200_VARIANT", "")
+OBJ_DIR = os.path.join(PKG_DIR, "_obj" + ("_" + VARIANT if VARIANT else ""))
+LIB_PATH = os.path.join(PKG_DIR, "libmas_b200.so") if not VARIANT else os.path.join(ROOT, "tools", "_variants", f"libmas_b200_{VARIANT}.so")
 
 SOURCES = ["engine.cu", "capi.cu", "centralized.cu", "model_st_lane.cu", "model_st_lane_con.cu", "model_st_circ.cu", "model_lqr4.cu", "model_pendulum.cu", "model_rocket.cu"]
 HEADERS = ["engine.cuh", "ilqr_core.cuh", "models.cuh", "centralized.cuh", "centralized_host.cuh"]

@@ -8,7 +8,7 @@ from typing import Optional
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_PKG, "libmas_b200.so")
+_LIB_PATH = os.environ.get("MAS_B200_LIB") or os.path.join(_PKG, "libmas_b200.so")  # MAS_B200_LIB: a tuning build (tools/_variants)
 _lib: Optional[ctypes.CDLL] = None
 
 MAX_CONTROL_DIM = 8
@@ -276,6 +276,9 @@ class Batch:
     def set_backward_mode(self, mode: int, max_problems: int = 0) -> None:
         """0 auto, 1 one thread per problem, 2 FD tasks over eight lanes, 3 time-parallel linearisation + Riccati sweep."""
         _check(load_library().mas_b200_batch_set_backward_mode(self._h, int(mode), int(max_problems)))
+
+    def set_concurrency_hint(self, solves_in_flight: int) -> None:
+        _check(load_library().mas_b200_batch_set_concurrency_hint(self._h, int(solves_in_flight)))
 
     def set_line_search_mode(self, mode: int) -> None:
         """0 auto, 1 concurrent lanes, 2 compacted rounds."""

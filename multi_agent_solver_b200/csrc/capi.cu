@@ -483,6 +483,13 @@ int mas_b200_batch_set_backward_mode(mas_b200_batch_t h, int mode, int max_probl
   return MAS_B200_OK;
 }
 
+int mas_b200_batch_set_concurrency_hint(mas_b200_batch_t h, int solves_in_flight) {
+  MAS_BATCH_GUARD(h);
+  if (solves_in_flight < 1) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "solves_in_flight must be >= 1");
+  b->concurrency_hint = solves_in_flight;
+  return MAS_B200_OK;
+}
+
 int mas_b200_batch_set_line_search_mode(mas_b200_batch_t h, int mode) {
   MAS_BATCH_GUARD(h);
   if (mode < 0 || mode > 3) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "line search mode must be 0 (auto), 1 (lanes), 2 (rounds) or 3 (warp-cooperative)");

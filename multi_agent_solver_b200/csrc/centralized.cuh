@@ -46,6 +46,7 @@ struct StackedProblem {
   double* out_cost;            // [1 + A]: stacked best_cost, then per-agent costs
   int* out_int;                // iterations, status, reg_retries, alpha_trials
   long long* phase_cycles;     // optional [kNumPhases]: SM cycles per phase of this scenario (diagnostics), or null
+  int use_dmma;                // opt-in (MAS_B200_CENTRALIZED_DMMA=1): dense gain / value-update products on the fp64 tensor cores
 };
 
 // Phases timed by MAS_PHASE (thread 0 of the scenario's CTA, clock64 between barriers).
@@ -123,6 +124,73 @@ struct StackedWork {
     total = o;
   }
 };
+
+// ---- opt-in fp64 tensor-core products (mma.sync.m8n8k4.f64 = DMMA.884) ------------------------------------------------
+// The dense products of the stacked gain and value update (ilqr.hpp:185-191 at n_s = 128, m_s = 64: K = -Q_uu^-1 Q_ux,
+// K^T Q_uu, and V_xx = Q_xx + K^T Q_ux + Q_ux^T K + (K^T Q_uu) K) are real matrix contractions of inner dimension m_s.
+// The default path evaluates every output element as a k-ascending sequence of separately rounded multiplications
+// and additions -- the reference's arithmetic, which the parity gate asserts bit for bit.  With use_dmma the same
+// products run on the tensor cores: fused multiply-adds, four k at a time, in the hardware's own accumulation order.
+// That changes rounding, and on this all-finite-difference configuration a rounding change moves the result as much
+// as a one-ulp change of the input does, so the mode is never the default and is excluded from parity;
+// tools/centralized_dmma.py reports its speed-up and its deviation next to the reference's own one-ulp band.
+// Fragment layout (PTX ISA, m8n8k4 .row.col f64): lane = 4 * g + c;  A[g][c], B[c][g], C/D[g][2c], [g][2c + 1].
+#if defined(__CUDACC__)
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// C[rows x cols] (+)= sum over `terms` of A_t * B_t, inner dimension kd (multiple of 4), rows % 8 == 0, cols % 16 == 0.
+// Element accessors: A_t(i, k) = a[t][i * a_is[t] + k * a_ks[t]] (times a_sign[t]), B_t(k, j) = b[t][k * b_ks[t] + j * b_js[t]].
+// Every warp owns 8 x 16 output blocks (two 8 x 8 tiles that share their A fragments).
+struct DmmaTerm {
+  const double* a;
+  size_t a_is, a_ks;
+  double a_sign;
+  const double* b;
+  size_t b_ks, b_js;
+};
+template <int NT>
+__device__ void dmma_product(const DmmaTerm (&term)[NT], int rows, int cols, int kd, const double* c_in, size_t c_ld, double* out0, size_t ld0, double* out1,
+                             size_t ld1, int tid, int nthr) {
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  const int g = lane >> 2, c = lane & 3;
+  const int ti = rows / 8, tj = cols / 16;
+  for (int blk = warp; blk < ti * tj; blk += nwarps) {
+    const int i0 = (blk % ti) * 8, j0 = (blk / ti) * 16;
+    const size_t i = i0 + g, ja = j0 + 2 * c, jb = j0 + 8 + 2 * c;
+    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+    if (c_in) {
+      c00 = c_in[i + ja * c_ld];
+      c01 = c_in[i + (ja + 1) * c_ld];
+      c10 = c_in[i + jb * c_ld];
+      c11 = c_in[i + (jb + 1) * c_ld];
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const double* pa = term[t].a + i * term[t].a_is + c * term[t].a_ks;
+      const double* pb0 = term[t].b + c * term[t].b_ks + static_cast<size_t>(j0 + g) * term[t].b_js;
+      const double* pb1 = pb0 + 8 * term[t].b_js;
+      const double sg = term[t].a_sign;
+#pragma unroll 4
+      for (int k0 = 0; k0 < kd; k0 += 4) {
+        const double av = sg * pa[k0 * term[t].a_ks];
+        dmma884(c00, c01, av, pb0[k0 * term[t].b_ks]);
+        dmma884(c10, c11, av, pb1[k0 * term[t].b_ks]);
+      }
+    }
+    out0[i + ja * ld0] = c00;
+    out0[i + (ja + 1) * ld0] = c01;
+    out0[i + jb * ld0] = c10;
+    out0[i + (jb + 1) * ld0] = c11;
+    if (out1) {
+      out1[i + ja * ld1] = c00;
+      out1[i + (ja + 1) * ld1] = c01;
+      out1[i + jb * ld1] = c10;
+      out1[i + (jb + 1) * ld1] = c11;
+    }
+  }
+}
+#endif
 
 // Barrier over a warp-aligned group of `count` threads of the CTA (named barrier `id`, 1..15); the whole CTA when
 // count == all.  Sequential host emulation: nothing.
@@ -625,7 +693,15 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
         kt[i] = s;
       }
     }
-    for (int e = tid; e < ms * ((ns + 3) / 4); e += nthr) {  // K: row i, four columns per thread
+    bool dmma = false;
+#if defined(__CUDA_ARCH__)
+    dmma = P.use_dmma && ns % 16 == 0 && ms % 16 == 0 && nthr % 32 == 0;
+    if (dmma) {  // K = (-inv) Q_ux on the tensor cores, into global K_t and the shared copy
+      const DmmaTerm tk[1] = {{inv, 1, static_cast<size_t>(ldk), -1.0, fQ, 1, static_cast<size_t>(ldk)}};
+      dmma_product<1>(tk, ms, ns, ms, nullptr, 0, Kt, ms, fK, ldk, tid, nthr);
+    }
+#endif
+    for (int e = tid; !dmma && e < ms * ((ns + 3) / 4); e += nthr) {  // K: row i, four columns per thread
       const int i = e % ms, j0 = (e / ms) * 4;
       int jc[4];
 #pragma unroll
@@ -651,7 +727,13 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
     MAS_CTA_SYNC();
     MAS_PHASE(PH_GAINS);
     // ---- K^T Q_uu (unregularised), then the value update (ilqr.hpp:188-192)
-    for (int e = tid; e < ns * ((ms + 3) / 4); e += nthr) {  // four columns of K^T Q_uu per thread, as in V_xx below
+#if defined(__CUDA_ARCH__)
+    if (dmma) {  // K^T Q_uu
+      const DmmaTerm tq[1] = {{fK, static_cast<size_t>(ldk), 1, 1.0, Quu, 1, static_cast<size_t>(ms)}};
+      dmma_product<1>(tq, ns, ms, ms, nullptr, 0, KtQ, ns, nullptr, 0, tid, nthr);
+    }
+#endif
+    for (int e = tid; !dmma && e < ns * ((ms + 3) / 4); e += nthr) {  // four columns of K^T Q_uu per thread, as in V_xx below
       const int i = e % ns, j0 = (e / ns) * 4;
       int jc[4];
 #pragma unroll
@@ -702,7 +784,15 @@ MAS_HD void stacked_backward(const StackedProblem<M>& P, const StackedWork& W, i
     }
     // V_xx: each thread owns one row index i and four consecutive columns, so that every operand it loads feeds four
     // (K, Q_ux of column i) or three (K, Q_ux of column j) of its twelve independent k-ascending sums
-    for (int e = tid; e < ns * ((ns + 3) / 4); e += nthr) {
+#if defined(__CUDA_ARCH__)
+    if (dmma) {  // V_xx = Q_xx + K^T Q_ux + Q_ux^T K + (K^T Q_uu) K, accumulated in that order
+      const DmmaTerm tv[3] = {{fK, static_cast<size_t>(ldk), 1, 1.0, fQ, 1, static_cast<size_t>(ldk)},
+                              {fQ, static_cast<size_t>(ldk), 1, 1.0, fK, 1, static_cast<size_t>(ldk)},
+                              {KtQ, 1, static_cast<size_t>(ns), 1.0, fK, 1, static_cast<size_t>(ldk)}};
+      dmma_product<3>(tv, ns, ns, ms, Qxx, ns, Vxx, ns, nullptr, 0, tid, nthr);
+    }
+#endif
+    for (int e = tid; !dmma && e < ns * ((ns + 3) / 4); e += nthr) {
       const int i = e % ns, j0 = (e / ns) * 4;
       int jc[4];
 #pragma unroll

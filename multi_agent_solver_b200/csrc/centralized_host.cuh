@@ -121,6 +121,8 @@ int run_centralized(Context* ctx, const mas_b200_ocp_desc& d, const mas_b200_ilq
   P.work = b.work;
   P.out_cost = b.oc;
   P.out_int = b.oi;
+  // opt-in, never the default, excluded from the parity gate: dense gain / value-update products on the fp64 tensor cores
+  P.use_dmma = std::getenv("MAS_B200_CENTRALIZED_DMMA") && std::atoi(std::getenv("MAS_B200_CENTRALIZED_DMMA")) != 0;
   // MAS_B200_CENTRALIZED_PHASES=1: SM cycles per phase of scenario 0 to stderr (how the time of a stacked solve splits
   // between finite differences, the dense Riccati algebra and the line-search rollouts)
   long long* d_phase = nullptr;

@@ -187,6 +187,59 @@ __global__ void __launch_bounds__(kSweepBlock) riccati_sweep_kernel(BatchView<M:
   if (r) v.reg_retries[p] += r;
 }
 
+// The Riccati recursion with the lanes of a problem sharing a step (RiccatiLanes, ilqr_core.cuh): LG lanes per problem,
+// 32 / LG problems per warp, one warp per CTA.  The derivative block of step t-1 is staged into shared memory by the whole
+// warp (coalesced over the warp's problems) while step t computes.
+template <class M, int MASK_CT>
+__global__ void __launch_bounds__(32) riccati_sweep_lanes_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
+                                                                 int* next_count, const double* __restrict__ D, int cap) {
+  using DB = DerivBlock<M>;
+  using RL = RiccatiLanes<M, MASK_CT>;
+  constexpr int LG = RL::LG, PW = 32 / LG;  // problems per warp
+  __shared__ double s_blk[2][PW][DB::size];
+  __shared__ double s_xch[PW][RL::XCH];
+  const int lane = threadIdx.x, q = lane / LG, j = lane % LG;
+  const int first = blockIdx.x * PW;
+  if (first == 0 && lane == 0) *next_count = 0;
+  const int n = *count;
+  if (first >= n) return;
+  const int i = first + q;
+  const bool active = i < n && j < M::NX;
+  const int p = i < n ? list[i] : 0;
+  // staging: lane -> (problem lane % PW, entries lane / PW, + LG, ...): PW consecutive slots of one entry per group of lanes
+  auto issue = [&](int t) {
+    const int sq = lane % PW, e0 = lane / PW;
+    const int ne = t == v.T ? DB::n_terminal_tasks : DB::size;
+    if (first + sq < n) {
+      const double* src = D + static_cast<size_t>(t) * DB::size * cap + (first + sq);
+      for (int e = e0; e < ne; e += LG) stage_copy8(&s_blk[t & 1][sq][e], src + static_cast<size_t>(e) * cap);
+    }
+    stage_commit();
+  };
+  RL r;
+  issue(v.T);
+  stage_wait();
+  __syncwarp();
+  if (v.T > 0) issue(v.T - 1);
+  if (active) r.init_terminal(s_blk[v.T & 1][q], j);
+  for (int t = v.T - 1; t >= 0; --t) {
+    stage_wait();
+    __syncwarp();  // block t is complete for every lane; nobody still reads block t+1's buffer... (it is the other buffer)
+    const double* blk = s_blk[t & 1][q];
+    if (active) r.phase_a(blk, j, s_xch[q]);
+    __syncwarp();
+    if (active) r.phase_b(blk, j, s_xch[q]);
+    __syncwarp();
+    if (active) r.phase_c(j, s_xch[q]);
+    __syncwarp();
+    if (active) r.phase_d(v, p, t, j, s_xch[q]);
+    __syncwarp();
+    if (t > 0) issue(t - 1);  // into the buffer block t+1 used: every lane is past its last read of it
+    if (active) r.phase_e(j, s_xch[q]);
+  }
+  if (active && j == 0 && r.retries) v.reg_retries[p] += r.retries;
+}
+
 // L lanes per problem (a power of two <= 16, aligned inside the warp); lane l rolls out step sizes
 // l, l+L, ...; the group picks the first improving candidate with shuffles; lane 0 commits.
 template <class M, int L, int C>
@@ -559,6 +612,8 @@ struct BatchBase {
   int deriv_cap = 0;
   int backward_mode = 0;
   int tp_max_problems = 8192;  // auto: largest active set that takes the time-parallel path (analytic-heavy modes)
+  int concurrency_hint = 1;  // independent solves expected in flight on this device: the lane mappings share the device with them
+  int sweep_lanes_max = 16384;  // largest active set whose Riccati sweep runs with the lanes of a problem sharing a step
   int ensure_deriv_store(int block_doubles);
   bool coop_store = false;  // mas_b200_batch_set_trial_store(b, 2): trial store in the cooperative kernel too
   int ensure_trial_store(long long min_slots);
@@ -724,8 +779,20 @@ struct BatchImpl : BatchBase {
     const long long threads = static_cast<long long>(n_pad) * G * (T + 1);
     linearize_kernel<M, MASK_CT><<<static_cast<int>((threads + kLinBlock - 1) / kLinBlock), kLinBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur,
                                                                                                                         d_deriv, deriv_cap, n_pad, G);
-    riccati_sweep_kernel<M, MASK_CT><<<div_up(n_upper, kSweepBlock), kSweepBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur,
-                                                                                                   d_count + (cur ^ 1), d_deriv, deriv_cap);
+    // the recursion itself: lanes of a problem share a step while that still leaves most of the device idle (latency
+    // bound), one thread per problem otherwise; models with path constraints always take the one-thread step
+    using RL = RiccatiLanes<M, MASK_CT>;
+    static const int env_sweep = std::getenv("MAS_B200_SWEEP_LANES") ? std::atoi(std::getenv("MAS_B200_SWEEP_LANES")) : -1;
+    const bool lanes_ok = !HasConstraints<M>::value && M::NX <= 8;
+    const bool use_lanes = lanes_ok && (env_sweep >= 0 ? env_sweep != 0 : static_cast<long long>(n_upper) * concurrency_hint <= sweep_lanes_max);
+    if (use_lanes) {
+      constexpr int PW = 32 / RL::LG;
+      riccati_sweep_lanes_kernel<M, MASK_CT><<<div_up(n_upper, PW), 32, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1), d_deriv,
+                                                                                           deriv_cap);
+    } else {
+      riccati_sweep_kernel<M, MASK_CT><<<div_up(n_upper, kSweepBlock), kSweepBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur,
+                                                                                                     d_count + (cur ^ 1), d_deriv, deriv_cap);
+    }
     stats.kernel_launches += 2;
   }
 
@@ -738,7 +805,7 @@ struct BatchImpl : BatchBase {
     const int tp_max_problems = env_tp_max > 0 ? env_tp_max : this->tp_max_problems;
     {
       const bool fd_heavy_tp = !(mask & D_LXX) && (mask == 0u || mask != M::EXAMPLE_MASK);
-      const bool want = backward_mode == 3 || (backward_mode == 0 && ls_mode == 0 && tune_L == 0 && (fd_heavy_tp || n_upper <= tp_max_problems));
+      const bool want = backward_mode == 3 || (backward_mode == 0 && ls_mode == 0 && tune_L == 0 && (fd_heavy_tp || static_cast<long long>(n_upper) * concurrency_hint <= tp_max_problems));
       if (want && ensure_deriv_store(DerivBlock<M>::size) == MAS_B200_OK && n_upper <= deriv_cap) {
         const int G = fd_heavy_tp ? 8 : 2;
         if (mask == M::EXAMPLE_MASK) launch_time_parallel<static_cast<int>(M::EXAMPLE_MASK)>(n_upper, cur, G);
@@ -851,7 +918,7 @@ struct BatchImpl : BatchBase {
       query_occupancy();
       l = 1;
       for (int k = 4; k >= 1; --k)
-        if (static_cast<long long>(n_active) * (1 << k) <= resident_lanes[k]) {
+        if (static_cast<long long>(n_active) * (1 << k) * concurrency_hint <= resident_lanes[k]) {
           l = 1 << k;
           break;
         }

@@ -85,7 +85,7 @@ MAS_HD double load_streaming(const double* p) {
 // step at a time with a long dependent fp64 chain per step; asking for step t+1's lines while step
 // t computes hides the ~800-cycle HBM latency without spending registers on double buffering.
 MAS_HD void prefetch_l1(const void* p) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(MAS_NO_L1_PREFETCH)
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 #else
   (void)p;
@@ -1309,6 +1309,193 @@ MAS_HD int riccati_sweep_thread(const BatchView<M::NX, M::NU>& v, int p, const F
   }
   return retries;
 }
+
+// ---- the Riccati recursion over the lanes of a problem (column-parallel) ---------------------------------------------
+// What is left of a backward step once the derivatives are precomputed is ~1,200 dependent instructions of one thread
+// (2.2 us per step on B200, measured), and small active sets pay exactly that latency T times per iteration.
+// RiccatiLanes spreads one problem's step over LG = NX lanes (lane j owns column j of V_xx, Q_xx, Q_ux, K and of the
+// value update; small quantities -- q_x, q_u, Q_uu, V_x -- are computed redundantly by every lane; the columns of
+// Q_uu^-1 are dealt out): every output element is produced by the same function, with the same operand order, as in
+// riccati_step, so the results are bit-identical (host emulation + GPU tests).  Four exchanges per step go through a
+// small per-problem area `xch` (shared memory on the device) with a group barrier after each phase.  Models with path
+// constraints keep the one-thread step (the augmented-Lagrangian terms touch every block of Q).
+template <int N>
+MAS_HD void llt_inverse_col(const double* L, int c, double* x) {  // column c of llt_inverse<N>
+#pragma unroll
+  for (int i = 0; i < N; ++i) x[i] = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = x[i];
+#pragma unroll
+    for (int j = 0; j < i; ++j) s -= L[i + j * N] * x[j];
+    x[i] = pm::div_(s, L[i + i * N]);
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    double s = x[i];
+#pragma unroll
+    for (int j = i + 1; j < N; ++j) s -= L[j + i * N] * x[j];
+    x[i] = pm::div_(s, L[i + i * N]);
+  }
+}
+// column j (run-time) of mat_nn_sb<R, KD, CC, NZ>(A, B, C): out[i] = sum over the k with bit (k + j*KD) of NZ set of
+// A[i + k*R] * bcol[k], same order, same "first term starts the sum" rule; no branches on j
+template <int R, int KD>
+MAS_HD void mat_nn_sb_col(const double* A, const double* bcol, unsigned long long nz, int j, double* out) {
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    double s = 0.0;
+    bool first = true;
+#pragma unroll
+    for (int k = 0; k < KD; ++k) {
+      const bool on = (nz >> (k + j * KD)) & 1ull;
+      const double prod = A[i + k * R] * bcol[k];
+      const double sum = s + prod;
+      s = on ? (first ? prod : sum) : s;
+      first = first && !on;
+    }
+    out[i] = s;
+  }
+}
+
+template <class M, int MASK_CT>
+struct RiccatiLanes {
+  static constexpr int NX = M::NX, NU = M::NU;
+  using D = DerivBlock<M>;
+  static constexpr int LG = NX <= 1 ? 1 : (NX <= 2 ? 2 : (NX <= 4 ? 4 : 8));  // lanes per problem (power of two >= NX)
+  static_assert(NX <= 8, "RiccatiLanes: one lane per state column, up to 8");
+  // exchange area (doubles): A^T V | B^T V | inv | K | Q_ux | V_xx
+  static constexpr int xAtV = 0, xBtV = xAtV + NX * NX, xInv = xBtV + NU * NX, xK = xInv + NU * NU, xQux = xK + NU * NX, xV = xQux + NU * NX,
+                       XCH = xV + NX * NX;
+  static constexpr unsigned long long kDense = ~0ull;
+  static constexpr unsigned long long a_nz = (MASK_CT >= 0 && (MASK_CT & D_A)) ? M::A_NZ : kDense;
+  static constexpr unsigned long long b_nz = (MASK_CT >= 0 && (MASK_CT & D_B)) ? M::B_NZ : kDense;
+
+  // per-lane state
+  double v_x[NX], vcol[NX];
+  double q_x[NX], q_u[NU], q_uu[NU * NU], L[NU * NU], qxx_col[NX], qux_col[NU], k_col[NU], kv[NU];
+  int retries = 0;
+
+  // terminal block [V_x | V_xx]: every lane symmetrises the whole matrix and keeps its column (ilqr.hpp:92-102)
+  MAS_HD void init_terminal(const double* blk, int j) {
+    double vxx[NX * NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) v_x[i] = blk[i];
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) vxx[i] = blk[NX + i];
+    symmetrize_aliased<NX>(vxx);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) vcol[i] = 0.0;
+#pragma unroll
+    for (int c = 0; c < NX; ++c) {
+      if (c == j) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) vcol[i] = vxx[i + c * NX];
+      }
+    }
+  }
+  // (A^T V)(:, j), (B^T V)(:, j)                                                      ilqr.hpp:117-119, first factors
+  MAS_HD void phase_a(const double* blk, int j, double* xch) const {
+    double atv[NX], btv[NU];
+    mat_tn_sa<NX, NX, 1, a_nz>(blk + D::oA, vcol, atv);
+    mat_tn_sa<NX, NU, 1, b_nz>(blk + D::oB, vcol, btv);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xch[xAtV + i + j * NX] = atv[i];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) xch[xBtV + i + j * NU] = btv[i];
+  }
+  // Q blocks (:115-119), Q_uu regularisation + LLT (:172-183), my columns of the inverse
+  MAS_HD void phase_b(const double* blk, int j, double* xch) {
+    const double* A = blk + D::oA;
+    const double* B = blk + D::oB;
+    double tmp[NX > NU ? NX : NU];
+    mat_tn_sa<NX, NX, 1, a_nz>(A, v_x, tmp);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) q_x[i] = blk[D::olx + i] + tmp[i];
+    mat_tn_sa<NX, NU, 1, b_nz>(B, v_x, tmp);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) q_u[i] = blk[D::olu + i] + tmp[i];
+    double acol[NX];
+#pragma unroll
+    for (int k = 0; k < NX; ++k) acol[k] = A[k + j * NX];
+    double t4[NX], t2[NU];
+    mat_nn_sb_col<NX, NX>(xch + xAtV, acol, a_nz, j, t4);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) qxx_col[i] = blk[D::olxx + i + j * NX] + t4[i];
+    mat_nn_sb_col<NU, NX>(xch + xBtV, acol, a_nz, j, t2);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) qux_col[i] = blk[D::olux + i + j * NU] + t2[i];
+    double tuu[NU * NU];
+    mat_nn_sb<NU, NX, NU, b_nz>(xch + xBtV, B, tuu);
+#pragma unroll
+    for (int i = 0; i < NU * NU; ++i) q_uu[i] = blk[D::oluu + i] + tuu[i];
+    double q_reg[NU * NU];
+#pragma unroll
+    for (int i = 0; i < NU * NU; ++i) q_reg[i] = q_uu[i];
+    double reg = 1e-6;
+    while (!llt_factor<NU>(q_reg, L)) {
+#pragma unroll
+      for (int i = 0; i < NU; ++i) q_reg[i + i * NU] += reg;
+      reg *= 10.0;
+      if (j == 0) ++retries;
+      if (!(reg < 1e300)) break;
+    }
+    for (int c = j; c < NU; c += LG) {
+      double x[NU];
+      llt_inverse_col<NU>(L, c, x);
+#pragma unroll
+      for (int i = 0; i < NU; ++i) xch[xInv + i + c * NU] = x[i];
+    }
+  }
+  // gains (:185-186): k on every lane, my column of K
+  MAS_HD void phase_c(int j, double* xch) {
+    double ninv[NU * NU];
+#pragma unroll
+    for (int i = 0; i < NU * NU; ++i) ninv[i] = -xch[xInv + i];
+    mat_nn<NU, NU, 1>(ninv, q_u, kv);
+    mat_nn<NU, NU, 1>(ninv, qux_col, k_col);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      xch[xK + i + j * NU] = k_col[i];
+      xch[xQux + i + j * NU] = qux_col[i];
+    }
+  }
+  // gains to HBM, value update (:188-191): V_x on every lane, my column of the unsymmetrised V_xx
+  MAS_HD void phase_d(const BatchView<NX, NU>& v, int p, int t, int j, double* xch) {
+    const double* Km = xch + xK;
+    const double* q_ux = xch + xQux;
+    if (j == 0) {
+#pragma unroll
+      for (int i = 0; i < NU; ++i) v.kff[soa_index<NU>(t, i, v.ld, p)] = kv[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NU; ++i) v.K[soa_index<NU * NX>(t, i + j * NU, v.ld, p)] = k_col[i];
+    double KtQuu[NX * NU], t1[NX], t2[NX], t3[NX];
+    mat_tn<NU, NX, NU>(Km, q_uu, KtQuu);
+    mat_tn<NU, NX, 1>(Km, q_u, t1);
+    mat_tn<NU, NX, 1>(q_ux, kv, t2);
+    mat_nn<NX, NU, 1>(KtQuu, kv, t3);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) v_x[i] = ((q_x[i] + t1[i]) + t2[i]) + t3[i];
+    double m1[NX], m2[NX], m3[NX];
+    mat_tn<NU, NX, 1>(Km, qux_col, m1);
+    mat_tn<NU, NX, 1>(q_ux, k_col, m2);
+    mat_nn<NX, NU, 1>(KtQuu, k_col, m3);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xch[xV + i + j * NX] = ((qxx_col[i] + m1[i]) + m2[i]) + m3[i];
+  }
+  // `v_xx = 0.5 * (v_xx + v_xx.transpose())` evaluated in place, columns outer (symmetrize_aliased), column j of the result:
+  // below the diagonal both operands are old; above it the transposed operand is the already-updated lower entry
+  MAS_HD void phase_e(int j, const double* xch) {
+    const double* V = xch + xV;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      const double a = V[i + j * NX], b = V[j + i * NX];
+      const double lower = 0.5 * (b + a);  // the value entry (j, i) took when column i < j was processed
+      vcol[i] = (i < j) ? 0.5 * (a + lower) : 0.5 * (a + b);
+    }
+  }
+};
 
 // ---- forward pass (ilqr.hpp:206-217) for C step sizes at once, merit only ------------------------
 // The C rollouts share the loads of the nominal trajectory and gains and give the fp64 pipe C

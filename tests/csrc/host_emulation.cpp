@@ -23,6 +23,7 @@ struct ALOptions {
   double penalty = 10.0, penalty_increase = 5.0, constraint_tolerance = 1e-4, activation_tolerance = 1e-6;
   int repeats = 1;
   bool trial_store = true;
+  bool sweep_lanes = false;  // time-parallel mode: the Riccati sweep column-parallel over the lanes of a problem (RiccatiLanes)
   int backward_lanes = 0;  // > 0: lane-parallel backward pass with that many lanes per problem; < 0: time-parallel with -n threads per point
   double* hist_cost = nullptr;
   int* hist_iters = nullptr;
@@ -75,6 +76,22 @@ int emulate_time_parallel(const BatchView<M::NX, M::NU>& v, int p, int G) {
   for (int t = v.T; t >= 0; --t)
     for (int g = G - 1; g >= 0; --g)
       linearize_point<M>(v, p, t, mask, g, G, [&](int off, double val) { store[static_cast<size_t>(t) * D::size + off] = val; });
+  if (g_al.sweep_lanes && !HasConstraints<M>::value) {
+    // riccati_sweep_lanes_kernel: the lanes of the problem run every phase one after the other, exchange area in between
+    using RL = RiccatiLanes<M, MASK_CT>;
+    RL lane[M::NX];
+    double xch[RL::XCH];
+    for (int j = 0; j < M::NX; ++j) lane[j].init_terminal(&store[static_cast<size_t>(v.T) * D::size], j);
+    for (int t = v.T - 1; t >= 0; --t) {
+      const double* blk = &store[static_cast<size_t>(t) * D::size];
+      for (int j = M::NX - 1; j >= 0; --j) lane[j].phase_a(blk, j, xch);
+      for (int j = 0; j < M::NX; ++j) lane[j].phase_b(blk, j, xch);
+      for (int j = M::NX - 1; j >= 0; --j) lane[j].phase_c(j, xch);
+      for (int j = 0; j < M::NX; ++j) lane[j].phase_d(v, p, t, j, xch);
+      for (int j = M::NX - 1; j >= 0; --j) lane[j].phase_e(j, xch);
+    }
+    return lane[0].retries;
+  }
   return riccati_sweep_thread<M, MASK_CT>(v, p, [&](int t, double* blk) {
     for (int k = 0; k < D::size; ++k) blk[k] = store[static_cast<size_t>(t) * D::size + k];
   });
@@ -290,6 +307,7 @@ extern "C" int emu_ilqr_solve_batch(int model, int batch, int T, double dt, unsi
 // Settings for the next emu_ilqr_solve_batch calls on constrained models (pass repeats = 1 and nulls to reset).
 extern "C" void emu_set_trial_store(int enable) { g_al.trial_store = enable != 0; }
 extern "C" void emu_set_backward_lanes(int lanes) { g_al.backward_lanes = lanes; }
+extern "C" void emu_set_sweep_lanes(int on) { g_al.sweep_lanes = on != 0; }
 
 extern "C" void emu_set_al_options(double penalty, double penalty_increase, double constraint_tolerance, double activation_tolerance, int repeats,
                                    double* hist_cost, int* hist_iters) {
@@ -341,6 +359,7 @@ int emulate_centralized(int A, int T, double dt, int has_bounds, const double* l
   P.out_cost = out_cost;
   P.out_int = out_int;
   P.phase_cycles = nullptr;
+  P.use_dmma = 0;
   stacked_solve<M>(P, 0, 1);
   return 0;
 }

@@ -194,8 +194,8 @@ def test_nonfinite_trajectories(emu, oracle):
     refs = [oracle.ilqr_solve_batch(0, x0, U_init=U, trig=oracle.TRIG_PORTABLE)]
     if ref_py.available():
         refs.append(ref_py.ilqr_solve_batch(0, x0, U_init=U, trig=1))
-    for L, C in ((1, 2), (4, 1), (16, 1)):
-        got = emu.solve(0, x0, U, 10, 1e-5, L=L, C=C)
+    for L, C, bl, sl in ((1, 2, 0, False), (4, 1, 0, False), (16, 1, 0, False), (16, 1, -2, False), (16, 1, -2, True)):
+        got = emu.solve(0, x0, U, 10, 1e-5, L=L, C=C, backward_lanes=bl, sweep_lanes=sl)
         for ref in refs:
             for k in ("X", "U", "cost", "iterations", "status"):
                 assert np.array_equal(got[k], ref[k], equal_nan=got[k].dtype.kind == "f"), (L, C, k)
@@ -221,8 +221,12 @@ def test_time_parallel_backward_pass_is_bit_identical(emu, oracle, model, mask, 
     U0 = np.zeros((10, T, m))
     one = emu.solve(model, x0, U0, max_it, tol, mask=mask)
     par = emu.solve(model, x0, U0, max_it, tol, mask=mask, backward_lanes=-threads)
+    # ... and with the recursion itself column-parallel over the lanes of a problem (RiccatiLanes)
+    lan = emu.solve(model, x0, U0, max_it, tol, mask=mask, backward_lanes=-threads, sweep_lanes=True)
     for k in ("X", "U", "cost", "iterations", "status", "alpha_trials", "reg_retries"):
         assert np.array_equal(one[k], par[k]), k
+        assert np.array_equal(one[k], lan[k]), k
     if mask == MODEL_TABLE[model][4]:
         ref = oracle.ilqr_solve_batch(model, x0, U_init=U0, max_iterations=max_it, tolerance=tol, trig=oracle.TRIG_PORTABLE)
         assert is_bit_exact(par, ref)
+        assert is_bit_exact(lan, ref)
