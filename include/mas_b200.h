@@ -201,6 +201,11 @@ int mas_b200_batch_set_trial_store(mas_b200_batch_t b, int enable);
  * problems (default 8192; 0 = keep) and for finite-difference-heavy derivative modes whenever the derivative blocks
  * fit 512 MB.  Results are bit-identical in every mode. */
 int mas_b200_batch_set_backward_mode(mas_b200_batch_t b, int mode, int max_problems);
+/* The per-iteration trace of the last solve, when it ran with params->debug != 0 (the reference prints these lines to
+ * std::cout, ilqr.hpp:79-80,262-267; a batch records them instead): records[r][6] for r = 0 .. *n_records - 1 of one
+ * problem -- r = 0: {initial cost, initial merit, nan, nan, nan, nan}; r = it: {cost, merit, d_merit, eq_violation,
+ * ineq_violation, accepted step-size index or -1} after iteration it.  Synchronises. */
+int mas_b200_batch_get_debug_trace(mas_b200_batch_t b, int problem, int max_records, double* records, int* n_records);
 /* How many independent solves the caller keeps in flight on this device (other batches on other streams; default 1).
  * The automatic lane mappings trade work for latency: a small active set evaluates all ten step sizes of the line
  * search at once on up to 16 lanes per problem when the device would otherwise idle.  With n solves in flight the
@@ -220,6 +225,9 @@ int mas_b200_batch_set_line_search_mode(mas_b200_batch_t b, int mode);
  */
 int mas_b200_ilqr_solve_batch(mas_b200_context_t ctx, const mas_b200_ocp_desc* desc, const mas_b200_ilqr_params* params, int batch,
                               const double* x0, const double* model_params, double* U, double* X, double* cost, int* iterations, int* status);
+
+/* mas_b200_batch_get_debug_trace for the batch behind the last mas_b200_ilqr_solve_batch of this context. */
+int mas_b200_ilqr_last_debug_trace(mas_b200_context_t ctx, int problem, int max_records, double* records, int* n_records);
 
 /* ---- multi-agent strategies: mas::solve(Strategy&, MultiAgentProblem&) (strategies/strategy.hpp:15-19)
  * on n_scenarios independent scenarios of n_agents agents each; agents have ids 0..n_agents-1 in

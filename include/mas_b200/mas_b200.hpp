@@ -21,6 +21,7 @@
 #include <cctype>
 #include <cmath>
 #include <cstring>
+#include <iostream>
 #include <limits>
 #include <memory>
 #include <optional>
@@ -247,6 +248,17 @@ class iLQR {
       o.best_cost = cost[b];
       o.last_iterations = it[b];
       o.last_status = st[b];
+    }
+    if (p_.debug) {  // the lines the reference prints while solving (ilqr.hpp:79-80,262-267), from the recorded trace
+      std::vector<double> rec(static_cast<std::size_t>(p_.max_iterations + 1) * 6);
+      for (int b = 0; b < B; ++b) {
+        int nrec = 0;
+        check(mas_b200_ilqr_last_debug_trace(Device::context(), b, p_.max_iterations + 1, rec.data(), &nrec));
+        if (nrec > 0) std::cout << "iLQR initial cost=" << rec[0] << " merit=" << rec[1] << '\n';
+        for (int r = 1; r < nrec; ++r)
+          std::cout << "iLQR iter " << (r - 1) << ": cost=" << rec[6 * r + 0] << " merit=" << rec[6 * r + 1] << " d_merit=" << rec[6 * r + 2]
+                    << " eq_violation=" << rec[6 * r + 3] << " ineq_violation=" << rec[6 * r + 4] << '\n';
+      }
     }
   }
 

@@ -277,6 +277,13 @@ class Batch:
         """0 auto, 1 one thread per problem, 2 FD tasks over eight lanes, 3 time-parallel linearisation + Riccati sweep."""
         _check(load_library().mas_b200_batch_set_backward_mode(self._h, int(mode), int(max_problems)))
 
+    def debug_trace(self, problem: int, max_records: int = 4096) -> np.ndarray:
+        """mas_b200_batch_get_debug_trace: [records, 6] = cost, merit, d_merit, eq_violation, ineq_violation, accepted index."""
+        rec = np.empty((max_records, 6))
+        n = ctypes.c_int()
+        _check(load_library().mas_b200_batch_get_debug_trace(self._h, int(problem), int(max_records), _dptr(rec), ctypes.byref(n)))
+        return rec[: n.value].copy()
+
     def set_concurrency_hint(self, solves_in_flight: int) -> None:
         _check(load_library().mas_b200_batch_set_concurrency_hint(self._h, int(solves_in_flight)))
 

@@ -483,6 +483,22 @@ int mas_b200_batch_set_backward_mode(mas_b200_batch_t h, int mode, int max_probl
   return MAS_B200_OK;
 }
 
+int mas_b200_batch_get_debug_trace(mas_b200_batch_t h, int problem, int max_records, double* records, int* n_records) {
+  MAS_BATCH_GUARD(h);
+  if (!records || !n_records || max_records < 0) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "bad arguments");
+  if (problem < 0 || problem >= b->batch) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "problem index out of range");
+  if (!b->dbg_valid || !b->d_dbg) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "no trace: the last solve of this batch did not have params.debug set");
+  const int want = std::min(max_records, b->dbg_records);
+  // one strided copy: `want * kDebugFields` doubles of column `problem`
+  MAS_CUDA_CHECK(cudaMemcpy2DAsync(records, sizeof(double), b->d_dbg + problem, static_cast<size_t>(b->ld) * sizeof(double), sizeof(double),
+                                   static_cast<size_t>(want) * kDebugFields, cudaMemcpyDeviceToHost, b->ctx->stream));
+  MAS_CUDA_CHECK(cudaStreamSynchronize(b->ctx->stream));
+  int n = 0;
+  while (n < want && !std::isnan(records[static_cast<size_t>(n) * kDebugFields + 5 * (n > 0)])) ++n;  // unused records are all-NaN
+  *n_records = n;
+  return MAS_B200_OK;
+}
+
 int mas_b200_batch_set_concurrency_hint(mas_b200_batch_t h, int solves_in_flight) {
   MAS_BATCH_GUARD(h);
   if (solves_in_flight < 1) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "solves_in_flight must be >= 1");
@@ -537,6 +553,11 @@ int mas_b200_ilqr_solve_batch(mas_b200_context_t ctx, const mas_b200_ocp_desc* d
   if (!rc) rc = mas_b200_batch_solve(h, params);
   if (!rc) rc = mas_b200_batch_get_solution(h, X, U, cost, iterations, status);
   return rc;
+}
+
+int mas_b200_ilqr_last_debug_trace(mas_b200_context_t ctx, int problem, int max_records, double* records, int* n_records) {
+  if (!ctx || !ctx->scratch_batch) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "no one-shot solve has run on this context");
+  return mas_b200_batch_get_debug_trace(ctx->scratch_batch, problem, max_records, records, n_records);
 }
 
 // ---- strategies ------------------------------------------------------------------------------------------

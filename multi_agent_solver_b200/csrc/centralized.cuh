@@ -18,6 +18,8 @@
 // The body is written as data-parallel phases `for (idx = tid; idx < n; idx += nthr)` separated by barriers, with
 // all cross-phase state in the workspace, so tests/csrc/host_emulation.cpp can run it with tid = 0, nthr = 1.
 #pragma once
+#include <ctime>
+
 #include "ilqr_core.cuh"
 
 namespace mas_b200 {
@@ -46,6 +48,8 @@ struct StackedProblem {
   double* out_cost;            // [1 + A]: stacked best_cost, then per-agent costs
   int* out_int;                // iterations, status, reg_retries, alpha_trials
   long long* phase_cycles;     // optional [kNumPhases]: SM cycles per phase of this scenario (diagnostics), or null
+  double max_ms;               // time budget of the stacked solve (ilqr.hpp:84-90): integer milliseconds since its start, checked at the
+                               // top of every iteration; +inf = none
   int use_dmma;                // opt-in (MAS_B200_CENTRALIZED_DMMA=1): dense gain / value-update products on the fp64 tensor cores
 };
 
@@ -205,7 +209,18 @@ MAS_HD void stacked_group_sync(int id, int count, int all) {
 #endif
 }
 
-enum StackedScalar { SC_COST = 0, SC_MERIT = 1, SC_TRIAL = 2, SC_REG = 3, SC_PIVOT = 4, SC_FLAG = 5, SC_INNER = 6 };
+enum StackedScalar { SC_COST = 0, SC_MERIT = 1, SC_TRIAL = 2, SC_REG = 3, SC_PIVOT = 4, SC_FLAG = 5, SC_INNER = 6, SC_TIMEOUT = 7 };
+
+// nanoseconds on a clock that all threads of the CTA agree on (device: %globaltimer; host emulation: steady_clock)
+MAS_HD unsigned long long stacked_now_ns() {
+#if defined(__CUDA_ARCH__)
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+#else
+  return static_cast<unsigned long long>(clock()) * (1000000000ull / CLOCKS_PER_SEC);
+#endif
+}
 
 // stacked value with agent a's term replaced by va: ((pref[a] + va) + c[a+1]) + ... + c[A-1]
 MAS_HD double stacked_sum1(const double* c, const double* pref, int A, int a, double va) {
@@ -934,7 +949,19 @@ MAS_HD void stacked_solve(const StackedProblem<M>& P, int tid, int nthr) {
     scal[SC_MERIT] = scal[SC_TRIAL];
   }
   MAS_CTA_SYNC();
+  const bool timed = P.max_ms < 1.7976931348623157e308;
+  const unsigned long long start_ns = timed ? stacked_now_ns() : 0ull;
   for (int iter = 0; iter < P.max_iterations; ++iter) {
+    if (timed) {  // `elapsed_ms > max_ms -> break`, whole milliseconds, only here (ilqr.hpp:84-90)
+      if (tid == 0) scal[SC_TIMEOUT] = static_cast<double>((stacked_now_ns() - start_ns) / 1000000ull) > P.max_ms ? 1.0 : 0.0;
+      MAS_CTA_SYNC();
+      const bool out_of_time = scal[SC_TIMEOUT] != 0.0;
+      MAS_CTA_SYNC();
+      if (out_of_time) {
+        if (tid == 0) P.out_int[1] = STATUS_TIME_LIMIT;
+        break;
+      }
+    }
     if (tid == 0) P.out_int[0] = iter + 1;
     stacked_backward<M, FAST_SHARED>(P, W, tid, nthr);
 #if defined(__CUDA_ARCH__)

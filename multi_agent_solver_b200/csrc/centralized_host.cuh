@@ -110,6 +110,7 @@ int run_centralized(Context* ctx, const mas_b200_ocp_desc& d, const mas_b200_ilq
   }
   P.tolerance = prm.tolerance;
   P.max_iterations = prm.max_iterations;
+  P.max_ms = prm.max_ms;  // per stacked solve, as for the reference's solve() of the global OCP
   P.x0 = b.x0;
   P.prm = b.prm;
   P.X = b.X;

@@ -75,6 +75,7 @@ BatchBase::~BatchBase() {
   if (download_pending) cudaEventSynchronize(ev_downloaded);
   if (d_out_stage) cudaFree(d_out_stage);
   if (d_deriv) cudaFree(d_deriv);
+  if (d_dbg) cudaFree(d_dbg);
   if (d_trial_X) cudaFree(d_trial_X);
   if (d_trial_U) cudaFree(d_trial_U);
   if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -185,6 +186,20 @@ int BatchBase::ensure_deriv_store(int block_doubles) {
     return MAS_B200_ERR_CUDA;
   }
   deriv_cap = static_cast<int>(cap);
+  return MAS_B200_OK;
+}
+
+// Trace buffer of `debug` solves; every record starts as NaN so that unused iterations are recognisable.
+int BatchBase::ensure_debug_trace(int records) {
+  if (records > dbg_records) {
+    if (d_dbg) cudaFree(d_dbg);
+    d_dbg = nullptr;
+    dbg_records = 0;
+    MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_dbg), static_cast<size_t>(records) * kDebugFields * ld * sizeof(double)));
+    dbg_records = records;
+  }
+  MAS_CUDA_CHECK(cudaMemsetAsync(d_dbg, 0xFF, static_cast<size_t>(dbg_records) * kDebugFields * ld * sizeof(double), ctx->stream));
+  dbg_valid = true;
   return MAS_B200_OK;
 }
 

@@ -94,6 +94,10 @@ __global__ void __launch_bounds__(kBlock) prologue_kernel(BatchView<M::NX, M::NU
   v.reg_retries[p] = 0;
   v.status[p] = STATUS_MAX_ITER;
   list[p] = p;
+  if (v.dbg && v.dbg_records > 0) {  // "iLQR initial cost=... merit=..." (ilqr.hpp:79-80)
+    v.dbg[p] = c;
+    v.dbg[static_cast<size_t>(v.ld) + p] = v.merit[p];
+  }
 }
 
 template <class M, int MASK_CT>
@@ -612,6 +616,10 @@ struct BatchBase {
   int deriv_cap = 0;
   int backward_mode = 0;
   int tp_max_problems = 8192;  // auto: largest active set that takes the time-parallel path (analytic-heavy modes)
+  double* d_dbg = nullptr;  // debug trace [dbg_records][kDebugFields][ld], allocated by the first solve with params.debug
+  int dbg_records = 0;
+  bool dbg_valid = false;
+  int ensure_debug_trace(int records);
   int concurrency_hint = 1;  // independent solves expected in flight on this device: the lane mappings share the device with them
   int sweep_lanes_max = 16384;  // largest active set whose Riccati sweep runs with the lanes of a problem sharing a step
   int ensure_deriv_store(int block_doubles);
@@ -722,6 +730,8 @@ struct BatchImpl : BatchBase {
     view.trial_X = trial_store ? d_trial_X : nullptr;
     view.trial_U = trial_store ? d_trial_U : nullptr;
     view.trial_slots = trial_store ? trial_slots : 0;
+    view.dbg = dbg_valid ? d_dbg : nullptr;
+    view.dbg_records = dbg_valid ? dbg_records : 0;
   }
 
   void apply_al_params(const mas_b200_ilqr_params& prm) {
@@ -937,6 +947,11 @@ struct BatchImpl : BatchBase {
     const auto start = clock::now();
     int rc = prepare_constraint_state(prm);
     if (rc) return rc;
+    dbg_valid = false;
+    if (prm.debug) {
+      rc = ensure_debug_trace(prm.max_iterations + 1);
+      if (rc) return rc;
+    }
     if (trial_store && prm.max_iterations > 0) {
       query_occupancy();
       // the widest launches that use the store: forward_kernel<L >= 4> with all lanes resident, or 16 lanes per problem

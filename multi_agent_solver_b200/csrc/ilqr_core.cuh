@@ -60,7 +60,13 @@ struct BatchView {
   double* trial_X;
   double* trial_U;
   int trial_slots;
+  // per-iteration trace of `debug` solves (ilqr.hpp:79-80,262-267): record r of problem p at dbg[(r * kDebugFields + f) * ld + p],
+  // r = 0 the initial cost / merit, r = it the values the reference prints after iteration it; null = off
+  double* dbg;
+  int dbg_records;  // capacity in records (max_iterations + 1)
 };
+
+constexpr int kDebugFields = 6;  // cost, merit, d_merit, eq_violation, ineq_violation, accepted step-size index (-1 = none)
 
 constexpr int kMaxALHorizon = 128;  // horizon bound of constrained models (merit addends are kept per step)
 
@@ -1796,12 +1802,21 @@ MAS_HD bool finish_iteration(const BatchView<M::NX, M::NU>& v, int p, const doub
   v.iters[p] = it;
   v.trials[p] += (best_j < kNumAlphas) ? best_j + 1 : kNumAlphas;
   bool feasible = true;
+  double eq_norm = 0.0, ineq_norm = 0.0;
   if (HasConstraints<M>::value) {
     // multipliers <- multipliers + rho * residual on the new trajectory, penalty growth, and the violation
     // norms that gate the stop test (ilqr.hpp:236-260,269-270)
-    double eq_norm, ineq_norm;
     al_update<M>(v, p, prm, &eq_norm, &ineq_norm);
     feasible = eq_norm < v.constraint_tolerance && ineq_norm < v.constraint_tolerance;
+  }
+  if (v.dbg && it < v.dbg_records) {  // what `debug` prints after the iteration (ilqr.hpp:262-267)
+    double* r = v.dbg + static_cast<size_t>(it) * kDebugFields * v.ld + p;
+    r[0 * static_cast<size_t>(v.ld)] = v.cost[p];
+    r[1 * static_cast<size_t>(v.ld)] = best_merit;
+    r[2 * static_cast<size_t>(v.ld)] = improvement;
+    r[3 * static_cast<size_t>(v.ld)] = eq_norm;
+    r[4 * static_cast<size_t>(v.ld)] = ineq_norm;
+    r[5 * static_cast<size_t>(v.ld)] = (best_j < kNumAlphas) ? static_cast<double>(best_j) : -1.0;
   }
   if (improvement < v.tolerance && feasible) {
     v.status[p] = STATUS_CONVERGED;

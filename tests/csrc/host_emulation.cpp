@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <vector>
 
 #include "ilqr_core.cuh"
@@ -360,6 +361,7 @@ int emulate_centralized(int A, int T, double dt, int has_bounds, const double* l
   P.out_int = out_int;
   P.phase_cycles = nullptr;
   P.use_dmma = 0;
+  P.max_ms = std::numeric_limits<double>::infinity();
   stacked_solve<M>(P, 0, 1);
   return 0;
 }

@@ -446,3 +446,29 @@ def test_backward_modes_are_bit_identical(mas, ctx, oracle, model, mask):
     if desc.deriv_mask == example_mask:
         ref = oracle.ilqr_solve_batch(model, x0, U_init=U0, max_iterations=max_it, tolerance=tol, trig=oracle.TRIG_PORTABLE)
         assert is_bit_exact(outs[2], ref)
+
+
+def test_debug_trace_matches_oracle(mas, ctx, oracle):
+    """params.debug: the values the reference prints per iteration (ilqr.hpp:79-80,262-267) are recorded per problem."""
+    x0 = random_x0(0, 70, seed=77)
+    b = mas.Batch(ctx, mas.example_desc(0), 70)
+    b.set_initial_states(x0)
+    b.set_controls(None)
+    prm = mas.IlqrParams.make(10, 1e-5)
+    prm.debug = 1
+    b.solve(prm)
+    got = b.get_solution()
+    for p in (0, 33, 69):
+        tr = oracle.ilqr_solve_trace(0, x0[p], max_iterations=10, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+        rec = b.debug_trace(p)
+        assert rec.shape[0] == got["iterations"][p] + 1
+        assert np.array_equal(rec[1:, 0], tr["cost_trace"])
+        assert np.array_equal(rec[1:, 5].astype(int), tr["alpha_index"])
+        assert rec[0, 0] == rec[0, 1] and np.isnan(rec[0, 5])
+        merit = np.concatenate([[rec[0, 1]], rec[1:, 1]])
+        assert np.array_equal(rec[1:, 2], merit[:-1] - merit[1:])  # d_merit
+    prm.debug = 0
+    b.solve(prm)
+    with pytest.raises(mas.MasB200Error):
+        b.debug_trace(0)
+    b.close()

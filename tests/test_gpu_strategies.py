@@ -106,3 +106,18 @@ def test_constrained_agents_inside_strategies(mas, ctx, oracle, kind):
     # a second run starts from fresh solvers again
     again = mas.strategy_run(ctx, strategy, desc, mas.IlqrParams.make(6, 1e-5), 3, x0)
     assert np.array_equal(again["U"], got["U"])
+
+
+def test_centralized_time_budget(mas, ctx):
+    """max_ms on the stacked solve (ilqr.hpp:84-90): a budget that is already spent stops before the first backward pass."""
+    x0, _ = circ_x0(2, 4)
+    prm = mas.IlqrParams.make(100, 1e-5, max_ms=-1.0)
+    got = mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, mas.example_desc(1), prm, 1, x0)
+    assert (got["trace_iters"][:, 0, 0] == 0).all()
+    assert (got["U"] == 0.0).all()
+    free = mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, mas.example_desc(1), mas.IlqrParams.make(100, 1e-5, max_ms=1e9), 1, x0)
+    ref = mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, mas.example_desc(1), mas.IlqrParams.make(100, 1e-5), 1, x0)
+    assert np.array_equal(free["U"], ref["U"]) and (free["trace_iters"][:, 0, 0] > 0).all()
+    # max_outer = 0 with trace pointers: nothing is written (the trace has no elements)
+    z = mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, mas.example_desc(1), mas.IlqrParams.make(100, 1e-5), 0, x0)
+    assert np.array_equal(z["U"], ref["U"]) and z["trace_iters"].size == 0
