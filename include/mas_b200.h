@@ -242,6 +242,32 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
                           int max_outer, int n_scenarios, int n_agents, const double* x0, const double* model_params, const double* U_init,
                           double* X, double* U, double* costs, double* total_cost, int* trace_iterations, int* trace_accepted, double* trace_cost);
 
+/* The same for agents of DIFFERENT models and shapes (MultiAgentProblem accepts any mix: compute_offsets /
+ * build_global_ocp, multi_agent_problem.hpp:37-127; the reference's own test stacks a 2x1 and a 1x2 agent,
+ * tests/ocp_tests.cpp:76-154): one description per agent; the per-agent arrays are given as arrays of n_agents
+ * pointers, agent a's array holding n_scenarios entries of ITS shape (x0[a]: [scenario][n_a], X[a]: [scenario][T_a+1][n_a],
+ * U[a]: [scenario][T_a][m_a], costs[a]: [scenario], model_params[a]: [scenario][np_a] or NULL, U_init[a] or NULL).
+ * Nash strategies (sequential, line search, trust region): agents of one description share a device batch, the
+ * groups advance round by round in lockstep, the line-search strategy's joint cost is summed over all agents in
+ * index order.  trace_iterations (optional): [scenario][outer][agent].  Centralized with agents that are not all of
+ * one description: MAS_B200_ERR_UNSUPPORTED (the stacked solve is compiled per model). */
+int mas_b200_strategy_run_mixed(mas_b200_context_t ctx, int strategy, const mas_b200_ocp_desc* agent_descs, const mas_b200_ilqr_params* params,
+                                int max_outer, int n_scenarios, int n_agents, const double* const* x0, const double* const* model_params,
+                                const double* const* U_init, double* const* X, double* const* U, double* const* costs, double* total_cost,
+                                int* trace_iterations);
+
+/* MultiAgentProblem::compute_offsets + build_global_ocp (multi_agent_problem.hpp:37-127) for agents of any mix of registered
+ * models, evaluated on the device: blocks sorted by agent id (agent_ids NULL = input order); dims_out = {total state dim,
+ * total control dim, horizon of the FIRST block, 1 if ALL agents have both input bounds}; dt of the first block; bounds_out
+ * [2][total_u] (lower, upper) written only in that case; block_agent / state_offsets / control_offsets [n_agents] in block
+ * order.  With X [total_x], U [total_u]: the stacked dynamics (block diagonal), stage cost at time_index and terminal cost,
+ * each cost the sum of the agents' terms in block order starting from 0.0.  X = U = NULL: structure only (no device).
+ * This is what tests/ocp_tests.cpp:76-154 of the reference checks for a 2x1 and a 1x2 agent. */
+int mas_b200_global_ocp_eval_mixed(mas_b200_context_t ctx, const mas_b200_ocp_desc* agent_descs, const unsigned long long* agent_ids, int n_agents,
+                                   const double* X, const double* U, int time_index, double* dynamics_out, double* stage_cost_out,
+                                   double* terminal_cost_out, int* dims_out, double* dt_out, double* bounds_out, int* block_agent, int* state_offsets,
+                                   int* control_offsets);
+
 /* ---- multi-GPU (one process per GPU).  unique_id: 128 bytes from mas_b200_nccl_unique_id on rank 0,
  * distributed by the caller (torch.distributed / MPI / file). ------------------------------------- */
 int mas_b200_nccl_unique_id(void* id128);

@@ -22,6 +22,8 @@ from .capi import (  # noqa: F401
     library_path,
     load_library,
     model_info,
+    global_ocp_eval_mixed,
     strategy_run,
+    strategy_run_mixed,
     synthetic_single_track_x0,
 )

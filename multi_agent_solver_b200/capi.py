@@ -367,3 +367,50 @@ def strategy_run(ctx: Context, strategy: int, desc: OcpDesc, params: IlqrParams,
                                                  _dptr(model_params), _dptr(U_init), _dptr(X), _dptr(U), _dptr(costs), _dptr(total), _iptr(t_it), _iptr(t_acc),
                                                  _dptr(t_cost)))
     return dict(X=X, U=U, costs=costs, total_cost=total, trace_iters=t_it, trace_accept=t_acc, trace_cost=t_cost)
+
+
+def strategy_run_mixed(ctx: Context, strategy: int, descs, params: IlqrParams, max_outer: int, x0_list, model_params=None, U_init=None):
+    """mas_b200_strategy_run_mixed.  descs: one OcpDesc per agent; x0_list[a]: [scenarios, n_a]."""
+    A = len(descs)
+    x0_list = [_f64(x) for x in x0_list]
+    S = x0_list[0].shape[0]
+    darr = (OcpDesc * A)(*descs)
+    PD = ctypes.POINTER(ctypes.c_double)
+
+    def ptrs(arrs):
+        return (PD * A)(*[(_dptr(a) if a is not None else PD()) for a in arrs])
+
+    X = [np.empty((S, d.horizon_steps + 1, d.state_dim)) for d in descs]
+    U = [np.empty((S, d.horizon_steps, d.control_dim)) for d in descs]
+    costs = [np.empty(S) for _ in descs]
+    total = np.empty(S)
+    t_it = np.zeros((S, max_outer, A), dtype=np.int32)
+    mp = [None] * A if model_params is None else [_f64(m) for m in model_params]
+    u0 = [None] * A if U_init is None else [_f64(u) for u in U_init]
+    _check(load_library().mas_b200_strategy_run_mixed(ctx._h, int(strategy), darr, ctypes.byref(params), int(max_outer), S, A, ptrs(x0_list), ptrs(mp),
+                                                       ptrs(u0), ptrs(X), ptrs(U), ptrs(costs), _dptr(total), _iptr(t_it)))
+    return dict(X=X, U=U, costs=np.stack(costs, -1), total_cost=total, trace_iters=t_it)
+
+
+def global_ocp_eval_mixed(ctx: Context, descs, agent_ids=None, X=None, U=None, time_index: int = 0):
+    """mas_b200_global_ocp_eval_mixed: structure (and, with X / U, values) of the stacked problem of mixed agents."""
+    A = len(descs)
+    darr = (OcpDesc * A)(*descs)
+    ids = None if agent_ids is None else (ctypes.c_ulonglong * A)(*[int(i) for i in agent_ids])
+    dims = np.zeros(4, dtype=np.int32)
+    dt = ctypes.c_double()
+    total_u = sum(d.control_dim for d in descs)
+    total_x = sum(d.state_dim for d in descs)
+    bounds = np.full((2, total_u), np.nan)
+    block_agent = np.zeros(A, dtype=np.int32)
+    soff = np.zeros(A, dtype=np.int32)
+    uoff = np.zeros(A, dtype=np.int32)
+    X = _f64(X)
+    U = _f64(U)
+    dyn = np.zeros(total_x)
+    stage, term = ctypes.c_double(), ctypes.c_double()
+    _check(load_library().mas_b200_global_ocp_eval_mixed(ctx._h if ctx is not None else None, darr, ids, A, _dptr(X), _dptr(U), int(time_index), _dptr(dyn), ctypes.byref(stage),
+                                                          ctypes.byref(term), _iptr(dims), ctypes.byref(dt), _dptr(bounds), _iptr(block_agent),
+                                                          _iptr(soff), _iptr(uoff)))
+    return dict(total_x=int(dims[0]), total_u=int(dims[1]), horizon=int(dims[2]), has_bounds=bool(dims[3]), dt=dt.value, bounds=bounds,
+                block_agent=block_agent, state_offsets=soff, control_offsets=uoff, dynamics=dyn, stage=stage.value, terminal=term.value)

@@ -2,6 +2,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <limits>
 #include <new>
 #include <random>
@@ -761,6 +762,302 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
   };
   rc = run();  // the batch stays with the context (borrow_scratch_batch)
   return rc;
+}
+
+// ---- strategies over agents of different models / shapes ------------------------------------------------------------
+namespace {
+struct AgentGroup {  // agents that share one description: one device batch [scenario][member]
+  mas_b200_ocp_desc desc;
+  std::vector<int> members;  // agent indices, ascending
+  mas_b200_batch* h = nullptr;
+  std::vector<double> cost;  // [scenario][member] after the last download
+};
+struct GroupSet {
+  std::vector<AgentGroup> g;
+  ~GroupSet() {
+    for (auto& a : g)
+      if (a.h) mas_b200_batch_destroy(a.h);
+  }
+};
+}  // namespace
+
+int mas_b200_strategy_run_mixed(mas_b200_context_t ctx, int strategy, const mas_b200_ocp_desc* agent_descs, const mas_b200_ilqr_params* params,
+                                int max_outer, int n_scenarios, int n_agents, const double* const* x0, const double* const* model_params,
+                                const double* const* U_init, double* const* X, double* const* U, double* const* costs, double* total_cost,
+                                int* trace_iterations) {
+  if (!ctx || !agent_descs || !x0) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "ctx / agent_descs / x0 is NULL");
+  int rc = validate_params(params);
+  if (rc) return rc;
+  if (n_scenarios <= 0 || n_agents <= 0 || max_outer < 0) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "bad scenario/agent/outer counts");
+  for (int a = 0; a < n_agents; ++a) {
+    rc = validate_desc(&agent_descs[a]);
+    if (rc) return rc;
+  }
+  bool same = true;
+  for (int a = 1; a < n_agents; ++a) same = same && std::memcmp(&agent_descs[a], &agent_descs[0], sizeof(mas_b200_ocp_desc)) == 0;
+  if (strategy == MAS_B200_STRATEGY_CENTRALIZED && !same)
+    return fail(MAS_B200_ERR_UNSUPPORTED,
+                "centralized strategy over agents of different models: the stacked solve is built per model (use mas_b200_global_ocp_eval_mixed for "
+                "the stacked functions; Nash strategies accept mixed agents)");
+  if (strategy != MAS_B200_STRATEGY_CENTRALIZED && strategy != MAS_B200_STRATEGY_SEQUENTIAL && strategy != MAS_B200_STRATEGY_TRUSTREGION &&
+      strategy != MAS_B200_STRATEGY_LINESEARCH)
+    return fail(MAS_B200_ERR_INVALID_ARGUMENT, "unknown strategy");
+  const int S = n_scenarios;
+  if (same) {  // one shape: pack the per-agent arrays into the [scenario][agent] layout and take the single-batch path
+    const mas_b200_ocp_desc& d = agent_descs[0];
+    const int n = d.state_dim, m = d.control_dim, T = d.horizon_steps, np = kModels[d.model_id].np;
+    const size_t SA = static_cast<size_t>(S) * n_agents;
+    std::vector<double> fx0(SA * n), fp, fU0, fX(SA * n * (T + 1)), fU(SA * m * T), fc(SA);
+    bool any_p = false, any_u = false;
+    for (int a = 0; a < n_agents; ++a) {
+      any_p = any_p || (model_params && model_params[a]);
+      any_u = any_u || (U_init && U_init[a]);
+    }
+    if (any_p) fp.assign(SA * np, 0.0);
+    if (any_u) fU0.assign(SA * m * T, 0.0);
+    for (int sc = 0; sc < S; ++sc)
+      for (int a = 0; a < n_agents; ++a) {
+        const size_t idx = static_cast<size_t>(sc) * n_agents + a;
+        std::memcpy(&fx0[idx * n], x0[a] + static_cast<size_t>(sc) * n, sizeof(double) * n);
+        if (any_p)
+          for (int i = 0; i < np; ++i) fp[idx * np + i] = (model_params[a]) ? model_params[a][static_cast<size_t>(sc) * np + i] : (d.num_params ? d.params[i] : kModels[d.model_id].default_params[i]);
+        if (any_u && U_init[a]) std::memcpy(&fU0[idx * m * T], U_init[a] + static_cast<size_t>(sc) * m * T, sizeof(double) * m * T);
+      }
+    rc = mas_b200_strategy_run(ctx, strategy, &d, params, max_outer, S, n_agents, fx0.data(), any_p ? fp.data() : nullptr, any_u ? fU0.data() : nullptr,
+                               fX.data(), fU.data(), fc.data(), total_cost, trace_iterations, nullptr, nullptr);
+    if (rc) return rc;
+    for (int sc = 0; sc < S; ++sc)
+      for (int a = 0; a < n_agents; ++a) {
+        const size_t idx = static_cast<size_t>(sc) * n_agents + a;
+        if (X && X[a]) std::memcpy(X[a] + static_cast<size_t>(sc) * n * (T + 1), &fX[idx * n * (T + 1)], sizeof(double) * n * (T + 1));
+        if (U && U[a]) std::memcpy(U[a] + static_cast<size_t>(sc) * m * T, &fU[idx * m * T], sizeof(double) * m * T);
+        if (costs && costs[a]) costs[a][sc] = fc[idx];
+      }
+    return MAS_B200_OK;
+  }
+  // ---- Nash strategies, mixed agents: agents never read each other's trajectories during a solve (nash.hpp:59-64,199-212),
+  // so agents of one description form one device batch and the groups advance round by round in lockstep; the only joint
+  // quantity, the line-search strategy's total cost (nash.hpp:39-51,103,121,143), is summed on the host in block order.
+  GroupSet gs;
+  for (int a = 0; a < n_agents; ++a) {
+    AgentGroup* found = nullptr;
+    for (auto& g : gs.g)
+      if (std::memcmp(&g.desc, &agent_descs[a], sizeof(mas_b200_ocp_desc)) == 0) found = &g;
+    if (!found) {
+      gs.g.push_back(AgentGroup{});
+      found = &gs.g.back();
+      found->desc = agent_descs[a];
+    }
+    found->members.push_back(a);
+  }
+  cudaStream_t st = ctx->c.stream;
+  const bool keeps_old = strategy != MAS_B200_STRATEGY_SEQUENTIAL;
+  for (auto& g : gs.g) {
+    const int G = static_cast<int>(g.members.size()), B = S * G;
+    const int n = g.desc.state_dim, m = g.desc.control_dim, T = g.desc.horizon_steps, np = kModels[g.desc.model_id].np;
+    rc = mas_b200_batch_create(ctx, &g.desc, B, &g.h);
+    if (rc) return rc;
+    std::vector<double> fx0(static_cast<size_t>(B) * n), fp, fU0;
+    bool any_p = false, any_u = false;
+    for (int a : g.members) {
+      any_p = any_p || (model_params && model_params[a]);
+      any_u = any_u || (U_init && U_init[a]);
+    }
+    if (any_p) fp.assign(static_cast<size_t>(B) * np, 0.0);
+    if (any_u) fU0.assign(static_cast<size_t>(B) * m * T, 0.0);
+    for (int sc = 0; sc < S; ++sc)
+      for (int k = 0; k < G; ++k) {
+        const int a = g.members[k];
+        const size_t idx = static_cast<size_t>(sc) * G + k;
+        std::memcpy(&fx0[idx * n], x0[a] + static_cast<size_t>(sc) * n, sizeof(double) * n);
+        if (any_p)
+          for (int i = 0; i < np; ++i) fp[idx * np + i] = model_params[a] ? model_params[a][static_cast<size_t>(sc) * np + i] : g.h->b->desc.params[i];
+        if (any_u && U_init[a]) std::memcpy(&fU0[idx * m * T], U_init[a] + static_cast<size_t>(sc) * m * T, sizeof(double) * m * T);
+      }
+    rc = mas_b200_batch_set_initial_states(g.h, fx0.data());
+    if (!rc) rc = mas_b200_batch_set_params(g.h, any_p ? fp.data() : nullptr);
+    if (!rc) rc = mas_b200_batch_set_controls(g.h, any_u ? fU0.data() : nullptr);
+    if (!rc) rc = g.h->b->initialize();
+    if (!rc && keeps_old) rc = g.h->b->ensure_strategy_scratch();
+    if (rc) return rc;
+    if (strategy == MAS_B200_STRATEGY_TRUSTREGION) {
+      std::vector<double> ones(g.h->b->ld, 1.0);
+      MAS_CUDA_CHECK(cudaMemcpyAsync(g.h->b->d_radius, ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+      MAS_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    g.cost.assign(B, 0.0);
+  }
+  // joint cost of every scenario: all agents in block (= index) order, from 0.0
+  std::vector<int> group_of(n_agents), slot_of(n_agents);
+  for (size_t gi = 0; gi < gs.g.size(); ++gi)
+    for (size_t k = 0; k < gs.g[gi].members.size(); ++k) {
+      group_of[gs.g[gi].members[k]] = static_cast<int>(gi);
+      slot_of[gs.g[gi].members[k]] = static_cast<int>(k);
+    }
+  auto download_costs = [&]() -> int {
+    for (auto& g : gs.g) MAS_CUDA_CHECK(cudaMemcpyAsync(g.cost.data(), g.h->b->d_cost, g.cost.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MAS_CUDA_CHECK(cudaStreamSynchronize(st));
+    return MAS_B200_OK;
+  };
+  auto joint = [&](int sc) {
+    double c = 0.0;
+    for (int a = 0; a < n_agents; ++a) {
+      const AgentGroup& g = gs.g[group_of[a]];
+      c += g.cost[static_cast<size_t>(sc) * g.members.size() + slot_of[a]];
+    }
+    return c;
+  };
+  std::vector<double> base(S, 0.0);
+  std::vector<int> state(S, 0);
+  auto upload_state = [&]() -> int {
+    for (auto& g : gs.g) MAS_CUDA_CHECK(cudaMemcpyAsync(g.h->b->d_ls_state, state.data(), S * sizeof(int), cudaMemcpyHostToDevice, st));
+    MAS_CUDA_CHECK(cudaStreamSynchronize(st));
+    return MAS_B200_OK;
+  };
+  if (strategy == MAS_B200_STRATEGY_LINESEARCH) {
+    rc = download_costs();
+    if (rc) return rc;
+    for (int sc = 0; sc < S; ++sc) base[sc] = joint(sc);  // nash.hpp:103
+  }
+  std::vector<int> it_tmp;
+  for (int outer = 0; outer < max_outer; ++outer) {
+    for (auto& g : gs.g) {
+      BatchBase* b = g.h->b;
+      const size_t L = static_cast<size_t>(b->ld), nXd = L * b->nx * (b->T + 1), nUd = L * b->nu * b->T;
+      if (keeps_old) {
+        MAS_CUDA_CHECK(cudaMemcpyAsync(b->d_U_old, b->d_U, nUd * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        MAS_CUDA_CHECK(cudaMemcpyAsync(b->d_X_old, b->d_X, nXd * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        MAS_CUDA_CHECK(cudaMemcpyAsync(b->d_cost_old, b->d_cost, L * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      }
+      rc = b->solve(*params);
+      if (!rc && strategy == MAS_B200_STRATEGY_TRUSTREGION) rc = b->trust_region_step();
+      if (rc) return rc;
+      if (trace_iterations) {
+        it_tmp.resize(b->batch);
+        MAS_CUDA_CHECK(cudaMemcpyAsync(it_tmp.data(), b->d_iters, b->batch * sizeof(int), cudaMemcpyDeviceToHost, st));
+        MAS_CUDA_CHECK(cudaStreamSynchronize(st));
+        const int G = static_cast<int>(g.members.size());
+        for (int sc = 0; sc < S; ++sc)
+          for (int k = 0; k < G; ++k)
+            trace_iterations[(static_cast<size_t>(sc) * max_outer + outer) * n_agents + g.members[k]] = it_tmp[static_cast<size_t>(sc) * G + k];
+      }
+      if (strategy == MAS_B200_STRATEGY_LINESEARCH)
+        MAS_CUDA_CHECK(cudaMemcpyAsync(b->d_U_cand, b->d_U, nUd * sizeof(double), cudaMemcpyDeviceToDevice, st));  // nash.hpp:123-125
+    }
+    if (strategy == MAS_B200_STRATEGY_LINESEARCH) {
+      rc = download_costs();
+      if (rc) return rc;
+      bool searching = false;
+      for (int sc = 0; sc < S; ++sc) {  // nash.hpp:119-121,173-176
+        const double c = joint(sc);
+        if (c >= base[sc]) {
+          state[sc] = 1;
+          searching = true;
+        } else {
+          base[sc] = c;
+          state[sc] = 0;
+        }
+      }
+      rc = upload_state();
+      if (rc) return rc;
+      for (double alpha = 0.5; searching && alpha > 1e-3; alpha *= 0.5) {  // nash.hpp:127-158
+        for (auto& g : gs.g) {
+          rc = g.h->b->nash_ls_trial(static_cast<int>(g.members.size()), alpha);
+          if (rc) return rc;
+        }
+        rc = download_costs();
+        if (rc) return rc;
+        searching = false;
+        for (int sc = 0; sc < S; ++sc) {
+          if (state[sc] != 1) continue;
+          const double c = joint(sc);
+          if (c < base[sc]) {
+            base[sc] = c;
+            state[sc] = 2;
+          } else {
+            searching = true;
+          }
+        }
+        rc = upload_state();
+        if (rc) return rc;
+      }
+      for (auto& g : gs.g) {  // nash.hpp:161-171
+        rc = g.h->b->nash_ls_restore(static_cast<int>(g.members.size()));
+        if (rc) return rc;
+      }
+    }
+  }
+  // collect_solution (nash.hpp:23-37)
+  for (auto& g : gs.g) {
+    BatchBase* b = g.h->b;
+    const int G = static_cast<int>(g.members.size());
+    const size_t per_x = static_cast<size_t>(b->nx) * (b->T + 1), per_u = static_cast<size_t>(b->nu) * b->T;
+    std::vector<double> fX(static_cast<size_t>(b->batch) * per_x), fU(static_cast<size_t>(b->batch) * per_u);
+    rc = mas_b200_batch_get_solution(g.h, fX.data(), fU.data(), g.cost.data(), nullptr, nullptr);
+    if (rc) return rc;
+    for (int sc = 0; sc < S; ++sc)
+      for (int k = 0; k < G; ++k) {
+        const int a = g.members[k];
+        const size_t idx = static_cast<size_t>(sc) * G + k;
+        if (X && X[a]) std::memcpy(X[a] + static_cast<size_t>(sc) * per_x, &fX[idx * per_x], sizeof(double) * per_x);
+        if (U && U[a]) std::memcpy(U[a] + static_cast<size_t>(sc) * per_u, &fU[idx * per_u], sizeof(double) * per_u);
+        if (costs && costs[a]) costs[a][sc] = g.cost[idx];
+      }
+  }
+  if (total_cost)
+    for (int sc = 0; sc < S; ++sc) total_cost[sc] = joint(sc);
+  return MAS_B200_OK;
+}
+
+int mas_b200_global_ocp_eval_mixed(mas_b200_context_t ctx, const mas_b200_ocp_desc* agent_descs, const unsigned long long* agent_ids, int n_agents,
+                                   const double* X, const double* U, int time_index, double* dynamics_out, double* stage_cost_out,
+                                   double* terminal_cost_out, int* dims_out, double* dt_out, double* bounds_out, int* block_agent, int* state_offsets,
+                                   int* control_offsets) {
+  if (!agent_descs || n_agents <= 0 || !dims_out) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "bad arguments");
+  if ((X || U) && !ctx) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "ctx is NULL (only the structure-only call works without a device)");
+  for (int a = 0; a < n_agents; ++a) {
+    const int rc = validate_desc(&agent_descs[a]);
+    if (rc) return rc;
+  }
+  // compute_offsets (multi_agent_problem.hpp:37-50): blocks sorted by agent id (stable for equal ids, like the order of the input)
+  std::vector<int> order(n_agents);
+  for (int a = 0; a < n_agents; ++a) order[a] = a;
+  if (agent_ids) std::stable_sort(order.begin(), order.end(), [&](int l, int r) { return agent_ids[l] < agent_ids[r]; });
+  std::vector<int> mid(n_agents), soff(n_agents), uoff(n_agents);
+  std::vector<double> prm(static_cast<size_t>(n_agents) * kMaxParams, 0.0);
+  int sx = 0, su = 0;
+  bool all_bounds = true;
+  for (int k = 0; k < n_agents; ++k) {
+    const mas_b200_ocp_desc& d = agent_descs[order[k]];
+    mid[k] = d.model_id;
+    soff[k] = sx;
+    uoff[k] = su;
+    sx += d.state_dim;
+    su += d.control_dim;
+    all_bounds = all_bounds && d.has_input_bounds;  // bounds only when ALL agents have both (:76-92)
+    for (int i = 0; i < kModels[d.model_id].np; ++i) prm[static_cast<size_t>(k) * kMaxParams + i] = d.num_params ? d.params[i] : kModels[d.model_id].default_params[i];
+    if (d.model_id == MAS_B200_MODEL_PENDULUM && d.num_params == 0) prm[static_cast<size_t>(k) * kMaxParams] = static_cast<double>(d.horizon_steps);
+    if (block_agent) block_agent[k] = order[k];
+    if (state_offsets) state_offsets[k] = soff[k];
+    if (control_offsets) control_offsets[k] = uoff[k];
+  }
+  dims_out[0] = sx;
+  dims_out[1] = su;
+  dims_out[2] = agent_descs[order[0]].horizon_steps;  // horizon and dt of the FIRST block only (:65-69)
+  dims_out[3] = all_bounds ? 1 : 0;
+  if (dt_out) *dt_out = agent_descs[order[0]].dt;
+  if (all_bounds && bounds_out)
+    for (int k = 0; k < n_agents; ++k) {
+      const mas_b200_ocp_desc& d = agent_descs[order[k]];
+      for (int i = 0; i < d.control_dim; ++i) {
+        bounds_out[uoff[k] + i] = d.input_lower[i];
+        bounds_out[su + uoff[k] + i] = d.input_upper[i];
+      }
+    }
+  if (!X || !U) return MAS_B200_OK;  // structure only
+  if (!dynamics_out || !stage_cost_out || !terminal_cost_out) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "output pointers are NULL");
+  return mixed_global_eval(&ctx->c, mid.data(), soff.data(), uoff.data(), prm.data(), n_agents, sx, su, X, U, time_index, dynamics_out, stage_cost_out,
+                           terminal_cost_out);
 }
 
 // ---- multi-GPU ---------------------------------------------------------------------------------------------

@@ -243,6 +243,93 @@ __global__ void nash_ls_reduce_kernel(const double* __restrict__ cost, int n_sce
   }
 }
 
+// ---- stacked functions of a MultiAgentProblem whose agents are of different models (build_global_ocp,
+// multi_agent_problem.hpp:94-125): block-diagonal dynamics, stage / terminal costs summed in block order from 0.0.
+// One thread per block evaluates its agent's registered functors (run-time dispatch on the model id); thread 0 then
+// forms the two sums in block order.
+struct MixedBlock {
+  int model_id, state_offset, control_offset;
+  double params[kMaxParams];
+};
+template <class M>
+__device__ void mixed_block_eval(const MixedBlock& b, const double* X, const double* U, int t, double* dyn, double* stage, double* terminal) {
+  double x[M::NX], u[M::NU], d[M::NX];
+  for (int i = 0; i < M::NX; ++i) x[i] = X[b.state_offset + i];
+  for (int i = 0; i < M::NU; ++i) u[i] = U[b.control_offset + i];
+  M::dynamics(x, u, b.params, d);
+  for (int i = 0; i < M::NX; ++i) dyn[b.state_offset + i] = d[i];
+  *stage = M::stage(x, u, t, b.params);
+  *terminal = M::terminal(x, b.params);
+}
+__global__ void mixed_global_eval_kernel(const MixedBlock* blocks, int n_blocks, const double* X, const double* U, int t, double* dyn, double* terms,
+                                         double* sums) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < n_blocks) {
+    const MixedBlock b = blocks[a];
+    double* st = terms + a;
+    double* te = terms + n_blocks + a;
+    switch (b.model_id) {
+      case StLane::ID: mixed_block_eval<StLane>(b, X, U, t, dyn, st, te); break;
+      case StCirc::ID: mixed_block_eval<StCirc>(b, X, U, t, dyn, st, te); break;
+      case Lqr4::ID: mixed_block_eval<Lqr4>(b, X, U, t, dyn, st, te); break;
+      case Pendulum::ID: mixed_block_eval<Pendulum>(b, X, U, t, dyn, st, te); break;
+      case Rocket::ID: mixed_block_eval<Rocket>(b, X, U, t, dyn, st, te); break;
+      case StLaneCon::ID: mixed_block_eval<StLaneCon>(b, X, U, t, dyn, st, te); break;
+    }
+  }
+}
+__global__ void mixed_global_sum_kernel(const double* terms, int n_blocks, double* sums) {
+  double s = 0.0, e = 0.0;
+  for (int a = 0; a < n_blocks; ++a) s += terms[a];
+  for (int a = 0; a < n_blocks; ++a) e += terms[n_blocks + a];
+  sums[0] = s;
+  sums[1] = e;
+}
+
+int mixed_global_eval(Context* ctx, const int* model_ids, const int* state_offsets, const int* control_offsets, const double* params /* [n][kMaxParams] */,
+                      int n_blocks, int total_x, int total_u, const double* X, const double* U, int t, double* dyn_out, double* stage_out,
+                      double* terminal_out) {
+  std::vector<MixedBlock> hb(n_blocks);
+  for (int a = 0; a < n_blocks; ++a) {
+    hb[a].model_id = model_ids[a];
+    hb[a].state_offset = state_offsets[a];
+    hb[a].control_offset = control_offsets[a];
+    for (int i = 0; i < kMaxParams; ++i) hb[a].params[i] = params[static_cast<size_t>(a) * kMaxParams + i];
+  }
+  MixedBlock* d_b = nullptr;
+  double* d_buf = nullptr;
+  const size_t nd = static_cast<size_t>(2) * total_x + total_u + 2 * n_blocks + 2;
+  MAS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_b), n_blocks * sizeof(MixedBlock)));
+  if (cudaMalloc(reinterpret_cast<void**>(&d_buf), nd * sizeof(double)) != cudaSuccess) {
+    cudaFree(d_b);
+    set_last_error("cudaMalloc failed");
+    return MAS_B200_ERR_CUDA;
+  }
+  double *dX = d_buf, *dU = dX + total_x, *dD = dU + total_u, *dT = dD + total_x, *dS = dT + 2 * n_blocks;
+  cudaStream_t st = ctx->stream;
+  int rc = MAS_B200_OK;
+  auto run = [&]() -> int {
+    MAS_CUDA_CHECK(cudaMemcpyAsync(d_b, hb.data(), n_blocks * sizeof(MixedBlock), cudaMemcpyHostToDevice, st));
+    MAS_CUDA_CHECK(cudaMemcpyAsync(dX, X, total_x * sizeof(double), cudaMemcpyHostToDevice, st));
+    MAS_CUDA_CHECK(cudaMemcpyAsync(dU, U, total_u * sizeof(double), cudaMemcpyHostToDevice, st));
+    mixed_global_eval_kernel<<<div_up(n_blocks, 64), 64, 0, st>>>(d_b, n_blocks, dX, dU, t, dD, dT, dS);
+    mixed_global_sum_kernel<<<1, 1, 0, st>>>(dT, n_blocks, dS);
+    MAS_CUDA_CHECK(cudaGetLastError());
+    double sums[2];
+    MAS_CUDA_CHECK(cudaMemcpyAsync(dyn_out, dD, total_x * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MAS_CUDA_CHECK(cudaMemcpyAsync(sums, dS, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MAS_CUDA_CHECK(cudaStreamSynchronize(st));
+    *stage_out = sums[0];
+    *terminal_out = sums[1];
+    return MAS_B200_OK;
+  };
+  rc = run();
+  cudaFree(d_b);
+  cudaFree(d_buf);
+  return rc;
+}
+
 int BatchBase::nash_ls_reduce(int n_scenarios, int n_agents, int phase) {
   nash_ls_reduce_kernel<<<div_up(n_scenarios, 128), 128, 0, ctx->stream>>>(d_cost, n_scenarios, n_agents, d_base_cost, d_ls_state, phase);
   stats.kernel_launches++;

@@ -1070,6 +1070,9 @@ int BatchImpl<M>::mark_time_limit(int cur) {
   return MAS_B200_OK;
 }
 
+int mixed_global_eval(Context* ctx, const int* model_ids, const int* state_offsets, const int* control_offsets, const double* params, int n_blocks,
+                      int total_x, int total_u, const double* X, const double* U, int t, double* dyn_out, double* stage_out, double* terminal_out);
+
 // factories, one translation unit per model (model_*.cu)
 BatchBase* make_batch_st_lane();
 BatchBase* make_batch_st_circ();

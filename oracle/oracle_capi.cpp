@@ -328,6 +328,104 @@ int oracle_strategy_run_batch(int kind, int model, int n_scenarios, int n_agents
   return err;
 }
 
+// The same for agents of different models (MultiAgentProblem takes any mix).  Ragged arrays: per scenario the agents'
+// entries are concatenated in agent order (x0: n_a; X: (T_a+1)*n_a; U: T_a*m_a); costs / iters_total are [scenario][agent].
+int oracle_strategy_run_mixed(int kind, int n_scenarios, int n_agents, const int* models, const double* x0, int max_outer, int max_iterations,
+                              double tolerance, int trig, double* X_out, double* U_out, double* costs_out, double* total_cost_out, int* iters_total) {
+  trig_mode() = trig;
+  std::vector<int> n(n_agents), m(n_agents), T(n_agents);
+  std::size_t sx0 = 0, sX = 0, sU = 0;
+  try {
+    for (int a = 0; a < n_agents; ++a) {
+      double dt;
+      model_dims(models[a], 0, &n[a], &m[a], &T[a], &dt);
+      sx0 += n[a];
+      sX += static_cast<std::size_t>(n[a]) * (T[a] + 1);
+      sU += static_cast<std::size_t>(m[a]) * T[a];
+    }
+  } catch (...) {
+    return 1;
+  }
+  int err = 0;
+#pragma omp parallel for schedule(static)
+  for (int s = 0; s < n_scenarios; ++s) {
+    try {
+      MultiAgentProblem problem;
+      std::size_t o = 0;
+      for (int a = 0; a < n_agents; ++a) {
+        auto ocp = std::make_shared<OCP>(build_ocp(models[a], x0 + s * sx0 + o, nullptr, 0, 0));
+        o += n[a];
+        problem.add_agent(std::make_shared<Agent>(static_cast<std::size_t>(a), ocp));
+      }
+      const SolverParams sp = make_params(max_iterations, tolerance, std::numeric_limits<double>::infinity());
+      OracleOptions opt;
+      StrategyTrace trace;
+      Solution sol;
+      if (kind == 1) sol = run_sequential(max_outer, sp, problem, opt, &trace);
+      else if (kind == 2) sol = run_line_search(max_outer, sp, problem, opt, &trace);
+      else if (kind == 3) sol = run_trust_region(max_outer, sp, problem, opt, &trace);
+      else throw std::invalid_argument("oracle: mixed agents need a Nash strategy");
+      std::size_t ox = 0, ou = 0;
+      for (int a = 0; a < n_agents; ++a) {
+        const std::size_t px = static_cast<std::size_t>(n[a]) * (T[a] + 1), pu = static_cast<std::size_t>(m[a]) * T[a];
+        std::memcpy(X_out + s * sX + ox, sol.states[a].d.data(), sizeof(double) * px);
+        std::memcpy(U_out + s * sU + ou, sol.controls[a].d.data(), sizeof(double) * pu);
+        ox += px;
+        ou += pu;
+        costs_out[static_cast<std::size_t>(s) * n_agents + a] = sol.costs[a];
+        int it = 0;
+        for (std::size_t r = a; r < trace.iterations.size(); r += n_agents) it += trace.iterations[r];
+        if (iters_total) iters_total[static_cast<std::size_t>(s) * n_agents + a] = it;
+      }
+      total_cost_out[s] = sol.total_cost;
+    } catch (...) {
+#pragma omp atomic write
+      err = 1;
+    }
+  }
+  return err;
+}
+
+// Stacked functions of a mixed MultiAgentProblem (build_global_ocp, multi_agent_problem.hpp:52-127): dims, horizon / dt of the
+// first block, concatenated bounds when ALL agents have both, block-diagonal dynamics, costs summed in block order.
+// Agents are added in REVERSE id order so that compute_offsets' sort is exercised.  bounds_out: [2][total_u] or untouched.
+int oracle_global_ocp_eval_mixed(int n_agents, const int* models, const double* x0, const double* X, const double* U, double* dyn_out, double* stage_out,
+                                 double* terminal_out, int* dims_out /* total_x,total_u,T,has_bounds */, double* dt_out, double* bounds_out) {
+  try {
+    trig_mode() = TRIG_PORTABLE;
+    MultiAgentProblem problem;
+    std::vector<std::shared_ptr<OCP>> ocps(n_agents);
+    std::size_t o = 0;
+    for (int a = 0; a < n_agents; ++a) {
+      int n, m, T;
+      double dt;
+      model_dims(models[a], 0, &n, &m, &T, &dt);
+      ocps[a] = std::make_shared<OCP>(build_ocp(models[a], x0 + o, nullptr, 0, 0));
+      o += n;
+    }
+    for (int a = n_agents - 1; a >= 0; --a) problem.add_agent(std::make_shared<Agent>(static_cast<std::size_t>(a), ocps[a]));
+    problem.compute_offsets();
+    OCP g = problem.build_global_ocp();
+    dims_out[0] = g.state_dim;
+    dims_out[1] = g.control_dim;
+    dims_out[2] = g.horizon_steps;
+    dims_out[3] = (g.input_lower_bounds && g.input_upper_bounds) ? 1 : 0;
+    *dt_out = g.dt;
+    if (dims_out[3] && bounds_out) {
+      std::memcpy(bounds_out, g.input_lower_bounds->data(), sizeof(double) * g.control_dim);
+      std::memcpy(bounds_out + g.control_dim, g.input_upper_bounds->data(), sizeof(double) * g.control_dim);
+    }
+    Vec Xv(X, X + g.state_dim), Uv(U, U + g.control_dim);
+    const Vec d = g.dynamics(Xv, Uv);
+    std::memcpy(dyn_out, d.data(), sizeof(double) * d.size());
+    *stage_out = g.stage_cost(Xv, Uv, 3);
+    *terminal_out = g.terminal_cost(Xv);
+  } catch (...) {
+    return 1;
+  }
+  return 0;
+}
+
 // Stacked-problem evaluation used to pin build_global_ocp against tests/ocp_tests.cpp:76-154.
 int oracle_global_ocp_eval(int model, int n_agents, const double* x0, const double* params, int np, int horizon, const double* X, const double* U,
                            double* dyn_out, double* stage_out, double* terminal_out, int* dims_out /* total_x,total_u,T */) {

@@ -24,6 +24,7 @@
 #include "ref_examples.hpp"
 
 extern "C" void ref_set_trig_mode(int mode);
+extern "C" void ref_set_thread_trig_override(int mode);
 
 namespace {
 
@@ -47,6 +48,10 @@ void model_dims(int model, int horizon, int* n, int* m, int* T, double* dt) {
 // example constants are compiled into the reference's lambdas).
 mas::OCP build_ocp(int model, const double* x0, const double* params, int np, int horizon, const double* U /* [T][m] or null */) {
   mas::OCP p;
+  ref_set_thread_trig_override(0);  // the example's own set-up code runs with libm, whatever mode the solve is compared in
+  struct Restore {
+    ~Restore() { ref_set_thread_trig_override(-1); }
+  } restore_after_builder;
   switch (model) {
     case MODEL_ST_LANE: p = create_single_track_lane_following_ocp(); break;
     case MODEL_ST_CIRC:
@@ -78,6 +83,7 @@ mas::OCP build_ocp(int model, const double* x0, const double* params, int np, in
     }
     default: throw std::invalid_argument("ref: unknown model id");
   }
+  ref_set_thread_trig_override(-1);
   for (int i = 0; i < p.state_dim; ++i) p.initial_state(i) = x0[i];
   if (U) {
     p.initial_controls.resize(p.control_dim, p.horizon_steps);
@@ -344,6 +350,108 @@ int ref_strategy_run_batch(int kind, int model, int n_scenarios, int n_agents, c
     }
   }
   return err;
+}
+
+// Agents of different models in one MultiAgentProblem (ragged arrays as in oracle_strategy_run_mixed).
+int ref_strategy_run_mixed(int kind, int n_scenarios, int n_agents, const int* models, const double* x0, int max_outer, int max_iterations,
+                           double tolerance, int trig, double* X_out, double* U_out, double* costs_out, double* total_cost_out, int* iters_total) {
+  ref_set_trig_mode(trig);
+  std::vector<int> n(n_agents), m(n_agents), T(n_agents);
+  std::size_t sx0 = 0, sX = 0, sU = 0;
+  try {
+    for (int a = 0; a < n_agents; ++a) {
+      double dt;
+      model_dims(models[a], 0, &n[a], &m[a], &T[a], &dt);
+      sx0 += n[a];
+      sX += static_cast<std::size_t>(n[a]) * (T[a] + 1);
+      sU += static_cast<std::size_t>(m[a]) * T[a];
+    }
+  } catch (...) {
+    return 1;
+  }
+  int err = 0;
+#pragma omp parallel for schedule(static)
+  for (int s = 0; s < n_scenarios; ++s) {
+    try {
+      omp_set_num_threads(1);
+      mas::MultiAgentProblem problem;
+      std::vector<std::shared_ptr<Probe>> probes;
+      std::size_t o = 0;
+      for (int a = 0; a < n_agents; ++a) {
+        auto ocp = std::make_shared<mas::OCP>(build_ocp(models[a], x0 + s * sx0 + o, nullptr, 0, 0, nullptr));
+        o += n[a];
+        probes.push_back(instrument(*ocp));
+        problem.add_agent(std::make_shared<mas::Agent>(static_cast<std::size_t>(a), ocp));
+      }
+      const mas::SolverParams sp = make_params(max_iterations, tolerance, std::numeric_limits<double>::infinity());
+      mas::Solver solver{std::in_place_type<mas::iLQR>};
+      mas::Strategy strategy = [&]() -> mas::Strategy {
+        switch (kind) {
+          case 1: return mas::SequentialNashStrategy{max_outer, std::move(solver), sp};
+          case 2: return mas::LineSearchNashStrategy{max_outer, std::move(solver), sp};
+          case 3: return mas::TrustRegionNashStrategy{max_outer, std::move(solver), sp};
+        }
+        throw std::invalid_argument("ref: mixed agents need a Nash strategy");
+      }();
+      const mas::Solution sol = mas::solve(strategy, problem);
+      std::size_t ox = 0, ou = 0;
+      for (int a = 0; a < n_agents; ++a) {
+        const std::size_t px = static_cast<std::size_t>(n[a]) * (T[a] + 1), pu = static_cast<std::size_t>(m[a]) * T[a];
+        std::memcpy(X_out + s * sX + ox, sol.states[a].data(), sizeof(double) * px);
+        std::memcpy(U_out + s * sU + ou, sol.controls[a].data(), sizeof(double) * pu);
+        ox += px;
+        ou += pu;
+        costs_out[static_cast<std::size_t>(s) * n_agents + a] = sol.costs[a];
+        if (iters_total) iters_total[static_cast<std::size_t>(s) * n_agents + a] = static_cast<int>(probes[a]->iteration_at.size());
+      }
+      total_cost_out[s] = sol.total_cost;
+    } catch (...) {
+#pragma omp atomic write
+      err = 1;
+    }
+  }
+  return err;
+}
+
+// compute_offsets + build_global_ocp of a mixed problem (agents added in reverse id order), evaluated at (X, U); portable trig.
+int ref_global_ocp_eval_mixed(int n_agents, const int* models, const double* x0, const double* X, const double* U, double* dyn_out, double* stage_out,
+                              double* terminal_out, int* dims_out, double* dt_out, double* bounds_out) {
+  try {
+    ref_set_trig_mode(1);
+    mas::MultiAgentProblem problem;
+    std::vector<std::shared_ptr<mas::OCP>> ocps(n_agents);
+    std::size_t o = 0;
+    for (int a = 0; a < n_agents; ++a) {
+      int n, m, T;
+      double dt;
+      model_dims(models[a], 0, &n, &m, &T, &dt);
+      ocps[a] = std::make_shared<mas::OCP>(build_ocp(models[a], x0 + o, nullptr, 0, 0, nullptr));
+      o += n;
+    }
+    for (int a = n_agents - 1; a >= 0; --a) problem.add_agent(std::make_shared<mas::Agent>(static_cast<std::size_t>(a), ocps[a]));
+    problem.compute_offsets();
+    mas::OCP g = problem.build_global_ocp();
+    dims_out[0] = g.state_dim;
+    dims_out[1] = g.control_dim;
+    dims_out[2] = g.horizon_steps;
+    dims_out[3] = (g.input_lower_bounds && g.input_upper_bounds) ? 1 : 0;
+    *dt_out = g.dt;
+    if (dims_out[3] && bounds_out) {
+      std::memcpy(bounds_out, g.input_lower_bounds->data(), sizeof(double) * g.control_dim);
+      std::memcpy(bounds_out + g.control_dim, g.input_upper_bounds->data(), sizeof(double) * g.control_dim);
+    }
+    mas::State Xv(g.state_dim);
+    mas::Control Uv(g.control_dim);
+    for (int i = 0; i < g.state_dim; ++i) Xv(i) = X[i];
+    for (int i = 0; i < g.control_dim; ++i) Uv(i) = U[i];
+    const mas::StateDerivative d = g.dynamics(Xv, Uv);
+    std::memcpy(dyn_out, d.data(), sizeof(double) * d.size());
+    *stage_out = g.stage_cost(Xv, Uv, 3);
+    *terminal_out = g.terminal_cost(Xv);
+  } catch (...) {
+    return 1;
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -15,6 +15,10 @@
 
 namespace {
 int g_mode = 0;
+// per-thread override (-1 = none): the example builders compute their initial guesses (pendulum_swing_up.cpp:110-113) with
+// libm when the program starts; the wrapper builds OCPs inside parallel loops, so it pins the builder call to libm per thread
+thread_local int t_override = -1;
+inline int mode() { return t_override >= 0 ? t_override : g_mode; }
 typedef double (*fn1)(double);
 typedef void (*fn_sc)(double, double*, double*);
 fn1 next_sin() {
@@ -37,13 +41,14 @@ fn_sc next_sincos() {
 
 extern "C" {
 void ref_set_trig_mode(int mode) { g_mode = mode; }
+void ref_set_thread_trig_override(int mode) { t_override = mode; }
 int ref_get_trig_mode() { return g_mode; }
 
-double sin(double x) { return g_mode ? mas_b200::pm::sin_(x) : next_sin()(x); }
-double cos(double x) { return g_mode ? mas_b200::pm::cos_(x) : next_cos()(x); }
-double tan(double x) { return g_mode ? mas_b200::pm::tan_(x) : next_tan()(x); }
+double sin(double x) { return mode() ? mas_b200::pm::sin_(x) : next_sin()(x); }
+double cos(double x) { return mode() ? mas_b200::pm::cos_(x) : next_cos()(x); }
+double tan(double x) { return mode() ? mas_b200::pm::tan_(x) : next_tan()(x); }
 void sincos(double x, double* s, double* c) {
-  if (g_mode)
+  if (mode())
     mas_b200::pm::sincos_(x, s, c);
   else
     next_sincos()(x, s, c);

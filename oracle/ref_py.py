@@ -155,3 +155,55 @@ def strategy_run_batch(kind, model, x0, params=None, horizon=0, max_outer=10, ma
     if rc:
         raise RuntimeError("ref_strategy_run_batch failed")
     return dict(X=X, U=U, costs=costs, total_cost=total, iterations_total=iters)
+
+
+def _mixed_shapes(models):
+    dims = [model_dims(m) for m in models]
+    return dims, sum(d[0] for d in dims), sum(d[0] * (d[2] + 1) for d in dims), sum(d[1] * d[2] for d in dims)
+
+
+def strategy_run_mixed(kind, models, x0_list, max_outer=10, max_iterations=100, tolerance=1e-5, trig=TRIG_GLIBC):
+    """Nash strategy over agents of different models.  x0_list[a]: [scenarios, n_a].  Per-agent lists of X, U back."""
+    models = [int(m) for m in models]
+    A = len(models)
+    dims, sx0, sX, sU = _mixed_shapes(models)
+    S = np.asarray(x0_list[0]).shape[0]
+    x0 = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float64).reshape(S, -1) for x in x0_list], axis=1))
+    X = np.zeros((S, sX))
+    U = np.zeros((S, sU))
+    costs = np.zeros((S, A))
+    total = np.zeros(S)
+    iters = np.zeros((S, A), dtype=np.int32)
+    marr = np.array(models, dtype=np.int32)
+    rc = lib().ref_strategy_run_mixed(int(kind), S, A, _p(marr, ctypes.c_int), _p(x0), int(max_outer), int(max_iterations), ctypes.c_double(tolerance),
+                                         int(trig), _p(X), _p(U), _p(costs), _p(total), _p(iters, ctypes.c_int))
+    if rc:
+        raise RuntimeError("strategy_run_mixed failed")
+    Xs, Us, ox, ou = [], [], 0, 0
+    for n, m, T, _ in dims:
+        Xs.append(X[:, ox:ox + n * (T + 1)].reshape(S, T + 1, n).copy())
+        Us.append(U[:, ou:ou + m * T].reshape(S, T, m).copy())
+        ox += n * (T + 1)
+        ou += m * T
+    return dict(X=Xs, U=Us, costs=costs, total_cost=total, iterations_total=iters)
+
+
+def global_ocp_eval_mixed(models, x0_list, X, U):
+    """build_global_ocp of mixed agents (ids = list order, added in reverse), evaluated at (X, U), stage cost at time index 3."""
+    models = [int(m) for m in models]
+    A = len(models)
+    dims, sx0, _, _ = _mixed_shapes(models)
+    x0 = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float64).reshape(-1) for x in x0_list]))
+    X = _f64(X)
+    U = _f64(U)
+    dyn = np.zeros(X.size)
+    stage, term, dt = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    d4 = np.zeros(4, dtype=np.int32)
+    bounds = np.full((2, U.size), np.nan)
+    marr = np.array(models, dtype=np.int32)
+    rc = lib().ref_global_ocp_eval_mixed(A, _p(marr, ctypes.c_int), _p(x0), _p(X), _p(U), _p(dyn), ctypes.byref(stage), ctypes.byref(term),
+                                            _p(d4, ctypes.c_int), ctypes.byref(dt), _p(bounds))
+    if rc:
+        raise RuntimeError("global_ocp_eval_mixed failed")
+    return dict(total_x=int(d4[0]), total_u=int(d4[1]), horizon=int(d4[2]), has_bounds=bool(d4[3]), dt=dt.value, bounds=bounds, dynamics=dyn,
+                stage=stage.value, terminal=term.value)

@@ -85,3 +85,18 @@ def test_oracle_is_not_reachable_from_the_product():
     lib = os.path.join(pkg, "libmas_b200.so")
     needed = os.popen(f"objdump -p {lib} | grep NEEDED").read()
     assert "oracle" not in needed
+
+
+def test_mixed_agent_structure_without_a_device(mas):
+    """mas_b200_global_ocp_eval_mixed, structure only (X = U = NULL needs no device): the reference's
+    MultiAgentProblemTest.BuildGlobalProblemMergesAgents checks (tests/ocp_tests.cpp:76-126) on registered models of
+    different shapes -- id-sorted blocks, offsets, summed dims, horizon / dt of the first block, bounds only if all have them."""
+    pend, rocket, lqr = mas.example_desc(3), mas.example_desc(4), mas.example_desc(2)
+    got = mas.global_ocp_eval_mixed(None, [rocket, pend], agent_ids=[2, 1])
+    assert list(got["block_agent"]) == [1, 0]  # the agent with id 1 (pendulum, 2 x 1) comes first
+    assert (got["total_x"], got["total_u"]) == (2 + 3, 1 + 1)
+    assert list(got["state_offsets"]) == [0, 2] and list(got["control_offsets"]) == [0, 1]
+    assert got["horizon"] == pend.horizon_steps and got["dt"] == pend.dt
+    assert got["has_bounds"] and list(got["bounds"][0]) == [-5.0, 0.0] and list(got["bounds"][1]) == [5.0, 20.0]
+    got = mas.global_ocp_eval_mixed(None, [rocket, pend, lqr], agent_ids=[2, 1, 0])
+    assert not got["has_bounds"] and got["total_x"] == 9 and got["horizon"] == lqr.horizon_steps  # LQR has no bounds and is block 0

@@ -121,3 +121,57 @@ def test_centralized_time_budget(mas, ctx):
     # max_outer = 0 with trace pointers: nothing is written (the trace has no elements)
     z = mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, mas.example_desc(1), mas.IlqrParams.make(100, 1e-5), 0, x0)
     assert np.array_equal(z["U"], ref["U"]) and z["trace_iters"].size == 0
+
+
+MIXED_MODELS = [0, 2, 3, 1, 4]  # ST-lane (4x2, T 80), LQR (4x4, T 10), pendulum (2x1, T 60), ST-circ (4x2, T 10), rocket (3x1, T 50)
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3])
+def test_mixed_agents_nash(mas, ctx, oracle, kind):
+    """mas_b200_strategy_run_mixed: agents of different registered models, shapes and horizons in one scenario; every Nash
+    strategy, bit-exact against the oracle (pinned to the reference's own code for the same mix in tests/test_ref_pin.py)."""
+    from conftest import random_x0
+
+    S = 5
+    x0 = [random_x0(m, S, seed=10 + m) for m in MIXED_MODELS]
+    descs = [mas.example_desc(m) for m in MIXED_MODELS]
+    U0 = [np.broadcast_to(mas.example_controls(m, d.horizon_steps), (S, d.horizon_steps, d.control_dim)).copy() for m, d in zip(MIXED_MODELS, descs)]
+    strategy = {1: mas.Strategy.SEQUENTIAL, 2: mas.Strategy.LINESEARCH, 3: mas.Strategy.TRUSTREGION}[kind]
+    got = mas.strategy_run_mixed(ctx, strategy, descs, mas.IlqrParams.make(8, 1e-5), 3, x0, U_init=U0)
+    ref = oracle.strategy_run_mixed(kind, MIXED_MODELS, x0, max_outer=3, max_iterations=8, trig=oracle.TRIG_PORTABLE)
+    for a in range(len(MIXED_MODELS)):
+        assert np.array_equal(got["X"][a], ref["X"][a]), a
+        assert np.array_equal(got["U"][a], ref["U"][a]), a
+    assert np.array_equal(got["costs"], ref["costs"]) and np.array_equal(got["total_cost"], ref["total_cost"])
+    assert np.array_equal(got["trace_iters"].sum(1), ref["iterations_total"])
+    # all agents of one description: the same entry point takes the single-batch path
+    d1 = [mas.example_desc(1)] * 3
+    x1, _ = circ_x0(4, 3)
+    same = mas.strategy_run_mixed(ctx, strategy, d1, mas.IlqrParams.make(100, 1e-5), 4, [x1[:, a] for a in range(3)])
+    flat = mas.strategy_run(ctx, strategy, mas.example_desc(1), mas.IlqrParams.make(100, 1e-5), 4, x1)
+    assert np.array_equal(same["costs"], flat["costs"]) and all(np.array_equal(same["U"][a], flat["U"][:, a]) for a in range(3))
+    with pytest.raises(mas.MasB200Error):
+        mas.strategy_run_mixed(ctx, mas.Strategy.CENTRALIZED, descs, mas.IlqrParams.make(8, 1e-5), 1, x0)
+
+
+def test_mixed_agents_stacked_functions(mas, ctx, oracle):
+    """mas_b200_global_ocp_eval_mixed on the device: compute_offsets + build_global_ocp of mixed agents, what the reference's
+    tests/ocp_tests.cpp:76-154 checks (ids out of order, offsets, bounds only if all agents have them, stacked values)."""
+    from conftest import random_x0
+
+    for models in (MIXED_MODELS, [3, 4, 0]):
+        descs = [mas.example_desc(m) for m in models]
+        nx, nu = sum(d.state_dim for d in descs), sum(d.control_dim for d in descs)
+        X, U = np.linspace(0.1, 1.5, nx), np.linspace(-0.3, 0.3, nu)
+        x0 = [random_x0(m, 1, seed=20 + m)[0] for m in models]
+        ref = oracle.global_ocp_eval_mixed(models, x0, X, U)
+        # agents handed over in reverse order with their ids: the blocks come out id-sorted
+        A = len(models)
+        got = mas.global_ocp_eval_mixed(ctx, descs[::-1], agent_ids=list(range(A))[::-1], X=X, U=U, time_index=3)
+        assert list(got["block_agent"]) == list(range(A))[::-1]
+        for k in ("total_x", "total_u", "horizon", "has_bounds", "dt", "stage", "terminal"):
+            assert got[k] == ref[k], k
+        assert np.array_equal(got["dynamics"], ref["dynamics"])
+        if ref["has_bounds"]:
+            assert np.array_equal(got["bounds"], ref["bounds"])
+        assert list(got["state_offsets"]) == list(np.cumsum([0] + [d.state_dim for d in descs[:-1]]))

