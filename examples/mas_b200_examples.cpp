@@ -146,6 +146,18 @@ int run_multi(const std::string& prog, const Options& o) {
         auto ocp = std::make_shared<mb::OCP>(mb::examples::create_single_track_circular_ocp(theta, 20.0, 5.0, 10));
         problem.add_agent(std::make_shared<mb::Agent>(i, ocp));
       }
+    } else if (prog == "multi_agent_mixed") {
+      // not a reference program: agents of different models, shapes and horizons in one MultiAgentProblem (which the
+      // reference's container accepts, multi_agent_problem.hpp:37-50) -- a lane-following car, an LQR agent and a
+      // circular-track car, repeated until --agents is reached
+      params = {{"max_iterations", 8}, {"tolerance", 1e-5}, {"max_ms", 1e9}};
+      for (int i = 0; i < o.agents; ++i) {
+        std::shared_ptr<mb::OCP> ocp;
+        if (i % 3 == 0) ocp = std::make_shared<mb::OCP>(mb::examples::create_single_track_lane_following_ocp());
+        else if (i % 3 == 1) ocp = std::make_shared<mb::OCP>(mb::examples::create_linear_lqr_ocp(4, 4, 0.1, 10));
+        else ocp = std::make_shared<mb::OCP>(mb::examples::create_single_track_circular_ocp(0.3 * i, 20.0, 5.0, 10));
+        problem.add_agent(std::make_shared<mb::Agent>(i, ocp));
+      }
     } else {  // multi_agent_lqr.cpp:108-122
       params = {{"max_iterations", 100}, {"tolerance", 1e-5}, {"max_ms", 100}};
       for (int i = 0; i < o.agents; ++i) {
@@ -184,7 +196,7 @@ int main(int argc, char** argv) {
   std::string prog = argv[0];
   prog = prog.substr(prog.find_last_of('/') + 1);
   int first = 1;
-  const char* names[] = {"single_track_ocp", "pendulum_swing_up", "rocket_max_altitude", "multi_agent_single_track", "multi_agent_lqr"};
+  const char* names[] = {"single_track_ocp", "pendulum_swing_up", "rocket_max_altitude", "multi_agent_single_track", "multi_agent_lqr", "multi_agent_mixed"};
   bool known = false;
   for (const char* n : names) known = known || prog == n;
   if (!known && argc > 1) {
@@ -193,7 +205,7 @@ int main(int argc, char** argv) {
     for (const char* n : names) known = known || prog == n;
   }
   if (!known) {
-    std::cerr << "usage: mas_b200_examples <single_track_ocp|pendulum_swing_up|rocket_max_altitude|multi_agent_single_track|multi_agent_lqr> [options]\n";
+    std::cerr << "usage: mas_b200_examples <single_track_ocp|pendulum_swing_up|rocket_max_altitude|multi_agent_single_track|multi_agent_lqr|multi_agent_mixed> [options]\n";
     return 2;
   }
   const bool multi = prog.rfind("multi_agent", 0) == 0;

@@ -338,13 +338,59 @@ inline Solution run_strategy(int kind, int max_outer, const mas_b200_ilqr_params
   mas_b200_ocp_desc d = first.desc();
   const int n = first.state_dim, m = first.control_dim, T = first.horizon_steps, A = static_cast<int>(problem.blocks.size());
   const int np = d.num_params;
+  bool mixed = false;
+  for (int a = 0; a < A; ++a) {
+    const OCP& o = *problem.blocks[a].agent->ocp;
+    mixed = mixed || o.state_dim != n || o.control_dim != m || o.horizon_steps != T || o.dt != first.dt || o.model_id != first.model_id ||
+            o.deriv_mask != first.deriv_mask || static_cast<int>(o.model_params.size()) != np;
+  }
+  if (mixed) {
+    // agents of different models / shapes (MultiAgentProblem accepts any mix): one description per agent, per-agent arrays
+    // (mas_b200_strategy_run_mixed); the centralized strategy over such a mix is MAS_B200_ERR_UNSUPPORTED -> std::runtime_error
+    std::vector<mas_b200_ocp_desc> descs(A);
+    std::vector<std::vector<double>> vx0(A), vp(A), vU0(A), vX(A), vU(A);
+    std::vector<const double*> px0(A), pp(A), pU0(A);
+    std::vector<double*> pX(A), pU(A), pc(A);
+    std::vector<double> c(A);
+    for (int a = 0; a < A; ++a) {
+      const OCP& o = *problem.blocks[a].agent->ocp;
+      descs[a] = o.desc();
+      vx0[a].assign(o.initial_state.begin(), o.initial_state.end());
+      vp[a].assign(o.model_params.begin(), o.model_params.end());
+      if (o.best_controls.rows() != o.control_dim || o.best_controls.cols() != o.horizon_steps)
+        throw std::invalid_argument("best_controls has the wrong shape; call initialize_problem()");
+      vU0[a].assign(o.best_controls.data(), o.best_controls.data() + static_cast<std::size_t>(o.control_dim) * o.horizon_steps);
+      vX[a].resize(static_cast<std::size_t>(o.state_dim) * (o.horizon_steps + 1));
+      vU[a].resize(static_cast<std::size_t>(o.control_dim) * o.horizon_steps);
+      px0[a] = vx0[a].data();
+      pp[a] = vp[a].empty() ? nullptr : vp[a].data();
+      pU0[a] = vU0[a].data();
+      pX[a] = vX[a].data();
+      pU[a] = vU[a].data();
+      pc[a] = &c[a];
+    }
+    double total = 0.0;
+    check(mas_b200_strategy_run_mixed(Device::context(), kind, descs.data(), &prm, max_outer, 1, A, px0.data(), pp.data(), pU0.data(), pX.data(),
+                                      pU.data(), pc.data(), &total, nullptr));
+    for (int a = 0; a < A; ++a) {
+      OCP& o = *problem.blocks[a].agent->ocp;
+      o.best_states = StateTrajectory(o.state_dim, o.horizon_steps + 1);
+      o.best_controls = ControlTrajectory(o.control_dim, o.horizon_steps);
+      std::copy(vX[a].begin(), vX[a].end(), o.best_states.data());
+      std::copy(vU[a].begin(), vU[a].end(), o.best_controls.data());
+      o.best_cost = c[a];
+      o.update_initial_with_best();
+      sol.states.push_back(o.best_states);
+      sol.controls.push_back(o.best_controls);
+      sol.costs.push_back(o.best_cost);
+    }
+    sol.total_cost = total;
+    return sol;
+  }
   std::vector<double> x0(static_cast<std::size_t>(A) * n), prms(static_cast<std::size_t>(A) * np), X(static_cast<std::size_t>(A) * n * (T + 1)),
       U(static_cast<std::size_t>(A) * m * T), U0(static_cast<std::size_t>(A) * m * T), costs(A);
   for (int a = 0; a < A; ++a) {
     const OCP& o = *problem.blocks[a].agent->ocp;
-    if (o.state_dim != n || o.control_dim != m || o.horizon_steps != T || o.dt != first.dt || o.model_id != first.model_id ||
-        o.deriv_mask != first.deriv_mask || static_cast<int>(o.model_params.size()) != np)
-      throw std::runtime_error("device strategies need agents of one shape and model (heterogeneous agents are not on the device path)");
     std::copy(o.initial_state.begin(), o.initial_state.end(), x0.begin() + static_cast<std::size_t>(a) * n);
     std::copy(o.model_params.begin(), o.model_params.end(), prms.begin() + static_cast<std::size_t>(a) * np);
     if (o.best_controls.rows() != m || o.best_controls.cols() != T) throw std::invalid_argument("best_controls has the wrong shape; call initialize_problem()");

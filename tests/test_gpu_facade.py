@@ -89,6 +89,25 @@ def test_multi_agent_programs(binaries, oracle):
     assert abs(float(f["cost"]) - ref["total_cost"][0]) < 1e-6
 
 
+def test_mixed_agents_through_the_facade(binaries, oracle):
+    """Agents of different models in one MultiAgentProblem, C++ facade -> mas_b200_strategy_run_mixed."""
+    import math
+
+    th = 0.3 * 2  # libm cos / sin like the C++ builder (the all-FD circular-track agent amplifies a last-bit difference)
+    x0 = [np.array([[0.0, 1.0, 0.0, 0.0]]), np.array([[1.0, 0.0, 0.0, 0.0]]),
+          np.array([[20.0 * math.cos(th), 20.0 * math.sin(th), 1.57 + th, 4.0]])]
+    for name, kind in (("sequential", 1), ("linesearch", 2), ("trustregion", 3)):
+        out = run(binaries, "multi_agent_mixed", "--agents", "3", "--strategy", name, "--max-outer", "3")
+        assert out.returncode == 0, out.stderr
+        f, _ = parse_line(out.stdout)
+        ref = oracle.strategy_run_mixed(kind, [0, 2, 1], x0, max_outer=3, max_iterations=8, trig=oracle.TRIG_PORTABLE)
+        assert abs(float(f["cost"]) - ref["total_cost"][0]) < 1e-6 * abs(ref["total_cost"][0])
+        _, U = parse_block(out.stdout, "agent_1_controls")
+        assert U.shape == (10, 5)
+    out = run(binaries, "multi_agent_mixed", "--agents", "3", "--strategy", "centralized")
+    assert out.returncode == 1 and "centralized strategy over agents of different models" in out.stderr
+
+
 def test_error_conventions(binaries):
     out = run(binaries, "single_track_ocp", "--solver", "cgd")
     assert out.returncode == 1 and "Unknown solver 'cgd'" in out.stderr and "Use --help" in out.stderr
