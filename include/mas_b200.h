@@ -55,6 +55,11 @@ extern "C" {
 #define MAS_B200_DERIV_LUX (1u << 6) /* OCP::cost_cross_term           (ocp.hpp:77)  */
 #define MAS_B200_DERIV_VX (1u << 7)  /* OCP::terminal_cost_gradient    (ocp.hpp:78)  */
 #define MAS_B200_DERIV_VXX (1u << 8) /* OCP::terminal_cost_hessian     (ocp.hpp:79)  */
+/* models with path constraints: analytic constraint Jacobians (clear = the central-difference defaults of ocp.hpp:137-171) */
+#define MAS_B200_DERIV_EQ_JX (1u << 9)    /* OCP::equality_constraints_state_jacobian     (ocp.hpp:65) */
+#define MAS_B200_DERIV_EQ_JU (1u << 10)   /* OCP::equality_constraints_control_jacobian   (ocp.hpp:66) */
+#define MAS_B200_DERIV_INEQ_JX (1u << 11) /* OCP::inequality_constraints_state_jacobian   (ocp.hpp:67) */
+#define MAS_B200_DERIV_INEQ_JU (1u << 12) /* OCP::inequality_constraints_control_jacobian (ocp.hpp:68) */
 
 /* per-problem result flag; the reference's solve() returns void, the definition is SURVEY 8a */
 #define MAS_B200_STATUS_CONVERGED 0  /* break at solvers/ilqr.hpp:269-271 */

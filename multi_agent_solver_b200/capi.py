@@ -28,7 +28,7 @@ class Strategy:
 
 
 class DerivBits:
-    A, B, LX, LU, LXX, LUU, LUX, VX, VXX = (1 << i for i in range(9))
+    A, B, LX, LU, LXX, LUU, LUX, VX, VXX, EQ_JX, EQ_JU, INEQ_JX, INEQ_JU = (1 << i for i in range(13))
 
 
 class MasB200Error(RuntimeError):

@@ -618,7 +618,9 @@ MAS_HD void al_backward_terms(const BatchView<M::NX, M::NU>& v, int p, int t, co
     constexpr int NC = M::NEQ > 0 ? M::NEQ : 1;
     double c[NC], Jx[NC * NX], Ju[NC * NU], dual[NC];
     M::eq(x, u, prm, c);
-    fd_constraint_jacobians<M, true>(x, u, prm, Jx, Ju);
+    fd_constraint_jacobians<M, true>(x, u, prm, Jx, Ju);  // the defaults of ocp.hpp:137-171 ...
+    if (v.deriv_mask & D_EQ_JX) M::eq_jac_x(x, u, prm, Jx);  // ... unless the problem installed its own (ocp.hpp:65-68)
+    if (v.deriv_mask & D_EQ_JU) M::eq_jac_u(x, u, prm, Ju);
 #pragma unroll
     for (int r = 0; r < NC; ++r) dual[r] = v.lam_eq[soa_index<NC>(t, r, v.ld, p)] + rho * c[r];
     al_add_linear<NC, NX>(Jx, dual, q_x);
@@ -632,6 +634,8 @@ MAS_HD void al_backward_terms(const BatchView<M::NX, M::NU>& v, int p, int t, co
     double g[NC], Jx[NC * NX], Ju[NC * NU], dual[NC], active[NC];
     M::ineq(x, u, prm, g);
     fd_constraint_jacobians<M, false>(x, u, prm, Jx, Ju);
+    if (v.deriv_mask & D_INEQ_JX) M::ineq_jac_x(x, u, prm, Jx);
+    if (v.deriv_mask & D_INEQ_JU) M::ineq_jac_u(x, u, prm, Ju);
     bool any_active = false;
 #pragma unroll
     for (int r = 0; r < NC; ++r) {

@@ -33,7 +33,13 @@ enum DerivBits : unsigned {
   D_LUX = 1u << 6,   // cost_cross_term
   D_VX = 1u << 7,    // terminal_cost_gradient
   D_VXX = 1u << 8,   // terminal_cost_hessian
-  D_ALL = 0x1FFu
+  D_ALL = 0x1FFu,
+  // analytic constraint Jacobians (OCP::equality_/inequality_constraints_{state,control}_jacobian, ocp.hpp:65-68); clear = the
+  // central-difference default initialize_problem() installs (ocp.hpp:137-171).  Only meaningful for models with constraints.
+  D_EQ_JX = 1u << 9,
+  D_EQ_JU = 1u << 10,
+  D_INEQ_JX = 1u << 11,
+  D_INEQ_JU = 1u << 12
 };
 
 // Column-major helpers: A is NX x NX (A[r + c*NX]), B is NX x NU, l_ux is NU x NX.
@@ -50,6 +56,11 @@ struct NoConstraints {
   static constexpr int NEQ = 0, NINEQ = 0;
   MAS_HD static void eq(const double*, const double*, const double*, double*) {}
   MAS_HD static void ineq(const double*, const double*, const double*, double*) {}
+  // analytic constraint Jacobians, row-major by constraint: Jx[r + c*NC] like the other column-major blocks
+  MAS_HD static void eq_jac_x(const double*, const double*, const double*, double*) {}
+  MAS_HD static void eq_jac_u(const double*, const double*, const double*, double*) {}
+  MAS_HD static void ineq_jac_x(const double*, const double*, const double*, double*) {}
+  MAS_HD static void ineq_jac_u(const double*, const double*, const double*, double*) {}
 };
 
 // ---- single-track kinematic bicycle, shared by StLane and StCirc ---------------------------------
@@ -154,8 +165,30 @@ struct StLaneCon : StLane {
   static constexpr int ID = 5;
   static constexpr int NP = 7;
   static constexpr int NEQ = 1, NINEQ = 1;
+  static constexpr unsigned AVAILABLE = StLane::AVAILABLE | D_EQ_JX | D_EQ_JU | D_INEQ_JX | D_INEQ_JU;
   MAS_HD static void eq(const double* x, const double* u, const double* p, double* c) { c[0] = u[1] - p[6] * (p[0] - x[3]); }
   MAS_HD static void ineq(const double* x, const double*, const double* p, double* g) { g[0] = x[3] - p[5]; }
+  // d eq / d x = (0, 0, 0, k), d eq / d u = (0, 1); d ineq / d x = (0, 0, 0, 1), d ineq / d u = (0, 0)   (1 x n blocks, entry (0, c) at c)
+  MAS_HD static void eq_jac_x(const double*, const double*, const double* p, double* J) {
+    J[0] = 0.0;
+    J[1] = 0.0;
+    J[2] = 0.0;
+    J[3] = p[6];
+  }
+  MAS_HD static void eq_jac_u(const double*, const double*, const double*, double* J) {
+    J[0] = 0.0;
+    J[1] = 1.0;
+  }
+  MAS_HD static void ineq_jac_x(const double*, const double*, const double*, double* J) {
+    J[0] = 0.0;
+    J[1] = 0.0;
+    J[2] = 0.0;
+    J[3] = 1.0;
+  }
+  MAS_HD static void ineq_jac_u(const double*, const double*, const double*, double* J) {
+    J[0] = 0.0;
+    J[1] = 0.0;
+  }
 };
 
 struct StCirc : NoConstraints {

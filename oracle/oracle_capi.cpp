@@ -57,7 +57,8 @@ OCP build_ocp(int model, const double* x0, const double* params, int np, int hor
         v_max = params[5];
         k_gain = params[6];
       }
-      return create_single_track_lane_constrained_ocp(&s, lp, v_max, k_gain);
+      const int jac_mask = (params && np >= 8) ? static_cast<int>(params[7]) : 0;  // analytic constraint Jacobians (test switch)
+      return create_single_track_lane_constrained_ocp(&s, lp, v_max, k_gain, jac_mask);
     }
   }
   throw std::invalid_argument("oracle: unknown model id");

@@ -79,6 +79,19 @@ mas::OCP build_ocp(int model, const double* x0, const double* params, int np, in
         c(0) = x(3) - v_max;
         return c;
       };
+      // params[7] (test switch): which constraint Jacobians are given analytically (ocp.hpp:65-68): 1 eq/state, 2 eq/control,
+      // 4 ineq/state, 8 ineq/control; the others get the finite-difference defaults from initialize_problem (ocp.hpp:137-171)
+      const int jac_mask = (params && np >= 8) ? static_cast<int>(params[7]) : 0;
+      auto row = [](std::initializer_list<double> v) {
+        mas::ConstraintsJacobian J = mas::ConstraintsJacobian::Zero(1, static_cast<int>(v.size()));
+        int c = 0;
+        for (double e : v) J(0, c++) = e;
+        return J;
+      };
+      if (jac_mask & 1) p.equality_constraints_state_jacobian = [=](const mas::State&, const mas::Control&) { return row({0.0, 0.0, 0.0, k_gain}); };
+      if (jac_mask & 2) p.equality_constraints_control_jacobian = [=](const mas::State&, const mas::Control&) { return row({0.0, 1.0}); };
+      if (jac_mask & 4) p.inequality_constraints_state_jacobian = [=](const mas::State&, const mas::Control&) { return row({0.0, 0.0, 0.0, 1.0}); };
+      if (jac_mask & 8) p.inequality_constraints_control_jacobian = [=](const mas::State&, const mas::Control&) { return row({0.0, 0.0}); };
       break;
     }
     default: throw std::invalid_argument("ref: unknown model id");

@@ -118,11 +118,23 @@ inline OCP create_single_track_lane_following_ocp(const Vec* x0 = nullptr, const
 // plus  c(x,u) = a - k_gain (v_des - v) = 0  and  g(x,u) = v - v_max <= 0, used to exercise the augmented-Lagrangian
 // part of iLQR::solve (ilqr.hpp:121-170,236-260,380-407).  Constraint Jacobians are the FD defaults that
 // initialize_problem installs (ocp.hpp:137-171).
-inline OCP create_single_track_lane_constrained_ocp(const Vec* x0, const LaneParams& lp, double v_max, double k_gain) {
+// jac_mask: which constraint Jacobians the problem installs itself (ocp.hpp:65-68) instead of the finite-difference defaults
+// (ocp.hpp:137-171): 1 eq/state, 2 eq/control, 4 ineq/state, 8 ineq/control.
+inline OCP create_single_track_lane_constrained_ocp(const Vec* x0, const LaneParams& lp, double v_max, double k_gain, int jac_mask = 0) {
   OCP p = create_single_track_lane_following_ocp(x0, lp);
   const double v_des = lp.desired_velocity;
   p.equality_constraints = [=](const State& s, const Control& c) { return Vec{c[1] - k_gain * (v_des - s[3])}; };
   p.inequality_constraints = [=](const State& s, const Control&) { return Vec{s[3] - v_max}; };
+  auto row = [](std::initializer_list<double> v) {
+    Mat J(1, static_cast<int>(v.size()));
+    int c = 0;
+    for (double e : v) J(0, c++) = e;
+    return J;
+  };
+  if (jac_mask & 1) p.equality_constraints_state_jacobian = [=](const State&, const Control&) { return row({0.0, 0.0, 0.0, k_gain}); };
+  if (jac_mask & 2) p.equality_constraints_control_jacobian = [=](const State&, const Control&) { return row({0.0, 1.0}); };
+  if (jac_mask & 4) p.inequality_constraints_state_jacobian = [=](const State&, const Control&) { return row({0.0, 0.0, 0.0, 1.0}); };
+  if (jac_mask & 8) p.inequality_constraints_control_jacobian = [=](const State&, const Control&) { return row({0.0, 0.0}); };
   p.initialize_problem();
   return p;
 }

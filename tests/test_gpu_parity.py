@@ -472,3 +472,29 @@ def test_debug_trace_matches_oracle(mas, ctx, oracle):
     with pytest.raises(mas.MasB200Error):
         b.debug_trace(0)
     b.close()
+
+
+@pytest.mark.parametrize("jm", [15, 9])
+def test_analytic_constraint_jacobians(mas, ctx, oracle, jm):
+    """deriv_mask bits 9-12 (analytic constraint Jacobians, ocp.hpp:65-68) through the C ABI."""
+    B = 100
+    x0 = random_x0(5, B, seed=303)
+    desc = mas.example_desc(5)
+    desc.deriv_mask = desc.deriv_mask | (jm << 9)
+    U0 = np.zeros((B, 80, 2))
+    prm = np.tile(np.array([1.0, 10.0, 1.0, 0.1, 0.1, 0.8, 0.5, float(jm)]), (B, 1))
+    ref = oracle.ilqr_solve_batch(5, x0, U_init=U0, params=prm, max_iterations=6, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    for mode in (1, 3):
+        b = mas.Batch(ctx, desc, B)
+        b.set_backward_mode(mode)
+        b.set_initial_states(x0)
+        b.set_controls(U0)
+        b.solve(mas.IlqrParams.make(6, 1e-5))
+        got = b.get_solution()
+        b.close()
+        assert_parity(got, ref)
+        assert is_bit_exact(got, ref)
+    bad = mas.example_desc(0)
+    bad.deriv_mask = bad.deriv_mask | (1 << 9)  # a model without constraints has no such callback
+    with pytest.raises(mas.MasB200Error):
+        mas.Batch(ctx, bad, 4)

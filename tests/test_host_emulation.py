@@ -230,3 +230,17 @@ def test_time_parallel_backward_pass_is_bit_identical(emu, oracle, model, mask, 
         ref = oracle.ilqr_solve_batch(model, x0, U_init=U0, max_iterations=max_it, tolerance=tol, trig=oracle.TRIG_PORTABLE)
         assert is_bit_exact(par, ref)
         assert is_bit_exact(lan, ref)
+
+
+@pytest.mark.parametrize("jm", [15, 5, 10])
+def test_analytic_constraint_jacobians(emu, oracle, jm):
+    """deriv_mask bits 9-12: the constraint Jacobians a problem installs itself (ocp.hpp:65-68) instead of the
+    finite-difference defaults (ocp.hpp:137-171), any subset; bit-exact against the oracle given the same callbacks."""
+    x0 = random_x0(5, 6, seed=41)
+    U0 = np.zeros((6, 80, 2))
+    prm = np.tile(np.array([1.0, 10.0, 1.0, 0.1, 0.1, 0.8, 0.5, float(jm)]), (6, 1))
+    ref = oracle.ilqr_solve_batch(5, x0, U_init=U0, params=prm, max_iterations=6, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    fd = oracle.ilqr_solve_batch(5, x0, U_init=U0, max_iterations=6, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    got = emu.solve(5, x0, U0, 6, 1e-5, mask=0x3F | (jm << 9))
+    assert is_bit_exact(got, ref) and np.array_equal(got["iterations"], ref["iterations"])
+    assert not np.array_equal(ref["U"], fd["U"])  # the analytic Jacobians do change the rounding

@@ -180,3 +180,13 @@ def test_mixed_agents_build_global_ocp(oracle, ref):
         assert np.array_equal(a["dynamics"], b["dynamics"])
         assert np.array_equal(a["bounds"], b["bounds"], equal_nan=True)
     assert not a["has_bounds"] or True
+
+
+@pytest.mark.parametrize("jm", [15, 6])
+def test_analytic_constraint_jacobians(oracle, ref, jm):
+    """OCP::*_constraints_*_jacobian given by the problem (ocp.hpp:65-68, used at ilqr.hpp:124-133,146-153)."""
+    prm = np.array([1.0, 10.0, 1.0, 0.1, 0.1, 0.8, 0.5, float(jm)])
+    x0 = np.array([0.0, 1.0, 0.0, 0.5])
+    a = oracle.ilqr_solve_repeat(5, x0, 3, params=prm, trig=1, max_iterations=10)
+    b = ref.ilqr_solve_repeat(5, x0, 3, params=prm, trig=1, max_iterations=10)
+    assert_same(a, b, ("X", "U", "cost", "iterations"))
