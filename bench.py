@@ -340,9 +340,17 @@ def run_other_configs(mas, torch, dist, rank, world, local_rank):
         t = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, d1, p100, 1, x5, trace=False), 2)
         rec["replicas"] = S5
         rec["scenarios_per_s"] = S5 / t
-        xj, gpj = circle_scenarios(296, 32, seed=5)
-        tj = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, d1, p100, 1, xj, model_params=gpj, trace=False), 1)
-        rec["jittered_radius_scenarios_per_s"] = 296 / tj
+        # track radius jittered per scenario: iteration counts spread from 4 to ~90, one scenario is one CTA, so a run is bounded
+        # below by its longest scenario; persistent CTAs pull scenarios from a queue, and with enough scenarios the rate
+        # approaches (SMs / mean scenario time)
+        for Sj in (296, 1184):
+            xj, gpj = circle_scenarios(Sj, 32, seed=5)
+            rj = mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, d1, p100, 1, xj, model_params=gpj)
+            tj = best_of(lambda: mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, d1, p100, 1, xj, model_params=gpj, trace=False), 1)
+            its = rj["trace_iters"][:, 0, 0]
+            rec[f"jittered_radius_{Sj}"] = {"scenarios_per_s": Sj / tj, "ms": tj * 1e3, "iterations_mean": float(its.mean()), "iterations_max": int(its.max()),
+                                            "longest_scenario_bound_ms": float(its.max()) * t1 * 1e3 / 4.0,
+                                            "work_bound_ms": float(its.sum()) * t1 * 1e3 / 4.0 / 148.0}
         return rec
 
     if rank == 0:

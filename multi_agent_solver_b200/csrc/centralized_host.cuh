@@ -9,34 +9,44 @@ namespace mas_b200 {
 
 constexpr int kCentralizedThreads = 256;
 
-// One CTA per scenario.  `base` holds the pointers of scenario 0; the strides select the others.
+// Persistent CTAs (one per SM slot the launch gets) pull scenarios from an atomic queue: `base` holds the pointers of
+// scenario 0 / CTA 0; inputs and results (x0, prm, X, U, out_*) are indexed by scenario, the scratch (trial trajectories,
+// gains, workspace) by CTA -- a run of thousands of scenarios needs the scratch of the resident CTAs only.  Scenarios differ
+// widely in iteration count (4 to 88 with jittered track radii), so a CTA that finishes early takes the next one.
 template <class M>
 __global__ void __launch_bounds__(kCentralizedThreads) centralized_kernel(StackedProblem<M> base, int n_scenarios, size_t work_stride,
-                                                                          size_t fast_offset, int fast_in_shared) {
+                                                                          size_t fast_offset, int fast_in_shared, int* queue) {
   extern __shared__ double mas_fast_scratch[];
-  const int s = blockIdx.x;
-  if (s >= n_scenarios) return;
+  __shared__ int s_next;
   constexpr int NPs = (M::NP > 0 ? M::NP : 1);
   const int ns = base.A * M::NX, ms = base.A * M::NU, T = base.T;
-  StackedProblem<M> P = base;
-  P.x0 = base.x0 + static_cast<size_t>(s) * ns;
-  P.prm = base.prm + static_cast<size_t>(s) * base.A * NPs;
-  P.X = base.X + static_cast<size_t>(s) * (T + 1) * ns;
-  P.Xt = base.Xt + static_cast<size_t>(s) * (T + 1) * ns;
-  P.U = base.U + static_cast<size_t>(s) * T * ms;
-  P.Ut = base.Ut + static_cast<size_t>(s) * T * ms;
-  P.K = base.K + static_cast<size_t>(s) * T * ms * ns;
-  P.kff = base.kff + static_cast<size_t>(s) * T * ms;
-  P.work = base.work + static_cast<size_t>(s) * work_stride;
-  P.fast = mas_fast_scratch;
-  P.out_cost = base.out_cost + static_cast<size_t>(s) * (1 + base.A);
-  P.out_int = base.out_int + static_cast<size_t>(s) * 4;
-  if (s != 0) P.phase_cycles = nullptr;  // diagnostics: scenario 0 only
-  if (fast_in_shared) {
-    stacked_solve<M, true>(P, threadIdx.x, blockDim.x);
-  } else {  // stacked problems too large for shared memory: the same scratch inside the global workspace
-    P.fast = P.work + fast_offset;
-    stacked_solve<M, false>(P, threadIdx.x, blockDim.x);
+  const int cta = blockIdx.x;
+  for (;;) {
+    __syncthreads();  // everybody is done with the previous scenario (and with s_next)
+    if (threadIdx.x == 0) s_next = atomicAdd(queue, 1);
+    __syncthreads();
+    const int s = s_next;
+    if (s >= n_scenarios) return;
+    StackedProblem<M> P = base;
+    P.x0 = base.x0 + static_cast<size_t>(s) * ns;
+    P.prm = base.prm + static_cast<size_t>(s) * base.A * NPs;
+    P.X = base.X + static_cast<size_t>(s) * (T + 1) * ns;
+    P.U = base.U + static_cast<size_t>(s) * T * ms;
+    P.out_cost = base.out_cost + static_cast<size_t>(s) * (1 + base.A);
+    P.out_int = base.out_int + static_cast<size_t>(s) * 4;
+    P.Xt = base.Xt + static_cast<size_t>(cta) * (T + 1) * ns;
+    P.Ut = base.Ut + static_cast<size_t>(cta) * T * ms;
+    P.K = base.K + static_cast<size_t>(cta) * T * ms * ns;
+    P.kff = base.kff + static_cast<size_t>(cta) * T * ms;
+    P.work = base.work + static_cast<size_t>(cta) * work_stride;
+    P.fast = mas_fast_scratch;
+    if (s != 0) P.phase_cycles = nullptr;  // diagnostics: scenario 0 only
+    if (fast_in_shared) {
+      stacked_solve<M, true>(P, threadIdx.x, blockDim.x);
+    } else {  // stacked problems too large for shared memory: the same scratch inside the global workspace
+      P.fast = P.work + fast_offset;
+      stacked_solve<M, false>(P, threadIdx.x, blockDim.x);
+    }
   }
 }
 
@@ -64,13 +74,23 @@ int run_centralized(Context* ctx, const mas_b200_ocp_desc& d, const mas_b200_ilq
   struct Buffers {
     double *x0 = nullptr, *prm = nullptr, *X = nullptr, *Xt = nullptr, *U = nullptr, *Ut = nullptr, *K = nullptr, *k = nullptr, *work = nullptr,
            *oc = nullptr;
-    int* oi = nullptr;
+    int *oi = nullptr, *queue = nullptr;
     ~Buffers() {
       for (double* p : {x0, prm, X, Xt, U, Ut, K, k, work, oc})
         if (p) cudaFree(p);
       if (oi) cudaFree(oi);
+      if (queue) cudaFree(queue);
     }
   };
+  // persistent CTAs: as many as the device holds at once (one per SM with the 200 KB shared-memory scratch), at most S
+  const size_t fast_bytes_q = W.fast_doubles * sizeof(double);
+  int max_optin_q = 0, per_sm = 1;
+  MAS_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin_q, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+  const bool shared_q = fast_bytes_q <= static_cast<size_t>(max_optin_q);
+  if (shared_q) MAS_CUDA_CHECK(cudaFuncSetAttribute(centralized_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fast_bytes_q)));
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, centralized_kernel<M>, kCentralizedThreads, shared_q ? fast_bytes_q : 0) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  const int G = std::min(S, ctx->sm_count * per_sm);
   const long long key[4] = {S, A, T, M::ID};
   const bool reuse = ctx->centralized_workspace && std::equal(key, key + 4, ctx->centralized_key);
   if (!reuse) {
@@ -85,12 +105,14 @@ int run_centralized(Context* ctx, const mas_b200_ocp_desc& d, const mas_b200_ilq
   MAS_CUDA_CHECK(dalloc(&b.x0, Ss * ns));
   MAS_CUDA_CHECK(dalloc(&b.prm, Ss * A * NPs));
   MAS_CUDA_CHECK(dalloc(&b.X, Ss * (T + 1) * ns));
-  MAS_CUDA_CHECK(dalloc(&b.Xt, Ss * (T + 1) * ns));
+  const size_t Gs = static_cast<size_t>(G);
+  MAS_CUDA_CHECK(dalloc(&b.Xt, Gs * (T + 1) * ns));
   MAS_CUDA_CHECK(dalloc(&b.U, Ss * T * ms));
-  MAS_CUDA_CHECK(dalloc(&b.Ut, Ss * T * ms));
-  MAS_CUDA_CHECK(dalloc(&b.K, Ss * T * ms * ns));
-  MAS_CUDA_CHECK(dalloc(&b.k, Ss * T * ms));
-  MAS_CUDA_CHECK(dalloc(&b.work, Ss * W.total));
+  MAS_CUDA_CHECK(dalloc(&b.Ut, Gs * T * ms));
+  MAS_CUDA_CHECK(dalloc(&b.K, Gs * T * ms * ns));
+  MAS_CUDA_CHECK(dalloc(&b.k, Gs * T * ms));
+  MAS_CUDA_CHECK(dalloc(&b.work, Gs * W.total));
+  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&b.queue), sizeof(int)));
   MAS_CUDA_CHECK(dalloc(&b.oc, Ss * (1 + A)));
   MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&b.oi), Ss * 4 * sizeof(int)));
   std::copy(key, key + 4, ctx->centralized_key);
@@ -139,7 +161,8 @@ int run_centralized(Context* ctx, const mas_b200_ocp_desc& d, const mas_b200_ilq
   const int in_shared = fast_bytes <= static_cast<size_t>(max_optin) ? 1 : 0;
   if (in_shared)
     MAS_CUDA_CHECK(cudaFuncSetAttribute(centralized_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fast_bytes)));
-  centralized_kernel<M><<<S, kCentralizedThreads, in_shared ? fast_bytes : 0, st>>>(P, S, W.total, W.fast, in_shared);
+  MAS_CUDA_CHECK(cudaMemsetAsync(b.queue, 0, sizeof(int), st));
+  centralized_kernel<M><<<G, kCentralizedThreads, in_shared ? fast_bytes : 0, st>>>(P, S, W.total, W.fast, in_shared, b.queue);
   if (launches) (*launches)++;
   MAS_CUDA_CHECK(cudaGetLastError());
 
