@@ -7,7 +7,10 @@
 
 namespace mas_b200 {
 
-constexpr int kCentralizedThreads = 256;
+#ifndef MAS_CENTRALIZED_THREADS
+#define MAS_CENTRALIZED_THREADS 512  /* 256 -> 512: 23.5 -> 18.5 ms per 32-agent scenario (4 warps per scheduler hide the latency of the barrier-separated phases); 640 / 768 / 1024: 19.9 / 21.2 / 23.5 ms */
+#endif
+constexpr int kCentralizedThreads = MAS_CENTRALIZED_THREADS;
 
 // Persistent CTAs (one per SM slot the launch gets) pull scenarios from an atomic queue: `base` holds the pointers of
 // scenario 0 / CTA 0; inputs and results (x0, prm, X, U, out_*) are indexed by scenario, the scratch (trial trajectories,
