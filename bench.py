@@ -246,12 +246,42 @@ def parity_gate(x0, got, threads):
     return out
 
 
+def bind_to_gpu_numa_node(torch, local_rank: int):
+    """Pins this rank (threads and, by first touch, its pinned host buffers) to the NUMA node its GPU hangs off, when the host
+    exposes one: results travel device -> host every step, and a rank whose buffers sit on the other socket pays the
+    inter-socket link on all of them.  Returns what was done, for the JSON line."""
+    info = {"numa_node": None, "bound": False}
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{dev}/numa_node") as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["bound"] = True
+            info["cpus"] = len(allowed)
+    except Exception as exc:  # noqa: BLE001
+        info["error"] = repr(exc)[:120]
+    return info
+
+
 class Lane:
     """One solve pipeline: its own CUDA stream, engine context, resident batch and pinned result buffers."""
 
     def __init__(self, torch, mas, device, desc, per_rank, args, with_host_buffers):
         self.stream = torch.cuda.Stream()
         self.ctx = mas.Context(device, self.stream.cuda_stream)
+        if args.blocking_sync:
+            self.ctx.set_blocking_sync(True)
         self.batch = mas.Batch(self.ctx, desc, per_rank)
         if args.lanes or args.chains:
             self.batch.set_tuning(args.lanes, args.chains)
@@ -425,6 +455,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if (world > 1 and not args.no_numa_bind) else {"numa_node": None, "bound": False}
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -444,6 +475,10 @@ def run_b200(args):
     depth = args.depth if args.depth > 0 else (3 if args.steps < 8 else (4 if shard >= PROBLEMS else (6 if shard >= PROBLEMS // 2 else 8)))
     if args.hint == 0 and shard < PROBLEMS:
         args.hint = 4
+    # more host threads than cores (8 ranks x 8 pipelines on a 32-vCPU box): wait on events sleeping, not spinning
+    cores = len(os.sched_getaffinity(0))
+    if args.blocking_sync < 0:
+        args.blocking_sync = 1 if world * (depth + 1) > cores else 0
 
     def barrier():
         if dist is not None:
@@ -593,7 +628,7 @@ def run_b200(args):
 
     weak = None
     if world > 1 and scaling == "strong" and not args.no_weak:
-        w = measure("weak", max(8, args.steps // 2), full=False)
+        w = measure("weak", args.steps, full=False)
         weak = {"value": w["value"], "unit": UNIT, "ms_per_step": w["ms_step"], "problems_per_gpu": w["per_rank"], "problems_total": w["total"],
                 "what": "one full 65,536-problem shard per rank, resident inputs (round 1's N > 1 headline)"}
         for ln in w["lanes"]:
@@ -677,10 +712,10 @@ def run_b200(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg,
             "engine": {"problems_per_gpu": per_rank, "parallelism": f"contiguous shards of independent problems x{n_gpus}, no data-path collective",
-                       "solves_in_flight": depth, "concurrency_hint": args.hint or 1,
+                       "solves_in_flight": depth, "concurrency_hint": args.hint or 1, "blocking_sync": bool(args.blocking_sync),
                        "pipelining": f"{depth} independent solves of the shard in flight per GPU, each a whole step on its own stream and host "
                                      "thread, starts staggered; ms_per_step = device time of the K steps / K",
-                       "single_solve_ms": single_ms,
+                       "single_solve_ms": single_ms, "host_cores": len(os.sched_getaffinity(0)), "numa": numa,
                        "l2": f"working set {per_rank * 10272 / 1e6:.0f} MB per solve (X,U,K,k) x {depth} in flight"
                              + (" > 126 MB L2, no flush needed" if per_rank * 10272 * depth > 126e6 else " (fits L2: flushed by the other lanes' traffic only)"),
                        "forward_lanes": st["forward_lanes"], "forward_chains": st["forward_chains"],
@@ -718,6 +753,8 @@ def main():
     ap.add_argument("--no-weak", action="store_true", help="skip the extra weak-scaling measurement at N > 1")
     ap.add_argument("--ls-mode", type=int, default=0, help="line search scheduling: 0 auto, 1 concurrent lanes, 2 compacted rounds")
     ap.add_argument("--shard", type=int, default=0, help="profiling aid (with --resident-only): problems per rank, overriding 65,536 / N")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin ranks to the NUMA node of their GPU (N > 1)")
+    ap.add_argument("--blocking-sync", type=int, default=-1, help="1: pipelines wait on events sleeping (mas_b200_context_set_blocking_sync); -1 = when oversubscribed")
     ap.add_argument("--hint", type=int, default=0, help="mas_b200_batch_set_concurrency_hint of every pipeline (0 = leave at 1)")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--chains", type=int, default=0)

@@ -155,6 +155,11 @@ int mas_b200_context_create(int device_id, void* stream, mas_b200_context_t* out
 int mas_b200_context_destroy(mas_b200_context_t ctx);
 int mas_b200_context_synchronize(mas_b200_context_t ctx);
 
+/* How the host waits for the device in the solve loop and in mas_b200_batch_wait_solution: 0 (default) spins, the lowest
+ * latency when every pipeline has a core of its own; 1 sleeps on the event (cudaEventBlockingSync) -- for hosts that drive
+ * more pipelines than they have cores (8 GPUs x 8 solves in flight on 32 vCPUs).  Applies to batches created afterwards. */
+int mas_b200_context_set_blocking_sync(mas_b200_context_t ctx, int enable);
+
 /* Pinned host memory for callers that want full-speed copies. */
 int mas_b200_host_alloc(size_t bytes, void** out);
 int mas_b200_host_free(void* p);

@@ -187,6 +187,9 @@ class Context:
         _check(load_library().mas_b200_nccl_unique_id(buf))
         return buf.raw
 
+    def set_blocking_sync(self, enable: bool) -> None:
+        _check(load_library().mas_b200_context_set_blocking_sync(self._h, int(bool(enable))))
+
     def set_agent_sharding(self, agents_sharded: bool) -> None:
         _check(load_library().mas_b200_context_set_agent_sharding(self._h, int(bool(agents_sharded))))
 

@@ -1085,6 +1085,12 @@ int mas_b200_context_init_nccl(mas_b200_context_t ctx, const void* id128, int ra
   return MAS_B200_OK;
 }
 
+int mas_b200_context_set_blocking_sync(mas_b200_context_t ctx, int enable) {
+  if (!ctx) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  ctx->c.blocking_sync = enable != 0;
+  return MAS_B200_OK;
+}
+
 int mas_b200_context_set_agent_sharding(mas_b200_context_t ctx, int agents_sharded) {
   if (!ctx) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
   ctx->agents_sharded = agents_sharded != 0;

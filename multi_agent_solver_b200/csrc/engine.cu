@@ -129,8 +129,9 @@ int BatchBase::allocate() {
   MAS_CUDA_CHECK(dalloc(&d_accept_merit, L));
   MAS_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&h_counts), 4 * sizeof(int), cudaHostAllocMapped));
   MAS_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h_counts_dev), h_counts, 0));
-  MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-  MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  const unsigned ev_flags = cudaEventDisableTiming | (ctx->blocking_sync ? cudaEventBlockingSync : 0u);
+  MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev[0], ev_flags));
+  MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev[1], ev_flags));
   return allocate_constraint_state();
 }
 
@@ -366,7 +367,7 @@ int BatchBase::begin_download(double* X, double* U, double* cost, int* iteration
     MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_out_stage), (nX + nU + batch) * sizeof(double) + 2 * static_cast<size_t>(batch) * sizeof(int)));
     MAS_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev_staged, cudaEventDisableTiming));
-    MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev_downloaded, cudaEventDisableTiming));
+    MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev_downloaded, cudaEventDisableTiming | (ctx->blocking_sync ? cudaEventBlockingSync : 0u)));
   }
   int rc = wait_download();  // the staging area and the previous host buffers are free again
   if (rc) return rc;

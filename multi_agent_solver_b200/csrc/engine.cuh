@@ -58,6 +58,7 @@ struct Context {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int sm_count = 148;
+  bool blocking_sync = false;  // host waits on events sleep instead of spinning (many pipelines per core: mas_b200_context_set_blocking_sync)
   void* nccl_comm = nullptr;  // ncclComm_t when multi-GPU is initialised
   int rank = 0, world = 1;
   // device workspace of the last centralized strategy call, kept for the next call of the same shape (a 592-scenario
