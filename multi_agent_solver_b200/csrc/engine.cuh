@@ -146,9 +146,12 @@ __global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) backward_lanes_kernel(Ba
 // with cp.async while step t computes.  FD-heavy derivative modes gain the whole stencil (118 cost + 12 dynamics
 // evaluations per step at n = 4, m = 2) spread over T x G threads per problem.
 constexpr int kLinBlock = 128;
+#ifndef MAS_LIN_MIN_CTAS
+#define MAS_LIN_MIN_CTAS 1
+#endif
 constexpr int kSweepBlock = 32;
 template <class M, int MASK_CT>
-__global__ void __launch_bounds__(kLinBlock) linearize_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
+__global__ void __launch_bounds__(kLinBlock, MAS_LIN_MIN_CTAS) linearize_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
                                                              double* __restrict__ D, int cap, int n_pad, int G) {
   using DB = DerivBlock<M>;
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
