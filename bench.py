@@ -37,6 +37,10 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# Hardware work queues of the CUDA context (default 8): every pipeline below is a stream, and streams that share a queue
+# serialise against each other.  With 8-24 pipelines in flight the default costs 9-17 % (profiles/r02_strong_scaling_tuning.txt).
+# Must be set before the CUDA context exists; a caller's own setting wins.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, ROOT)
 
 METRIC = "iLQR OCP solves/sec (batched single-track, fp64)"
@@ -277,8 +281,8 @@ def bind_to_gpu_numa_node(torch, local_rank: int):
 class Lane:
     """One solve pipeline: its own CUDA stream, engine context, resident batch and pinned result buffers."""
 
-    def __init__(self, torch, mas, device, desc, per_rank, args, with_host_buffers):
-        self.stream = torch.cuda.Stream()
+    def __init__(self, torch, mas, device, desc, per_rank, args, with_host_buffers, priority=0):
+        self.stream = torch.cuda.Stream(priority=priority)
         self.ctx = mas.Context(device, self.stream.cuda_stream)
         if args.blocking_sync:
             self.ctx.set_blocking_sync(True)
@@ -472,10 +476,24 @@ def run_b200(args):
     # in flight, and every batch is told that it shares the device (mas_b200_batch_set_concurrency_hint: narrower lane
     # mappings, i.e. less speculative work).  Measured on one B200 (profiles/r02_strong_scaling_tuning.txt).
     shard = args.shard or (PROBLEMS if scaling == "weak" else PROBLEMS // world)
-    depth = args.depth if args.depth > 0 else (3 if args.steps < 8 else (4 if shard >= PROBLEMS else (6 if shard >= PROBLEMS // 2 else 8)))
+
+    def depth_for(per_rank: int) -> int:
+        """Solves in flight per GPU.  A full 65,536-problem shard fills the device in its first iterations and four pipelines
+        hide its latency-bound tail.  The smaller shards of strong scaling are latency-bound from the start (every
+        iteration costs the latency of its 80 sequential time steps whatever the problem count), so the device only fills
+        with many of them in flight: up to 12 for 32,768 problems, up to 24 below -- never more than there are steps.
+        Measured on one B200 (profiles/r02_strong_scaling_tuning.txt)."""
+        if args.depth > 0:
+            return args.depth
+        if args.steps < 8:
+            return min(3, max(args.steps, 1))
+        cap = 4 if per_rank >= PROBLEMS else (12 if per_rank >= PROBLEMS // 2 else 24)
+        return max(1, min(cap, args.steps))
+
+    depth = depth_for(shard)
     if args.hint == 0 and shard < PROBLEMS:
-        args.hint = 4
-    # more host threads than cores (8 ranks x 8 pipelines on a 32-vCPU box): wait on events sleeping, not spinning
+        args.hint = 4  # every batch is told that it shares the device: narrower lane mappings, less speculative work
+    # more host threads than cores (8 ranks x many pipelines on a 32-vCPU box): wait on events sleeping, not spinning
     cores = len(os.sched_getaffinity(0))
     if args.blocking_sync < 0:
         args.blocking_sync = 1 if world * (depth + 1) > cores else 0
@@ -497,7 +515,18 @@ def run_b200(args):
         else:
             x0 = x0_all[(rank * per_rank) % PROBLEMS:(rank * per_rank) % PROBLEMS + per_rank].copy()
         x0_host = torch.from_numpy(x0).pin_memory().numpy()
-        lanes = [Lane(torch, mas, local_rank, desc, per_rank, args, with_host_buffers=full and not args.resident_only) for _ in range(depth)]
+        n_lanes = depth_for(per_rank)
+        # end to end, deep pipelines of small shards run one or two steps each: a download that only starts after the solve
+        # queues on the copy engine behind everyone else's at the end of the run, so their results are streamed out while the
+        # solves run (result sink).  A 65,536-problem shard with 4 pipelines is better off with the copy engine (measured both
+        # ways: profiles/r02_strong_scaling_tuning.txt)
+        use_sink = bool(args.sink) if args.sink >= 0 else per_rank < PROBLEMS
+        # --priorities 1: stream priorities falling with the lane index, so that the solves complete one after the other
+        # instead of all at the end (an alternative to the result sink for overlapping downloads with other lanes' solves)
+        use_prio = max(args.priorities, 0)  # measured: +17 % e2e without the result sink, -12 % resident; off by default
+        prio_lo, prio_hi = (0, -5) if use_prio else (0, 0)  # B200: cudaDeviceGetStreamPriorityRange = [0, -5]; torch clamps
+        lanes = [Lane(torch, mas, local_rank, desc, per_rank, args, with_host_buffers=full and not args.resident_only,
+                      priority=prio_hi + (i * (prio_lo - prio_hi + 1)) // n_lanes) for i in range(n_lanes)]
         for ln in lanes:
             ln.batch.set_initial_states(x0_host)  # resident input of the `value` measurement
 
@@ -509,15 +538,25 @@ def run_b200(args):
             ln.batch.set_initial_states(x0_host)  # H2D from pinned memory
             ln.batch.set_controls(None)
             ln.batch.solve(prm)
-            # D2H of X, U, cost, iterations, status into pinned memory: staged in HBM on the solve stream, copied on the
-            # batch's copy stream while this lane's next solve starts; e2e_finish() waits for the last one inside the
-            # timed region, and every begin waits for the previous download of the lane
+            # D2H of X, U, cost, iterations, status into pinned memory.  Default: the lane's pinned buffers are registered as the
+            # batch's result sink (mas_b200_batch_set_result_sink) and the solve itself streams every problem's rows out as soon as
+            # the problem leaves the active set -- the transfer overlaps the remaining iterations.  --no-sink: staged in HBM on the
+            # solve stream after the solve and copied on the batch's copy stream (mas_b200_batch_begin_get_solution).  Either way
+            # e2e_finish() waits for the lane's last results inside the timed region.
+            if use_sink:
+                return
             ln.batch.begin_get_solution(ln.out if keys is None else {k: v for k, v in ln.out.items() if k in keys})
 
         def e2e_finish(ln):
             ln.batch.wait_solution()
 
-        def timed(fn, nsteps, use_lanes, stagger_ms, finish=None):
+        def set_sinks(use_lanes, keys=None):
+            if not use_sink:
+                return
+            for ln in use_lanes:
+                ln.batch.set_result_sink(ln.out if keys is None else {k: v for k, v in ln.out.items() if k in keys})
+
+        def timed(fn, nsteps, use_lanes, stagger_ms, finish=None, stagger_units=None):
             """Runs exactly `nsteps` steps spread over `use_lanes` pipelines, each driven by its own host thread and
             started stagger_ms/len(use_lanes) apart so one solve's latency-bound tail overlaps another's bulk.
             Device time = latest end event - earliest start event over the lanes' streams (then max over ranks)."""
@@ -533,8 +572,12 @@ def run_b200(args):
                     torch.cuda.set_device(local_rank)  # the current device is per host thread
                     ln = use_lanes[i]
                     go.wait()
-                    if i:
-                        time.sleep(i * stagger_ms * args.stagger * 1e-3 / n)
+                    # starts staggered when every pipeline runs several steps (one solve's latency-bound tail then overlaps
+                    # another's bulk for the whole run); with one or two steps per pipeline the offsets would only delay the
+                    # last start, so they all start together (measured: profiles/r02_strong_scaling_tuning.txt)
+                    stagger = stagger_units if stagger_units is not None else (args.stagger if args.stagger >= 0 else (1.0 if nsteps > 2 * n else 0.0))
+                    if i and stagger > 0:
+                        time.sleep(i * stagger_ms * stagger * 1e-3 / n)
                     e0[i].record(ln.stream)
                     for _ in range(counts[i]):
                         fn(ln)
@@ -568,7 +611,7 @@ def run_b200(args):
                 ms, wall = float(t[0]), float(t[1]) / 1e3
             return ms / nsteps, wall / nsteps
 
-        res = {"per_rank": per_rank, "total": total, "x0": x0, "lanes": lanes}
+        res = {"per_rank": per_rank, "total": total, "x0": x0, "lanes": lanes, "depth": n_lanes, "sink": use_sink}
         # ---- one solve at a time: latency of one solve of the shard, and the reference for kernel shares -----------
         for _ in range(max(args.warmup, 3)):
             for ln in lanes:
@@ -584,24 +627,34 @@ def run_b200(args):
         if not full or args.resident_only:
             return res
         # ---- e2e: host buffers in, host buffers out, every step ---------------------------------------------------
+        set_sinks(lanes)
         for ln in lanes:
             e2e_step(ln)
             e2e_finish(ln)
-        e2e_ms, e2e_wall = timed(e2e_step, steps, lanes, res["single_ms"], finish=e2e_finish)
+        # end to end the pipelines always start staggered: a lane's download then overlaps the other lanes' solves instead
+        # of queueing behind everyone else's on the copy engine after the last solve
+        e2e_lanes = lanes[:args.e2e_depth] if args.e2e_depth > 0 else lanes
+        e2e_stagger = args.e2e_stagger if args.e2e_stagger >= 0 else 1.0
+        res["e2e_depth"] = len(e2e_lanes)
+        e2e_ms, e2e_wall = timed(e2e_step, steps, e2e_lanes, res["single_ms"], finish=e2e_finish, stagger_units=e2e_stagger)
         res["e2e"] = {"value": total / (max(e2e_ms * 1e-3, e2e_wall)), "unit": UNIT, "h2d_bytes_per_step": per_rank * NX * 8,
-                      "d2h_bytes_per_step": per_rank * (((T + 1) * NX + T * NU + 1) * 8 + 2 * 4), "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall * 1e3}
+                      "d2h_bytes_per_step": per_rank * (((T + 1) * NX + T * NU + 1) * 8 + 2 * 4), "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall * 1e3,
+                      "results_via": "result sink: rows stored to pinned host memory by the engine as problems finish (mas_b200_batch_set_result_sink)"
+                                     if use_sink else "staged in HBM after the solve, copy engine on a second stream (mas_b200_batch_begin_get_solution)"}
         # what the timed batch produced (lane 0's last download): input of the parity gate
         res["timed_output"] = {k: v.copy() for k, v in lanes[0].out.items()}
         # the same loop for a caller that only wants the controls (X = NULL): a third of the download, reported next to the
         # headline e2e because at N > 1 the host's D2H bandwidth sets e2e
         ukeys = ("U", "cost", "iterations", "status")
+        set_sinks(lanes, ukeys)
         for ln in lanes:
             e2e_step(ln, ukeys)
             e2e_finish(ln)
-        u_ms, u_wall = timed(lambda ln: e2e_step(ln, ukeys), steps, lanes, res["single_ms"], finish=e2e_finish)
+        u_ms, u_wall = timed(lambda ln: e2e_step(ln, ukeys), steps, e2e_lanes, res["single_ms"], finish=e2e_finish, stagger_units=e2e_stagger)
         res["e2e_controls_only"] = {"value": total / (max(u_ms * 1e-3, u_wall)), "unit": UNIT, "h2d_bytes_per_step": per_rank * NX * 8,
                                     "d2h_bytes_per_step": per_rank * ((T * NU + 1) * 8 + 2 * 4), "ms_per_step": u_ms,
                                     "note": "same loop without downloading the state trajectories (X = NULL in the C ABI); not the headline"}
+        set_sinks(lanes, ())  # unregister
         # ---- per-kernel timing for the roofline: one solve at a time, CUDA events around every launch inside the engine
         batch = lanes[0].batch
         batch.set_profiling(True)
@@ -712,9 +765,10 @@ def run_b200(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg,
             "engine": {"problems_per_gpu": per_rank, "parallelism": f"contiguous shards of independent problems x{n_gpus}, no data-path collective",
-                       "solves_in_flight": depth, "concurrency_hint": args.hint or 1, "blocking_sync": bool(args.blocking_sync),
+                       "solves_in_flight": depth, "cuda_device_max_connections": int(os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "8")),
+                       "concurrency_hint": args.hint or 1, "blocking_sync": bool(args.blocking_sync),
                        "pipelining": f"{depth} independent solves of the shard in flight per GPU, each a whole step on its own stream and host "
-                                     "thread, starts staggered; ms_per_step = device time of the K steps / K",
+                                     "thread (starts staggered when a pipeline runs more than two steps); ms_per_step = device time of the K steps / K",
                        "single_solve_ms": single_ms, "host_cores": len(os.sched_getaffinity(0)), "numa": numa,
                        "l2": f"working set {per_rank * 10272 / 1e6:.0f} MB per solve (X,U,K,k) x {depth} in flight"
                              + (" > 126 MB L2, no flush needed" if per_rank * 10272 * depth > 126e6 else " (fits L2: flushed by the other lanes' traffic only)"),
@@ -743,9 +797,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"], help="auto = strong (65,536 split over the ranks) at N > 1")
-    ap.add_argument("--depth", type=int, default=0, help="independent solves in flight per GPU (1 = one at a time; 0 = by step count: "
-                    "3 below 8 steps, else 4 -- fewer pipelines fill and drain faster when K is small)")
-    ap.add_argument("--stagger", type=float, default=1.0, help="start offset between pipelines, in units of single_solve_ms / depth")
+    ap.add_argument("--depth", type=int, default=0, help="independent solves in flight per GPU (1 = one at a time; 0 = by shard size and step count: "
+                    "4 for a 65,536-problem shard, up to 12 / 24 for the 32,768 / smaller shards of strong scaling, never more than --steps)")
+    ap.add_argument("--stagger", type=float, default=-1.0, help="start offset between pipelines, in units of single_solve_ms / depth (-1 = auto: 1 when "
+                    "every pipeline runs more than two steps, else 0)")
+    ap.add_argument("--sink", type=int, default=-1, help="e2e results: 1 = streamed into a result sink while the solve runs (mas_b200_batch_set_result_sink), "
+                    "0 = downloaded after the solve (mas_b200_batch_begin_get_solution), -1 = sink for shards below 65,536 problems (measured)")
+    ap.add_argument("--priorities", type=int, default=0, help="1: stream priorities falling with the pipeline index (experiment; see profiles/r02_strong_scaling_tuning.txt)")
+    ap.add_argument("--e2e-depth", type=int, default=0, help="pipelines used by the e2e measurement (0 = all)")
+    ap.add_argument("--e2e-stagger", type=float, default=-1.0, help="start offset between pipelines of the e2e measurement (-1 = 1.0)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems per CPU-baseline pass (0 = sized automatically)")
     ap.add_argument("--resident-only", action="store_true", help="run only warm-up + timed resident steps (for ncu)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity gate (profiling runs)")

@@ -187,6 +187,16 @@ int mas_b200_batch_get_solution(mas_b200_batch_t b, double* X, double* U, double
  * asynchronous copy) are valid after mas_b200_batch_wait_solution; a second begin waits for the first. */
 int mas_b200_batch_begin_get_solution(mas_b200_batch_t b, double* X, double* U, double* cost, int* iterations, int* status);
 int mas_b200_batch_wait_solution(mas_b200_batch_t b);
+/* Results streamed to the host WHILE the solve runs.  Registers page-locked host buffers (cudaHostAlloc /
+ * cudaHostRegister; any may be NULL, shapes as in mas_b200_batch_get_solution) as the destination of every following
+ * mas_b200_batch_solve: the reference's solve leaves its result in the caller's OCP (best_states, best_controls,
+ * best_cost; solvers/ilqr.hpp:71-73), and so does this -- whenever problems leave the active set (stop test :269-271,
+ * iteration cap, time budget :85-90) a kernel on a side stream writes their rows straight into the buffers over PCIe,
+ * concurrently with the remaining iterations of the other problems, so that by the end of the solve only the last
+ * finishers are still travelling.  mas_b200_batch_wait_solution fences the buffers; the next solve / set_controls of the
+ * batch waits on the device for the previous export.  Buffers that are not page-locked: MAS_B200_ERR_INVALID_ARGUMENT.
+ * All NULL: unregister.  Synchronises the context stream (a setup call, not a per-solve one). */
+int mas_b200_batch_set_result_sink(mas_b200_batch_t b, double* X, double* U, double* cost, int* iterations, int* status);
 int mas_b200_batch_get_device_view(mas_b200_batch_t b, mas_b200_device_view* out);
 /* Constrained models only: the multipliers and the penalty parameter persist from solve to solve like the members
  * of a reference solver object (ilqr.hpp:331-338,415); this makes the next solve start from a fresh solver

@@ -311,6 +311,14 @@ class Batch:
     def wait_solution(self) -> None:
         _check(load_library().mas_b200_batch_wait_solution(self._h))
 
+    def set_result_sink(self, out) -> None:
+        """mas_b200_batch_set_result_sink: every following solve streams its results into `out` (page-locked arrays, e.g.
+        torch pin_memory) while it runs; wait_solution() fences them.  None unregisters."""
+        out = out or {}
+        self._sink_keep = out
+        _check(load_library().mas_b200_batch_set_result_sink(self._h, _dptr(out.get("X")), _dptr(out.get("U")), _dptr(out.get("cost")),
+                                                              _iptr(out.get("iterations")), _iptr(out.get("status"))))
+
     def device_view(self) -> DeviceView:
         v = DeviceView()
         _check(load_library().mas_b200_batch_get_device_view(self._h, ctypes.byref(v)))

@@ -370,6 +370,8 @@ int mas_b200_batch_set_params(mas_b200_batch_t h, const double* params) {
 
 int mas_b200_batch_set_controls(mas_b200_batch_t h, const double* U) {
   MAS_BATCH_GUARD(h);
+  int frc = b->fence_exports();  // the last solve's results may still be travelling out of U
+  if (frc) return frc;
   if (!U) {
     MAS_CUDA_CHECK(cudaMemsetAsync(b->d_U, 0, static_cast<size_t>(b->ld) * b->nu * b->T * sizeof(double), b->ctx->stream));
     return MAS_B200_OK;
@@ -379,6 +381,8 @@ int mas_b200_batch_set_controls(mas_b200_batch_t h, const double* U) {
 
 int mas_b200_batch_initialize(mas_b200_batch_t h) {
   MAS_BATCH_GUARD(h);
+  int frc = b->fence_exports();
+  if (frc) return frc;
   return b->initialize();
 }
 
@@ -409,6 +413,11 @@ int mas_b200_batch_begin_get_solution(mas_b200_batch_t h, double* X, double* U, 
 int mas_b200_batch_wait_solution(mas_b200_batch_t h) {
   MAS_BATCH_GUARD(h);
   return b->wait_download();
+}
+
+int mas_b200_batch_set_result_sink(mas_b200_batch_t h, double* X, double* U, double* cost, int* iterations, int* status) {
+  MAS_BATCH_GUARD(h);
+  return b->set_result_sink(X, U, cost, iterations, status);
 }
 
 int mas_b200_batch_get_device_view(mas_b200_batch_t h, mas_b200_device_view* out) {

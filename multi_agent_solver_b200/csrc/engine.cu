@@ -45,6 +45,64 @@ __global__ void time_limit_kernel(const int* __restrict__ list, const int* __res
   if (i < *count) status[list[i]] = STATUS_TIME_LIMIT;
 }
 
+// Result sink: rows of finished problems straight to page-locked host memory (device-mapped), [batch][rows] row-major --
+// per problem exactly the bytes of the reference's column-major best_states / best_controls.  A warp looks at 32
+// neighbouring problems, then moves the finished ones one after the other: its lanes read 32 rows of the problem's
+// [rows][ld] column and store them as one 256-byte run over PCIe.  mode 0: problems whose iteration counter equals
+// `finished_at` and whose flag is final (they left the active set in the iteration that has just ended and are never
+// written again); mode 1: problems stopped by the time budget; mode 2: all.
+__global__ void export_results_kernel(const double* __restrict__ dX, const double* __restrict__ dU, const double* __restrict__ dcost,
+                                      const int* __restrict__ iters, const int* __restrict__ status, int batch, int ld, int rowsX, int rowsU, int mode,
+                                      int finished_at, int max_iterations, double* hX, double* hU, double* hcost, int* hiters, int* hstatus) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int groups = (batch + 31) >> 5;
+  for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < groups; g += warps) {
+    const int p = g * 32 + lane;
+    bool done = false;
+    if (p < batch) {
+      const int it = iters[p], st = status[p];
+      done = mode == 2 || (mode == 1 ? st == STATUS_TIME_LIMIT : (it == finished_at && (st == STATUS_CONVERGED || it >= max_iterations)));
+      if (done) {
+        if (hcost) hcost[p] = dcost[p];
+        if (hiters) hiters[p] = it;
+        if (hstatus) hstatus[p] = st;
+      }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, done);
+    while (todo) {
+      const int q = g * 32 + (__ffs(todo) - 1);
+      todo &= todo - 1;
+      if (hX) {
+        double* dst = hX + static_cast<size_t>(q) * rowsX;
+        int r = lane;
+        for (; r + 96 < rowsX; r += 128) {  // four independent loads in flight per lane
+          const double a = __ldcs(dX + static_cast<size_t>(r) * ld + q), b = __ldcs(dX + static_cast<size_t>(r + 32) * ld + q),
+                       c = __ldcs(dX + static_cast<size_t>(r + 64) * ld + q), d = __ldcs(dX + static_cast<size_t>(r + 96) * ld + q);
+          dst[r] = a;
+          dst[r + 32] = b;
+          dst[r + 64] = c;
+          dst[r + 96] = d;
+        }
+        for (; r < rowsX; r += 32) dst[r] = __ldcs(dX + static_cast<size_t>(r) * ld + q);
+      }
+      if (hU) {
+        double* dst = hU + static_cast<size_t>(q) * rowsU;
+        int r = lane;
+        for (; r + 96 < rowsU; r += 128) {
+          const double a = __ldcs(dU + static_cast<size_t>(r) * ld + q), b = __ldcs(dU + static_cast<size_t>(r + 32) * ld + q),
+                       c = __ldcs(dU + static_cast<size_t>(r + 64) * ld + q), d = __ldcs(dU + static_cast<size_t>(r + 96) * ld + q);
+          dst[r] = a;
+          dst[r + 32] = b;
+          dst[r + 64] = c;
+          dst[r + 96] = d;
+        }
+        for (; r < rowsU; r += 32) dst[r] = __ldcs(dU + static_cast<size_t>(r) * ld + q);
+      }
+    }
+  }
+}
+
 // 8 independent DFMA chains per thread; reports 2 flops per fma.
 __global__ void dfma_probe_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-3, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
@@ -73,6 +131,10 @@ BatchBase::~BatchBase() {
   if (h_counts) cudaFreeHost(h_counts);
   if (d_count_hist) cudaFree(d_count_hist);
   if (download_pending) cudaEventSynchronize(ev_downloaded);
+  if (export_pending) cudaEventSynchronize(ev_exported);
+  if (export_stream) cudaStreamDestroy(export_stream);
+  if (ev_exported) cudaEventDestroy(ev_exported);
+  if (ev_export_src) cudaEventDestroy(ev_export_src);
   if (d_out_stage) cudaFree(d_out_stage);
   if (d_deriv) cudaFree(d_deriv);
   if (d_dbg) cudaFree(d_dbg);
@@ -424,9 +486,83 @@ int BatchBase::ensure_trial_store(long long min_slots) {
 }
 
 int BatchBase::wait_download() {
+  if (export_pending) {  // results streamed into the sink by the last solve
+    MAS_CUDA_CHECK(cudaEventSynchronize(ev_exported));
+    export_pending = false;
+  }
   if (!download_pending) return MAS_B200_OK;
   MAS_CUDA_CHECK(cudaEventSynchronize(ev_downloaded));
   download_pending = false;
+  return MAS_B200_OK;
+}
+
+// Host buffers must be page-locked: the export kernel stores into them through their device-mapped addresses.
+int BatchBase::set_result_sink(double* X, double* U, double* cost, int* iterations, int* status) {
+  int rc = wait_download();
+  if (rc) return rc;
+  MAS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (export_stream) MAS_CUDA_CHECK(cudaStreamSynchronize(export_stream));
+  sink_X = sink_U = sink_cost = nullptr;
+  sink_iters = sink_status = nullptr;
+  sink_set = false;
+  if (!X && !U && !cost && !iterations && !status) return MAS_B200_OK;
+  auto mapped = [&](void* host, void** dev) -> int {
+    *dev = nullptr;
+    if (!host) return MAS_B200_OK;
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, host) != cudaSuccess || attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
+      cudaGetLastError();
+      set_last_error("result sink: the buffers must be page-locked host memory (cudaHostAlloc / cudaHostRegister)");
+      return MAS_B200_ERR_INVALID_ARGUMENT;
+    }
+    *dev = attr.devicePointer;
+    return MAS_B200_OK;
+  };
+  void* d[5];
+  void* h[5] = {X, U, cost, iterations, status};
+  for (int i = 0; i < 5; ++i)
+    if ((rc = mapped(h[i], &d[i]))) return rc;
+  if (!export_stream) {
+    int lo = 0, hi = 0;
+    MAS_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    MAS_CUDA_CHECK(cudaStreamCreateWithPriority(&export_stream, cudaStreamNonBlocking, hi));  // its few CTAs should not queue behind the solves
+    MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev_exported, cudaEventDisableTiming | (ctx->blocking_sync ? cudaEventBlockingSync : 0u)));
+    MAS_CUDA_CHECK(cudaEventCreateWithFlags(&ev_export_src, cudaEventDisableTiming));
+  }
+  sink_X = static_cast<double*>(d[0]);
+  sink_U = static_cast<double*>(d[1]);
+  sink_cost = static_cast<double*>(d[2]);
+  sink_iters = static_cast<int*>(d[3]);
+  sink_status = static_cast<int*>(d[4]);
+  sink_set = true;
+  return MAS_B200_OK;
+}
+
+int BatchBase::export_results(int mode, int finished_at, int max_iterations, cudaEvent_t after) {
+  if (!after) {
+    MAS_CUDA_CHECK(cudaEventRecord(ev_export_src, ctx->stream));
+    after = ev_export_src;
+  }
+  MAS_CUDA_CHECK(cudaStreamWaitEvent(export_stream, after, 0));
+  // a few CTAs: the kernel is bound by PCIe (one 256-byte store per warp instruction), not by the SMs it occupies
+  static const int env_ctas = std::getenv("MAS_B200_EXPORT_CTAS") ? std::atoi(std::getenv("MAS_B200_EXPORT_CTAS")) : 0;
+  const int grid = std::max(1, std::min(env_ctas > 0 ? env_ctas : kExportCtas, div_up(div_up(batch, 32), kExportBlock / 32)));
+  export_results_kernel<<<grid, kExportBlock, 0, export_stream>>>(d_X, d_U, d_cost, d_iters, d_status, batch, ld, nx * (T + 1), nu * T, mode, finished_at,
+                                                                  max_iterations, sink_X, sink_U, sink_cost, sink_iters, sink_status);
+  stats.kernel_launches++;
+  MAS_CUDA_CHECK(cudaGetLastError());
+  return MAS_B200_OK;
+}
+
+int BatchBase::finish_exports() {
+  MAS_CUDA_CHECK(cudaEventRecord(ev_exported, export_stream));
+  export_pending = true;
+  return MAS_B200_OK;
+}
+
+int BatchBase::fence_exports() {
+  // the last solve's exports read X, U, cost and the flags on their own stream: whoever overwrites them waits (on the device)
+  if (ev_exported && sink_set) MAS_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ev_exported, 0));
   return MAS_B200_OK;
 }
 

@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) backward_lanes_kernel(Ba
 // riccati_sweep_kernel then runs the recursion alone, one thread per problem, fetching block t-1 into shared memory
 // with cp.async while step t computes.  FD-heavy derivative modes gain the whole stencil (118 cost + 12 dynamics
 // evaluations per step at n = 4, m = 2) spread over T x G threads per problem.
+constexpr int kExportBlock = 256, kExportCtas = 64;  // result-sink kernel: PCIe-bound, a few CTAs suffice
 constexpr int kLinBlock = 128;
 #ifndef MAS_LIN_MIN_CTAS
 #define MAS_LIN_MIN_CTAS 1
@@ -631,6 +632,19 @@ struct BatchBase {
   int ensure_trial_store(long long min_slots);
   int begin_download(double* X, double* U, double* cost, int* iterations, int* status);
   int wait_download();
+  // result sink (mas_b200_batch_set_result_sink): page-locked host buffers that every solve streams its results into
+  // while it runs -- after every iteration a kernel on `export_stream` writes the rows of the problems that have just
+  // left the active set straight to the host (device-mapped addresses below), concurrently with the next iterations
+  double *sink_X = nullptr, *sink_U = nullptr, *sink_cost = nullptr;
+  int *sink_iters = nullptr, *sink_status = nullptr;
+  bool sink_set = false, export_pending = false;
+  cudaStream_t export_stream = nullptr;
+  cudaEvent_t ev_exported = nullptr, ev_export_src = nullptr;
+  int set_result_sink(double* X, double* U, double* cost, int* iterations, int* status);
+  // mode 0: problems whose iteration counter equals `finished_at` and that are final; 1: status TIME_LIMIT; 2: all
+  int export_results(int mode, int finished_at, int max_iterations, cudaEvent_t after);
+  int finish_exports();   // end of a solve: event for wait_download() and for the next writer of X / U
+  int fence_exports();    // the context stream waits for the last solve's exports before X / U are overwritten
   // strategy scratch (allocated on demand)
   double *d_U_old = nullptr, *d_X_old = nullptr, *d_cost_old = nullptr, *d_radius = nullptr;
   int* d_accepted = nullptr;
@@ -949,7 +963,9 @@ struct BatchImpl : BatchBase {
   int solve(const mas_b200_ilqr_params& prm) override {
     using clock = std::chrono::steady_clock;
     const auto start = clock::now();
-    int rc = prepare_constraint_state(prm);
+    int rc = fence_exports();
+    if (rc) return rc;
+    rc = prepare_constraint_state(prm);
     if (rc) return rc;
     dbg_valid = false;
     if (prm.debug) {
@@ -992,6 +1008,7 @@ struct BatchImpl : BatchBase {
         if (elapsed_ms > prm.max_ms) {
           rc = mark_time_limit(cur);
           if (rc) return rc;
+          if (sink_set && (rc = export_results(1, 0, prm.max_iterations, nullptr))) return rc;
           break;
         }
       }
@@ -1046,6 +1063,8 @@ struct BatchImpl : BatchBase {
         stats.kernel_launches++;
       }
       MAS_CUDA_CHECK(cudaEventRecord(ev[it & 1], ctx->stream));
+      // the problems that left the active set in this iteration travel to the host while the next iterations run
+      if (sink_set && (rc = export_results(0, it + 1, prm.max_iterations, ev[it & 1]))) return rc;
       if (it >= 1) {
         // active count after iteration it-1: an upper bound for iteration it+1 (the list only shrinks)
         MAS_CUDA_CHECK(cudaEventSynchronize(ev[(it - 1) & 1]));
@@ -1053,6 +1072,10 @@ struct BatchImpl : BatchBase {
       }
       cur ^= 1;
       ++trips;
+    }
+    if (sink_set) {
+      if (prm.max_iterations <= 0 && (rc = export_results(2, 0, 0, nullptr))) return rc;  // the prologue's rollout is the result
+      if ((rc = finish_exports())) return rc;
     }
     stats.outer_iterations_run = trips;
     stats.forward_lanes = last_L;

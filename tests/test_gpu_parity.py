@@ -313,6 +313,60 @@ def test_constraint_state_persists_and_resets(mas, ctx, oracle):
     assert np.array_equal(again["cost"], hist[0]["cost"]) and np.array_equal(again["X"], hist[0]["X"])
 
 
+def test_result_sink_streams_the_same_results(mas, ctx, oracle):
+    """mas_b200_batch_set_result_sink: results written to page-locked host memory while the solve runs (per iteration, the
+    problems that left the active set) are the bits get_solution returns -- two solves back to back, a ragged batch, every
+    stop reason: converged, iteration cap (max_iterations 2), zero iterations; unpinned buffers are refused."""
+    import torch
+
+    B = 1237
+    xa, xb = random_x0(0, B, seed=411), random_x0(0, B, seed=412)
+    b = mas.Batch(ctx, mas.example_desc(0), B)
+
+    def pinned():
+        return dict(X=torch.empty((B, 81, 4), dtype=torch.float64).pin_memory().numpy(), U=torch.empty((B, 80, 2), dtype=torch.float64).pin_memory().numpy(),
+                    cost=torch.empty(B, dtype=torch.float64).pin_memory().numpy(), iterations=torch.empty(B, dtype=torch.int32).pin_memory().numpy(),
+                    status=torch.empty(B, dtype=torch.int32).pin_memory().numpy())
+
+    sink = pinned()
+    with pytest.raises(Exception):
+        b.set_result_sink(dict(X=np.empty((B, 81, 4))))  # pageable memory
+    b.set_result_sink(sink)
+    for x0, iters in ((xa, 10), (xb, 10), (xa, 2), (xb, 0)):
+        for v in sink.values():
+            v[...] = -7
+        b.set_initial_states(x0)
+        b.set_controls(None)
+        b.solve(mas.IlqrParams.make(iters, 1e-5))
+        b.wait_solution()
+        streamed = {k: v.copy() for k, v in sink.items()}
+        direct = b.get_solution()
+        for k in streamed:
+            assert np.array_equal(streamed[k], direct[k], equal_nan=(k in ("X", "U", "cost"))), k
+        ref = oracle.ilqr_solve_batch(0, x0, max_iterations=iters, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+        assert is_bit_exact(streamed, ref)
+    # time budget already spent (ilqr.hpp:84-90): every problem is written with TIME_LIMIT and its initial rollout
+    for v in sink.values():
+        v[...] = -7
+    b.set_initial_states(xa)
+    b.set_controls(None)
+    b.solve(mas.IlqrParams.make(10, 1e-5, max_ms=-1.0))
+    b.wait_solution()
+    direct = b.get_solution()
+    assert (sink["status"] == mas.Status.TIME_LIMIT).all() and (sink["iterations"] == 0).all()
+    for k in sink:
+        assert np.array_equal(sink[k], direct[k]), k
+    b.set_result_sink(None)
+    b.set_initial_states(xa)
+    b.set_controls(None)
+    for v in sink.values():
+        v[...] = -7
+    b.solve(mas.IlqrParams.make(10, 1e-5))
+    b.wait_solution()
+    assert np.all(sink["iterations"] == -7)  # unregistered: nothing is written
+    b.close()
+
+
 def test_asynchronous_download_survives_the_next_solve(mas, ctx, oracle):
     """begin_get_solution stages the results in HBM; a following solve on other inputs must not disturb them."""
     import torch
