@@ -516,17 +516,22 @@ def run_b200(args):
             x0 = x0_all[(rank * per_rank) % PROBLEMS:(rank * per_rank) % PROBLEMS + per_rank].copy()
         x0_host = torch.from_numpy(x0).pin_memory().numpy()
         n_lanes = depth_for(per_rank)
-        # end to end, deep pipelines of small shards run one or two steps each: a download that only starts after the solve
-        # queues on the copy engine behind everyone else's at the end of the run, so their results are streamed out while the
-        # solves run (result sink).  A 65,536-problem shard with 4 pipelines is better off with the copy engine (measured both
-        # ways: profiles/r02_strong_scaling_tuning.txt)
-        use_sink = bool(args.sink) if args.sink >= 0 else per_rank < PROBLEMS
-        # --priorities 1: stream priorities falling with the lane index, so that the solves complete one after the other
-        # instead of all at the end (an alternative to the result sink for overlapping downloads with other lanes' solves)
-        use_prio = max(args.priorities, 0)  # measured: +17 % e2e without the result sink, -12 % resident; off by default
-        prio_lo, prio_hi = (0, -5) if use_prio else (0, 0)  # B200: cudaDeviceGetStreamPriorityRange = [0, -5]; torch clamps
-        lanes = [Lane(torch, mas, local_rank, desc, per_rank, args, with_host_buffers=full and not args.resident_only,
-                      priority=prio_hi + (i * (prio_lo - prio_hi + 1)) // n_lanes) for i in range(n_lanes)]
+        # e2e results: downloaded after the solve by the copy engine (default), or streamed into a result sink while the solve
+        # runs (--sink 1; mas_b200_batch_set_result_sink).  Measured both ways (profiles/r02_strong_scaling_tuning.txt): the
+        # sink wins on a single-GPU host when pipelines run one or two steps each, the copy engine wins for 65,536-problem
+        # shards and on the multi-GPU hosts, where SM stores of several GPUs reach less host bandwidth than their copy engines
+        use_sink = args.sink > 0
+
+        def make_lanes(n, host_buffers, prio):
+            # prio: stream priorities falling with the lane index, so that deep pipelines complete their solves one after the
+            # other instead of all at the end -- a finished lane's download then overlaps the other lanes' solves instead of
+            # queueing on the copy engine behind everyone else's after the last kernel (e2e of small shards +17-21 %; the
+            # resident measurement loses 12 % with it and does not use it)
+            lo, hi = (0, -5) if prio else (0, 0)  # B200: cudaDeviceGetStreamPriorityRange = [0, -5]; torch clamps
+            return [Lane(torch, mas, local_rank, desc, per_rank, args, with_host_buffers=host_buffers, priority=hi + (i * (lo - hi + 1)) // n)
+                    for i in range(n)]
+
+        lanes = make_lanes(n_lanes, False, args.priorities > 0)
         for ln in lanes:
             ln.batch.set_initial_states(x0_host)  # resident input of the `value` measurement
 
@@ -627,34 +632,45 @@ def run_b200(args):
         if not full or args.resident_only:
             return res
         # ---- e2e: host buffers in, host buffers out, every step ---------------------------------------------------
-        set_sinks(lanes)
-        for ln in lanes:
+        # its own pipelines: pinned result buffers, and for the small shards of strong scaling fewer of them than the resident
+        # measurement keeps in flight.  At N > 1 the e2e run is bound by the host's aggregate device-to-host bandwidth (255 MB per
+        # step whatever N: profiles/r02_pcie_probe_*), so what counts is that the first results start travelling early and the copy
+        # engines never idle -- 6 / 8 staggered pipelines did better than 12 / 20 with or without stream priorities (2 and 8 GPUs)
+        n_e2e = args.e2e_depth if args.e2e_depth > 0 else (n_lanes if per_rank >= PROBLEMS else min(n_lanes, 6 if per_rank >= PROBLEMS // 2 else 8))
+        e2e_prio = args.priorities > 0
+        for ln in lanes[1:]:
+            ln.close()
+        e2e_lanes = make_lanes(n_e2e, True, e2e_prio)
+        lanes = lanes[:1]
+        res["lanes"] = lanes + e2e_lanes
+        for ln in e2e_lanes:
+            ln.batch.set_initial_states(x0_host)
+        set_sinks(e2e_lanes)
+        for ln in e2e_lanes:
             e2e_step(ln)
             e2e_finish(ln)
-        # end to end the pipelines always start staggered: a lane's download then overlaps the other lanes' solves instead
-        # of queueing behind everyone else's on the copy engine after the last solve
-        e2e_lanes = lanes[:args.e2e_depth] if args.e2e_depth > 0 else lanes
+        # end to end the pipelines always start staggered: a lane's download then overlaps the other lanes' solves
         e2e_stagger = args.e2e_stagger if args.e2e_stagger >= 0 else 1.0
-        res["e2e_depth"] = len(e2e_lanes)
+        res["e2e_depth"], res["e2e_priorities"] = n_e2e, bool(e2e_prio)
         e2e_ms, e2e_wall = timed(e2e_step, steps, e2e_lanes, res["single_ms"], finish=e2e_finish, stagger_units=e2e_stagger)
         res["e2e"] = {"value": total / (max(e2e_ms * 1e-3, e2e_wall)), "unit": UNIT, "h2d_bytes_per_step": per_rank * NX * 8,
                       "d2h_bytes_per_step": per_rank * (((T + 1) * NX + T * NU + 1) * 8 + 2 * 4), "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall * 1e3,
                       "results_via": "result sink: rows stored to pinned host memory by the engine as problems finish (mas_b200_batch_set_result_sink)"
                                      if use_sink else "staged in HBM after the solve, copy engine on a second stream (mas_b200_batch_begin_get_solution)"}
         # what the timed batch produced (lane 0's last download): input of the parity gate
-        res["timed_output"] = {k: v.copy() for k, v in lanes[0].out.items()}
+        res["timed_output"] = {k: v.copy() for k, v in e2e_lanes[0].out.items()}
         # the same loop for a caller that only wants the controls (X = NULL): a third of the download, reported next to the
         # headline e2e because at N > 1 the host's D2H bandwidth sets e2e
         ukeys = ("U", "cost", "iterations", "status")
-        set_sinks(lanes, ukeys)
-        for ln in lanes:
+        set_sinks(e2e_lanes, ukeys)
+        for ln in e2e_lanes:
             e2e_step(ln, ukeys)
             e2e_finish(ln)
         u_ms, u_wall = timed(lambda ln: e2e_step(ln, ukeys), steps, e2e_lanes, res["single_ms"], finish=e2e_finish, stagger_units=e2e_stagger)
         res["e2e_controls_only"] = {"value": total / (max(u_ms * 1e-3, u_wall)), "unit": UNIT, "h2d_bytes_per_step": per_rank * NX * 8,
                                     "d2h_bytes_per_step": per_rank * ((T * NU + 1) * 8 + 2 * 4), "ms_per_step": u_ms,
                                     "note": "same loop without downloading the state trajectories (X = NULL in the C ABI); not the headline"}
-        set_sinks(lanes, ())  # unregister
+        set_sinks(e2e_lanes, ())  # unregister
         # ---- per-kernel timing for the roofline: one solve at a time, CUDA events around every launch inside the engine
         batch = lanes[0].batch
         batch.set_profiling(True)
@@ -765,7 +781,8 @@ def run_b200(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg,
             "engine": {"problems_per_gpu": per_rank, "parallelism": f"contiguous shards of independent problems x{n_gpus}, no data-path collective",
-                       "solves_in_flight": depth, "cuda_device_max_connections": int(os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "8")),
+                       "solves_in_flight": depth, "e2e_solves_in_flight": main.get("e2e_depth"), "e2e_stream_priorities": main.get("e2e_priorities"),
+                       "cuda_device_max_connections": int(os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "8")),
                        "concurrency_hint": args.hint or 1, "blocking_sync": bool(args.blocking_sync),
                        "pipelining": f"{depth} independent solves of the shard in flight per GPU, each a whole step on its own stream and host "
                                      "thread (starts staggered when a pipeline runs more than two steps); ms_per_step = device time of the K steps / K",
@@ -802,8 +819,9 @@ def main():
     ap.add_argument("--stagger", type=float, default=-1.0, help="start offset between pipelines, in units of single_solve_ms / depth (-1 = auto: 1 when "
                     "every pipeline runs more than two steps, else 0)")
     ap.add_argument("--sink", type=int, default=-1, help="e2e results: 1 = streamed into a result sink while the solve runs (mas_b200_batch_set_result_sink), "
-                    "0 = downloaded after the solve (mas_b200_batch_begin_get_solution), -1 = sink for shards below 65,536 problems (measured)")
-    ap.add_argument("--priorities", type=int, default=0, help="1: stream priorities falling with the pipeline index (experiment; see profiles/r02_strong_scaling_tuning.txt)")
+                    "0 / -1 = downloaded after the solve by the copy engine (mas_b200_batch_begin_get_solution; default, measured faster on the multi-GPU hosts)")
+    ap.add_argument("--priorities", type=int, default=-1, help="1: stream priorities falling with the pipeline index (an experiment: +17-21 % e2e for deep pipelines of small shards on a "
+                    "single-GPU host, -12 % resident; profiles/r02_strong_scaling_tuning.txt); default off")
     ap.add_argument("--e2e-depth", type=int, default=0, help="pipelines used by the e2e measurement (0 = all)")
     ap.add_argument("--e2e-stagger", type=float, default=-1.0, help="start offset between pipelines of the e2e measurement (-1 = 1.0)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems per CPU-baseline pass (0 = sized automatically)")
