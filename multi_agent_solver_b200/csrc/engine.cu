@@ -122,6 +122,9 @@ __global__ void dfma_probe_kernel(double* out, int iters) {
 
 BatchBase::~BatchBase() {
   if (ctx) cudaSetDevice(ctx->device);
+  // transfers that still read the buffers freed below
+  if (download_pending) cudaEventSynchronize(ev_downloaded);
+  if (export_pending) cudaEventSynchronize(ev_exported);
   double* dptrs[] = {d_x0, d_X, d_U, d_K, d_k, d_cost, d_merit, d_params, d_stage, d_U_old, d_X_old, d_cost_old, d_radius, d_accept_merit, d_U_cand, d_base_cost, d_lam_eq, d_lam_ineq, d_penalty};
   for (double* p : dptrs)
     if (p) cudaFree(p);
@@ -130,8 +133,6 @@ BatchBase::~BatchBase() {
     if (p) cudaFree(p);
   if (h_counts) cudaFreeHost(h_counts);
   if (d_count_hist) cudaFree(d_count_hist);
-  if (download_pending) cudaEventSynchronize(ev_downloaded);
-  if (export_pending) cudaEventSynchronize(ev_exported);
   if (export_stream) cudaStreamDestroy(export_stream);
   if (ev_exported) cudaEventDestroy(ev_exported);
   if (ev_export_src) cudaEventDestroy(ev_export_src);
