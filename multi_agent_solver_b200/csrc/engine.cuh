@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) backward_lanes_kernel(Ba
 // riccati_sweep_kernel then runs the recursion alone, one thread per problem, fetching block t-1 into shared memory
 // with cp.async while step t computes.  FD-heavy derivative modes gain the whole stencil (118 cost + 12 dynamics
 // evaluations per step at n = 4, m = 2) spread over T x G threads per problem.
-constexpr int kExportBlock = 256, kExportCtas = 64;  // result-sink kernel: PCIe-bound, a few CTAs suffice
+constexpr int kExportBlock = 256, kExportCtas = 16;  // result-sink kernel: PCIe-bound, a few CTAs suffice
 constexpr int kLinBlock = 128;
 #ifndef MAS_LIN_MIN_CTAS
 #define MAS_LIN_MIN_CTAS 1
