@@ -249,6 +249,63 @@ __global__ void __launch_bounds__(32) riccati_sweep_lanes_kernel(BatchView<M::NX
   if (active && j == 0 && r.retries) v.reg_retries[p] += r.retries;
 }
 
+// The Riccati recursion with one lane per entry of the NX x NX matrices (RiccatiWide, ilqr_core.cuh): NX*NX lanes per
+// problem, 32 / (NX*NX) problems per warp, one warp per CTA -- the mapping for the smallest active sets, where a launch
+// costs T times the latency of one step and nothing else.  Staging of the derivative blocks as in the kernel above.
+template <class M, int MASK_CT>
+__global__ void __launch_bounds__(32) riccati_sweep_wide_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
+                                                                int* next_count, const double* __restrict__ D, int cap) {
+  using DB = DerivBlock<M>;
+  using RW = RiccatiWide<M, MASK_CT>;
+  constexpr int LW = RW::LW, PW = 32 / LW;  // problems per warp
+  __shared__ double s_blk[2][PW][DB::size];
+  __shared__ double s_xch[PW][RW::XCH];
+  const int lane = threadIdx.x, q = lane / LW, e = lane % LW;
+  const int first = blockIdx.x * PW;
+  if (first == 0 && lane == 0) *next_count = 0;
+  const int n = *count;
+  if (first >= n) return;
+  const int i = first + q;
+  const bool active = i < n;
+  const int p = active ? list[i] : 0;
+  auto issue = [&](int t) {
+    const int sq = lane % PW, e0 = lane / PW;
+    const int ne = t == v.T ? DB::n_terminal_tasks : DB::size;
+    if (first + sq < n) {
+      const double* src = D + static_cast<size_t>(t) * DB::size * cap + (first + sq);
+      for (int k = e0; k < ne; k += LW) stage_copy8(&s_blk[t & 1][sq][k], src + static_cast<size_t>(k) * cap);
+    }
+    stage_commit();
+  };
+  RW r;
+  double* xch = s_xch[q];
+  issue(v.T);
+  stage_wait();
+  __syncwarp();
+  if (v.T > 0) issue(v.T - 1);
+  if (active) RW::init_terminal(s_blk[v.T & 1][q], e, xch);
+  __syncwarp();
+  if (active) RW::phase6(e, xch);
+  for (int t = v.T - 1; t >= 0; --t) {
+    stage_wait();
+    __syncwarp();  // block t has landed for every lane, and the symmetrised V_xx of step t+1 is complete
+    const double* blk = s_blk[t & 1][q];
+    if (active) r.phase1(blk, e, xch);
+    __syncwarp();
+    if (active) r.phase2(blk, e, xch);
+    __syncwarp();
+    if (t > 0) issue(t - 1);  // into the buffer block t+1 used; block t is not read after phase 2
+    if (active) r.phase3(v, p, t, e, xch);
+    __syncwarp();
+    if (active) r.phase4(e, xch);
+    __syncwarp();
+    if (active) r.phase5(e, xch);
+    __syncwarp();
+    if (active) RW::phase6(e, xch);
+  }
+  if (active && e == 0 && r.retries) v.reg_retries[p] += r.retries;
+}
+
 // L lanes per problem (a power of two <= 16, aligned inside the warp); lane l rolls out step sizes
 // l, l+L, ...; the group picks the first improving candidate with shuffles; lane 0 commits.
 template <class M, int L, int C>
@@ -627,6 +684,7 @@ struct BatchBase {
   int ensure_debug_trace(int records);
   int concurrency_hint = 1;  // independent solves expected in flight on this device: the lane mappings share the device with them
   int sweep_lanes_max = 16384;  // largest active set whose Riccati sweep runs with the lanes of a problem sharing a step
+  int sweep_wide_max = 0;       // ... with one lane per matrix entry (RiccatiWide): off, measured no faster (MAS_B200_SWEEP_WIDE=1 enables)
   int ensure_deriv_store(int block_doubles);
   bool coop_store = false;  // mas_b200_batch_set_trial_store(b, 2): trial store in the cooperative kernel too
   int ensure_trial_store(long long min_slots);
@@ -813,7 +871,15 @@ struct BatchImpl : BatchBase {
     static const int env_sweep = std::getenv("MAS_B200_SWEEP_LANES") ? std::atoi(std::getenv("MAS_B200_SWEEP_LANES")) : -1;
     const bool lanes_ok = !HasConstraints<M>::value && M::NX <= 8;
     const bool use_lanes = lanes_ok && (env_sweep >= 0 ? env_sweep != 0 : static_cast<long long>(n_upper) * concurrency_hint <= sweep_lanes_max);
-    if (use_lanes) {
+    // one lane per matrix entry (RiccatiWide): opt-in; on B200 one problem 0.834 vs 0.836 ms, 256-8,192 problems 3-5 % slower
+    // than the four-lane sweep (profiles/r02_wide_probe.jsonl) -- the barriers between its six phases cost what the shorter
+    // chains save
+    using RW = RiccatiWide<M, MASK_CT>;
+    static const int env_wide = std::getenv("MAS_B200_SWEEP_WIDE") ? std::atoi(std::getenv("MAS_B200_SWEEP_WIDE")) : -1;
+    const bool use_wide = RW::kSupported && (env_wide >= 0 ? env_wide != 0 : static_cast<long long>(n_upper) * concurrency_hint <= sweep_wide_max);
+    if (use_wide) {
+      launch_sweep_wide<MASK_CT>(n_upper, cur);
+    } else if (use_lanes) {
       constexpr int PW = 32 / RL::LG;
       riccati_sweep_lanes_kernel<M, MASK_CT><<<div_up(n_upper, PW), 32, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1), d_deriv,
                                                                                            deriv_cap);
@@ -822,6 +888,16 @@ struct BatchImpl : BatchBase {
                                                                                                      d_count + (cur ^ 1), d_deriv, deriv_cap);
     }
     stats.kernel_launches += 2;
+  }
+
+  template <int MASK_CT>
+  void launch_sweep_wide(int n_upper, int cur) {
+    using RW = RiccatiWide<M, MASK_CT>;
+    if constexpr (RW::kSupported) {
+      constexpr int PW = 32 / RW::LW;
+      riccati_sweep_wide_kernel<M, MASK_CT><<<div_up(n_upper, PW), 32, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_count + (cur ^ 1), d_deriv,
+                                                                                          deriv_cap);
+    }
   }
 
   void launch_backward(int n_upper, int cur) {

@@ -1507,6 +1507,170 @@ struct RiccatiLanes {
   }
 };
 
+// ---- the Riccati recursion over NX*NX lanes of a problem (element-parallel) ------------------------------------------
+// RiccatiLanes leaves every lane ~340 dependent fp64 instructions per step (q_x, q_u, Q_uu, the factorisation and K^T Q_uu
+// are computed redundantly), and a lone warp issues them at ~5.5 cycles each: 2.1 us per step, T times per iteration,
+// whatever the problem count.  RiccatiWide gives a problem one lane per ENTRY (i, j) of the NX x NX matrices: a lane
+// produces one entry of A^T V_xx, Q_xx, m1, m2, m3 and V_xx per step plus one entry of the smaller products (B^T V_xx,
+// Q_ux, Q_uu, K, K^T Q_uu, q_x, q_u, k, V_x), dealt out by lane index; only the NU x NU factorisation + inverse is
+// repeated on every lane.  Every entry is the same k-ascending sum with the same structural zeros left out as in
+// riccati_step (sparse_dot == one entry of mat_tn_sa / mat_nn_sb / mat_tn / mat_nn), so the results are bit-identical
+// (host emulation + GPU tests).  Operands travel through a per-problem area of shared memory, one barrier per phase.
+// a[k*sa] * b[k*sb] summed over the k whose bit (bit0 + k) of nz is set, k ascending, the first term starts the sum;
+// branch-free so that the lanes of a warp may differ in (a, b, nz, bit0)
+template <int KD>
+MAS_HD double sparse_dot(const double* a, int sa, const double* b, int sb, unsigned long long nz, int bit0) {
+  double s = 0.0;
+  bool first = true;
+#pragma unroll
+  for (int k = 0; k < KD; ++k) {
+    const bool on = (nz >> (bit0 + k)) & 1ull;
+    const double prod = a[k * sa] * b[k * sb];
+    const double sum = s + prod;
+    s = on ? (first ? prod : sum) : s;
+    first = first && !on;
+  }
+  return s;
+}
+template <int KD>
+MAS_HD double dense_dot(const double* a, int sa, const double* b, int sb) {
+  double s = a[0] * b[0];
+#pragma unroll
+  for (int k = 1; k < KD; ++k) s = s + a[k * sa] * b[k * sb];
+  return s;
+}
+
+template <class M, int MASK_CT>
+struct RiccatiWide {
+  static constexpr int NX = M::NX, NU = M::NU;
+  using D = DerivBlock<M>;
+  static constexpr int LW = NX * NX;  // lanes per problem
+  static constexpr bool kSupported = (LW == 4 || LW == 8 || LW == 16 || LW == 32) && NU * NX + NX + NU <= LW && NU * NX + NU * NU <= LW &&
+                                     NU * NX + 2 * NX <= LW && !HasConstraints<M>::value;
+  // lane roles beside the (i, j) entry every lane owns: [0, UX) an entry of the NU x NX (or NX x NU) matrices, then ranges of NX / NU lanes
+  static constexpr int UX = NU * NX, rQx = UX, rQu = UX + NX, rQuu = UX, rKv = UX, rT1 = UX, rT2 = UX + NX;
+  // exchange area (doubles)
+  static constexpr int xAtV = 0, xBtV = xAtV + NX * NX, xQux = xBtV + UX, xQuu = xQux + UX, xqu = xQuu + NU * NU, xK = xqu + NU, xkv = xK + UX,
+                       xKtQuu = xkv + NU, xt2 = xKtQuu + UX, xVu = xt2 + NX, xV = xVu + NX * NX, xvx = xV + NX * NX, XCH = xvx + NX;
+  static constexpr unsigned long long kDense = ~0ull;
+  static constexpr unsigned long long a_nz = (MASK_CT >= 0 && (MASK_CT & D_A)) ? M::A_NZ : kDense;
+  static constexpr unsigned long long b_nz = (MASK_CT >= 0 && (MASK_CT & D_B)) ? M::B_NZ : kDense;
+
+  // per-lane state
+  double qxx = 0.0;   // Q_xx(i, j), then (Q_xx + m1) + m2
+  double qx = 0.0;    // lanes [rQx, rQx + NX): q_x(i), then q_x + t1
+  int retries = 0;
+
+  // terminal block [V_x | V_xx] (ilqr.hpp:92-100); the aliased symmetrisation (:102) is phase 6
+  static MAS_HD void init_terminal(const double* blk, int e, double* xch) {
+    xch[xVu + e] = blk[NX + e];
+    if (e < NX) xch[xvx + e] = blk[e];
+  }
+  // first factors (:115-119): (A^T V_xx)(i, j); (B^T V_xx)(r, j); q_x(i) = l_x + A^T V_x; q_u(r) = l_u + B^T V_x
+  MAS_HD void phase1(const double* blk, int e, double* xch) {
+    const int i = e % NX, j = e / NX;
+    xch[xAtV + e] = sparse_dot<NX>(blk + D::oA + i * NX, 1, xch + xV + j * NX, 1, a_nz, i * NX);
+    if (e < rQu + NU) {
+      const bool isBtV = e < UX, isQx = !isBtV && e < rQu;
+      const int r = isBtV ? e % NU : e - rQu, jb = e / NU, ix = e - rQx;
+      const int col = isQx ? ix : r;  // column of A (q_x) or of B (B^T V, q_u)
+      const double* a = blk + (isQx ? D::oA : D::oB) + col * NX;
+      const double* b = isBtV ? xch + xV + jb * NX : xch + xvx;
+      const double dot = sparse_dot<NX>(a, 1, b, 1, isQx ? a_nz : b_nz, col * NX);
+      if (isBtV) {
+        xch[xBtV + e] = dot;
+      } else if (isQx) {
+        qx = blk[D::olx + ix] + dot;
+      } else {
+        xch[xqu + r] = blk[D::olu + r] + dot;
+      }
+    }
+  }
+  // second factors (:117-119): Q_xx(i, j); Q_ux(r, j); Q_uu(r, s)
+  MAS_HD void phase2(const double* blk, int e, double* xch) {
+    const int i = e % NX, j = e / NX;
+    qxx = blk[D::olxx + e] + sparse_dot<NX>(xch + xAtV + i, NX, blk + D::oA + j * NX, 1, a_nz, j * NX);
+    if (e < rQuu + NU * NU) {
+      const bool isQux = e < UX;
+      const int f = isQux ? e : e - rQuu, r = f % NU, c = f / NU;  // c: column of A (Q_ux) or of B (Q_uu)
+      const double dot = sparse_dot<NX>(xch + xBtV + r, NU, blk + (isQux ? D::oA : D::oB) + c * NX, 1, isQux ? a_nz : b_nz, c * NX);
+      if (isQux) xch[xQux + f] = blk[D::olux + f] + dot;
+      else xch[xQuu + f] = blk[D::oluu + f] + dot;
+    }
+  }
+  // Q_uu regularisation + LLT + inverse on every lane (:172-183), then the gains (:185-186): K(r, j), k(r)
+  MAS_HD void phase3(const BatchView<NX, NU>& v, int p, int t, int e, double* xch) {
+    double q_reg[NU * NU], L[NU * NU], inv[NU * NU];
+#pragma unroll
+    for (int n = 0; n < NU * NU; ++n) q_reg[n] = xch[xQuu + n];
+    double reg = 1e-6;
+    while (!llt_factor<NU>(q_reg, L)) {
+#pragma unroll
+      for (int n = 0; n < NU; ++n) q_reg[n + n * NU] += reg;
+      reg *= 10.0;
+      if (e == 0) ++retries;
+      if (!(reg < 1e300)) break;
+    }
+    llt_inverse<NU>(L, inv);
+    if (e < rKv + NU) {
+      const bool isK = e < UX;
+      const int r = isK ? e % NU : e - rKv, j = e / NU;
+      double nrow[NU];  // row r of -Q_uu^-1, picked with selects (r is a run-time value)
+#pragma unroll
+      for (int sidx = 0; sidx < NU; ++sidx) {
+        double val = -inv[0 + sidx * NU];
+#pragma unroll
+        for (int rr = 1; rr < NU; ++rr) val = (r == rr) ? -inv[rr + sidx * NU] : val;
+        nrow[sidx] = val;
+      }
+      const double g = dense_dot<NU>(nrow, 1, isK ? xch + xQux + j * NU : xch + xqu, 1);
+      if (isK) {
+        xch[xK + e] = g;
+        v.K[soa_index<NU * NX>(t, e, v.ld, p)] = g;
+      } else {
+        xch[xkv + r] = g;
+        v.kff[soa_index<NU>(t, r, v.ld, p)] = g;
+      }
+    }
+  }
+  // value update, first half (:188-191): m1, m2 of my entry; (K^T Q_uu)(i, s); K^T q_u; Q_ux^T k
+  MAS_HD void phase4(int e, double* xch) {
+    const int i = e % NX, j = e / NX;
+    const double m1 = dense_dot<NU>(xch + xK + i * NU, 1, xch + xQux + j * NU, 1);
+    const double m2 = dense_dot<NU>(xch + xQux + i * NU, 1, xch + xK + j * NU, 1);
+    qxx = (qxx + m1) + m2;
+    if (e < rT2 + NX) {
+      const bool isKtQ = e < UX, isT1 = !isKtQ && e < rT2;
+      const int ii = isKtQ ? e % NX : (isT1 ? e - rT1 : e - rT2), sc = e / NX;
+      const double* a = (isKtQ || isT1) ? xch + xK + ii * NU : xch + xQux + ii * NU;
+      const double* b = isKtQ ? xch + xQuu + sc * NU : (isT1 ? xch + xqu : xch + xkv);
+      const double d = dense_dot<NU>(a, 1, b, 1);
+      if (isKtQ) xch[xKtQuu + e] = d;
+      else if (isT1) qx = qx + d;
+      else xch[xt2 + ii] = d;
+    }
+  }
+  // value update, second half: m3 and the unsymmetrised V_xx(i, j); V_x(i)
+  MAS_HD void phase5(int e, double* xch) {
+    const int i = e % NX, j = e / NX;
+    const double m3 = dense_dot<NU>(xch + xKtQuu + i, NX, xch + xK + j * NU, 1);
+    xch[xVu + e] = qxx + m3;
+    if (e >= rT1 && e < rT1 + NX) {
+      const int ii = e - rT1;
+      const double t3 = dense_dot<NU>(xch + xKtQuu + ii, NX, xch + xkv, 1);
+      xch[xvx + ii] = (qx + xch[xt2 + ii]) + t3;
+    }
+  }
+  // `v_xx = 0.5 * (v_xx + v_xx.transpose())` evaluated in place, columns outer (symmetrize_aliased), entry (i, j): below the
+  // diagonal both operands are old; above it the transposed operand is the already-updated lower entry
+  static MAS_HD void phase6(int e, double* xch) {
+    const int i = e % NX, j = e / NX;
+    const double a = xch[xVu + i + j * NX], b = xch[xVu + j + i * NX];
+    const double lower = 0.5 * (b + a);
+    xch[xV + e] = (i < j) ? 0.5 * (a + lower) : 0.5 * (a + b);
+  }
+};
+
 // ---- forward pass (ilqr.hpp:206-217) for C step sizes at once, merit only ------------------------
 // The C rollouts share the loads of the nominal trajectory and gains and give the fp64 pipe C
 // independent dependency chains.  merit[c] = sum_t stage + terminal, accumulated in t order.

@@ -75,7 +75,7 @@ class HostEmulation:
         self.lib = ctypes.CDLL(_build_emulation())
 
     def solve(self, model, x0, U, max_iterations, tolerance, L=1, C=2, mask=None, per_problem_params=None, penalty=10.0, repeats=1,
-              trial_store=True, backward_lanes=0, sweep_lanes=False):
+              trial_store=True, backward_lanes=0, sweep_lanes=False, sweep_wide=0):
         """repeats > 1: the same solver state (multipliers, penalty) and warm start solving again; adds cost_history /
         iterations_history [repeats, B]."""
         n, m, T, dt, emask, hb, lo, hi, prm = MODEL_TABLE[model]
@@ -101,6 +101,7 @@ class HostEmulation:
         self.lib.emu_set_trial_store(int(trial_store))
         self.lib.emu_set_backward_lanes(int(backward_lanes))
         self.lib.emu_set_sweep_lanes(int(bool(sweep_lanes)))
+        self.lib.emu_set_sweep_wide(int(sweep_wide))
         hc = np.zeros((repeats, B))
         hi_ = np.zeros((repeats, B), np.int32)
         self.lib.emu_set_al_options(ctypes.c_double(penalty), ctypes.c_double(5.0), ctypes.c_double(1e-4), ctypes.c_double(1e-6), int(repeats),
@@ -112,6 +113,7 @@ class HostEmulation:
         self.lib.emu_set_al_options(ctypes.c_double(10.0), ctypes.c_double(5.0), ctypes.c_double(1e-4), ctypes.c_double(1e-6), 1, None, None)
         self.lib.emu_set_backward_lanes(0)
         self.lib.emu_set_sweep_lanes(0)
+        self.lib.emu_set_sweep_wide(0)
         assert rc == 0
         return dict(X=X, U=U, cost=cost, iterations=it, status=st, alpha_trials=tr, reg_retries=rg, cost_history=hc, iterations_history=hi_)
 

@@ -25,6 +25,7 @@ struct ALOptions {
   int repeats = 1;
   bool trial_store = true;
   bool sweep_lanes = false;  // time-parallel mode: the Riccati sweep column-parallel over the lanes of a problem (RiccatiLanes)
+  int sweep_wide = 0;        // time-parallel mode: one lane per matrix entry (RiccatiWide); 1 / 2 = lanes run a phase in ascending / mixed order
   int backward_lanes = 0;  // > 0: lane-parallel backward pass with that many lanes per problem; < 0: time-parallel with -n threads per point
   double* hist_cost = nullptr;
   int* hist_iters = nullptr;
@@ -77,6 +78,38 @@ int emulate_time_parallel(const BatchView<M::NX, M::NU>& v, int p, int G) {
   for (int t = v.T; t >= 0; --t)
     for (int g = G - 1; g >= 0; --g)
       linearize_point<M>(v, p, t, mask, g, G, [&](int off, double val) { store[static_cast<size_t>(t) * D::size + off] = val; });
+  if constexpr (RiccatiWide<M, MASK_CT>::kSupported) {
+    if (g_al.sweep_wide) {
+      // riccati_sweep_wide_kernel: the LW lanes of the problem run every phase one after the other (a barrier separates the
+      // phases on the device), in an order that changes from phase to phase so that a dependence inside a phase would show
+      using RW = RiccatiWide<M, MASK_CT>;
+      constexpr int LW = RW::LW;
+      RW lane[LW];
+      double xch[RW::XCH];
+      for (int k = 0; k < RW::XCH; ++k) xch[k] = std::numeric_limits<double>::quiet_NaN();
+      int phase = 0;
+      auto each = [&](auto fn) {
+        ++phase;
+        for (int k = 0; k < LW; ++k) {
+          const int e = g_al.sweep_wide == 1 ? k : ((phase & 1) ? LW - 1 - k : (k * 5 + phase) % LW);
+          fn(e);
+        }
+      };
+      const double* tb = &store[static_cast<size_t>(v.T) * D::size];
+      each([&](int e) { RW::init_terminal(tb, e, xch); });
+      each([&](int e) { RW::phase6(e, xch); });
+      for (int t = v.T - 1; t >= 0; --t) {
+        const double* blk = &store[static_cast<size_t>(t) * D::size];
+        each([&](int e) { lane[e].phase1(blk, e, xch); });
+        each([&](int e) { lane[e].phase2(blk, e, xch); });
+        each([&](int e) { lane[e].phase3(v, p, t, e, xch); });
+        each([&](int e) { lane[e].phase4(e, xch); });
+        each([&](int e) { lane[e].phase5(e, xch); });
+        each([&](int e) { RW::phase6(e, xch); });
+      }
+      return lane[0].retries;
+    }
+  }
   if (g_al.sweep_lanes && !HasConstraints<M>::value) {
     // riccati_sweep_lanes_kernel: the lanes of the problem run every phase one after the other, exchange area in between
     using RL = RiccatiLanes<M, MASK_CT>;
@@ -309,6 +342,7 @@ extern "C" int emu_ilqr_solve_batch(int model, int batch, int T, double dt, unsi
 extern "C" void emu_set_trial_store(int enable) { g_al.trial_store = enable != 0; }
 extern "C" void emu_set_backward_lanes(int lanes) { g_al.backward_lanes = lanes; }
 extern "C" void emu_set_sweep_lanes(int on) { g_al.sweep_lanes = on != 0; }
+extern "C" void emu_set_sweep_wide(int mode) { g_al.sweep_wide = mode; }
 
 extern "C" void emu_set_al_options(double penalty, double penalty_increase, double constraint_tolerance, double activation_tolerance, int repeats,
                                    double* hist_cost, int* hist_iters) {

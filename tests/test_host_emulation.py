@@ -194,8 +194,8 @@ def test_nonfinite_trajectories(emu, oracle):
     refs = [oracle.ilqr_solve_batch(0, x0, U_init=U, trig=oracle.TRIG_PORTABLE)]
     if ref_py.available():
         refs.append(ref_py.ilqr_solve_batch(0, x0, U_init=U, trig=1))
-    for L, C, bl, sl in ((1, 2, 0, False), (4, 1, 0, False), (16, 1, 0, False), (16, 1, -2, False), (16, 1, -2, True)):
-        got = emu.solve(0, x0, U, 10, 1e-5, L=L, C=C, backward_lanes=bl, sweep_lanes=sl)
+    for L, C, bl, sl, sw in ((1, 2, 0, False, 0), (4, 1, 0, False, 0), (16, 1, 0, False, 0), (16, 1, -2, False, 0), (16, 1, -2, True, 0), (16, 1, -2, False, 2)):
+        got = emu.solve(0, x0, U, 10, 1e-5, L=L, C=C, backward_lanes=bl, sweep_lanes=sl, sweep_wide=sw)
         for ref in refs:
             for k in ("X", "U", "cost", "iterations", "status"):
                 assert np.array_equal(got[k], ref[k], equal_nan=got[k].dtype.kind == "f"), (L, C, k)
@@ -223,9 +223,14 @@ def test_time_parallel_backward_pass_is_bit_identical(emu, oracle, model, mask, 
     par = emu.solve(model, x0, U0, max_it, tol, mask=mask, backward_lanes=-threads)
     # ... and with the recursion itself column-parallel over the lanes of a problem (RiccatiLanes)
     lan = emu.solve(model, x0, U0, max_it, tol, mask=mask, backward_lanes=-threads, sweep_lanes=True)
+    # ... and with one lane per entry of the NX x NX matrices (RiccatiWide; models it does not cover fall back), the lanes of
+    # a phase run in ascending and in mixed order
+    wides = [emu.solve(model, x0, U0, max_it, tol, mask=mask, backward_lanes=-threads, sweep_wide=w) for w in (1, 2)]
     for k in ("X", "U", "cost", "iterations", "status", "alpha_trials", "reg_retries"):
         assert np.array_equal(one[k], par[k]), k
         assert np.array_equal(one[k], lan[k]), k
+        for wd in wides:
+            assert np.array_equal(one[k], wd[k]), k
     if mask == MODEL_TABLE[model][4]:
         ref = oracle.ilqr_solve_batch(model, x0, U_init=U0, max_iterations=max_it, tolerance=tol, trig=oracle.TRIG_PORTABLE)
         assert is_bit_exact(par, ref)
