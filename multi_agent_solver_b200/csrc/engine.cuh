@@ -776,11 +776,7 @@ struct BatchImpl : BatchBase {
     view.T = T;
     view.dt = desc.dt;
     view.deriv_mask = desc.deriv_mask;
-    view.has_bounds = desc.has_input_bounds;
-    for (int i = 0; i < M::NU; ++i) {
-      view.lo[i] = desc.input_lower[i];
-      view.hi[i] = desc.input_upper[i];
-    }
+    view.set_bounds(desc.has_input_bounds, desc.input_lower, desc.input_upper);
     view.per_problem_params = per_problem_params ? 1 : 0;
     for (int i = 0; i < kMaxParams; ++i) view.shared_p[i] = i < desc.num_params ? desc.params[i] : 0.0;
     view.params = d_params;

@@ -31,6 +31,16 @@ struct BatchView {
   unsigned deriv_mask;
   int has_bounds;  // both input bounds present (ilqr.hpp:213)
   double lo[NU], hi[NU];
+  double clamp_lo[NU], clamp_hi[NU];  // the same, or -inf / +inf without bounds: the trial rollouts clamp without a branch
+  void set_bounds(int has, const double* lower, const double* upper) {
+    has_bounds = has;
+    for (int i = 0; i < NU; ++i) {
+      lo[i] = lower[i];
+      hi[i] = upper[i];
+      clamp_lo[i] = has ? lower[i] : -__builtin_huge_val();
+      clamp_hi[i] = has ? upper[i] : __builtin_huge_val();
+    }
+  }
   int per_problem_params;  // 0: shared_p, 1: params[NP][ld]
   double shared_p[kMaxParams];
   const double* params;
@@ -270,6 +280,39 @@ MAS_HD void rk4_step(const double* x, const double* u, const double* prm, double
   const double sixth = MAS_DIV_CONST(dt, 6.0);
 #pragma unroll
   for (int i = 0; i < NX; ++i) xn[i] = x[i] + sixth * (((k1[i] + 2.0 * k2[i]) + 2.0 * k3[i]) + k4[i]);
+}
+
+// The same step as one basic block, for the trial rollouts of the line search: every division on its fast path with
+// selects instead of branches (portable_math.h: tan_spec, div_const_spec), `sixth` = dt / 6 computed by the caller once per
+// rollout.  Returns false when a division would have needed its slow path (operands outside 2^+-896: trajectories that
+// have left the finite range) -- the caller then repeats the step with rk4_step; otherwise xn holds the bits of rk4_step.
+// With the branches gone the compiler interleaves the four stages' sin / cos chains and the C candidates of a lane.
+template <class M>
+MAS_HD bool rk4_step_spec(const double* x, const double* u, const double* prm, double dt, double sixth, double* xn) {
+  if constexpr (M::SPEC_STEP) {
+    constexpr int NX = M::NX;
+    double k1[NX], k2[NX], k3[NX], k4[NX], xs[NX];
+    const double hdt = 0.5 * dt;
+    double cu[M::NCU];
+    bool exact = true;
+    M::control_terms_spec(u, prm, cu, &exact);
+    M::dynamics_c_spec(x, u, cu, prm, k1, &exact);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xs[i] = x[i] + hdt * k1[i];
+    M::dynamics_c_spec(xs, u, cu, prm, k2, &exact);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xs[i] = x[i] + hdt * k2[i];
+    M::dynamics_c_spec(xs, u, cu, prm, k3, &exact);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xs[i] = x[i] + dt * k3[i];
+    M::dynamics_c_spec(xs, u, cu, prm, k4, &exact);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xn[i] = x[i] + sixth * (((k1[i] + 2.0 * k2[i]) + 2.0 * k3[i]) + k4[i]);
+    return exact;
+  } else {
+    rk4_step<M>(x, u, prm, dt, xn);
+    return true;
+  }
 }
 
 // ---- prologue: X = integrate_horizon(x0, U); cost = objective(X, U)  (ilqr.hpp:75-78) -----------
@@ -1692,6 +1735,9 @@ MAS_HD void trial_rollout(const BatchView<M::NX, M::NU>& v, int p, const double*
 #pragma unroll
     for (int i = 0; i < NX; ++i) xt[c][i] = v.x0[static_cast<size_t>(i) * v.ld + p];
   }
+  const double sixth = MAS_DIV_CONST(v.dt, 6.0);
+  const size_t ld = static_cast<size_t>(v.ld);
+  const double *rX = v.X + p, *rU = v.U + p, *rk = v.kff + p, *rK = v.K + p;  // rows of step t (plain-load path)
   for (int t = 0; t < v.T; ++t) {
     double xn[NX], un[NU], kv[NU], Km[NU * NX];
     if (stage) {
@@ -1699,28 +1745,36 @@ MAS_HD void trial_rollout(const BatchView<M::NX, M::NU>& v, int p, const double*
       stage_read_step<NX, NU>(stage, t & 1, xn, un, kv, Km);
       if (t + 1 < v.T) stage_issue_step<NX, NU>(v, p, t + 1, t + 1, stage, (t + 1) & 1);
     } else {
+      // running row pointers (one add per array and step instead of a 64-bit index product per element); the rows of
+      // step t+1 are prefetched without a branch: on the last step the offset is zero and the current rows are named again
 #pragma unroll
-      for (int i = 0; i < NX; ++i) xn[i] = v.X[soa_index<NX>(t, i, v.ld, p)];
+      for (int i = 0; i < NX; ++i) xn[i] = rX[i * ld];
 #pragma unroll
-      for (int i = 0; i < NU; ++i) un[i] = v.U[soa_index<NU>(t, i, v.ld, p)];
+      for (int i = 0; i < NU; ++i) un[i] = rU[i * ld];
 #pragma unroll
-      for (int i = 0; i < NU; ++i) kv[i] = v.kff[soa_index<NU>(t, i, v.ld, p)];
+      for (int i = 0; i < NU; ++i) kv[i] = rk[i * ld];
 #pragma unroll
-      for (int i = 0; i < NU * NX; ++i) Km[i] = v.K[soa_index<NU * NX>(t, i, v.ld, p)];
-      if (t + 1 < v.T) {
+      for (int i = 0; i < NU * NX; ++i) Km[i] = rK[i * ld];
+      const size_t nxt = t + 1 < v.T ? 1 : 0;
+      const double *nX = rX + nxt * (NX * ld), *nU = rU + nxt * (NU * ld), *nk = rk + nxt * (NU * ld), *nK = rK + nxt * (NU * NX * ld);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) prefetch_l1(&v.X[soa_index<NX>(t + 1, i, v.ld, p)]);
+      for (int i = 0; i < NX; ++i) prefetch_l1(&nX[i * ld]);
 #pragma unroll
-        for (int i = 0; i < NU; ++i) prefetch_l1(&v.U[soa_index<NU>(t + 1, i, v.ld, p)]);
+      for (int i = 0; i < NU; ++i) prefetch_l1(&nU[i * ld]);
 #pragma unroll
-        for (int i = 0; i < NU; ++i) prefetch_l1(&v.kff[soa_index<NU>(t + 1, i, v.ld, p)]);
+      for (int i = 0; i < NU; ++i) prefetch_l1(&nk[i * ld]);
 #pragma unroll
-        for (int i = 0; i < NU * NX; ++i) prefetch_l1(&v.K[soa_index<NU * NX>(t + 1, i, v.ld, p)]);
-      }
+      for (int i = 0; i < NU * NX; ++i) prefetch_l1(&nK[i * ld]);
+      rX = nX;
+      rU = nU;
+      rk = nk;
+      rK = nK;
     }
+    double u[C][NU], xnext[C][NX];
+    bool exact = true;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      double dx[NX], u[NU], xnext[NX];
+      double dx[NX];
 #pragma unroll
       for (int i = 0; i < NX; ++i) dx[i] = xt[c][i] - xn[i];
 #pragma unroll
@@ -1729,23 +1783,29 @@ MAS_HD void trial_rollout(const BatchView<M::NX, M::NU>& v, int p, const double*
 #pragma unroll
         for (int j = 1; j < NX; ++j) kdx = kdx + Km[i + j * NU] * dx[j];
         double ui = (un[i] + alpha[c] * kv[i]) + kdx;
-        if (v.has_bounds) {  // clamp_controls: cwiseMin(upper) then cwiseMax(lower)
-          ui = (v.hi[i] < ui) ? v.hi[i] : ui;
-          ui = (v.lo[i] > ui) ? v.lo[i] : ui;
-        }
-        u[i] = ui;
+        ui = (v.clamp_hi[i] < ui) ? v.clamp_hi[i] : ui;  // clamp_controls: cwiseMin(upper) then cwiseMax(lower); +-inf = no bounds
+        ui = (v.clamp_lo[i] > ui) ? v.clamp_lo[i] : ui;
+        u[c][i] = ui;
       }
-      cost[c] += M::stage(xt[c], u, t, prm);
-      if (kAL) al_merit_addends<M>(v, p, t, xt[c], u, prm, al_rho, &al_terms[c][3 * t]);
-      rk4_step<M>(xt[c], u, prm, v.dt, xnext);
+      cost[c] += M::stage(xt[c], u[c], t, prm);
+      if (kAL) al_merit_addends<M>(v, p, t, xt[c], u[c], prm, al_rho, &al_terms[c][3 * t]);
+      const bool e = rk4_step_spec<M>(xt[c], u[c], prm, v.dt, sixth, xnext[c]);  // one basic block for all C candidates
+      exact = exact && e;
+    }
+    if (!exact) {  // a division off its fast path (non-finite trajectories): the step again, branch by branch
 #pragma unroll
-      for (int i = 0; i < NX; ++i) xt[c][i] = xnext[i];
+      for (int c = 0; c < C; ++c) rk4_step<M>(xt[c], u[c], prm, v.dt, xnext[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) xt[c][i] = xnext[c][i];
       if (STORE) {
         const size_t slot = static_cast<size_t>(slot0 + c * slot_stride);
 #pragma unroll
-        for (int i = 0; i < NU; ++i) store_streaming(&v.trial_U[(static_cast<size_t>(t) * NU + i) * n_slots + slot], u[i]);
+        for (int i = 0; i < NU; ++i) store_streaming(&v.trial_U[(static_cast<size_t>(t) * NU + i) * n_slots + slot], u[c][i]);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) store_streaming(&v.trial_X[(static_cast<size_t>(t) * NX + i) * n_slots + slot], xnext[i]);
+        for (int i = 0; i < NX; ++i) store_streaming(&v.trial_X[(static_cast<size_t>(t) * NX + i) * n_slots + slot], xnext[c][i]);
       }
     }
   }

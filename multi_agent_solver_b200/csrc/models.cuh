@@ -54,6 +54,7 @@ enum DerivBits : unsigned {
 struct NoConstraints {
   static constexpr unsigned long long A_NZ = ~0ull, B_NZ = ~0ull;
   static constexpr int NEQ = 0, NINEQ = 0;
+  static constexpr bool SPEC_STEP = false;  // no straight-line variant of the dynamics (rk4_step_spec falls back to rk4_step)
   MAS_HD static void eq(const double*, const double*, const double*, double*) {}
   MAS_HD static void ineq(const double*, const double*, const double*, double*) {}
   // analytic constraint Jacobians, row-major by constraint: Jx[r + c*NC] like the other column-major blocks
@@ -87,6 +88,19 @@ struct SingleTrackDyn {
     control_terms(u, cu);
     f_c(x, u, cu, d);
   }
+  // The same two functions as straight-line code (pm::tan_spec, pm::div_const_spec): identical bits whenever *exact stays
+  // true; the rollout step of the line search runs them and repeats the step with the functions above otherwise.
+  MAS_HD static void control_terms_spec(const double* u, double* cu, bool* exact) { cu[0] = pm::tan_spec(u[0], exact); }
+  MAS_HD static void f_c_spec(const double* x, const double* u, const double* cu, double* d, bool* exact) {
+    const double psi = x[2], v = x[3], a = u[1];
+    const double L = 2.5;
+    double s, c;
+    pm::sincos_(psi, &s, &c);
+    d[0] = v * c;
+    d[1] = v * s;
+    d[2] = MAS_DIV_CONST_SPEC(v * cu[0], L, exact);
+    d[3] = a;
+  }
   MAS_HD static void jac_x(const double* x, const double* u, double* A) {
     const double psi = x[2], v = x[3], delta = u[0];
     const double L = 2.5;
@@ -119,6 +133,11 @@ struct StLane : NoConstraints {
   static constexpr int NCU = 1;
   MAS_HD static void control_terms(const double* u, const double*, double* cu) { SingleTrackDyn::control_terms(u, cu); }
   MAS_HD static void dynamics_c(const double* x, const double* u, const double* cu, const double*, double* d) { SingleTrackDyn::f_c(x, u, cu, d); }
+  static constexpr bool SPEC_STEP = true;  // straight-line rollout step available (rk4_step_spec)
+  MAS_HD static void control_terms_spec(const double* u, const double*, double* cu, bool* exact) { SingleTrackDyn::control_terms_spec(u, cu, exact); }
+  MAS_HD static void dynamics_c_spec(const double* x, const double* u, const double* cu, const double*, double* d, bool* exact) {
+    SingleTrackDyn::f_c_spec(x, u, cu, d, exact);
+  }
   MAS_HD static void dynamics(const double* x, const double* u, const double*, double* d) { SingleTrackDyn::f(x, u, d); }
   MAS_HD static double stage(const double* x, const double* u, int, const double* p) {
     const double lane_error = x[1], speed_error = (x[3] - p[0]);
@@ -201,6 +220,11 @@ struct StCirc : NoConstraints {
   static constexpr int NCU = 1;
   MAS_HD static void control_terms(const double* u, const double*, double* cu) { SingleTrackDyn::control_terms(u, cu); }
   MAS_HD static void dynamics_c(const double* x, const double* u, const double* cu, const double*, double* d) { SingleTrackDyn::f_c(x, u, cu, d); }
+  static constexpr bool SPEC_STEP = true;  // straight-line rollout step available (rk4_step_spec)
+  MAS_HD static void control_terms_spec(const double* u, const double*, double* cu, bool* exact) { SingleTrackDyn::control_terms_spec(u, cu, exact); }
+  MAS_HD static void dynamics_c_spec(const double* x, const double* u, const double* cu, const double*, double* d, bool* exact) {
+    SingleTrackDyn::f_c_spec(x, u, cu, d, exact);
+  }
   MAS_HD static void dynamics(const double* x, const double* u, const double*, double* d) { SingleTrackDyn::f(x, u, d); }
   MAS_HD static double stage(const double* s, const double* c, int, const double* p) {
     const double x = s[0], y = s[1], vx = s[3];

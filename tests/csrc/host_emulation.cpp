@@ -151,11 +151,7 @@ int emulate(int batch, int T, double dt, unsigned mask, int has_bounds, const do
   v.T = T;
   v.dt = dt;
   v.deriv_mask = mask;
-  v.has_bounds = has_bounds;
-  for (int i = 0; i < NU; ++i) {
-    v.lo[i] = lo[i];
-    v.hi[i] = hi[i];
-  }
+  v.set_bounds(has_bounds, lo, hi);
   v.per_problem_params = per_problem_p ? 1 : 0;
   for (int i = 0; i < kMaxParams; ++i) v.shared_p[i] = shared_p ? shared_p[i] : 0.0;
   v.params = sp.data();
