@@ -317,6 +317,12 @@ int mas_b200_synthetic_single_track_x0(unsigned long long seed, int batch, doubl
 /* fp64 pipe peak probe (DFMA throughput in TFLOP/s on the context device) for roofline reporting */
 int mas_b200_probe_fp64_peak(mas_b200_context_t ctx, double* tflops);
 
+/* Device self-test of the straight-line divisions the line search's rollout step uses (portable_math.h: div_spec,
+ * div_const_spec) against the division instruction, on `pairs` generated operand pairs: counts[0] pairs checked,
+ * counts[1] pairs div_spec accepted as exact, counts[2] of those that differ from a / b (must be 0), counts[3] /
+ * counts[4] the same for div_const_spec with the divisors 2.5 and 6. */
+int mas_b200_selftest_division(mas_b200_context_t ctx, unsigned long long seed, long long pairs, long long* counts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -212,6 +212,11 @@ class Context:
         _check(load_library().mas_b200_probe_fp64_peak(self._h, ctypes.byref(tf)))
         return tf.value
 
+    def selftest_division(self, pairs: int, seed: int = 1) -> dict:
+        counts = (ctypes.c_longlong * 5)()
+        _check(load_library().mas_b200_selftest_division(self._h, ctypes.c_ulonglong(seed), ctypes.c_longlong(pairs), counts))
+        return dict(checked=counts[0], div_exact=counts[1], div_mismatch=counts[2], div_const_exact=counts[3], div_const_mismatch=counts[4])
+
     def close(self) -> None:
         if self._h:
             load_library().mas_b200_context_destroy(self._h)

@@ -1178,4 +1178,24 @@ int mas_b200_probe_fp64_peak(mas_b200_context_t ctx, double* tflops) {
   return MAS_B200_OK;
 }
 
+int mas_b200_selftest_division(mas_b200_context_t ctx, unsigned long long seed, long long pairs, long long* counts) {
+  if (!ctx || !counts || pairs < 1) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "bad arguments");
+  MAS_CUDA_CHECK(cudaSetDevice(ctx->c.device));
+  const int threads = 256, blocks = ctx->c.sm_count * 8;
+  const long long per_thread = (pairs + static_cast<long long>(threads) * blocks - 1) / (static_cast<long long>(threads) * blocks);
+  if (per_thread > 1000000) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "too many pairs");
+  unsigned long long* d = nullptr;
+  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d), 5 * sizeof(unsigned long long)));
+  cudaMemsetAsync(d, 0, 5 * sizeof(unsigned long long), ctx->c.stream);
+  division_selftest_kernel<<<blocks, threads, 0, ctx->c.stream>>>(seed, static_cast<int>(per_thread), d);
+  unsigned long long h[5] = {0, 0, 0, 0, 0};
+  const cudaError_t e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->c.stream);
+  const cudaError_t e2 = cudaStreamSynchronize(ctx->c.stream);
+  cudaFree(d);
+  MAS_CUDA_CHECK(e);
+  MAS_CUDA_CHECK(e2);
+  for (int i = 0; i < 5; ++i) counts[i] = static_cast<long long>(h[i]);
+  return MAS_B200_OK;
+}
+
 }  // extern "C"

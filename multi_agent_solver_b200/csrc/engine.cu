@@ -120,6 +120,57 @@ __global__ void dfma_probe_kernel(double* out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// Brute-force check of the straight-line divisions of portable_math.h against the instructions they stand for, on
+// operands drawn from a counter-based generator: out[0] pairs checked, out[1] pairs on which div_spec kept `exact`,
+// out[2] of those whose bits differ from div.rn.f64, out[3] / out[4] the same two counts for div_const_spec against `/`
+// (divisors 2.5 and 6).  Operand classes by (index mod 4): any 64-bit pattern; exponents within 2^+-40 of 1; the same
+// with the numerator's low mantissa bits cleared (quotients near ties); numerator from a cos-like range.
+__global__ void division_selftest_kernel(unsigned long long seed, int per_thread, unsigned long long* out) {
+  auto mix = [](unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  };
+  const unsigned long long tid = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+  unsigned long long n_exact = 0, n_bad = 0, nc_exact = 0, nc_bad = 0;
+  for (int k = 0; k < per_thread; ++k) {
+    const unsigned long long idx = tid * per_thread + k;
+    unsigned long long ra = mix(seed + 2 * idx), rb = mix(seed + 2 * idx + 1);
+    const int cls = static_cast<int>(idx & 3);
+    if (cls != 0) {
+      const unsigned long long ea = 1023 - 40 + (ra >> 52) % 81, eb = 1023 - 40 + (rb >> 52) % 81;
+      ra = (ra & 0x800FFFFFFFFFFFFFull) | (ea << 52);
+      rb = (rb & 0x800FFFFFFFFFFFFFull) | (eb << 52);
+      if (cls == 2) ra &= ~0xFFFFFFFFull;
+      if (cls == 3) rb = (rb & 0x800FFFFFFFFFFFFFull) | (1022ull << 52);
+    }
+    const double a = __longlong_as_double(static_cast<long long>(ra)), b = __longlong_as_double(static_cast<long long>(rb));
+    double ref;
+    asm volatile("div.rn.f64 %0, %1, %2;" : "=d"(ref) : "d"(a), "d"(b));
+    bool exact = true;
+    const double q = pm::div_spec(a, b, &exact);
+    if (exact) {
+      ++n_exact;
+      if (__double_as_longlong(q) != __double_as_longlong(ref) && !(q != q && ref != ref)) ++n_bad;
+    }
+    const double divisor = (idx & 4) ? 2.5 : 6.0, recip = (idx & 4) ? 1.0 / 2.5 : 1.0 / 6.0;
+    double refc;
+    asm volatile("div.rn.f64 %0, %1, %2;" : "=d"(refc) : "d"(a), "d"(divisor));
+    bool exact_c = true;
+    const double qc = pm::div_const_spec(a, divisor, recip, &exact_c);
+    if (exact_c) {
+      ++nc_exact;
+      if (__double_as_longlong(qc) != __double_as_longlong(refc) && !(qc != qc && refc != refc)) ++nc_bad;
+    }
+  }
+  atomicAdd(out + 0, static_cast<unsigned long long>(per_thread));
+  atomicAdd(out + 1, n_exact);
+  atomicAdd(out + 2, n_bad);
+  atomicAdd(out + 3, nc_exact);
+  atomicAdd(out + 4, nc_bad);
+}
+
 BatchBase::~BatchBase() {
   if (ctx) cudaSetDevice(ctx->device);
   // transfers that still read the buffers freed below

@@ -72,6 +72,7 @@ struct Context {
 __global__ void aos_to_soa_kernel(const double* __restrict__ src, double* __restrict__ dst, int batch, int rows, int ld);
 __global__ void soa_to_aos_kernel(const double* __restrict__ src, double* __restrict__ dst, int batch, int rows, int ld);
 __global__ void dfma_probe_kernel(double* out, int iters);
+__global__ void division_selftest_kernel(unsigned long long seed, int per_thread, unsigned long long* out);
 __global__ void publish_count_kernel(const int* __restrict__ count, int* mapped_host_word);
 
 // OCP::initialize_problem / iLQR prologue: rollout + cost, reset of the per-solve counters and of
@@ -379,7 +380,9 @@ __global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) forward_kernel(BatchView
 // search costs about (candidates actually needed)/32 rollout times instead of 10.  Then owners commit / stop-test.
 // STORE: lanes keep their trial trajectories (BatchView::trial_*) and an owner copies its accepted candidate right
 // after the round that produced it, instead of rolling it out again at the end.
-template <class M, int C, bool STORE>
+// SP: the parameters are the batch's shared ones (no per-problem table): they are read where they lie in the kernel's
+// parameter block (constant-bank operands) instead of occupying registers for the whole rollout.
+template <class M, int C, bool STORE, bool SP>
 __global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) forward_coop_kernel(BatchView<M::NX, M::NU> v, const int* __restrict__ list, const int* __restrict__ count,
                                                                 int* next_list, int* next_count) {
   constexpr int kWarps = kBlock / 32;
@@ -416,8 +419,12 @@ __global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) forward_coop_kernel(Batc
       const int o = s_plan[w].owner[lane];
       if (o >= 0) {
         const int po = s_p[w][o], j = s_plan[w].cand[lane];
-        double prm[M::NP > 0 ? M::NP : 1];
-        load_params<M>(v, po, prm);
+        double prm_local[M::NP > 0 ? M::NP : 1];
+        const double* prm = v.shared_p;
+        if constexpr (!SP) {
+          load_params<M>(v, po, prm_local);
+          prm = prm_local;
+        }
         double alpha[C], merit[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) alpha[c] = alpha_of(j + c < kNumAlphas ? j + c : kNumAlphas - 1);
@@ -452,8 +459,12 @@ __global__ void __launch_bounds__(kBlock, MAS_MIN_CTAS) forward_coop_kernel(Batc
   }
   bool again = false;
   if (owner) {
-    double prm[M::NP > 0 ? M::NP : 1];
-    load_params<M>(v, p, prm);
+    double prm_local[M::NP > 0 ? M::NP : 1];
+    const double* prm = v.shared_p;
+    if constexpr (!SP) {
+      load_params<M>(v, p, prm_local);
+      prm = prm_local;
+    }
     again = finish_iteration<M>(v, p, prm, current_merit, accepted >= 0 ? accepted : kNumAlphas, accepted >= 0 ? accepted_merit : current_merit,
                                 committed ? kSlotCommitted : -1, accepted_objective);
   }
@@ -774,7 +785,7 @@ struct BatchImpl : BatchBase {
   void make_view() {
     view.ld = ld;
     view.T = T;
-    view.dt = desc.dt;
+    view.set_dt(desc.dt);
     view.deriv_mask = desc.deriv_mask;
     view.set_bounds(desc.has_input_bounds, desc.input_lower, desc.input_upper);
     view.per_problem_params = per_problem_params ? 1 : 0;
@@ -1107,12 +1118,15 @@ struct BatchImpl : BatchBase {
         // two step sizes per lane by default: +3% with several solves in flight, neutral alone (B200, 65,536 problems)
         const int cgrid = div_up(n_upper, kBlock);
         const bool cstore = coop_store && view.trial_X != nullptr && 2ll * cgrid * kBlock <= view.trial_slots;
+        const bool sp = !view.per_problem_params;
         if (tune_C != 1 && cstore)
-          forward_coop_kernel<M, 2, true><<<cgrid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1], d_count + (cur ^ 1));
+          forward_coop_kernel<M, 2, true, false><<<cgrid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1], d_count + (cur ^ 1));
+        else if (tune_C != 1 && sp)
+          forward_coop_kernel<M, 2, false, true><<<cgrid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1], d_count + (cur ^ 1));
         else if (tune_C != 1)
-          forward_coop_kernel<M, 2, false><<<cgrid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1], d_count + (cur ^ 1));
+          forward_coop_kernel<M, 2, false, false><<<cgrid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1], d_count + (cur ^ 1));
         else
-          forward_coop_kernel<M, 1, false><<<cgrid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1], d_count + (cur ^ 1));
+          forward_coop_kernel<M, 1, false, false><<<cgrid, kBlock, 0, ctx->stream>>>(view, d_list[cur], d_count + cur, d_list[cur ^ 1], d_count + (cur ^ 1));
         stats.kernel_launches++;
         last_L = 32;
         last_C = tune_C != 1 ? 2 : 1;

@@ -28,6 +28,12 @@ struct BatchView {
   int ld;
   int T;
   double dt;
+  double half_dt, sixth_dt;  // 0.5 * dt and dt / 6 (integrator.hpp:22-27), formed once on the host: IEEE operations, the same bits
+  void set_dt(double step) {
+    dt = step;
+    half_dt = 0.5 * step;
+    sixth_dt = step / 6.0;
+  }
   unsigned deriv_mask;
   int has_bounds;  // both input bounds present (ilqr.hpp:213)
   double lo[NU], hi[NU];
@@ -283,16 +289,20 @@ MAS_HD void rk4_step(const double* x, const double* u, const double* prm, double
 }
 
 // The same step as one basic block, for the trial rollouts of the line search: every division on its fast path with
-// selects instead of branches (portable_math.h: tan_spec, div_const_spec), `sixth` = dt / 6 computed by the caller once per
-// rollout.  Returns false when a division would have needed its slow path (operands outside 2^+-896: trajectories that
+// selects instead of branches (portable_math.h: tan_spec, div_const_spec), `hdt` = dt / 2 and `sixth` = dt / 6 from the view
+// (constant-bank operands).  Returns false when a division would have needed its slow path (operands outside 2^+-896: trajectories that
 // have left the finite range) -- the caller then repeats the step with rk4_step; otherwise xn holds the bits of rk4_step.
 // With the branches gone the compiler interleaves the four stages' sin / cos chains and the C candidates of a lane.
 template <class M>
-MAS_HD bool rk4_step_spec(const double* x, const double* u, const double* prm, double dt, double sixth, double* xn) {
-  if constexpr (M::SPEC_STEP) {
+MAS_HD bool rk4_step_spec(const double* x, const double* u, const double* prm, double dt, double hdt, double sixth, double* xn) {
+#if defined(MAS_NO_SPEC_STEP)  // tuning builds: the branchy step everywhere (A/B measurement of the straight-line step)
+  constexpr bool kSpec = false;
+#else
+  constexpr bool kSpec = M::SPEC_STEP;
+#endif
+  if constexpr (kSpec) {
     constexpr int NX = M::NX;
     double k1[NX], k2[NX], k3[NX], k4[NX], xs[NX];
-    const double hdt = 0.5 * dt;
     double cu[M::NCU];
     bool exact = true;
     M::control_terms_spec(u, prm, cu, &exact);
@@ -1735,7 +1745,6 @@ MAS_HD void trial_rollout(const BatchView<M::NX, M::NU>& v, int p, const double*
 #pragma unroll
     for (int i = 0; i < NX; ++i) xt[c][i] = v.x0[static_cast<size_t>(i) * v.ld + p];
   }
-  const double sixth = MAS_DIV_CONST(v.dt, 6.0);
   const size_t ld = static_cast<size_t>(v.ld);
   const double *rX = v.X + p, *rU = v.U + p, *rk = v.kff + p, *rK = v.K + p;  // rows of step t (plain-load path)
   for (int t = 0; t < v.T; ++t) {
@@ -1789,7 +1798,7 @@ MAS_HD void trial_rollout(const BatchView<M::NX, M::NU>& v, int p, const double*
       }
       cost[c] += M::stage(xt[c], u[c], t, prm);
       if (kAL) al_merit_addends<M>(v, p, t, xt[c], u[c], prm, al_rho, &al_terms[c][3 * t]);
-      const bool e = rk4_step_spec<M>(xt[c], u[c], prm, v.dt, sixth, xnext[c]);  // one basic block for all C candidates
+      const bool e = rk4_step_spec<M>(xt[c], u[c], prm, v.dt, v.half_dt, v.sixth_dt, xnext[c]);  // one basic block for all C candidates
       exact = exact && e;
     }
     if (!exact) {  // a division off its fast path (non-finite trajectories): the step again, branch by branch
@@ -1888,15 +1897,13 @@ MAS_HD double commit_rollout(const BatchView<M::NX, M::NU>& v, int p, const doub
 #pragma unroll
       for (int j = 1; j < NX; ++j) kdx = kdx + Km[i + j * NU] * dx[j];
       double ui = (un[i] + alpha * kv[i]) + kdx;
-      if (v.has_bounds) {
-        ui = (v.hi[i] < ui) ? v.hi[i] : ui;
-        ui = (v.lo[i] > ui) ? v.lo[i] : ui;
-      }
+      ui = (v.clamp_hi[i] < ui) ? v.clamp_hi[i] : ui;
+      ui = (v.clamp_lo[i] > ui) ? v.clamp_lo[i] : ui;
       u[i] = ui;
       v.U[soa_index<NU>(t, i, v.ld, p)] = ui;
     }
     cost += M::stage(xt, u, t, prm);
-    rk4_step<M>(xt, u, prm, v.dt, xnext);
+    if (!rk4_step_spec<M>(xt, u, prm, v.dt, v.half_dt, v.sixth_dt, xnext)) rk4_step<M>(xt, u, prm, v.dt, xnext);
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       xt[i] = xnext[i];

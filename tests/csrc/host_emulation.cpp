@@ -149,7 +149,7 @@ int emulate(int batch, int T, double dt, unsigned mask, int has_bounds, const do
   BatchView<NX, NU> v{};
   v.ld = ld;
   v.T = T;
-  v.dt = dt;
+  v.set_dt(dt);
   v.deriv_mask = mask;
   v.set_bounds(has_bounds, lo, hi);
   v.per_problem_params = per_problem_p ? 1 : 0;

@@ -552,3 +552,15 @@ def test_analytic_constraint_jacobians(mas, ctx, oracle, jm):
     bad.deriv_mask = bad.deriv_mask | (1 << 9)  # a model without constraints has no such callback
     with pytest.raises(mas.MasB200Error):
         mas.Batch(ctx, bad, 4)
+
+
+def test_straight_line_divisions_equal_the_division_instruction(mas, ctx):
+    """The trial rollouts divide with straight-line code (portable_math.h: div_spec = the compiler's division sequence minus
+    its branch, div_const_spec = Markstein's correction) and repeat a step with the plain division whenever those flag an
+    operand as outside their fast path.  Brute force on the device: wherever the fast path is accepted the bits are those of
+    div.rn.f64 -- 2^28 pairs over all exponents, near-tie quotients and the cos-like divisor range of tan."""
+    r = ctx.selftest_division(1 << 28, seed=20240607)
+    assert r["checked"] >= 1 << 28
+    assert r["div_mismatch"] == 0 and r["div_const_mismatch"] == 0, r
+    # three quarters of the pairs are ordinary magnitudes: the fast path must be the rule there, not the exception
+    assert r["div_exact"] > 0.74 * r["checked"] and r["div_const_exact"] > 0.74 * r["checked"], r
