@@ -269,8 +269,12 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
  * U[a]: [scenario][T_a][m_a], costs[a]: [scenario], model_params[a]: [scenario][np_a] or NULL, U_init[a] or NULL).
  * Nash strategies (sequential, line search, trust region): agents of one description share a device batch, the
  * groups advance round by round in lockstep, the line-search strategy's joint cost is summed over all agents in
- * index order.  trace_iterations (optional): [scenario][outer][agent].  Centralized with agents that are not all of
- * one description: MAS_B200_ERR_UNSUPPORTED (the stacked solve is compiled per model). */
+ * index order.  trace_iterations (optional): [scenario][outer][agent].
+ * Centralized over a mix (strategies/centralized.hpp:18-38 on build_global_ocp of the mix): one stacked iLQR solve per
+ * scenario with run-time block shapes, every derivative by finite differences, horizon and dt of the FIRST agent, bounds
+ * only when every agent has both, zero initial controls (U_init is not read).  The results keep the stacked horizon T_0:
+ * X[a] is [scenario][T_0+1][n_a], U[a] is [scenario][T_0][m_a], costs[a] the agent's own objective on its rows, total_cost
+ * the stacked best_cost; the iteration count goes to trace_iterations[scenario][0][0] when max_outer >= 1. */
 int mas_b200_strategy_run_mixed(mas_b200_context_t ctx, int strategy, const mas_b200_ocp_desc* agent_descs, const mas_b200_ilqr_params* params,
                                 int max_outer, int n_scenarios, int n_agents, const double* const* x0, const double* const* model_params,
                                 const double* const* U_init, double* const* X, double* const* U, double* const* costs, double* total_cost,

@@ -346,7 +346,9 @@ inline Solution run_strategy(int kind, int max_outer, const mas_b200_ilqr_params
   }
   if (mixed) {
     // agents of different models / shapes (MultiAgentProblem accepts any mix): one description per agent, per-agent arrays
-    // (mas_b200_strategy_run_mixed); the centralized strategy over such a mix is MAS_B200_ERR_UNSUPPORTED -> std::runtime_error
+    // (mas_b200_strategy_run_mixed); the centralized strategy returns every agent's rows of the stacked solution, whose
+    // horizon is the first block's (multi_agent_problem.hpp:65-69, centralized.hpp:27-36)
+    const bool central = kind == MAS_B200_STRATEGY_CENTRALIZED;
     std::vector<mas_b200_ocp_desc> descs(A);
     std::vector<std::vector<double>> vx0(A), vp(A), vU0(A), vX(A), vU(A);
     std::vector<const double*> px0(A), pp(A), pU0(A);
@@ -360,8 +362,9 @@ inline Solution run_strategy(int kind, int max_outer, const mas_b200_ilqr_params
       if (o.best_controls.rows() != o.control_dim || o.best_controls.cols() != o.horizon_steps)
         throw std::invalid_argument("best_controls has the wrong shape; call initialize_problem()");
       vU0[a].assign(o.best_controls.data(), o.best_controls.data() + static_cast<std::size_t>(o.control_dim) * o.horizon_steps);
-      vX[a].resize(static_cast<std::size_t>(o.state_dim) * (o.horizon_steps + 1));
-      vU[a].resize(static_cast<std::size_t>(o.control_dim) * o.horizon_steps);
+      const int Tr = central ? T : o.horizon_steps;
+      vX[a].resize(static_cast<std::size_t>(o.state_dim) * (Tr + 1));
+      vU[a].resize(static_cast<std::size_t>(o.control_dim) * Tr);
       px0[a] = vx0[a].data();
       pp[a] = vp[a].empty() ? nullptr : vp[a].data();
       pU0[a] = vU0[a].data();
@@ -374,12 +377,13 @@ inline Solution run_strategy(int kind, int max_outer, const mas_b200_ilqr_params
                                       pU.data(), pc.data(), &total, nullptr));
     for (int a = 0; a < A; ++a) {
       OCP& o = *problem.blocks[a].agent->ocp;
-      o.best_states = StateTrajectory(o.state_dim, o.horizon_steps + 1);
-      o.best_controls = ControlTrajectory(o.control_dim, o.horizon_steps);
+      const int Tr = central ? T : o.horizon_steps;
+      o.best_states = StateTrajectory(o.state_dim, Tr + 1);
+      o.best_controls = ControlTrajectory(o.control_dim, Tr);
       std::copy(vX[a].begin(), vX[a].end(), o.best_states.data());
       std::copy(vU[a].begin(), vU[a].end(), o.best_controls.data());
       o.best_cost = c[a];
-      o.update_initial_with_best();
+      if (!central) o.update_initial_with_best();  // the centralized strategy does not (centralized.hpp:18-38)
       sol.states.push_back(o.best_states);
       sol.controls.push_back(o.best_controls);
       sol.costs.push_back(o.best_cost);

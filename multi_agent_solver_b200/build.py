@@ -22,7 +22,7 @@ OBJ_DIR = os.path.join(PKG_DIR, "_obj" + ("_" + VARIANT if VARIANT else ""))
 LIB_PATH = os.path.join(PKG_DIR, "libmas_b200.so") if not VARIANT else os.path.join(ROOT, "tools", "_variants", f"libmas_b200_{VARIANT}.so")
 
 SOURCES = ["engine.cu", "capi.cu", "centralized.cu", "model_st_lane.cu", "model_st_lane_con.cu", "model_st_circ.cu", "model_lqr4.cu", "model_pendulum.cu", "model_rocket.cu"]
-HEADERS = ["engine.cuh", "ilqr_core.cuh", "models.cuh", "centralized.cuh", "centralized_host.cuh"]
+HEADERS = ["engine.cuh", "ilqr_core.cuh", "models.cuh", "centralized.cuh", "centralized_host.cuh", "stacked_mixed.cuh", "stacked_mixed_host.cuh"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",

@@ -396,8 +396,10 @@ def strategy_run_mixed(ctx: Context, strategy: int, descs, params: IlqrParams, m
     def ptrs(arrs):
         return (PD * A)(*[(_dptr(a) if a is not None else PD()) for a in arrs])
 
-    X = [np.empty((S, d.horizon_steps + 1, d.state_dim)) for d in descs]
-    U = [np.empty((S, d.horizon_steps, d.control_dim)) for d in descs]
+    # the centralized strategy returns every agent's rows of the stacked solution: horizon of the first agent
+    T_of = (lambda d: descs[0].horizon_steps) if int(strategy) == int(Strategy.CENTRALIZED) else (lambda d: d.horizon_steps)
+    X = [np.empty((S, T_of(d) + 1, d.state_dim)) for d in descs]
+    U = [np.empty((S, T_of(d), d.control_dim)) for d in descs]
     costs = [np.empty(S) for _ in descs]
     total = np.empty(S)
     t_it = np.zeros((S, max_outer, A), dtype=np.int32)

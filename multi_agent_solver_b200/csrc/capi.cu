@@ -804,10 +804,61 @@ int mas_b200_strategy_run_mixed(mas_b200_context_t ctx, int strategy, const mas_
   }
   bool same = true;
   for (int a = 1; a < n_agents; ++a) same = same && std::memcmp(&agent_descs[a], &agent_descs[0], sizeof(mas_b200_ocp_desc)) == 0;
-  if (strategy == MAS_B200_STRATEGY_CENTRALIZED && !same)
-    return fail(MAS_B200_ERR_UNSUPPORTED,
-                "centralized strategy over agents of different models: the stacked solve is built per model (use mas_b200_global_ocp_eval_mixed for "
-                "the stacked functions; Nash strategies accept mixed agents)");
+  if (strategy == MAS_B200_STRATEGY_CENTRALIZED && !same) {
+    // build_global_ocp of a mixed problem (multi_agent_problem.hpp:52-127): blocks in agent order (ids 0..n-1), horizon and dt of the
+    // first block, bounds only when every agent has both; the stacked solve starts from zero controls (U_init is not read)
+    const int S = n_scenarios, T = agent_descs[0].horizon_steps;
+    std::vector<int> mid(n_agents), soff(n_agents), uoff(n_agents);
+    int ns = 0, ms = 0;
+    bool all_bounds = true;
+    for (int a = 0; a < n_agents; ++a) {
+      const mas_b200_ocp_desc& d = agent_descs[a];
+      mid[a] = d.model_id;
+      soff[a] = ns;
+      uoff[a] = ms;
+      ns += d.state_dim;
+      ms += d.control_dim;
+      all_bounds = all_bounds && d.has_input_bounds;
+    }
+    std::vector<double> lo(ms, 0.0), hi(ms, 0.0), fx0(static_cast<size_t>(S) * ns), fp(static_cast<size_t>(S) * n_agents * kMaxParams, 0.0);
+    for (int a = 0; a < n_agents; ++a) {
+      const mas_b200_ocp_desc& d = agent_descs[a];
+      const int np = kModels[d.model_id].np;
+      for (int i = 0; i < d.control_dim; ++i) {
+        lo[uoff[a] + i] = d.input_lower[i];
+        hi[uoff[a] + i] = d.input_upper[i];
+      }
+      for (int sc = 0; sc < S; ++sc) {
+        std::memcpy(&fx0[static_cast<size_t>(sc) * ns + soff[a]], x0[a] + static_cast<size_t>(sc) * d.state_dim, sizeof(double) * d.state_dim);
+        double* dst = &fp[(static_cast<size_t>(sc) * n_agents + a) * kMaxParams];
+        for (int i = 0; i < np; ++i)
+          dst[i] = (model_params && model_params[a]) ? model_params[a][static_cast<size_t>(sc) * np + i]
+                                                     : (d.num_params ? d.params[i] : kModels[d.model_id].default_params[i]);
+        if (d.model_id == MAS_B200_MODEL_PENDULUM && d.num_params == 0 && !(model_params && model_params[a])) dst[0] = static_cast<double>(d.horizon_steps);
+      }
+    }
+    std::vector<double> gX(static_cast<size_t>(S) * (T + 1) * ns), gU(static_cast<size_t>(S) * T * ms), gc(static_cast<size_t>(S) * (1 + n_agents));
+    std::vector<int> gi(static_cast<size_t>(S) * 4);
+    rc = centralized_mixed_entry(&ctx->c, n_agents, mid.data(), T, agent_descs[0].dt, all_bounds ? 1 : 0, lo.data(), hi.data(), *params, S, fx0.data(),
+                                 fp.data(), gX.data(), gU.data(), gc.data(), gi.data(), nullptr);
+    if (rc) return rc;
+    // every agent gets its rows of the stacked result (centralized.hpp:27-36): shapes [scenario][T+1][n_a] / [scenario][T][m_a], T of the first block
+    for (int sc = 0; sc < S; ++sc) {
+      for (int a = 0; a < n_agents; ++a) {
+        const int n = agent_descs[a].state_dim, m = agent_descs[a].control_dim;
+        if (X && X[a])
+          for (int t = 0; t <= T; ++t)
+            std::memcpy(X[a] + (static_cast<size_t>(sc) * (T + 1) + t) * n, &gX[(static_cast<size_t>(sc) * (T + 1) + t) * ns + soff[a]], sizeof(double) * n);
+        if (U && U[a])
+          for (int t = 0; t < T; ++t)
+            std::memcpy(U[a] + (static_cast<size_t>(sc) * T + t) * m, &gU[(static_cast<size_t>(sc) * T + t) * ms + uoff[a]], sizeof(double) * m);
+        if (costs && costs[a]) costs[a][sc] = gc[static_cast<size_t>(sc) * (1 + n_agents) + 1 + a];
+      }
+      if (total_cost) total_cost[sc] = gc[static_cast<size_t>(sc) * (1 + n_agents)];
+      if (trace_iterations && max_outer >= 1) trace_iterations[static_cast<size_t>(sc) * max_outer * n_agents] = gi[static_cast<size_t>(sc) * 4];
+    }
+    return MAS_B200_OK;
+  }
   if (strategy != MAS_B200_STRATEGY_CENTRALIZED && strategy != MAS_B200_STRATEGY_SEQUENTIAL && strategy != MAS_B200_STRATEGY_TRUSTREGION &&
       strategy != MAS_B200_STRATEGY_LINESEARCH)
     return fail(MAS_B200_ERR_INVALID_ARGUMENT, "unknown strategy");

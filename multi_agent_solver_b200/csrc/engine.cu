@@ -362,12 +362,12 @@ __global__ void nash_ls_reduce_kernel(const double* __restrict__ cost, int n_sce
 // multi_agent_problem.hpp:94-125): block-diagonal dynamics, stage / terminal costs summed in block order from 0.0.
 // One thread per block evaluates its agent's registered functors (run-time dispatch on the model id); thread 0 then
 // forms the two sums in block order.
-struct MixedBlock {
+struct EvalBlock {
   int model_id, state_offset, control_offset;
   double params[kMaxParams];
 };
 template <class M>
-__device__ void mixed_block_eval(const MixedBlock& b, const double* X, const double* U, int t, double* dyn, double* stage, double* terminal) {
+__device__ void mixed_block_eval(const EvalBlock& b, const double* X, const double* U, int t, double* dyn, double* stage, double* terminal) {
   double x[M::NX], u[M::NU], d[M::NX];
   for (int i = 0; i < M::NX; ++i) x[i] = X[b.state_offset + i];
   for (int i = 0; i < M::NU; ++i) u[i] = U[b.control_offset + i];
@@ -376,11 +376,11 @@ __device__ void mixed_block_eval(const MixedBlock& b, const double* X, const dou
   *stage = M::stage(x, u, t, b.params);
   *terminal = M::terminal(x, b.params);
 }
-__global__ void mixed_global_eval_kernel(const MixedBlock* blocks, int n_blocks, const double* X, const double* U, int t, double* dyn, double* terms,
+__global__ void mixed_global_eval_kernel(const EvalBlock* blocks, int n_blocks, const double* X, const double* U, int t, double* dyn, double* terms,
                                          double* sums) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a < n_blocks) {
-    const MixedBlock b = blocks[a];
+    const EvalBlock b = blocks[a];
     double* st = terms + a;
     double* te = terms + n_blocks + a;
     switch (b.model_id) {
@@ -404,18 +404,18 @@ __global__ void mixed_global_sum_kernel(const double* terms, int n_blocks, doubl
 int mixed_global_eval(Context* ctx, const int* model_ids, const int* state_offsets, const int* control_offsets, const double* params /* [n][kMaxParams] */,
                       int n_blocks, int total_x, int total_u, const double* X, const double* U, int t, double* dyn_out, double* stage_out,
                       double* terminal_out) {
-  std::vector<MixedBlock> hb(n_blocks);
+  std::vector<EvalBlock> hb(n_blocks);
   for (int a = 0; a < n_blocks; ++a) {
     hb[a].model_id = model_ids[a];
     hb[a].state_offset = state_offsets[a];
     hb[a].control_offset = control_offsets[a];
     for (int i = 0; i < kMaxParams; ++i) hb[a].params[i] = params[static_cast<size_t>(a) * kMaxParams + i];
   }
-  MixedBlock* d_b = nullptr;
+  EvalBlock* d_b = nullptr;
   double* d_buf = nullptr;
   const size_t nd = static_cast<size_t>(2) * total_x + total_u + 2 * n_blocks + 2;
   MAS_CUDA_CHECK(cudaSetDevice(ctx->device));
-  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_b), n_blocks * sizeof(MixedBlock)));
+  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_b), n_blocks * sizeof(EvalBlock)));
   if (cudaMalloc(reinterpret_cast<void**>(&d_buf), nd * sizeof(double)) != cudaSuccess) {
     cudaFree(d_b);
     set_last_error("cudaMalloc failed");
@@ -425,7 +425,7 @@ int mixed_global_eval(Context* ctx, const int* model_ids, const int* state_offse
   cudaStream_t st = ctx->stream;
   int rc = MAS_B200_OK;
   auto run = [&]() -> int {
-    MAS_CUDA_CHECK(cudaMemcpyAsync(d_b, hb.data(), n_blocks * sizeof(MixedBlock), cudaMemcpyHostToDevice, st));
+    MAS_CUDA_CHECK(cudaMemcpyAsync(d_b, hb.data(), n_blocks * sizeof(EvalBlock), cudaMemcpyHostToDevice, st));
     MAS_CUDA_CHECK(cudaMemcpyAsync(dX, X, total_x * sizeof(double), cudaMemcpyHostToDevice, st));
     MAS_CUDA_CHECK(cudaMemcpyAsync(dU, U, total_u * sizeof(double), cudaMemcpyHostToDevice, st));
     mixed_global_eval_kernel<<<div_up(n_blocks, 64), 64, 0, st>>>(d_b, n_blocks, dX, dU, t, dD, dT, dS);

@@ -1183,6 +1183,9 @@ int BatchImpl<M>::mark_time_limit(int cur) {
   return MAS_B200_OK;
 }
 
+int centralized_mixed_entry(Context* ctx, int n_blocks, const int* model_ids, int T, double dt, int has_bounds, const double* lo, const double* hi,
+                            const mas_b200_ilqr_params& prm, int S, const double* x0, const double* params, double* X, double* U, double* costs, int* ints,
+                            long long* launches);
 int mixed_global_eval(Context* ctx, const int* model_ids, const int* state_offsets, const int* control_offsets, const double* params, int n_blocks,
                       int total_x, int total_u, const double* X, const double* U, int t, double* dyn_out, double* stage_out, double* terminal_out);
 

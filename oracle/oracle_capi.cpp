@@ -340,6 +340,7 @@ int oracle_strategy_run_mixed(int kind, int n_scenarios, int n_agents, const int
     for (int a = 0; a < n_agents; ++a) {
       double dt;
       model_dims(models[a], 0, &n[a], &m[a], &T[a], &dt);
+      if (kind == 0) T[a] = T[0];  // centralized: every agent gets its rows of the stacked solution, horizon of the first block
       sx0 += n[a];
       sX += static_cast<std::size_t>(n[a]) * (T[a] + 1);
       sU += static_cast<std::size_t>(m[a]) * T[a];
@@ -362,10 +363,18 @@ int oracle_strategy_run_mixed(int kind, int n_scenarios, int n_agents, const int
       OracleOptions opt;
       StrategyTrace trace;
       Solution sol;
-      if (kind == 1) sol = run_sequential(max_outer, sp, problem, opt, &trace);
+      int stacked_iterations = 0;
+      if (kind == 0) {  // strategies/centralized.hpp:18-38 on the mixed problem
+        iLQR solver;
+        solver.set_params(sp);
+        solver.options = opt;
+        SolveStats st;
+        sol = run_centralized(solver, problem, &st);
+        stacked_iterations = st.iterations;
+      } else if (kind == 1) sol = run_sequential(max_outer, sp, problem, opt, &trace);
       else if (kind == 2) sol = run_line_search(max_outer, sp, problem, opt, &trace);
       else if (kind == 3) sol = run_trust_region(max_outer, sp, problem, opt, &trace);
-      else throw std::invalid_argument("oracle: mixed agents need a Nash strategy");
+      else throw std::invalid_argument("oracle: unknown strategy kind");
       std::size_t ox = 0, ou = 0;
       for (int a = 0; a < n_agents; ++a) {
         const std::size_t px = static_cast<std::size_t>(n[a]) * (T[a] + 1), pu = static_cast<std::size_t>(m[a]) * T[a];
@@ -376,7 +385,7 @@ int oracle_strategy_run_mixed(int kind, int n_scenarios, int n_agents, const int
         costs_out[static_cast<std::size_t>(s) * n_agents + a] = sol.costs[a];
         int it = 0;
         for (std::size_t r = a; r < trace.iterations.size(); r += n_agents) it += trace.iterations[r];
-        if (iters_total) iters_total[static_cast<std::size_t>(s) * n_agents + a] = it;
+        if (iters_total) iters_total[static_cast<std::size_t>(s) * n_agents + a] = (kind == 0) ? (a == 0 ? stacked_iterations : 0) : it;
       }
       total_cost_out[s] = sol.total_cost;
     } catch (...) {

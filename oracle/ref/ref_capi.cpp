@@ -375,6 +375,7 @@ int ref_strategy_run_mixed(int kind, int n_scenarios, int n_agents, const int* m
     for (int a = 0; a < n_agents; ++a) {
       double dt;
       model_dims(models[a], 0, &n[a], &m[a], &T[a], &dt);
+      if (kind == 0) T[a] = T[0];  // centralized: rows of the stacked solution, horizon of the first block
       sx0 += n[a];
       sX += static_cast<std::size_t>(n[a]) * (T[a] + 1);
       sU += static_cast<std::size_t>(m[a]) * T[a];
@@ -387,24 +388,29 @@ int ref_strategy_run_mixed(int kind, int n_scenarios, int n_agents, const int* m
   for (int s = 0; s < n_scenarios; ++s) {
     try {
       omp_set_num_threads(1);
-      mas::MultiAgentProblem problem;
       std::vector<std::shared_ptr<Probe>> probes;
-      std::size_t o = 0;
-      for (int a = 0; a < n_agents; ++a) {
-        auto ocp = std::make_shared<mas::OCP>(build_ocp(models[a], x0 + s * sx0 + o, nullptr, 0, 0, nullptr));
-        o += n[a];
-        probes.push_back(instrument(*ocp));
-        problem.add_agent(std::make_shared<mas::Agent>(static_cast<std::size_t>(a), ocp));
-      }
+      auto make_problem = [&](bool with_probes) {
+        mas::MultiAgentProblem pr;
+        std::size_t o = 0;
+        for (int a = 0; a < n_agents; ++a) {
+          auto ocp = std::make_shared<mas::OCP>(build_ocp(models[a], x0 + s * sx0 + o, nullptr, 0, 0, nullptr));
+          o += n[a];
+          if (with_probes) probes.push_back(instrument(*ocp));
+          pr.add_agent(std::make_shared<mas::Agent>(static_cast<std::size_t>(a), ocp));
+        }
+        return pr;
+      };
+      mas::MultiAgentProblem problem = make_problem(kind != 0);
       const mas::SolverParams sp = make_params(max_iterations, tolerance, std::numeric_limits<double>::infinity());
       mas::Solver solver{std::in_place_type<mas::iLQR>};
       mas::Strategy strategy = [&]() -> mas::Strategy {
         switch (kind) {
+          case 0: mas::set_params(solver, sp); return mas::CentralizedStrategy{std::move(solver)};
           case 1: return mas::SequentialNashStrategy{max_outer, std::move(solver), sp};
           case 2: return mas::LineSearchNashStrategy{max_outer, std::move(solver), sp};
           case 3: return mas::TrustRegionNashStrategy{max_outer, std::move(solver), sp};
         }
-        throw std::invalid_argument("ref: mixed agents need a Nash strategy");
+        throw std::invalid_argument("ref: unknown strategy kind");
       }();
       const mas::Solution sol = mas::solve(strategy, problem);
       std::size_t ox = 0, ou = 0;
@@ -415,9 +421,19 @@ int ref_strategy_run_mixed(int kind, int n_scenarios, int n_agents, const int* m
         ox += px;
         ou += pu;
         costs_out[static_cast<std::size_t>(s) * n_agents + a] = sol.costs[a];
-        if (iters_total) iters_total[static_cast<std::size_t>(s) * n_agents + a] = static_cast<int>(probes[a]->iteration_at.size());
+        if (iters_total) iters_total[static_cast<std::size_t>(s) * n_agents + a] = kind == 0 ? 0 : static_cast<int>(probes[a]->iteration_at.size());
       }
       total_cost_out[s] = sol.total_cost;
+      if (iters_total && kind == 0) {  // iterations of the stacked solve: a second, instrumented build_global_ocp() + solve
+        mas::MultiAgentProblem again = make_problem(false);
+        again.compute_offsets();
+        mas::OCP global = again.build_global_ocp();
+        auto probe = instrument(global);
+        mas::Solver s2{std::in_place_type<mas::iLQR>};
+        mas::set_params(s2, sp);
+        mas::solve(s2, global);
+        iters_total[static_cast<std::size_t>(s) * n_agents] = static_cast<int>(probe->iteration_at.size());
+      }
     } catch (...) {
 #pragma omp atomic write
       err = 1;

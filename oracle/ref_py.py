@@ -157,16 +157,19 @@ def strategy_run_batch(kind, model, x0, params=None, horizon=0, max_outer=10, ma
     return dict(X=X, U=U, costs=costs, total_cost=total, iterations_total=iters)
 
 
-def _mixed_shapes(models):
+def _mixed_shapes(models, kind=1):
     dims = [model_dims(m) for m in models]
+    if int(kind) == 0:  # centralized: every agent's rows of the stacked solution, horizon of the first block
+        dims = [(d[0], d[1], dims[0][2], d[3]) for d in dims]
     return dims, sum(d[0] for d in dims), sum(d[0] * (d[2] + 1) for d in dims), sum(d[1] * d[2] for d in dims)
 
 
 def strategy_run_mixed(kind, models, x0_list, max_outer=10, max_iterations=100, tolerance=1e-5, trig=TRIG_GLIBC):
-    """Nash strategy over agents of different models.  x0_list[a]: [scenarios, n_a].  Per-agent lists of X, U back."""
+    """Strategy (0 centralized, 1 sequential, 2 line search, 3 trust region) over agents of different models.
+    x0_list[a]: [scenarios, n_a].  Per-agent lists of X, U back; centralized: iterations_total[:, 0] = stacked iterations."""
     models = [int(m) for m in models]
     A = len(models)
-    dims, sx0, sX, sU = _mixed_shapes(models)
+    dims, sx0, sX, sU = _mixed_shapes(models, kind)
     S = np.asarray(x0_list[0]).shape[0]
     x0 = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float64).reshape(S, -1) for x in x0_list], axis=1))
     X = np.zeros((S, sX))

@@ -47,7 +47,7 @@ _EMU_LIB = os.path.join(ROOT, "tests", "_build", "libhost_emulation.so")
 
 
 def _build_emulation() -> str:
-    deps = [_EMU_SRC] + [os.path.join(ROOT, "multi_agent_solver_b200", "csrc", f) for f in ("ilqr_core.cuh", "models.cuh", "centralized.cuh")]
+    deps = [_EMU_SRC] + [os.path.join(ROOT, "multi_agent_solver_b200", "csrc", f) for f in ("ilqr_core.cuh", "models.cuh", "centralized.cuh", "stacked_mixed.cuh")]
     deps.append(os.path.join(ROOT, "include", "mas_b200", "portable_math.h"))
     if not os.path.exists(_EMU_LIB) or os.path.getmtime(_EMU_LIB) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(_EMU_LIB), exist_ok=True)
@@ -138,6 +138,41 @@ class HostEmulation:
         assert rc == 0
         return dict(X=X.reshape(T + 1, A, n).transpose(1, 0, 2).copy(), U=U.reshape(T, A, m).transpose(1, 0, 2).copy(), total_cost=oc[0],
                     costs=oc[1:].copy(), iterations=int(oi[0]), status=int(oi[1]), reg_retries=int(oi[2]), alpha_trials=int(oi[3]))
+
+
+    def solve_centralized_mixed(self, models, x0_list, max_iterations=100, tolerance=1e-5):
+        """mixed_stacked_solve (stacked_mixed.cuh) with tid = 0, nthr = 1: one scenario, agents of different models.
+        x0_list[a]: [n_a].  Horizon / dt of the first agent, bounds only if every agent has them (build_global_ocp)."""
+        rows = [MODEL_TABLE[m] for m in models]
+        A = len(models)
+        T, dt = rows[0][2], rows[0][3]
+        ns, ms = sum(r[0] for r in rows), sum(r[1] for r in rows)
+        hb = int(all(r[5] for r in rows))
+        lo = np.concatenate([np.asarray(r[6], dtype=np.float64) for r in rows])
+        hi = np.concatenate([np.asarray(r[7], dtype=np.float64) for r in rows])
+        pp = np.zeros((A, 8))
+        for a, r in enumerate(rows):
+            pp[a, :len(r[8])] = r[8]
+        x0 = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float64).reshape(-1) for x in x0_list]))
+        X = np.zeros((T + 1, ns))
+        U = np.zeros((T, ms))
+        oc = np.zeros(1 + A)
+        oi = np.zeros(4, np.int32)
+        marr = np.array(models, dtype=np.int32)
+        P = ctypes.POINTER(ctypes.c_double)
+        PI = ctypes.POINTER(ctypes.c_int)
+        rc = self.lib.emu_centralized_mixed(A, marr.ctypes.data_as(PI), T, ctypes.c_double(dt), hb, lo.ctypes.data_as(P), hi.ctypes.data_as(P),
+                                            pp.ctypes.data_as(P), x0.ctypes.data_as(P), X.ctypes.data_as(P), U.ctypes.data_as(P), oc.ctypes.data_as(P),
+                                            oi.ctypes.data_as(PI), int(max_iterations), ctypes.c_double(tolerance))
+        assert rc == 0
+        Xs, Us, ox, ou = [], [], 0, 0
+        for r in rows:
+            Xs.append(X[:, ox:ox + r[0]].copy())
+            Us.append(U[:, ou:ou + r[1]].copy())
+            ox += r[0]
+            ou += r[1]
+        return dict(X=Xs, U=Us, total_cost=oc[0], costs=oc[1:].copy(), iterations=int(oi[0]), status=int(oi[1]), reg_retries=int(oi[2]),
+                    alpha_trials=int(oi[3]))
 
 
 @pytest.fixture(scope="session")

@@ -406,3 +406,54 @@ extern "C" int emu_centralized_solve(int model, int A, int T, double dt, int has
   }
   return 1;
 }
+
+// ---- centralized strategy over agents of different models: stacked_mixed.cuh with tid = 0, nthr = 1 --------------------------
+#include "stacked_mixed.cuh"
+
+extern "C" int emu_centralized_mixed(int n_agents, const int* models, int T, double dt, int has_bounds, const double* lo, const double* hi,
+                                     const double* params /* [n_agents][kMaxParams] */, const double* x0, double* X, double* U, double* out_cost,
+                                     int* out_int, int max_iterations, double tolerance) {
+  std::vector<MixedBlock> blocks(n_agents);
+  int ns = 0, ms = 0;
+  for (int a = 0; a < n_agents; ++a) {
+    MixedBlock& b = blocks[a];
+    b.model_id = models[a];
+    if (!mixed_model_dims(b.model_id, &b.nx, &b.nu)) return 1;
+    b.state_offset = ns;
+    b.control_offset = ms;
+    ns += b.nx;
+    ms += b.nu;
+    for (int i = 0; i < kMaxParams; ++i) b.params[i] = 0.0;
+  }
+  std::vector<int> box(ns), bou(ms);
+  for (int a = 0; a < n_agents; ++a) {
+    for (int i = 0; i < blocks[a].nx; ++i) box[blocks[a].state_offset + i] = a;
+    for (int i = 0; i < blocks[a].nu; ++i) bou[blocks[a].control_offset + i] = a;
+  }
+  const MixedWork W(ns, ms, T, n_agents);
+  std::vector<double> work(W.total, 0.0);
+  MixedStacked P{};
+  P.n_blocks = n_agents;
+  P.ns = ns;
+  P.ms = ms;
+  P.T = T;
+  P.dt = dt;
+  P.has_bounds = has_bounds;
+  P.tolerance = tolerance;
+  P.max_iterations = max_iterations;
+  P.max_ms = std::numeric_limits<double>::infinity();
+  P.blocks = blocks.data();
+  P.block_of_x = box.data();
+  P.block_of_u = bou.data();
+  P.lo = lo;
+  P.hi = hi;
+  P.x0 = x0;
+  P.prm = params;
+  P.X = X;
+  P.U = U;
+  P.work = work.data();
+  P.out_cost = out_cost;
+  P.out_int = out_int;
+  mixed_stacked_solve(P, 0, 1);
+  return 0;
+}

@@ -104,8 +104,14 @@ def test_mixed_agents_through_the_facade(binaries, oracle):
         assert abs(float(f["cost"]) - ref["total_cost"][0]) < 1e-6 * abs(ref["total_cost"][0])
         _, U = parse_block(out.stdout, "agent_1_controls")
         assert U.shape == (10, 5)
+    # centralized over the same mix: one stacked solve, horizon of the first agent (80 steps of the lane follower)
     out = run(binaries, "multi_agent_mixed", "--agents", "3", "--strategy", "centralized")
-    assert out.returncode == 1 and "centralized strategy over agents of different models" in out.stderr
+    assert out.returncode == 0, out.stderr
+    f, _ = parse_line(out.stdout)
+    ref = oracle.strategy_run_mixed(0, [0, 2, 1], x0, max_iterations=8, trig=oracle.TRIG_PORTABLE)
+    assert abs(float(f["cost"]) - ref["total_cost"][0]) < 1e-6 * abs(ref["total_cost"][0])
+    _, U = parse_block(out.stdout, "agent_1_controls")
+    assert U.shape == (80, 5)
 
 
 def test_error_conventions(binaries):

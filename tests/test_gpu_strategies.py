@@ -150,8 +150,28 @@ def test_mixed_agents_nash(mas, ctx, oracle, kind):
     same = mas.strategy_run_mixed(ctx, strategy, d1, mas.IlqrParams.make(100, 1e-5), 4, [x1[:, a] for a in range(3)])
     flat = mas.strategy_run(ctx, strategy, mas.example_desc(1), mas.IlqrParams.make(100, 1e-5), 4, x1)
     assert np.array_equal(same["costs"], flat["costs"]) and all(np.array_equal(same["U"][a], flat["U"][:, a]) for a in range(3))
-    with pytest.raises(mas.MasB200Error):
-        mas.strategy_run_mixed(ctx, mas.Strategy.CENTRALIZED, descs, mas.IlqrParams.make(8, 1e-5), 1, x0)
+
+
+@pytest.mark.parametrize("models", [[3, 4], [1, 0, 3, 2, 4], [2, 1, 2], [4, 3, 1]])
+def test_mixed_agents_centralized(mas, ctx, oracle, models):
+    """CentralizedStrategy over agents of different models and shapes (stacked_mixed.cuh; one CTA per scenario, run-time block
+    structure, every derivative of the stacked functions by finite differences): stacked trajectories, per-agent costs, total
+    and iteration count bit-equal to the oracle's build_global_ocp + iLQR, which tests/test_ref_pin.py pins to the reference's
+    own code for the same mixes.  Result horizon = the first agent's (multi_agent_problem.hpp:65-69)."""
+    from conftest import random_x0
+
+    S = 3
+    x0 = [random_x0(m, S, seed=40 + m) for m in models]
+    descs = [mas.example_desc(m) for m in models]
+    got = mas.strategy_run_mixed(ctx, mas.Strategy.CENTRALIZED, descs, mas.IlqrParams.make(6, 1e-5), 1, x0)
+    ref = oracle.strategy_run_mixed(0, models, x0, max_iterations=6, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    T0 = descs[0].horizon_steps
+    for a in range(len(models)):
+        assert got["X"][a].shape == (S, T0 + 1, descs[a].state_dim)
+        assert np.array_equal(got["X"][a], ref["X"][a]), a
+        assert np.array_equal(got["U"][a], ref["U"][a]), a
+    assert np.array_equal(got["costs"], ref["costs"]) and np.array_equal(got["total_cost"], ref["total_cost"])
+    assert np.array_equal(got["trace_iters"][:, 0, 0], ref["iterations_total"][:, 0])
 
 
 def test_mixed_agents_stacked_functions(mas, ctx, oracle):

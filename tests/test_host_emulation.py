@@ -249,3 +249,20 @@ def test_analytic_constraint_jacobians(emu, oracle, jm):
     got = emu.solve(5, x0, U0, 6, 1e-5, mask=0x3F | (jm << 9))
     assert is_bit_exact(got, ref) and np.array_equal(got["iterations"], ref["iterations"])
     assert not np.array_equal(ref["U"], fd["U"])  # the analytic Jacobians do change the rounding
+
+
+@pytest.mark.parametrize("models", [[3, 4], [1, 0, 3, 2, 4], [2, 1, 2], [4, 3, 1]])
+def test_centralized_over_mixed_agents_is_bit_identical(emu, oracle, models):
+    """CentralizedStrategy on agents of different models and shapes (stacked_mixed.cuh, the device source on the host) against the
+    oracle's stacked solve -- which tests/test_ref_pin.py pins to the reference's own build_global_ocp + iLQR for the same mixes.
+    [3, 4] is the shape of the reference's own stacking test (a 2x1 and a 3x1 agent; tests/ocp_tests.cpp:76-154 uses 2x1 and 1x2)."""
+    from conftest import random_x0
+
+    x0 = [random_x0(m, 1, seed=40 + m) for m in models]
+    ref = oracle.strategy_run_mixed(0, models, x0, max_iterations=6, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    got = emu.solve_centralized_mixed(models, [x[0] for x in x0], max_iterations=6, tolerance=1e-5)
+    for a in range(len(models)):
+        assert np.array_equal(got["X"][a], ref["X"][a][0]), a
+        assert np.array_equal(got["U"][a], ref["U"][a][0]), a
+    assert np.array_equal(got["costs"], ref["costs"][0]) and got["total_cost"] == ref["total_cost"][0]
+    assert got["iterations"] == ref["iterations_total"][0, 0]

@@ -165,6 +165,19 @@ def test_mixed_agents_nash(oracle, ref, kind):
     assert_same(a, b, ("costs", "total_cost", "iterations_total"))
 
 
+@pytest.mark.parametrize("models", [[3, 4], [1, 0, 3, 2, 4], [2, 1, 2], [4, 3, 1]])
+def test_mixed_agents_centralized(oracle, ref, models):
+    """CentralizedStrategy (centralized.hpp:18-38) on agents of different models: build_global_ocp of the mix, iLQR on the
+    stacked OCP with every derivative by finite differences, every agent's rows and own objective back."""
+    x0 = [random_x0(m, 2, seed=40 + m) for m in models]
+    a = oracle.strategy_run_mixed(0, models, x0, max_iterations=6, trig=1)
+    b = ref.strategy_run_mixed(0, models, x0, max_iterations=6, trig=1)
+    for k in ("X", "U"):
+        for xa, xb in zip(a[k], b[k]):
+            assert np.array_equal(xa, xb), k
+    assert_same(a, b, ("costs", "total_cost", "iterations_total"))
+
+
 def test_mixed_agents_build_global_ocp(oracle, ref):
     """compute_offsets + build_global_ocp on mixed agents (tests/ocp_tests.cpp:76-154 does this for a 2x1 and a 1x2 agent):
     dims, horizon / dt of the first block, bounds only when every agent has both, block-diagonal dynamics, block-order sums."""
