@@ -7,7 +7,7 @@
 // then runs iLQR::solve (ilqr.hpp:59-273) on that OCP.  centralized.cuh does this for agents of ONE model, with the block
 // structure compiled in; this file is the general case: block shapes and models are run-time data (MixedBlock), every
 // model call goes through a switch on the model id, and all matrices are dense, i.e. every sum has exactly the terms, in
-// exactly the order, of the reference's dense Eigen expressions (oracle/dense.hpp states that order).
+// exactly the order, of the reference's dense Eigen expressions (k ascending, the first product starts the sum).
 //
 // One CTA per scenario, data-parallel phases `for (idx = tid; idx < n; idx += nthr)` between barriers with all state in the
 // scenario's workspace, so tests/csrc/host_emulation.cpp runs the same source with tid = 0, nthr = 1.
@@ -198,7 +198,7 @@ MAS_HD_NI double mixed_terminal_at(const MixedStacked& P, const double* cb, cons
   return s;
 }
 
-// dense column-major products with the reference's summation order (oracle/dense.hpp): the first product starts the sum
+// dense column-major products with the reference's summation order: k ascending, the first product starts the sum
 MAS_HD double mixed_dot_tn(const double* a, int lda, int i, const double* b, int ldb, int j, int kd) {  // sum_k a(k,i) b(k,j)
   double s = a[static_cast<size_t>(i) * lda] * b[static_cast<size_t>(j) * ldb];
   for (int k = 1; k < kd; ++k) s = s + a[k + static_cast<size_t>(i) * lda] * b[k + static_cast<size_t>(j) * ldb];
