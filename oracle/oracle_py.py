@@ -24,7 +24,9 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile the oracle with its Makefile (g++ only, a few seconds)."""
-    if force or not os.path.exists(_LIB_PATH):
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "dense.hpp", "ref_core.hpp", "ref_ilqr.hpp", "ref_models.hpp", "ref_multi_agent.hpp")]
+    stale = not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs)
+    if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "all"] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
