@@ -257,7 +257,9 @@ int mas_b200_ilqr_last_debug_trace(mas_b200_context_t ctx, int problem, int max_
  * [scenario][outer][agent] inner iteration counts / accepted flags / best_cost after the round.
  * MAS_B200_STRATEGY_CENTRALIZED: the stacked problem always starts from zero controls (build_global_ocp never sets
  * initial_controls, multi_agent_problem.hpp:52-127) -- U_init is ignored; max_outer has no meaning, and the
- * iteration count of the stacked solve is written to trace_iterations[scenario][0][0] only when max_outer >= 1. */
+ * iteration count of the stacked solve is written to trace_iterations[scenario][0][0] only when max_outer >= 1.
+ * Stacks above 256 states (n_agents * state_dim) run the general stacked solve that mas_b200_strategy_run_mixed uses for
+ * agents of different models: same results, workspace in HBM instead of shared memory. */
 int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_ocp_desc* agent_desc, const mas_b200_ilqr_params* params,
                           int max_outer, int n_scenarios, int n_agents, const double* x0, const double* model_params, const double* U_init,
                           double* X, double* U, double* costs, double* total_cost, int* trace_iterations, int* trace_accepted, double* trace_cost);

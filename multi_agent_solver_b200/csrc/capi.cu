@@ -571,6 +571,68 @@ int mas_b200_ilqr_last_debug_trace(mas_b200_context_t ctx, int problem, int max_
 }
 
 // ---- strategies ------------------------------------------------------------------------------------------
+// CentralizedStrategy through the general stacked solve (stacked_mixed.cuh: run-time block shapes, workspace in HBM): agents of
+// different models, and stacks of one model that are too large for the compiled-in kernel of centralized.cuh.  Per-agent
+// pointer arrays as in mas_b200_strategy_run_mixed.
+static int run_centralized_general(mas_b200_context_t ctx, const mas_b200_ocp_desc* agent_descs, const mas_b200_ilqr_params* params, int max_outer,
+                                   int n_scenarios, int n_agents, const double* const* x0, const double* const* model_params, double* const* X,
+                                   double* const* U, double* const* costs, double* total_cost, int* trace_iterations) {
+  int rc = MAS_B200_OK;
+  // build_global_ocp of a mixed problem (multi_agent_problem.hpp:52-127): blocks in agent order (ids 0..n-1), horizon and dt of the
+  // first block, bounds only when every agent has both; the stacked solve starts from zero controls (U_init is not read)
+  const int S = n_scenarios, T = agent_descs[0].horizon_steps;
+  std::vector<int> mid(n_agents), soff(n_agents), uoff(n_agents);
+  int ns = 0, ms = 0;
+  bool all_bounds = true;
+  for (int a = 0; a < n_agents; ++a) {
+    const mas_b200_ocp_desc& d = agent_descs[a];
+    mid[a] = d.model_id;
+    soff[a] = ns;
+    uoff[a] = ms;
+    ns += d.state_dim;
+    ms += d.control_dim;
+    all_bounds = all_bounds && d.has_input_bounds;
+  }
+  std::vector<double> lo(ms, 0.0), hi(ms, 0.0), fx0(static_cast<size_t>(S) * ns), fp(static_cast<size_t>(S) * n_agents * kMaxParams, 0.0);
+  for (int a = 0; a < n_agents; ++a) {
+    const mas_b200_ocp_desc& d = agent_descs[a];
+    const int np = kModels[d.model_id].np;
+    for (int i = 0; i < d.control_dim; ++i) {
+      lo[uoff[a] + i] = d.input_lower[i];
+      hi[uoff[a] + i] = d.input_upper[i];
+    }
+    for (int sc = 0; sc < S; ++sc) {
+      std::memcpy(&fx0[static_cast<size_t>(sc) * ns + soff[a]], x0[a] + static_cast<size_t>(sc) * d.state_dim, sizeof(double) * d.state_dim);
+      double* dst = &fp[(static_cast<size_t>(sc) * n_agents + a) * kMaxParams];
+      for (int i = 0; i < np; ++i)
+        dst[i] = (model_params && model_params[a]) ? model_params[a][static_cast<size_t>(sc) * np + i]
+                                                   : (d.num_params ? d.params[i] : kModels[d.model_id].default_params[i]);
+      if (d.model_id == MAS_B200_MODEL_PENDULUM && d.num_params == 0 && !(model_params && model_params[a])) dst[0] = static_cast<double>(d.horizon_steps);
+    }
+  }
+  std::vector<double> gX(static_cast<size_t>(S) * (T + 1) * ns), gU(static_cast<size_t>(S) * T * ms), gc(static_cast<size_t>(S) * (1 + n_agents));
+  std::vector<int> gi(static_cast<size_t>(S) * 4);
+  rc = centralized_mixed_entry(&ctx->c, n_agents, mid.data(), T, agent_descs[0].dt, all_bounds ? 1 : 0, lo.data(), hi.data(), *params, S, fx0.data(),
+                               fp.data(), gX.data(), gU.data(), gc.data(), gi.data(), nullptr);
+  if (rc) return rc;
+  // every agent gets its rows of the stacked result (centralized.hpp:27-36): shapes [scenario][T+1][n_a] / [scenario][T][m_a], T of the first block
+  for (int sc = 0; sc < S; ++sc) {
+    for (int a = 0; a < n_agents; ++a) {
+      const int n = agent_descs[a].state_dim, m = agent_descs[a].control_dim;
+      if (X && X[a])
+        for (int t = 0; t <= T; ++t)
+          std::memcpy(X[a] + (static_cast<size_t>(sc) * (T + 1) + t) * n, &gX[(static_cast<size_t>(sc) * (T + 1) + t) * ns + soff[a]], sizeof(double) * n);
+      if (U && U[a])
+        for (int t = 0; t < T; ++t)
+          std::memcpy(U[a] + (static_cast<size_t>(sc) * T + t) * m, &gU[(static_cast<size_t>(sc) * T + t) * ms + uoff[a]], sizeof(double) * m);
+      if (costs && costs[a]) costs[a][sc] = gc[static_cast<size_t>(sc) * (1 + n_agents) + 1 + a];
+    }
+    if (total_cost) total_cost[sc] = gc[static_cast<size_t>(sc) * (1 + n_agents)];
+    if (trace_iterations && max_outer >= 1) trace_iterations[static_cast<size_t>(sc) * max_outer * n_agents] = gi[static_cast<size_t>(sc) * 4];
+  }
+  return MAS_B200_OK;
+}
+
 int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_ocp_desc* agent_desc, const mas_b200_ilqr_params* params,
                           int max_outer, int n_scenarios, int n_agents, const double* x0, const double* model_params, const double* U_init,
                           double* X, double* U, double* costs, double* total_cost, int* trace_iterations, int* trace_accepted, double* trace_cost) {
@@ -582,7 +644,40 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
     // stack -> one solve -> scatter (strategies/centralized.hpp:18-38); the stacked problem is always all-FD
     rc = validate_desc(agent_desc);
     if (rc) return rc;
-    if (n_agents * agent_desc->state_dim > 256) return fail(MAS_B200_ERR_UNSUPPORTED, "stacked state dimension above 256");
+    if (n_agents * agent_desc->state_dim > 256) {
+      // the kernel of centralized.cuh keeps its index arithmetic and scratch sized for stacked states up to 256; larger stacks
+      // take the general solve with its workspace in HBM (bit-identical results, slower): re-pack [scenario][agent][...]
+      // into the per-agent arrays it works on
+      const int S = n_scenarios, A = n_agents, n = agent_desc->state_dim, m = agent_desc->control_dim, T = agent_desc->horizon_steps;
+      const int np = kModels[agent_desc->model_id].np;
+      const size_t Ss = static_cast<size_t>(S);
+      std::vector<mas_b200_ocp_desc> descs(A, *agent_desc);
+      std::vector<double> ax0(Ss * A * n), ap(model_params ? Ss * A * np : 0), aX(Ss * A * (T + 1) * n), aU(Ss * A * T * m), ac(Ss * A);
+      std::vector<const double*> px0(A), pp(A, nullptr);
+      std::vector<double*> pX(A), pU(A), pc(A);
+      for (int a = 0; a < A; ++a) {
+        px0[a] = &ax0[Ss * a * n];
+        if (model_params) pp[a] = &ap[Ss * a * np];
+        pX[a] = &aX[Ss * a * (T + 1) * n];
+        pU[a] = &aU[Ss * a * T * m];
+        pc[a] = &ac[Ss * a];
+        for (int sc = 0; sc < S; ++sc) {
+          std::memcpy(&ax0[(Ss * a + sc) * n], x0 + (static_cast<size_t>(sc) * A + a) * n, sizeof(double) * n);
+          if (model_params) std::memcpy(&ap[(Ss * a + sc) * np], model_params + (static_cast<size_t>(sc) * A + a) * np, sizeof(double) * np);
+        }
+      }
+      rc = run_centralized_general(ctx, descs.data(), params, max_outer, S, A, px0.data(), model_params ? pp.data() : nullptr, pX.data(), pU.data(),
+                                   pc.data(), total_cost, trace_iterations);  // [scenario][outer][agent] in both layouts
+      if (rc) return rc;
+      for (int sc = 0; sc < S; ++sc)
+        for (int a = 0; a < A; ++a) {
+          const size_t sa = static_cast<size_t>(sc) * A + a;
+          if (X) std::memcpy(X + sa * (T + 1) * n, &aX[(Ss * a + sc) * (T + 1) * n], sizeof(double) * (T + 1) * n);
+          if (U) std::memcpy(U + sa * T * m, &aU[(Ss * a + sc) * T * m], sizeof(double) * T * m);
+          if (costs) costs[sa] = ac[Ss * a + sc];
+        }
+      return MAS_B200_OK;
+    }
     CentralizedFn fn = centralized_entry(agent_desc->model_id);
     if (!fn) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "unknown model_id");
     mas_b200_ocp_desc d = *agent_desc;
@@ -804,61 +899,8 @@ int mas_b200_strategy_run_mixed(mas_b200_context_t ctx, int strategy, const mas_
   }
   bool same = true;
   for (int a = 1; a < n_agents; ++a) same = same && std::memcmp(&agent_descs[a], &agent_descs[0], sizeof(mas_b200_ocp_desc)) == 0;
-  if (strategy == MAS_B200_STRATEGY_CENTRALIZED && !same) {
-    // build_global_ocp of a mixed problem (multi_agent_problem.hpp:52-127): blocks in agent order (ids 0..n-1), horizon and dt of the
-    // first block, bounds only when every agent has both; the stacked solve starts from zero controls (U_init is not read)
-    const int S = n_scenarios, T = agent_descs[0].horizon_steps;
-    std::vector<int> mid(n_agents), soff(n_agents), uoff(n_agents);
-    int ns = 0, ms = 0;
-    bool all_bounds = true;
-    for (int a = 0; a < n_agents; ++a) {
-      const mas_b200_ocp_desc& d = agent_descs[a];
-      mid[a] = d.model_id;
-      soff[a] = ns;
-      uoff[a] = ms;
-      ns += d.state_dim;
-      ms += d.control_dim;
-      all_bounds = all_bounds && d.has_input_bounds;
-    }
-    std::vector<double> lo(ms, 0.0), hi(ms, 0.0), fx0(static_cast<size_t>(S) * ns), fp(static_cast<size_t>(S) * n_agents * kMaxParams, 0.0);
-    for (int a = 0; a < n_agents; ++a) {
-      const mas_b200_ocp_desc& d = agent_descs[a];
-      const int np = kModels[d.model_id].np;
-      for (int i = 0; i < d.control_dim; ++i) {
-        lo[uoff[a] + i] = d.input_lower[i];
-        hi[uoff[a] + i] = d.input_upper[i];
-      }
-      for (int sc = 0; sc < S; ++sc) {
-        std::memcpy(&fx0[static_cast<size_t>(sc) * ns + soff[a]], x0[a] + static_cast<size_t>(sc) * d.state_dim, sizeof(double) * d.state_dim);
-        double* dst = &fp[(static_cast<size_t>(sc) * n_agents + a) * kMaxParams];
-        for (int i = 0; i < np; ++i)
-          dst[i] = (model_params && model_params[a]) ? model_params[a][static_cast<size_t>(sc) * np + i]
-                                                     : (d.num_params ? d.params[i] : kModels[d.model_id].default_params[i]);
-        if (d.model_id == MAS_B200_MODEL_PENDULUM && d.num_params == 0 && !(model_params && model_params[a])) dst[0] = static_cast<double>(d.horizon_steps);
-      }
-    }
-    std::vector<double> gX(static_cast<size_t>(S) * (T + 1) * ns), gU(static_cast<size_t>(S) * T * ms), gc(static_cast<size_t>(S) * (1 + n_agents));
-    std::vector<int> gi(static_cast<size_t>(S) * 4);
-    rc = centralized_mixed_entry(&ctx->c, n_agents, mid.data(), T, agent_descs[0].dt, all_bounds ? 1 : 0, lo.data(), hi.data(), *params, S, fx0.data(),
-                                 fp.data(), gX.data(), gU.data(), gc.data(), gi.data(), nullptr);
-    if (rc) return rc;
-    // every agent gets its rows of the stacked result (centralized.hpp:27-36): shapes [scenario][T+1][n_a] / [scenario][T][m_a], T of the first block
-    for (int sc = 0; sc < S; ++sc) {
-      for (int a = 0; a < n_agents; ++a) {
-        const int n = agent_descs[a].state_dim, m = agent_descs[a].control_dim;
-        if (X && X[a])
-          for (int t = 0; t <= T; ++t)
-            std::memcpy(X[a] + (static_cast<size_t>(sc) * (T + 1) + t) * n, &gX[(static_cast<size_t>(sc) * (T + 1) + t) * ns + soff[a]], sizeof(double) * n);
-        if (U && U[a])
-          for (int t = 0; t < T; ++t)
-            std::memcpy(U[a] + (static_cast<size_t>(sc) * T + t) * m, &gU[(static_cast<size_t>(sc) * T + t) * ms + uoff[a]], sizeof(double) * m);
-        if (costs && costs[a]) costs[a][sc] = gc[static_cast<size_t>(sc) * (1 + n_agents) + 1 + a];
-      }
-      if (total_cost) total_cost[sc] = gc[static_cast<size_t>(sc) * (1 + n_agents)];
-      if (trace_iterations && max_outer >= 1) trace_iterations[static_cast<size_t>(sc) * max_outer * n_agents] = gi[static_cast<size_t>(sc) * 4];
-    }
-    return MAS_B200_OK;
-  }
+  if (strategy == MAS_B200_STRATEGY_CENTRALIZED && !same)
+    return run_centralized_general(ctx, agent_descs, params, max_outer, n_scenarios, n_agents, x0, model_params, X, U, costs, total_cost, trace_iterations);
   if (strategy != MAS_B200_STRATEGY_CENTRALIZED && strategy != MAS_B200_STRATEGY_SEQUENTIAL && strategy != MAS_B200_STRATEGY_TRUSTREGION &&
       strategy != MAS_B200_STRATEGY_LINESEARCH)
     return fail(MAS_B200_ERR_INVALID_ARGUMENT, "unknown strategy");

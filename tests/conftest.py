@@ -140,12 +140,13 @@ class HostEmulation:
                     costs=oc[1:].copy(), iterations=int(oi[0]), status=int(oi[1]), reg_retries=int(oi[2]), alpha_trials=int(oi[3]))
 
 
-    def solve_centralized_mixed(self, models, x0_list, max_iterations=100, tolerance=1e-5):
+    def solve_centralized_mixed(self, models, x0_list, max_iterations=100, tolerance=1e-5, horizon=0):
         """mixed_stacked_solve (stacked_mixed.cuh) with tid = 0, nthr = 1: one scenario, agents of different models.
-        x0_list[a]: [n_a].  Horizon / dt of the first agent, bounds only if every agent has them (build_global_ocp)."""
+        x0_list[a]: [n_a].  Horizon / dt of the first agent (horizon > 0 overrides the example's), bounds only if every agent
+        has them (build_global_ocp)."""
         rows = [MODEL_TABLE[m] for m in models]
         A = len(models)
-        T, dt = rows[0][2], rows[0][3]
+        T, dt = horizon or rows[0][2], rows[0][3]
         ns, ms = sum(r[0] for r in rows), sum(r[1] for r in rows)
         hb = int(all(r[5] for r in rows))
         lo = np.concatenate([np.asarray(r[6], dtype=np.float64) for r in rows])

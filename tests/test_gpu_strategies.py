@@ -174,6 +174,23 @@ def test_mixed_agents_centralized(mas, ctx, oracle, models):
     assert np.array_equal(got["trace_iters"][:, 0, 0], ref["iterations_total"][:, 0])
 
 
+def test_centralized_stack_above_256_states(mas, ctx, oracle):
+    """mas_b200_strategy_run(CENTRALIZED) with 65 LQR agents (260 stacked states and controls): stacks too large for the
+    compiled-in kernel of centralized.cuh go to the general solve in HBM (stacked_mixed.cuh) instead of
+    MAS_B200_ERR_UNSUPPORTED.  Horizon 2, one iteration (the oracle needs 0.8 M stacked cost calls per step for the Hessians)."""
+    from conftest import random_x0
+
+    S, A, T = 2, 65, 2
+    x0 = random_x0(2, S * A, seed=77).reshape(S, A, 4)
+    desc = mas.example_desc(2)
+    desc.horizon_steps = T
+    got = mas.strategy_run(ctx, mas.Strategy.CENTRALIZED, desc, mas.IlqrParams.make(1, 1e-5), 1, x0)
+    ref = oracle.strategy_run_batch(0, 2, x0, horizon=T, max_outer=1, max_iterations=1, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    for k in ("X", "U", "costs", "total_cost"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert np.array_equal(got["trace_iters"][:, 0, 0], ref["trace_iters"][:, 0, 0]) and np.abs(got["U"]).max() > 0
+
+
 def test_mixed_agents_stacked_functions(mas, ctx, oracle):
     """mas_b200_global_ocp_eval_mixed on the device: compute_offsets + build_global_ocp of mixed agents, what the reference's
     tests/ocp_tests.cpp:76-154 checks (ids out of order, offsets, bounds only if all agents have them, stacked values)."""

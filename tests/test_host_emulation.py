@@ -266,3 +266,18 @@ def test_centralized_over_mixed_agents_is_bit_identical(emu, oracle, models):
         assert np.array_equal(got["U"][a], ref["U"][a][0]), a
     assert np.array_equal(got["costs"], ref["costs"][0]) and got["total_cost"] == ref["total_cost"][0]
     assert got["iterations"] == ref["iterations_total"][0, 0]
+
+
+def test_centralized_stack_above_256_states(emu, oracle):
+    """65 LQR agents = 260 stacked states and controls: past the size the compiled-in kernel of centralized.cuh is laid out for,
+    so the C ABI sends the stack to the general solve (stacked_mixed.cuh); the same source on the host against the oracle's
+    CentralizedStrategy.  Horizon 2 and one iteration: a finite-difference Hessian of this size is 0.8 M stacked cost calls per step."""
+    from conftest import random_x0
+
+    A, T = 65, 2
+    x0 = random_x0(2, A, seed=77)
+    ref = oracle.strategy_run_batch(0, 2, x0[None], horizon=T, max_outer=1, max_iterations=1, tolerance=1e-5, trig=oracle.TRIG_PORTABLE)
+    got = emu.solve_centralized_mixed([2] * A, list(x0), max_iterations=1, tolerance=1e-5, horizon=T)
+    assert np.array_equal(np.stack(got["X"]), ref["X"][0]) and np.array_equal(np.stack(got["U"]), ref["U"][0])
+    assert np.array_equal(got["costs"], ref["costs"][0]) and got["total_cost"] == ref["total_cost"][0]
+    assert got["iterations"] == ref["trace_iters"][0, 0, 0] == 1 and np.abs(got["U"][0]).max() > 0
