@@ -1246,11 +1246,20 @@ int mas_b200_probe_fp64_peak(mas_b200_context_t ctx, double* tflops) {
   if (!ctx || !tflops) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "bad arguments");
   MAS_CUDA_CHECK(cudaSetDevice(ctx->c.device));
   const int blocks = ctx->c.sm_count * 8, threads = 256, iters = 20000;
-  double* d = nullptr;
-  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d), static_cast<size_t>(blocks) * threads * sizeof(double)));
-  cudaEvent_t e0, e1;
-  MAS_CUDA_CHECK(cudaEventCreate(&e0));
-  MAS_CUDA_CHECK(cudaEventCreate(&e1));
+  struct Scratch {  // freed on every return path
+    double* d = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Scratch() {
+      if (e0) cudaEventDestroy(e0);
+      if (e1) cudaEventDestroy(e1);
+      if (d) cudaFree(d);
+    }
+  } sc;
+  MAS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&sc.d), static_cast<size_t>(blocks) * threads * sizeof(double)));
+  MAS_CUDA_CHECK(cudaEventCreate(&sc.e0));
+  MAS_CUDA_CHECK(cudaEventCreate(&sc.e1));
+  double* d = sc.d;
+  cudaEvent_t e0 = sc.e0, e1 = sc.e1;
   dfma_probe_kernel<<<blocks, threads, 0, ctx->c.stream>>>(d, 1000);
   double best = 0.0;
   for (int rep = 0; rep < 5; ++rep) {
@@ -1264,9 +1273,6 @@ int mas_b200_probe_fp64_peak(mas_b200_context_t ctx, double* tflops) {
     const double tf = flops / (ms * 1e-3) / 1e12;
     if (tf > best) best = tf;
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(d);
   *tflops = best;
   return MAS_B200_OK;
 }
