@@ -1,10 +1,12 @@
 """Generates tests/golden/*.npz.
 
-PROVENANCE: the reference (markomiz/multi_agent_solver) cannot be built or run in this image (it needs
-Eigen 3.4; no network), and its repository holds no golden vectors for iLQR.  These fixtures are therefore
-REGRESSION PINS produced by oracle/ (the CPU restatement of the reference), not reference outputs:
-they freeze today's oracle so that later edits to the oracle or to the shared portable trig cannot drift
-unnoticed, and they let the GPU tests compare against committed numbers.  Both libm modes are stored.
+PROVENANCE: the fixtures are written from oracle/ (the CPU restatement of the reference), and every one of them is an
+output of the reference's OWN code as well: oracle/_ref/libref.so -- /root/reference's unmodified headers and example OCP
+builders compiled against oracle/eigen_shim (the image has no Eigen) -- returns the same bits for the same inputs.
+main() asserts that before it writes anything (where libref.so is available), tests/test_golden.py::
+test_fixtures_are_outputs_of_the_reference_build re-checks the committed files, and tests/test_ref_pin.py holds the
+wider oracle == reference-build comparison.  The reference repository itself holds no golden vectors for iLQR.  Both
+libm modes are stored; only the portable-trig arrays are compared bit for bit across hosts.
 
     python tests/golden/make_golden.py
 """
@@ -27,7 +29,37 @@ def config3_x0(n):
     return mas.synthetic_single_track_x0(n)
 
 
+def check_against_reference_build():
+    """oracle == reference build on the fixtures' inputs (the strongest statement available offline)."""
+    from oracle import ref_py as ref
+
+    if not ref.available():
+        print("oracle/_ref/libref.so not available: fixtures written from the oracle alone")
+        return
+    ref.build()
+    x1 = np.array([[0.0, 1.0, 0.0, 0.0]])
+    x96 = config3_x0(96)
+    for trig in (o.TRIG_GLIBC, o.TRIG_PORTABLE):
+        for x0 in (x1, x96):
+            a = o.ilqr_solve_batch(o.MODEL_ST_LANE, x0, max_iterations=10, tolerance=1e-5, trig=trig)
+            b = ref.ilqr_solve_batch(ref.MODEL_ST_LANE, x0, max_iterations=10, tolerance=1e-5, trig=trig)
+            assert all(np.array_equal(a[k], b[k]) for k in ("X", "U", "cost", "iterations", "status", "alpha_trials"))
+    th = 2.0 * np.pi * np.arange(3) / 3
+    cases = [(o.STRATEGY_TRUSTREGION, o.MODEL_ST_CIRC, np.stack([20 * np.cos(th), 20 * np.sin(th), 1.57 + th, np.full(3, 4.0)], -1)[None], 10),
+             (o.STRATEGY_SEQUENTIAL, o.MODEL_LQR, np.tile([1.0, 0.0, 0.0, 0.0], (1, 4, 1)), 10)]
+    for A in (4, 32):
+        th = 2.0 * np.pi * np.arange(A) / A
+        cases.append((o.STRATEGY_CENTRALIZED, o.MODEL_ST_CIRC, np.stack([20 * np.cos(th), 20 * np.sin(th), 1.57 + th, np.full(A, 4.0)], -1)[None], 1))
+    for kind, model, x0, outer in cases:
+        a = o.strategy_run_batch(kind, model, x0, max_outer=outer, max_iterations=100, tolerance=1e-5, trig=o.TRIG_PORTABLE)
+        b = ref.strategy_run_batch(kind, model, x0, max_outer=outer, max_iterations=100, tolerance=1e-5, trig=ref.TRIG_PORTABLE)
+        assert all(np.array_equal(a[k], b[k]) for k in ("X", "U", "costs", "total_cost"))
+        assert np.array_equal(a["trace_iters"].sum(1), b["iterations_total"])
+    print("oracle == reference build (oracle/_ref/libref.so) on every fixture input")
+
+
 def main():
+    check_against_reference_build()
     out = {}
     # config 1: single_track_ocp
     for trig, tag in ((o.TRIG_GLIBC, "glibc"), (o.TRIG_PORTABLE, "portable")):

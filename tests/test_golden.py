@@ -1,7 +1,7 @@
-"""The oracle against the committed fixtures in tests/golden/ (regression pins generated by
-tests/golden/make_golden.py from the oracle itself -- see that file for why they are not reference
-outputs).  The portable-trig fixtures must reproduce bit for bit; the glibc ones to 1e-9 / 1e-7 on the
-problems that are not ill-conditioned (libm may differ between hosts in the last bit).
+"""The committed fixtures in tests/golden/ (tests/golden/make_golden.py) against the oracle, against a build of the
+reference's own sources (oracle/_ref/libref.so: test_fixtures_are_outputs_of_the_reference_build) and, in the gpu tests,
+against the CUDA path with no checker involved at run time.  The portable-trig fixtures must reproduce bit for bit; the
+glibc ones to 1e-9 / 1e-7 on the problems that are not ill-conditioned (libm may differ between hosts in the last bit).
 """
 import os
 
@@ -63,6 +63,49 @@ def test_config5_centralized_small(oracle):
     for k in ("X", "U", "costs", "total_cost"):
         assert np.array_equal(r[k], g[k]), k
     assert r["trace_iters"][0, 0, 0] == g["iterations"][0]
+
+
+def test_fixtures_are_outputs_of_the_reference_build():
+    """Every portable-trig fixture equals, bit for bit, what the reference's OWN code returns for the fixture's inputs
+    (oracle/_ref/libref.so: /root/reference's unmodified headers and example OCP builders on oracle/eigen_shim).  The
+    32-agent config-5 fixture is covered by tests/test_ref_pin.py::test_config5_centralized_32_agents (same inputs)."""
+    from oracle import ref_py as ref
+
+    if not ref.available():
+        pytest.skip("oracle/_ref/libref.so absent and no reference sources to build it from")
+    ref.build()
+    g = load("config1_single_track.npz")
+    for trig, tag in ((ref.TRIG_GLIBC, "glibc"), (ref.TRIG_PORTABLE, "portable")):
+        r = ref.ilqr_solve_batch(ref.MODEL_ST_LANE, np.array([[0.0, 1.0, 0.0, 0.0]]), max_iterations=10, tolerance=1e-5, trig=trig)
+        if trig == ref.TRIG_PORTABLE:
+            for k in ("X", "U", "cost", "iterations", "status"):
+                assert np.array_equal(r[k], g[f"config1_{tag}_{k}"]), k
+        else:  # the host's libm may differ from the generating host's in the last bit
+            assert abs(r["cost"][0] - g["config1_glibc_cost"][0]) <= 1e-9 * abs(g["config1_glibc_cost"][0])
+    g = load("config3_first96.npz")
+    assert np.array_equal(ref.synthetic_single_track_x0(96), g["x0"])
+    r = ref.ilqr_solve_batch(ref.MODEL_ST_LANE, g["x0"], max_iterations=10, tolerance=1e-5, trig=ref.TRIG_PORTABLE)
+    for k in ("cost", "iterations", "status", "alpha_trials"):
+        assert np.array_equal(r[k], g[f"portable_{k}"]), k
+    assert np.array_equal(r["U"][:, 0, :], g["portable_U_final_step0"]) and np.array_equal(r["X"][:, -1, :], g["portable_X_terminal"])
+    g = load("config2_trust_region_3agents.npz")
+    r = ref.strategy_run_batch(ref.STRATEGY_TRUSTREGION, ref.MODEL_ST_CIRC, g["x0"], max_outer=10, max_iterations=100, tolerance=1e-5,
+                               trig=ref.TRIG_PORTABLE)
+    for k in ("X", "U", "costs", "total_cost"):
+        assert np.array_equal(r[k], g[f"portable_{k}"]), k
+    assert np.array_equal(r["iterations_total"], g["portable_trace_iters"].sum(1))
+    g = load("config4_sequential_lqr.npz")
+    r = ref.strategy_run_batch(ref.STRATEGY_SEQUENTIAL, ref.MODEL_LQR, g["x0"], max_outer=10, max_iterations=100, tolerance=1e-5,
+                               trig=ref.TRIG_PORTABLE)
+    for k in ("X", "U", "costs", "total_cost"):
+        assert np.array_equal(r[k], g[k]), k
+    assert np.array_equal(r["iterations_total"], g["trace_iters"].sum(1))
+    g = load("config5_centralized_4agents.npz")
+    r = ref.strategy_run_batch(ref.STRATEGY_CENTRALIZED, ref.MODEL_ST_CIRC, g["x0"], max_outer=1, max_iterations=100, tolerance=1e-5,
+                               trig=ref.TRIG_PORTABLE)
+    for k in ("X", "U", "costs", "total_cost"):
+        assert np.array_equal(r[k], g[k]), k
+    assert r["iterations_total"][0, 0] == g["iterations"][0]
 
 
 def test_config5_centralized_32_agents_device_source(emu):
