@@ -1,4 +1,5 @@
-// ORACLE -- TEST INFRASTRUCTURE ONLY (see dense.hpp header).  PARITY UNPINNED (see dense.hpp).
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see dense.hpp header).  Pinned bit for bit to a build of the reference's own sources
+// (oracle/_ref, tests/test_ref_pin.py; see dense.hpp).
 //
 // oracle_capi.cpp: plain-C entry points over the restated reference so tests/ and bench.py's
 // cpu_baseline leg can drive it through ctypes.  The batch loops are

@@ -1,7 +1,8 @@
 """ORACLE -- TEST INFRASTRUCTURE ONLY.  ctypes front-end to oracle/_build/liboracle.so.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
-PARITY UNPINNED: see oracle/dense.hpp.
+Parity pin: oracle == oracle/_ref/libref.so (the reference's own sources) bit for bit, tests/test_ref_pin.py;
+see oracle/dense.hpp.
 """
 from __future__ import annotations
 

@@ -1,4 +1,5 @@
-// ORACLE -- TEST INFRASTRUCTURE ONLY (see dense.hpp header).  PARITY UNPINNED (see dense.hpp).
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see dense.hpp header).  Pinned bit for bit to a build of the reference's own sources
+// (oracle/_ref, tests/test_ref_pin.py; see dense.hpp).
 //
 // ref_core.hpp: CPU restatement of the reference's problem model and numerical kernels, in the
 // reference's own shape (std::function callbacks over dynamically sized vectors):

@@ -1,4 +1,5 @@
-// ORACLE -- TEST INFRASTRUCTURE ONLY (see dense.hpp header).  PARITY UNPINNED (see dense.hpp).
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see dense.hpp header).  Pinned bit for bit to a build of the reference's own sources
+// (oracle/_ref, tests/test_ref_pin.py; see dense.hpp).
 //
 // ref_ilqr.hpp: CPU restatement of the reference's augmented-Lagrangian iLQR,
 // include/multi_agent_solver/solvers/ilqr.hpp:26-55 (params), :59-273 (solve), :278-377 (buffers),

@@ -1,4 +1,5 @@
-// ORACLE -- TEST INFRASTRUCTURE ONLY (see dense.hpp header).  PARITY UNPINNED (see dense.hpp).
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see dense.hpp header).  Pinned bit for bit to a build of the reference's own sources
+// (oracle/_ref, tests/test_ref_pin.py; see dense.hpp).
 //
 // ref_models.hpp: the reference's example dynamics and OCP definitions, restated:
 //   examples/models/single_track_model.hpp:23-82, pendulum_model.hpp:8-44, rocket_model.hpp:13-76

@@ -1,4 +1,5 @@
-// ORACLE -- TEST INFRASTRUCTURE ONLY (see dense.hpp header).  PARITY UNPINNED (see dense.hpp).
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see dense.hpp header).  Pinned bit for bit to a build of the reference's own sources
+// (oracle/_ref, tests/test_ref_pin.py; see dense.hpp).
 //
 // ref_multi_agent.hpp: CPU restatement of the reference's multi-agent layer as far as the iLQR
 // path uses it:

@@ -1,7 +1,7 @@
-"""The oracle (oracle/, CPU restatement of the reference) against every known answer available for this
-path.  PARITY UNPINNED: the reference cannot be executed here (needs Eigen 3.4) and its own tests never
-call iLQR, so the pins are: closed-form anchors, the reference's unit-test values for the layers under
-iLQR (oracle_selftest), and the SURVEY section 9 probe values (an independent numpy restatement).
+"""The oracle (oracle/, CPU restatement of the reference) against the known answers that do not need the reference
+build: closed-form anchors, the reference's unit-test values for the layers under iLQR (oracle_selftest.cpp follows
+tests/ocp_tests.cpp:21-154), and the SURVEY section 9 probe values (an independent numpy restatement).  The pin to the
+reference's own executed code is tests/test_ref_pin.py (oracle == oracle/_ref/libref.so bit for bit).
 """
 import os
 import subprocess
