@@ -30,6 +30,14 @@ static const ModelInfo kModels[MAS_B200_NUM_MODELS] = {
      make_batch_st_lane_con},
 };
 
+// The parameter block a description stands for: its own params, or the model's example defaults when it carries none
+// (the pendulum's first parameter is its horizon: pendulum_swing_up.cpp:62-98 weights the stage cost by t / T).
+static void effective_params(const mas_b200_ocp_desc& d, double* out) {
+  const ModelInfo& m = kModels[d.model_id];
+  for (int i = 0; i < m.np; ++i) out[i] = d.num_params ? d.params[i] : m.default_params[i];
+  if (d.model_id == MAS_B200_MODEL_PENDULUM && d.num_params == 0) out[0] = static_cast<double>(d.horizon_steps);
+}
+
 static int fail(int code, const std::string& msg) {
   set_last_error(msg);
   return code;
@@ -318,9 +326,8 @@ int mas_b200_batch_create(mas_b200_context_t ctx, const mas_b200_ocp_desc* desc,
   b->ctx = &ctx->c;
   b->desc = *desc;
   if (desc->num_params == 0) {
+    effective_params(*desc, b->desc.params);
     b->desc.num_params = m.np;
-    for (int i = 0; i < m.np; ++i) b->desc.params[i] = m.default_params[i];
-    if (desc->model_id == MAS_B200_MODEL_PENDULUM) b->desc.params[0] = static_cast<double>(desc->horizon_steps);
   }
   b->batch = batch;
   b->nx = m.nx;
@@ -604,10 +611,10 @@ static int run_centralized_general(mas_b200_context_t ctx, const mas_b200_ocp_de
     for (int sc = 0; sc < S; ++sc) {
       std::memcpy(&fx0[static_cast<size_t>(sc) * ns + soff[a]], x0[a] + static_cast<size_t>(sc) * d.state_dim, sizeof(double) * d.state_dim);
       double* dst = &fp[(static_cast<size_t>(sc) * n_agents + a) * kMaxParams];
-      for (int i = 0; i < np; ++i)
-        dst[i] = (model_params && model_params[a]) ? model_params[a][static_cast<size_t>(sc) * np + i]
-                                                   : (d.num_params ? d.params[i] : kModels[d.model_id].default_params[i]);
-      if (d.model_id == MAS_B200_MODEL_PENDULUM && d.num_params == 0 && !(model_params && model_params[a])) dst[0] = static_cast<double>(d.horizon_steps);
+      if (model_params && model_params[a])
+        for (int i = 0; i < np; ++i) dst[i] = model_params[a][static_cast<size_t>(sc) * np + i];
+      else
+        effective_params(d, dst);
     }
   }
   std::vector<double> gX(static_cast<size_t>(S) * (T + 1) * ns), gU(static_cast<size_t>(S) * T * ms), gc(static_cast<size_t>(S) * (1 + n_agents));
@@ -682,9 +689,8 @@ int mas_b200_strategy_run(mas_b200_context_t ctx, int strategy, const mas_b200_o
     if (!fn) return fail(MAS_B200_ERR_INVALID_ARGUMENT, "unknown model_id");
     mas_b200_ocp_desc d = *agent_desc;
     if (d.num_params == 0) {
+      effective_params(*agent_desc, d.params);
       d.num_params = kModels[d.model_id].np;
-      for (int i = 0; i < d.num_params; ++i) d.params[i] = kModels[d.model_id].default_params[i];
-      if (d.model_id == MAS_B200_MODEL_PENDULUM) d.params[0] = static_cast<double>(d.horizon_steps);
     }
     std::vector<int> its(n_scenarios);
     rc = fn(&ctx->c, d, *params, n_scenarios, n_agents, x0, model_params, U_init, X, U, costs, total_cost, its.data(), nullptr, nullptr);
@@ -921,8 +927,12 @@ int mas_b200_strategy_run_mixed(mas_b200_context_t ctx, int strategy, const mas_
       for (int a = 0; a < n_agents; ++a) {
         const size_t idx = static_cast<size_t>(sc) * n_agents + a;
         std::memcpy(&fx0[idx * n], x0[a] + static_cast<size_t>(sc) * n, sizeof(double) * n);
-        if (any_p)
-          for (int i = 0; i < np; ++i) fp[idx * np + i] = (model_params[a]) ? model_params[a][static_cast<size_t>(sc) * np + i] : (d.num_params ? d.params[i] : kModels[d.model_id].default_params[i]);
+        if (any_p) {
+          if (model_params[a])
+            for (int i = 0; i < np; ++i) fp[idx * np + i] = model_params[a][static_cast<size_t>(sc) * np + i];
+          else
+            effective_params(d, &fp[idx * np]);
+        }
         if (any_u && U_init[a]) std::memcpy(&fU0[idx * m * T], U_init[a] + static_cast<size_t>(sc) * m * T, sizeof(double) * m * T);
       }
     rc = mas_b200_strategy_run(ctx, strategy, &d, params, max_outer, S, n_agents, fx0.data(), any_p ? fp.data() : nullptr, any_u ? fU0.data() : nullptr,
@@ -1137,8 +1147,7 @@ int mas_b200_global_ocp_eval_mixed(mas_b200_context_t ctx, const mas_b200_ocp_de
     sx += d.state_dim;
     su += d.control_dim;
     all_bounds = all_bounds && d.has_input_bounds;  // bounds only when ALL agents have both (:76-92)
-    for (int i = 0; i < kModels[d.model_id].np; ++i) prm[static_cast<size_t>(k) * kMaxParams + i] = d.num_params ? d.params[i] : kModels[d.model_id].default_params[i];
-    if (d.model_id == MAS_B200_MODEL_PENDULUM && d.num_params == 0) prm[static_cast<size_t>(k) * kMaxParams] = static_cast<double>(d.horizon_steps);
+    effective_params(d, &prm[static_cast<size_t>(k) * kMaxParams]);
     if (block_agent) block_agent[k] = order[k];
     if (state_offsets) state_offsets[k] = soff[k];
     if (control_offsets) control_offsets[k] = uoff[k];
