@@ -100,3 +100,22 @@ def test_mixed_agent_structure_without_a_device(mas):
     assert got["has_bounds"] and list(got["bounds"][0]) == [-5.0, 0.0] and list(got["bounds"][1]) == [5.0, 20.0]
     got = mas.global_ocp_eval_mixed(None, [rocket, pend, lqr], agent_ids=[2, 1, 0])
     assert not got["has_bounds"] and got["total_x"] == 9 and got["horizon"] == lqr.horizon_steps  # LQR has no bounds and is block 0
+
+
+def test_cpp_facade_host_behaviour(mas):
+    """include/mas_b200/mas_b200.hpp without a device (tests/csrc/facade_host_test.cpp): set_params' std::out_of_range on a
+    missing key (ilqr.hpp:42-44), the name registries' std::invalid_argument (example_utils.hpp:32-110), column-major
+    Matrix, verify_problem, the OCP description handed to the C ABI, compute_offsets on out-of-order ids the way the
+    reference's tests/ocp_tests.cpp:76-154 checks it, and -- here, where there is no GPU -- std::runtime_error from the
+    first call that needs the device (no host implementation behind the facade)."""
+    import subprocess
+
+    src = os.path.join(ROOT, "tests", "csrc", "facade_host_test.cpp")
+    out_dir = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, "facade_host_test")
+    lib_dir = os.path.join(ROOT, "multi_agent_solver_b200")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"), src, "-o", exe, "-L" + lib_dir,
+                           "-lmas_b200", "-Wl,-rpath," + lib_dir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout + out.stderr
