@@ -97,7 +97,7 @@ void print_block(const mb::Matrix& m, double dt, const std::string& label, const
 
 void usage(const std::string& prog, bool multi) {
   if (multi) std::cout << "Usage: " << prog << " [--agents N] [--solver NAME] [--strategy NAME] [--max-outer N]\n       " << prog << " N\n\n";
-  else std::cout << "Usage: " << prog << " [--solver NAME]\n\n";
+  else std::cout << "Usage: " << prog << " [--solver NAME]" << (prog == "rocket_max_altitude" ? " [--dump]" : "") << "\n\n";  // rocket_max_altitude.cpp:141
   std::cout << "Available solvers: ilqr\nAvailable strategies: centralized, sequential, linesearch, trustregion\n";
 }
 
@@ -217,7 +217,8 @@ int main(int argc, char** argv) {
     }
     return multi ? run_multi(prog, o) : run_single(prog, o);
   } catch (const std::exception& e) {
-    std::cerr << "Error: " << e.what() << "\nUse --help to see available options.\n";
+    std::cerr << "Error: " << e.what() << '\n';
+    if (prog != "rocket_max_altitude") std::cerr << "Use --help to see available options.\n";  // rocket_max_altitude.cpp:192-196 prints no hint
     return 1;
   }
 }
