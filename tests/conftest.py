@@ -47,11 +47,20 @@ _EMU_LIB = os.path.join(ROOT, "tests", "_build", "libhost_emulation.so")
 
 
 def _build_emulation() -> str:
+    # MAS_B200_EMU_SANITIZE=1: the same source with -fsanitize=address,undefined into a second library (run the emulation
+    # tests with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0): index errors of the device
+    # code that would be silent on the GPU; tools/README.md
+    if os.environ.get("MAS_B200_EMU_SANITIZE") == "1":
+        return _build_emulation_variant(_EMU_LIB.replace(".so", "_asan.so"), ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"])
+    return _build_emulation_variant(_EMU_LIB, ["-O2"])
+
+
+def _build_emulation_variant(_EMU_LIB: str, opt) -> str:
     deps = [_EMU_SRC] + [os.path.join(ROOT, "multi_agent_solver_b200", "csrc", f) for f in ("ilqr_core.cuh", "models.cuh", "centralized.cuh", "stacked_mixed.cuh")]
     deps.append(os.path.join(ROOT, "include", "mas_b200", "portable_math.h"))
     if not os.path.exists(_EMU_LIB) or os.path.getmtime(_EMU_LIB) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(_EMU_LIB), exist_ok=True)
-        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-x", "c++",
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", *opt, "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-x", "c++",
                                "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "multi_agent_solver_b200", "csrc"), _EMU_SRC,
                                "-o", _EMU_LIB])
     return _EMU_LIB
