@@ -24,8 +24,12 @@
 
 namespace mas_b200 {
 
+// Host builds run a solve with one thread (barriers are nothing), or -- tests/csrc/*_threads_test.cpp, the race check under
+// ThreadSanitizer -- with host threads as the threads of a CTA and MAS_HOST_THREADS_SYNC(id, count, all) as their barrier.
 #if defined(__CUDA_ARCH__)
 #define MAS_CTA_SYNC() __syncthreads()
+#elif defined(MAS_HOST_THREADS_SYNC)
+#define MAS_CTA_SYNC() MAS_HOST_THREADS_SYNC(0, 0, 0)
 #else
 #define MAS_CTA_SYNC() ((void)0)
 #endif
@@ -197,11 +201,14 @@ __device__ void dmma_product(const DmmaTerm (&term)[NT], int rows, int cols, int
 #endif
 
 // Barrier over a warp-aligned group of `count` threads of the CTA (named barrier `id`, 1..15); the whole CTA when
-// count == all.  Sequential host emulation: nothing.
+// count == all.  Sequential host emulation: nothing; threaded host test: its barrier hook.
 MAS_HD void stacked_group_sync(int id, int count, int all) {
 #if defined(__CUDA_ARCH__)
   if (count == all) __syncthreads();
   else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#elif defined(MAS_HOST_THREADS_SYNC)
+  if (count == all) MAS_HOST_THREADS_SYNC(0, 0, 0);
+  else MAS_HOST_THREADS_SYNC(id, count, all);
 #else
   (void)id;
   (void)count;

@@ -281,3 +281,52 @@ def test_centralized_stack_above_256_states(emu, oracle):
     assert np.array_equal(np.stack(got["X"]), ref["X"][0]) and np.array_equal(np.stack(got["U"]), ref["U"][0])
     assert np.array_equal(got["costs"], ref["costs"][0]) and got["total_cost"] == ref["total_cost"][0]
     assert got["iterations"] == ref["trace_iters"][0, 0, 0] == 1 and np.abs(got["U"][0]).max() > 0
+
+
+def _race_check(source, exe_name, args, drop_var, drop_ks):
+    """Builds tests/csrc/<source> with -fsanitize=thread, runs it clean (no report, results identical to one thread), then with
+    single barriers dropped: the sanitizer / the comparison has to catch those."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out_dir = os.path.join(root, "tests", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, exe_name)
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-mfma", "-fsanitize=thread", "-w",
+                           "-I" + os.path.join(root, "include"), "-I" + os.path.join(root, "multi_agent_solver_b200", "csrc"), "-x", "c++",
+                           os.path.join(root, "tests", "csrc", source), "-o", exe, "-lpthread"])
+    env = dict(os.environ)
+    env.pop(drop_var, None)
+    env.pop("LD_PRELOAD", None)
+    clean = subprocess.run([exe, *args], capture_output=True, text=True, timeout=900, env=env)
+    if "FATAL: ThreadSanitizer" in clean.stderr:  # e.g. an address-space layout the runtime cannot map
+        pytest.skip("ThreadSanitizer cannot run here: " + clean.stderr.strip().splitlines()[0])
+    assert clean.returncode == 0 and "ALL OK" in clean.stdout and "ThreadSanitizer" not in clean.stderr, clean.stdout + clean.stderr
+    caught = 0
+    for k in drop_ks:
+        env[drop_var] = str(k)
+        mutant = subprocess.run([exe, *args], capture_output=True, text=True, timeout=900, env=env)
+        caught += int(mutant.returncode != 0 and ("WARNING: ThreadSanitizer: data race" in mutant.stderr or "DIFFERS" in mutant.stdout))
+    assert caught >= len(drop_ks) - 1, caught
+    return clean.stdout
+
+
+def test_mixed_stacked_solve_has_no_races_between_barriers():
+    """stacked_mixed.cuh with real threads as the threads of a CTA (tests/csrc/mixed_threads_test.cpp): MAS_CTA_SYNC() becomes a
+    pthread barrier, 2 / 5 / 8 threads run the same source under ThreadSanitizer on four agent mixes.  No report = every pair of
+    conflicting accesses to the workspace and the result arrays is ordered by a barrier (what __syncthreads() must do on the
+    GPU), and the results equal the one-thread run bit for bit.  The harness is checked on itself: with one barrier dropped
+    (MIXED_DROP_BARRIER=k) the sanitizer has to report the race (152 of the first 160 barriers are caught when dropped; the
+    rest are redundant ones, e.g. two barriers in a row)."""
+    _race_check("mixed_threads_test.cpp", "mixed_threads_tsan", [], "MIXED_DROP_BARRIER", (40, 75, 100, 130))
+
+
+def test_centralized_kernel_has_no_races_between_barriers():
+    """centralized.cuh (config 5's kernel) the same way (tests/csrc/centralized_threads_test.cpp): 7 / 32 / 128 / 160 host threads;
+    from 128 threads on the Q_uu factorisation (threads 0-63, named barrier 1) runs beside the next step's finite differences
+    (the other threads, named barrier 2) exactly as in the CUDA kernel, the named barriers mapped to pthread barriers whose
+    participant counts are checked.  4 stacked circular-track agents, 10 steps, 4 iterations with 18 regularisation retries.
+    Dropped CTA barriers are caught 26 times out of 30 sampled."""
+    out = _race_check("centralized_threads_test.cpp", "centralized_threads_tsan", ["4", "10", "4"], "CENTRALIZED_DROP_BARRIER", (41, 65, 89, 113))
+    assert "retries 18" in out and out.count("identical to one thread") == 4
