@@ -330,3 +330,13 @@ def test_centralized_kernel_has_no_races_between_barriers():
     Dropped CTA barriers are caught 26 times out of 30 sampled."""
     out = _race_check("centralized_threads_test.cpp", "centralized_threads_tsan", ["4", "10", "4"], "CENTRALIZED_DROP_BARRIER", (41, 65, 89, 113))
     assert "retries 18" in out and out.count("identical to one thread") == 4
+
+
+def test_lane_cooperative_backward_passes_have_no_races():
+    """RiccatiLanes (the column-parallel Riccati sweep of small active sets: four lanes per problem exchanging columns through
+    shared memory, a __syncwarp() between phases a..e) and backward_lanes (eight lanes dealing out the finite-difference
+    stencil points) with one host thread per lane and pthread barriers placed as in riccati_sweep_lanes_kernel /
+    backward_lanes_kernel, under ThreadSanitizer (tests/csrc/lanes_threads_test.cpp): no report, gains bit-equal to the
+    one-thread sweep.  Every one of the first 60 barriers is caught when dropped."""
+    out = _race_check("lanes_threads_test.cpp", "lanes_threads_tsan", [], "LANES_DROP_BARRIER", (2, 9, 23, 41))
+    assert out.count("identical to the one-thread sweep") == 6
